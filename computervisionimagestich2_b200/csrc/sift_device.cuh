@@ -1,0 +1,335 @@
+// sift_device.cuh -- per-item bodies of the SIFT kernels (detector, refinement, gradient, orientation, descriptor).
+//
+// Each body is the work of ONE logical item (a pixel, a candidate extremum, a keypoint, a descriptor job) written
+// as a __host__ __device__ function, so that the very same arithmetic can be exercised on a CPU-only box by the
+// test-only emulator in tests/emul.  The CUDA kernels in sift_kernels.cu map items onto threads and call these.
+//
+// Reference semantics restated here (file:line relative to the reference tree):
+//   blur taps + column convolution ... vl/sift.c:116-159, vl/imopv.c:118-201
+//   DoG + 26-neighbour extrema ....... vl/sift.c:521-603
+//   3-D quadratic refinement ......... vl/sift.c:610-772
+//   gradient (mod, angle) map ........ vl/sift.c:792-876
+//   orientation histogram ............ vl/sift.c:904-1037
+//   4x4x8 descriptor ................. vl/sift.c:1268-1438
+#pragma once
+#include "exact_math.cuh"
+
+namespace pb {
+
+// One octave of the Gaussian scale space resident in HBM.  Rows are `pitch` floats apart (pitch % 32 == 0 so
+// that every row starts on a 128-byte line); level l (= s - s_min) starts at gss + l * pitch * h.
+// grad holds interleaved (modulus, angle) pairs for the detection levels s = s_min+1 .. s_max-2:
+// grad[((l * h + y) * pitch + x) * 2 + {0,1}].
+struct OctaveView {
+    int w, h, pitch;
+    int nlevels;  // s_max - s_min + 1
+    const float* gss;
+    const float* grad;
+};
+
+struct SiftConsts {
+    int s_min, s_max, S;
+    double peak_thresh, edge_thresh, norm_thresh, magnif, window_size;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// separable blur, one output sample (vl/imopv.c:137-198 with VL_PAD_BY_CONTINUITY): taps are applied in
+// increasing source index, the j-th source sample (p = centre - W + j, clamped) meets filt[2W - j].
+// ---------------------------------------------------------------------------------------------------------
+PB_HD float blur_sample(const float* __restrict__ line, int stride, int n, int centre, const float* __restrict__ filt,
+                        int W) {
+    float acc = 0.0f;
+    for (int j = 0; j <= 2 * W; ++j) {
+        int p = centre - W + j;
+        p = p < 0 ? 0 : (p > n - 1 ? n - 1 : p);
+        acc = acc + line[(long)p * stride] * filt[2 * W - j];
+    }
+    return acc;
+}
+
+// DoG value on the fly: dog[l](x,y) = gss[l+1](x,y) - gss[l](x,y)   (vl/sift.c:521-530)
+PB_HD float dog_at(const OctaveView& ov, int x, int y, int l) {
+    const long ls = (long)ov.pitch * ov.h;
+    const long o = (long)y * ov.pitch + x;
+    return ov.gss[(l + 1) * ls + o] - ov.gss[l * ls + o];
+}
+
+// 26-neighbour strict extremum test at interior pixel (x, y) of DoG level l (1 <= l <= nlevels-3).
+// vl/sift.c:536-577 (CHECK_NEIGHBORS); tp = peak threshold.
+PB_HD bool is_extremum(const OctaveView& ov, int x, int y, int l, double tp) {
+    const float v = dog_at(ov, x, y, l);
+    bool gt = ((double)v >= 0.8 * tp), lt = ((double)v <= -0.8 * tp);
+    if (!gt && !lt) return false;
+    for (int dl = -1; dl <= 1 && (gt || lt); ++dl)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dl == 0 && dy == 0 && dx == 0) continue;
+                const float n = dog_at(ov, x + dx, y + dy, l + dl);
+                gt = gt && (v > n);
+                lt = lt && (v < n);
+            }
+    return gt || lt;
+}
+
+struct RefinedKey {
+    int ix0, iy0, is0;  // the candidate as detected (raster order key)
+    int good;
+    int ix, iy, is;     // after the <=5 moves
+    float x, y, s;      // k->x, k->y, k->s   (sigma is finished on the host: it needs pow())
+    double sn;          // s + b[2] in double, input of sigma0 * pow(2, sn / S) * xper
+};
+
+// vl/sift.c:610-772.  (x, y, s) is the detected extremum, s in reference units (s_min+1 .. s_max-2).
+PB_HD RefinedKey refine_key(const OctaveView& ov, const SiftConsts& sc, int x, int y, int s, double xper) {
+    RefinedKey out;
+    out.ix0 = x; out.iy0 = y; out.is0 = s;
+    const int w = ov.w, h = ov.h;
+    const int l = s - sc.s_min;
+    double Dx = 0, Dy = 0, Ds = 0, Dxx = 0, Dyy = 0, Dss = 0, Dxy = 0, Dxs = 0, Dys = 0;
+    double A[9], b[3];
+    b[0] = b[1] = b[2] = 0;
+    int dx = 0, dy = 0;
+#define PB_AT(ddx, ddy, dds) dog_at(ov, x + (ddx), y + (ddy), l + (dds))
+#define PB_A(i, j) (A[(i) + (j)*3])
+    for (int iter = 0; iter < 5; ++iter) {
+        x += dx;
+        y += dy;
+        // float differences first (the reference subtracts/adds floats, then widens)
+        Dx = 0.5 * (double)(PB_AT(+1, 0, 0) - PB_AT(-1, 0, 0));
+        Dy = 0.5 * (double)(PB_AT(0, +1, 0) - PB_AT(0, -1, 0));
+        Ds = 0.5 * (double)(PB_AT(0, 0, +1) - PB_AT(0, 0, -1));
+        const double c2 = 2.0 * (double)PB_AT(0, 0, 0);
+        Dxx = ((double)(PB_AT(+1, 0, 0) + PB_AT(-1, 0, 0)) - c2);
+        Dyy = ((double)(PB_AT(0, +1, 0) + PB_AT(0, -1, 0)) - c2);
+        Dss = ((double)(PB_AT(0, 0, +1) + PB_AT(0, 0, -1)) - c2);
+        Dxy = 0.25 * (double)(PB_AT(+1, +1, 0) + PB_AT(-1, -1, 0) - PB_AT(-1, +1, 0) - PB_AT(+1, -1, 0));
+        Dxs = 0.25 * (double)(PB_AT(+1, 0, +1) + PB_AT(-1, 0, -1) - PB_AT(-1, 0, +1) - PB_AT(+1, 0, -1));
+        Dys = 0.25 * (double)(PB_AT(0, +1, +1) + PB_AT(0, -1, -1) - PB_AT(0, -1, +1) - PB_AT(0, +1, -1));
+
+        PB_A(0, 0) = Dxx; PB_A(1, 1) = Dyy; PB_A(2, 2) = Dss;
+        PB_A(0, 1) = PB_A(1, 0) = Dxy;
+        PB_A(0, 2) = PB_A(2, 0) = Dxs;
+        PB_A(1, 2) = PB_A(2, 1) = Dys;
+        b[0] = -Dx; b[1] = -Dy; b[2] = -Ds;
+
+        // Gauss elimination with maximal-magnitude pivot (vl/sift.c:661-712)
+        bool singular = false;
+        for (int j = 0; j < 3; ++j) {
+            double maxa = 0, maxabsa = 0;
+            int maxi = -1;
+            for (int i = j; i < 3; ++i) {
+                double a = PB_A(i, j);
+                double absa = abs_d(a);
+                if (absa > maxabsa) { maxa = a; maxabsa = absa; maxi = i; }
+            }
+            if (maxabsa < (double)1e-10f) {
+                b[0] = 0; b[1] = 0; b[2] = 0;
+                singular = true;
+                break;
+            }
+            const int i = maxi;
+            for (int jj = j; jj < 3; ++jj) {
+                double tmp = PB_A(i, jj); PB_A(i, jj) = PB_A(j, jj); PB_A(j, jj) = tmp;
+                PB_A(j, jj) /= maxa;
+            }
+            double tmp = b[j]; b[j] = b[i]; b[i] = tmp;
+            b[j] /= maxa;
+            for (int ii = j + 1; ii < 3; ++ii) {
+                double xx = PB_A(ii, j);
+                for (int jj = j; jj < 3; ++jj) PB_A(ii, jj) -= xx * PB_A(j, jj);
+                b[ii] -= xx * b[j];
+            }
+        }
+        (void)singular;
+        // backward substitution (runs after a singular break as well, on b = 0: harmless, as in the reference)
+        for (int i = 2; i > 0; --i) {
+            double xx = b[i];
+            for (int ii = i - 1; ii >= 0; --ii) b[ii] -= xx * PB_A(ii, i);
+        }
+        dx = ((b[0] > 0.6 && x < w - 2) ? 1 : 0) + ((b[0] < -0.6 && x > 1) ? -1 : 0);
+        dy = ((b[1] > 0.6 && y < h - 2) ? 1 : 0) + ((b[1] < -0.6 && y > 1) ? -1 : 0);
+        if (dx == 0 && dy == 0) break;
+    }
+    {
+        const double te = sc.edge_thresh, tp = sc.peak_thresh;
+        double val = (double)PB_AT(0, 0, 0) + 0.5 * (Dx * b[0] + Dy * b[1] + Ds * b[2]);
+        double score = (Dxx + Dyy) * (Dxx + Dyy) / (Dxx * Dyy - Dxy * Dxy);
+        double xn = x + b[0];
+        double yn = y + b[1];
+        double sn = s + b[2];
+        bool good = abs_d(val) > tp && score < (te + 1) * (te + 1) / te && score >= 0 && abs_d(b[0]) < 1.5 &&
+                    abs_d(b[1]) < 1.5 && abs_d(b[2]) < 1.5 && xn >= 0 && xn <= w - 1 && yn >= 0 && yn <= h - 1 &&
+                    sn >= sc.s_min && sn <= sc.s_max;
+        out.good = good ? 1 : 0;
+        out.ix = x; out.iy = y; out.is = s;
+        out.s = (float)sn;
+        out.x = (float)(xn * xper);
+        out.y = (float)(yn * xper);
+        out.sn = sn;
+    }
+#undef PB_AT
+#undef PB_A
+    return out;
+}
+
+// vl/sift.c:792-876: gradient modulus and angle of GSS level l at (x, y); one-sided differences on the border.
+PB_HD void gradient_at(const float* __restrict__ lev, int w, int h, int pitch, int x, int y, float* mod, float* ang) {
+    const float* p = lev + (long)y * pitch + x;
+    float gx, gy;
+    if (x == 0) gx = p[1] - p[0];
+    else if (x == w - 1) gx = p[0] - p[-1];
+    else gx = 0.5f * (p[1] - p[-1]);
+    if (y == 0) gy = p[pitch] - p[0];
+    else if (y == h - 1) gy = p[0] - p[-pitch];
+    else gy = 0.5f * (p[pitch] - p[-pitch]);
+    *mod = fast_sqrt_f(gx * gx + gy * gy);
+    *ang = mod_2pi_f((float)((double)fast_atan2_f(gy, gx) + 2 * kPi));
+}
+
+// vl/sift.c:904-1037.  hist: 36 doubles, element b at hist[b * hstride] (hstride = 32 on the device where the
+// histograms of a warp's 32 keypoints are interleaved in shared memory; 1 on the host).
+// Returns the number of angles (0..4).
+PB_HD int orientations_of(const OctaveView& ov, const SiftConsts& sc, const double* __restrict__ expn_tab, int o_cur,
+                          int ko, int kis, float kx, float ky, float ksigma, double xper, double* hist, int hstride,
+                          double angles[4]) {
+    const double winf = 1.5;
+    const int w = ov.w, h = ov.h;
+    const double x = (double)kx / xper;
+    const double y = (double)ky / xper;
+    const double sigma = (double)ksigma / xper;
+    const int xi = (int)(x + 0.5);
+    const int yi = (int)(y + 0.5);
+    const int si = kis;
+    const double sigmaw = winf * sigma;
+    const double Wd = floor(3.0 * sigmaw);
+    const int W = (int)(Wd > 1 ? Wd : 1);
+    enum { nbins = 36 };
+    if (ko != o_cur) return 0;
+    if (xi < 0 || xi > w - 1 || yi < 0 || yi > h - 1 || si < sc.s_min + 1 || si > sc.s_max - 2) return 0;
+    for (int i = 0; i < nbins; ++i) hist[i * hstride] = 0;
+    const float* pt = ov.grad + 2 * ((long)(si - sc.s_min - 1) * ov.h * ov.pitch);
+    const int ys0 = (-W > -yi) ? -W : -yi, ys1 = (W < h - 1 - yi) ? W : h - 1 - yi;
+    const int xs0 = (-W > -xi) ? -W : -xi, xs1 = (W < w - 1 - xi) ? W : w - 1 - xi;
+    const double r2max = W * W + 0.6;
+    const double den = 2 * sigmaw * sigmaw;
+    for (int ys = ys0; ys <= ys1; ++ys) {
+        const float* row = pt + 2 * ((long)(yi + ys) * ov.pitch);
+        const double dy = (double)(yi + ys) - y;
+        for (int xs = xs0; xs <= xs1; ++xs) {
+            const double dx = (double)(xi + xs) - x;
+            const double r2 = dx * dx + dy * dy;
+            if (r2 >= r2max) continue;
+            const double wgt = fast_expn(expn_tab, r2 / den);
+            const double mod = row[2 * (xi + xs)];
+            const double ang = row[2 * (xi + xs) + 1];
+            const double fbin = nbins * ang / (2 * kPi);
+            const int bin = floor_d(fbin - 0.5);
+            const double rbin = fbin - bin - 0.5;
+            hist[((bin + nbins) % nbins) * hstride] += (1 - rbin) * mod * wgt;
+            hist[((bin + 1) % nbins) * hstride] += (rbin)*mod * wgt;
+        }
+    }
+    for (int iter = 0; iter < 6; iter++) {
+        double prev = hist[(nbins - 1) * hstride];
+        double first = hist[0];
+        int i;
+        for (i = 0; i < nbins - 1; i++) {
+            double newh = (prev + hist[i * hstride] + hist[((i + 1) % nbins) * hstride]) / 3.0;
+            prev = hist[i * hstride];
+            hist[i * hstride] = newh;
+        }
+        hist[i * hstride] = (prev + hist[i * hstride] + first) / 3.0;
+    }
+    double maxh = 0;
+    for (int i = 0; i < nbins; ++i) maxh = (maxh > hist[i * hstride]) ? maxh : hist[i * hstride];
+    int nangles = 0;
+    for (int i = 0; i < nbins; ++i) {
+        double h0 = hist[i * hstride];
+        double hm = hist[((i - 1 + nbins) % nbins) * hstride];
+        double hp = hist[((i + 1 + nbins) % nbins) * hstride];
+        if (h0 > 0.8 * maxh && h0 > hm && h0 > hp) {
+            double di = -0.5 * (hp - hm) / (hp + hm - 2 * h0);
+            double th = 2 * kPi * (i + di + 0.5) / nbins;
+            angles[nangles++] = th;
+            if (nangles == 4) break;
+        }
+    }
+    return nangles;
+}
+
+// vl/sift.c:1268-1438.  st0 / ct0 = sin / cos of the keypoint angle, evaluated on the HOST with glibc.
+// hist: 128 floats, bin b at hist[b * hstride].  descr: 128 contiguous floats written only when the keypoint
+// passes the bounds test; returns 1 if written, 0 if the reference would have returned early (vl/sift.c:1321-1328).
+PB_HD int descriptor_of(const OctaveView& ov, const SiftConsts& sc, const double* __restrict__ expn_tab, int o_cur,
+                        int ko, int kis, float kx, float ky, float ksigma, double xper, double angle0, double st0,
+                        double ct0, float* hist, int hstride, float* __restrict__ descr) {
+    enum { NBO = 8, NBP = 4 };
+    const int w = ov.w, h = ov.h;
+    const double x = (double)kx / xper;
+    const double y = (double)ky / xper;
+    const double sigma = (double)ksigma / xper;
+    const int xi = (int)(x + 0.5);
+    const int yi = (int)(y + 0.5);
+    const int si = kis;
+    const double SBP = sc.magnif * sigma + kEpsD;
+    const int W = (int)floor(1.4142135623730951 * SBP * (NBP + 1) / 2.0 + 0.5);
+    if (ko != o_cur || xi < 0 || xi >= w || yi < 0 || yi >= h - 1 || si < sc.s_min + 1 || si > sc.s_max - 2) return 0;
+    for (int i = 0; i < NBO * NBP * NBP; ++i) hist[i * hstride] = 0.0f;
+    const float* pt = ov.grad + 2 * ((long)(si - sc.s_min - 1) * ov.h * ov.pitch);
+    const float wsigma = (float)sc.window_size;
+    const double wden = 2.0 * wsigma * wsigma;
+    const int dy0 = (-W > 1 - yi) ? -W : 1 - yi, dy1 = (W < h - yi - 2) ? W : h - yi - 2;
+    const int dx0 = (-W > 1 - xi) ? -W : 1 - xi, dx1 = (W < w - xi - 2) ? W : w - xi - 2;
+    for (int dyi = dy0; dyi <= dy1; ++dyi) {
+        const float* row = pt + 2 * ((long)(yi + dyi) * ov.pitch);
+        const float dy = (float)((double)(yi + dyi) - y);
+        for (int dxi = dx0; dxi <= dx1; ++dxi) {
+            const float mod = row[2 * (xi + dxi)];
+            const float angle = row[2 * (xi + dxi) + 1];
+            const float theta = mod_2pi_f((float)((double)angle - angle0));
+            const float dx = (float)((double)(xi + dxi) - x);
+            const float nx = (float)((ct0 * (double)dx + st0 * (double)dy) / SBP);
+            const float ny = (float)((-st0 * (double)dx + ct0 * (double)dy) / SBP);
+            const float nt = (float)((double)((float)NBO * theta) / (2 * kPi));
+            const float win = (float)fast_expn(expn_tab, (double)(nx * nx + ny * ny) / wden);
+            const int binx = floor_f((float)((double)nx - 0.5));
+            const int biny = floor_f((float)((double)ny - 0.5));
+            const int bint = floor_f(nt);
+            const float rbinx = (float)((double)nx - ((double)binx + 0.5));
+            const float rbiny = (float)((double)ny - ((double)biny + 0.5));
+            const float rbint = nt - (float)bint;
+            for (int dbinx = 0; dbinx < 2; ++dbinx)
+                for (int dbiny = 0; dbiny < 2; ++dbiny)
+                    for (int dbint = 0; dbint < 2; ++dbint) {
+                        if (binx + dbinx >= -(NBP / 2) && binx + dbinx < (NBP / 2) && biny + dbiny >= -(NBP / 2) &&
+                            biny + dbiny < (NBP / 2)) {
+                            const float weight = win * mod * fabs_f((float)(1 - dbinx) - rbinx) *
+                                                 fabs_f((float)(1 - dbiny) - rbiny) *
+                                                 fabs_f((float)(1 - dbint) - rbint);
+                            const int bi = (biny + dbiny + NBP / 2) * (NBO * NBP) + (binx + dbinx + NBP / 2) * NBO +
+                                           ((bint + dbint) % NBO);
+                            hist[bi * hstride] += weight;
+                        }
+                    }
+        }
+    }
+    // normalize -> clamp 0.2 -> normalize (vl/sift.c:1048-1063, 1415-1436)
+    const int n = NBO * NBP * NBP;
+    float norm = 0.0f;
+    for (int i = 0; i < n; ++i) norm += hist[i * hstride] * hist[i * hstride];
+    norm = fast_sqrt_f(norm) + kEpsF;
+    for (int i = 0; i < n; ++i) hist[i * hstride] /= norm;
+    if (sc.norm_thresh != 0 && (double)norm < sc.norm_thresh) {
+        for (int i = 0; i < n; ++i) descr[i] = 0;
+        return 1;
+    }
+    for (int i = 0; i < n; ++i)
+        if ((double)hist[i * hstride] > 0.2) hist[i * hstride] = (float)0.2;
+    norm = 0.0f;
+    for (int i = 0; i < n; ++i) norm += hist[i * hstride] * hist[i * hstride];
+    norm = fast_sqrt_f(norm) + kEpsF;
+    for (int i = 0; i < n; ++i) descr[i] = hist[i * hstride] / norm;
+    return 1;
+}
+
+}  // namespace pb

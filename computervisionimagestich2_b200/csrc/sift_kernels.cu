@@ -1,0 +1,369 @@
+// sift_kernels.cu -- sm_100a kernels for the Gaussian scale space, DoG extrema, refinement, gradient map,
+// orientation histograms and 128-d descriptors.  Arithmetic lives in sift_device.cuh (bit-exact bodies); this file
+// maps items to threads, stages tiles in shared memory and vectorises HBM access.
+//
+// Compiled with -fmad=false (no FMA contraction): the blur is a chain of separate FMUL + FADD per tap, exactly
+// the reference's `acc += v * c` (vl/imopv.c:163-187).
+#include "sift_kernels.h"
+#include "common.h"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------------------------------------
+// format conversion
+// ---------------------------------------------------------------------------------------------------------
+__global__ void u8_to_f32_kernel(const unsigned char* __restrict__ src, int src_pitch, float* __restrict__ dst, int w,
+                                 int h, int pitch) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < w && y < h) dst[(long)y * pitch + x] = (float)src[(long)y * src_pitch + x];
+}
+void launch_u8_to_f32(const unsigned char* src, int src_pitch, float* dst, int w, int h, int pitch, cudaStream_t st) {
+    dim3 b(128, 2), g(div_up(w, 128), div_up(h, 2));
+    u8_to_f32_kernel<<<g, b, 0, st>>>(src, src_pitch, dst, w, h, pitch);
+    PB_KERNEL_CHECK();
+}
+void launch_copy_f32(const float* src, int src_pitch, float* dst, int w, int h, int pitch, cudaStream_t st) {
+    PB_CUDA(cudaMemcpy2DAsync(dst, (size_t)pitch * 4, src, (size_t)src_pitch * 4, (size_t)w * 4, h,
+                              cudaMemcpyDeviceToDevice, st));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// separable Gaussian blur
+// ---------------------------------------------------------------------------------------------------------
+// Vertical pass: each thread owns one column x and R consecutive rows.  It loads the R + 2W source samples it
+// needs once into registers (coalesced across the warp) and reuses every sample for up to R outputs.
+template <int W, int R>
+__global__ void __launch_bounds__(256) blur_v_kernel(const float* __restrict__ src, float* __restrict__ dst, int w,
+                                                     int h, int pitch, const BlurTaps taps) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y0 = (blockIdx.y * 8 + threadIdx.y) * R;
+    if (x >= w || y0 >= h) return;
+    float v[R + 2 * W];
+#pragma unroll
+    for (int i = 0; i < R + 2 * W; ++i) {
+        int yy = y0 - W + i;
+        yy = yy < 0 ? 0 : (yy > h - 1 ? h - 1 : yy);
+        v[i] = src[(long)yy * pitch + x];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j <= 2 * W; ++j) acc = acc + v[r + j] * taps.c[2 * W - j];
+        if (y0 + r < h) dst[(long)(y0 + r) * pitch + x] = acc;
+    }
+}
+
+// Horizontal pass: a CTA stages TY rows x (TX + 2 WP) columns in shared memory (edge columns replicated), then
+// every thread produces 4 adjacent outputs from 2WP+4 samples fetched with 128-bit shared loads and writes them
+// with one 128-bit store.  DS: also emit the 2:1 sub-sampled image for the next octave (vl/sift.c:179-194).
+template <int W, bool DS>
+__global__ void __launch_bounds__(256) blur_h_kernel(const float* __restrict__ src, float* __restrict__ dst, int w,
+                                                     int h, int pitch, const BlurTaps taps, float* __restrict__ ds,
+                                                     int ds_pitch, int w2, int h2) {
+    constexpr int WP = (W + 3) / 4 * 4;
+    constexpr int TX = 512, TY = 8;
+    constexpr int L = TX + 2 * WP;
+    __shared__ __align__(16) float tile[TY][L];
+    const int tile_x0 = blockIdx.x * TX;
+    const int tile_y0 = blockIdx.y * TY;
+    const int tid = threadIdx.y * 128 + threadIdx.x;
+    for (int r = 0; r < TY; ++r) {
+        int y = tile_y0 + r;
+        if (y >= h) break;
+        const float* row = src + (long)y * pitch;
+        for (int c = tid; c < L; c += 256) {
+            int gx = tile_x0 - WP + c;
+            gx = gx < 0 ? 0 : (gx > w - 1 ? w - 1 : gx);
+            tile[r][c] = row[gx];
+        }
+    }
+    __syncthreads();
+    const int xl = threadIdx.x * 4;
+    const int x0 = tile_x0 + xl;
+    if (x0 >= w) return;
+    constexpr int NV = (2 * WP + 4) / 4;
+    constexpr int D = WP - W;
+    for (int r = threadIdx.y; r < TY; r += 2) {
+        const int y = tile_y0 + r;
+        if (y >= h) break;
+        float in[NV * 4];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            float4 t = *reinterpret_cast<const float4*>(&tile[r][xl + 4 * q]);
+            in[4 * q + 0] = t.x; in[4 * q + 1] = t.y; in[4 * q + 2] = t.z; in[4 * q + 3] = t.w;
+        }
+        float acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j <= 2 * W; ++j) a = a + in[D + i + j] * taps.c[2 * W - j];
+            acc[i] = a;
+        }
+        *reinterpret_cast<float4*>(dst + (long)y * pitch + x0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (DS) {
+            if ((y & 1) == 0 && (y >> 1) < h2) {
+                float* drow = ds + (long)(y >> 1) * ds_pitch;
+                const int xd = x0 >> 1;
+                if (xd + 1 < w2) *reinterpret_cast<float2*>(drow + xd) = make_float2(acc[0], acc[2]);
+                else if (xd < w2) drow[xd] = acc[0];
+            }
+        }
+    }
+}
+
+// Any half-width: one thread per output sample, taps from the parameter table.
+__global__ void blur_generic_kernel(const float* __restrict__ src, float* __restrict__ dst, int w, int h, int pitch,
+                                    const BlurTaps taps, int vertical) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float r = vertical ? blur_sample(src + x, pitch, h, y, taps.c, taps.W)
+                       : blur_sample(src + (long)y * pitch, 1, w, x, taps.c, taps.W);
+    dst[(long)y * pitch + x] = r;
+}
+
+__global__ void downsample2_kernel(const float* __restrict__ src, int pitch, float* __restrict__ dst, int dst_pitch,
+                                   int w2, int h2) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < w2 && y < h2) dst[(long)y * dst_pitch + x] = src[(long)(2 * y) * pitch + 2 * x];
+}
+void launch_downsample2(const float* src, int w, int h, int pitch, float* dst, int dst_pitch, cudaStream_t st) {
+    int w2 = w / 2, h2 = h / 2;
+    if (w2 <= 0 || h2 <= 0) return;
+    dim3 b(128, 2), g(div_up(w2, 128), div_up(h2, 2));
+    downsample2_kernel<<<g, b, 0, st>>>(src, pitch, dst, dst_pitch, w2, h2);
+    PB_KERNEL_CHECK();
+}
+
+template <int W>
+static void launch_blur_w(const float* src, float* tmp, float* dst, int w, int h, int pitch, const BlurTaps& taps,
+                          float* ds, int ds_pitch, cudaStream_t st) {
+    constexpr int R = 8;
+    dim3 bv(32, 8), gv(div_up(w, 32), div_up(h, 8 * R));
+    blur_v_kernel<W, R><<<gv, bv, 0, st>>>(src, tmp, w, h, pitch, taps);
+    PB_KERNEL_CHECK();
+    dim3 bh(128, 2), gh(div_up(w, 512), div_up(h, 8));
+    if (ds)
+        blur_h_kernel<W, true><<<gh, bh, 0, st>>>(tmp, dst, w, h, pitch, taps, ds, ds_pitch, w / 2, h / 2);
+    else
+        blur_h_kernel<W, false><<<gh, bh, 0, st>>>(tmp, dst, w, h, pitch, taps, nullptr, 0, 0, 0);
+    PB_KERNEL_CHECK();
+}
+
+void launch_blur(const float* src, float* tmp, float* dst, int w, int h, int pitch, const BlurTaps& taps, float* ds,
+                 int ds_pitch, cudaStream_t st) {
+    switch (taps.W) {
+    case 7: launch_blur_w<7>(src, tmp, dst, w, h, pitch, taps, ds, ds_pitch, st); return;
+    case 10: launch_blur_w<10>(src, tmp, dst, w, h, pitch, taps, ds, ds_pitch, st); return;
+    case 13: launch_blur_w<13>(src, tmp, dst, w, h, pitch, taps, ds, ds_pitch, st); return;
+    case 19: launch_blur_w<19>(src, tmp, dst, w, h, pitch, taps, ds, ds_pitch, st); return;
+    default: break;
+    }
+    dim3 b(128, 2), g(div_up(w, 128), div_up(h, 2));
+    blur_generic_kernel<<<g, b, 0, st>>>(src, tmp, w, h, pitch, taps, 1);
+    PB_KERNEL_CHECK();
+    blur_generic_kernel<<<g, b, 0, st>>>(tmp, dst, w, h, pitch, taps, 0);
+    PB_KERNEL_CHECK();
+    if (ds) launch_downsample2(dst, w, h, pitch, ds, ds_pitch, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DoG (only materialised for the vl_sift shim mirror and the parity tests; the detector forms it on the fly)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void dog_kernel(OctaveView ov, float* __restrict__ dog) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int l = blockIdx.z;
+    if (x < ov.w && y < ov.h) dog[((long)l * ov.h + y) * ov.pitch + x] = dog_at(ov, x, y, l);
+}
+void launch_dog(const OctaveView& ov, float* dog, cudaStream_t st) {
+    dim3 b(128, 2), g(div_up(ov.w, 128), div_up(ov.h, 2), ov.nlevels - 1);
+    dog_kernel<<<g, b, 0, st>>>(ov, dog);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// extrema detection: a CTA stages a (TX+2) x (TY+2) window of all DoG levels in shared memory (DoG is formed
+// from the GSS levels while loading, so it never travels through HBM) and tests the interior pixels of the
+// detection levels against their 26 neighbours.
+// ---------------------------------------------------------------------------------------------------------
+template <int NL>  // number of GSS levels (5 for S = 2)
+__global__ void __launch_bounds__(256) detect_kernel(OctaveView ov, SiftConsts sc, Cand* __restrict__ cand,
+                                                     int* __restrict__ count, int cap) {
+    constexpr int TX = 64, TY = 16;
+    constexpr int ND = NL - 1;
+    __shared__ float d[ND][TY + 2][TX + 2];
+    const int tx0 = blockIdx.x * TX, ty0 = blockIdx.y * TY;
+    const long ls = (long)ov.pitch * ov.h;
+    for (int i = threadIdx.x; i < (TY + 2) * (TX + 2); i += 256) {
+        int ry = i / (TX + 2), rx = i - ry * (TX + 2);
+        int gx = tx0 - 1 + rx, gy = ty0 - 1 + ry;
+        if (gx >= 0 && gx < ov.w && gy >= 0 && gy < ov.h) {
+            const float* p = ov.gss + (long)gy * ov.pitch + gx;
+            float prev = p[0];
+#pragma unroll
+            for (int l = 0; l < ND; ++l) {
+                float cur = p[(l + 1) * ls];
+                d[l][ry][rx] = cur - prev;
+                prev = cur;
+            }
+        } else {
+#pragma unroll
+            for (int l = 0; l < ND; ++l) d[l][ry][rx] = 0.0f;
+        }
+    }
+    __syncthreads();
+    const double tp = sc.peak_thresh;
+    for (int i = threadIdx.x; i < TX * TY; i += 256) {
+        int ry = i / TX, rx = i - ry * TX;
+        int gx = tx0 + rx, gy = ty0 + ry;
+        if (gx < 1 || gx > ov.w - 2 || gy < 1 || gy > ov.h - 2) continue;
+#pragma unroll
+        for (int l = 1; l <= ND - 2; ++l) {
+            const float v = d[l][ry + 1][rx + 1];
+            bool gt = ((double)v >= 0.8 * tp), lt = ((double)v <= -0.8 * tp);
+#pragma unroll
+            for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+                for (int dy = 0; dy <= 2; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx <= 2; ++dx) {
+                        if (dl == 0 && dy == 1 && dx == 1) continue;
+                        const float n = d[l + dl][ry + dy][rx + dx];
+                        gt = gt && (v > n);
+                        lt = lt && (v < n);
+                    }
+            if (gt || lt) {
+                int idx = atomicAdd(count, 1);
+                if (idx < cap) cand[idx] = Cand{gx, gy, l + sc.s_min};
+            }
+        }
+    }
+}
+
+__global__ void detect_generic_kernel(OctaveView ov, SiftConsts sc, Cand* __restrict__ cand, int* __restrict__ count,
+                                      int cap) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < 1 || x > ov.w - 2 || y < 1 || y > ov.h - 2) return;
+    for (int l = 1; l <= ov.nlevels - 3; ++l)
+        if (is_extremum(ov, x, y, l, sc.peak_thresh)) {
+            int idx = atomicAdd(count, 1);
+            if (idx < cap) cand[idx] = Cand{x, y, l + sc.s_min};
+        }
+}
+
+void launch_detect(const OctaveView& ov, const SiftConsts& sc, Cand* cand, int* count, int cap, cudaStream_t st) {
+    if (ov.w < 3 || ov.h < 3) return;
+    if (ov.nlevels == 5) {
+        dim3 g(div_up(ov.w, 64), div_up(ov.h, 16));
+        detect_kernel<5><<<g, 256, 0, st>>>(ov, sc, cand, count, cap);
+    } else {
+        dim3 b(128, 2), g(div_up(ov.w, 128), div_up(ov.h, 2));
+        detect_generic_kernel<<<g, b, 0, st>>>(ov, sc, cand, count, cap);
+    }
+    PB_KERNEL_CHECK();
+}
+
+__global__ void refine_kernel(OctaveView ov, SiftConsts sc, const Cand* __restrict__ cand,
+                              const int* __restrict__ count, int cap, RefinedKey* __restrict__ out, double xper) {
+    int n = *count;
+    n = n < cap ? n : cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Cand c = cand[i];
+        out[i] = refine_key(ov, sc, c.x, c.y, c.s, xper);
+    }
+}
+void launch_refine(const OctaveView& ov, const SiftConsts& sc, const Cand* cand, const int* count, int cap,
+                   RefinedKey* out, double xper, cudaStream_t st) {
+    int blocks = div_up(cap, 128);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    refine_kernel<<<blocks, 128, 0, st>>>(ov, sc, cand, count, cap, out, xper);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gradient map of the detection levels (modulus, angle) interleaved
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gradient_kernel(OctaveView ov, int first_level, float* __restrict__ grad) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int l = blockIdx.z;
+    if (x >= ov.w || y >= ov.h) return;
+    const float* lev = ov.gss + (long)(first_level + l) * ov.pitch * ov.h;
+    float m, a;
+    gradient_at(lev, ov.w, ov.h, ov.pitch, x, y, &m, &a);
+    reinterpret_cast<float2*>(grad)[((long)l * ov.h + y) * ov.pitch + x] = make_float2(m, a);
+}
+void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cudaStream_t st) {
+    int nl = (sc.s_max - 2) - (sc.s_min + 1) + 1;
+    if (nl <= 0) return;
+    dim3 b(128, 2), g(div_up(ov.w, 128), div_up(ov.h, 2), nl);
+    gradient_kernel<<<g, b, 0, st>>>(ov, 1, grad);  // grad level l <-> s = s_min+1+l <-> GSS level index 1+l
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// orientation + descriptor: one thread per keypoint / per (keypoint, angle); the accumulation order inside a
+// histogram bin is the raster order of the patch, exactly as in the reference, so results are bit-identical.
+// The histograms of a warp's 32 items are interleaved in shared memory (bin b of lane l at [b * 32 + l]):
+// conflict-free whatever bins the lanes touch.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) orient_kernel(OctaveView ov, SiftConsts sc, const double* __restrict__ expn_tab,
+                                                     int o_cur, const KeyIn* __restrict__ keys, int nkeys, double xper,
+                                                     int* __restrict__ nangles, double* __restrict__ angles) {
+    extern __shared__ double hsm[];
+    __shared__ double tab[257];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nkeys) return;
+    double* hist = hsm + (threadIdx.x >> 5) * 36 * 32 + (threadIdx.x & 31);
+    KeyIn k = keys[i];
+    double a[4] = {0, 0, 0, 0};
+    int n = orientations_of(ov, sc, tab, o_cur, o_cur, k.is, k.x, k.y, k.sigma, xper, hist, 32, a);
+    nangles[i] = n;
+    for (int j = 0; j < 4; ++j) angles[i * 4 + j] = a[j];
+}
+void launch_orient(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
+                   int nkeys, double xper, int* nangles, double* angles, cudaStream_t st) {
+    if (nkeys <= 0) return;
+    const int threads = 128;
+    size_t smem = (size_t)(threads / 32) * 36 * 32 * sizeof(double);
+    orient_kernel<<<div_up(nkeys, threads), threads, smem, st>>>(ov, sc, expn_tab, o_cur, keys, nkeys, xper, nangles,
+                                                                 angles);
+    PB_KERNEL_CHECK();
+}
+
+__global__ void __launch_bounds__(64) descr_kernel(OctaveView ov, SiftConsts sc, const double* __restrict__ expn_tab,
+                                                   int o_cur, const KeyIn* __restrict__ keys,
+                                                   const DescJob* __restrict__ jobs, int njobs, double xper,
+                                                   float* __restrict__ descr, int* __restrict__ written) {
+    extern __shared__ float fsm[];
+    __shared__ double tab[257];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= njobs) return;
+    float* hist = fsm + (threadIdx.x >> 5) * 128 * 32 + (threadIdx.x & 31);
+    DescJob j = jobs[i];
+    KeyIn k = keys[j.key];
+    written[i] = descriptor_of(ov, sc, tab, o_cur, o_cur, k.is, k.x, k.y, k.sigma, xper, j.angle, j.st0, j.ct0, hist,
+                               32, descr + (long)i * 128);
+}
+void launch_descr(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
+                  const DescJob* jobs, int njobs, double xper, float* descr, int* written, cudaStream_t st) {
+    if (njobs <= 0) return;
+    const int threads = 64;
+    size_t smem = (size_t)(threads / 32) * 128 * 32 * sizeof(float);
+    descr_kernel<<<div_up(njobs, threads), threads, smem, st>>>(ov, sc, expn_tab, o_cur, keys, jobs, njobs, xper,
+                                                                descr, written);
+    PB_KERNEL_CHECK();
+}
+
+}  // namespace pb
