@@ -1,0 +1,253 @@
+"""computervisionimagestich2_b200 -- B200-native (sm_100a) panorama-stitching hot path.
+
+The product is the C-ABI shared library ``libpano_b200.so`` built from ``csrc/`` (hand-written CUDA kernels + a C++ host
+orchestrator mirroring the reference's ``ImageProcess`` class).  This Python package is only a thin ctypes binding over
+that ABI, used by the tests and by ``bench.py``; it contains no numerical code and has no CPU fallback: every call
+fails loudly when the library is missing or no CUDA device is present.
+
+Reference interface mirrored (chensh236/ComputerVisionImageStich2): ``ImageProcess(dir, n)`` -> ``Stitcher``,
+``Projection::imageProjection`` -> ``project``, ``siftAlgorithm`` -> ``sift_features``, ``getImgPair`` -> ``match``,
+``RANSAC`` -> ``ransac``, ``warpingImageByHomography`` / ``movingImageByOffset`` -> ``warp_shift``,
+``blendTwoImages`` -> ``blend``, the equalisation tail of ``matching`` -> ``equalize_mix``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpano_b200.so")
+
+KEY_DTYPE = np.dtype(
+    [("o", "<i4"), ("ix", "<i4"), ("iy", "<i4"), ("is", "<i4"), ("x", "<f4"), ("y", "<f4"), ("s", "<f4"), ("sigma", "<f4")]
+)  # VlSiftKeypoint, vl/sift.h:19-31
+PAIR_DTYPE = np.dtype([("src", KEY_DTYPE), ("dst", KEY_DTYPE)])  # ImgPair, ImageProcess.h:43-47
+
+
+class Times(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("project", "sift", "table", "match", "ransac", "warp", "blend", "tail", "total")] + [
+        ("match_pairs_evaluated", C.c_int64), ("sift_pixels", C.c_int64), ("n_match_calls", C.c_int), ("n_blends", C.c_int)]
+
+
+class PanoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpano_b200.so; raises if it was not built (python -m computervisionimagestich2_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PanoError(f"{LIB_PATH} is missing: build it with `python -m computervisionimagestich2_b200.build` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.pano_b200_last_error.restype = C.c_char_p
+        L.pano_b200_last_error.argtypes = [C.c_void_p]
+        L.pano_b200_free.argtypes = [C.c_void_p]
+        L.pano_b200_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+class Context:
+    """One CUDA device + stream + workspaces (pano_b200_ctx)."""
+
+    def __init__(self, device: int = 0):
+        L = lib()
+        if L.pano_b200_device_count() <= 0:
+            raise PanoError("no CUDA device visible: the B200 path cannot run (there is no CPU fallback)")
+        h = C.c_void_p()
+        rc = L.pano_b200_create(device, C.byref(h))
+        if rc != 0 or not h.value:
+            raise PanoError(f"pano_b200_create failed ({rc})")
+        self.h = h
+        self.L = L
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.pano_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PanoError(f"{what} failed ({rc}): {self.L.pano_b200_last_error(self.h).decode()}")
+
+    # ---- stages ------------------------------------------------------------------------------------------------
+    def project(self, img, want_gray=False):
+        img = _u8(img)
+        _, h, w = img.shape
+        out = np.empty_like(img)
+        g = np.empty((h, w), np.uint8) if want_gray else None
+        self._check(self.L.pano_b200_project(self.h, _p(img), w, h, _p(out), _p(g) if want_gray else None), "project")
+        return (out, g) if want_gray else out
+
+    def gray(self, img):
+        img = _u8(img)
+        _, h, w = img.shape
+        g = np.empty((h, w), np.uint8)
+        self._check(self.L.pano_b200_gray(self.h, _p(img), w, h, _p(g)), "gray")
+        return g
+
+    def sift_features(self, gray_u8):
+        g = _u8(gray_u8)
+        h, w = g.shape
+        pd, pk, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        self._check(self.L.pano_b200_sift_features(self.h, _p(g), w, h, C.byref(pd), C.byref(pk), C.byref(n)), "sift_features")
+        n = n.value
+        descr = np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_float)), (max(n, 1), 128))[:n].copy()
+        keys = np.frombuffer(C.string_at(pk, n * KEY_DTYPE.itemsize), KEY_DTYPE).copy()
+        self.L.pano_b200_free(pd)
+        self.L.pano_b200_free(pk)
+        return descr, keys
+
+    def sift_raw(self, im_f32, noctaves=4, nlevels=2):
+        im = np.ascontiguousarray(im_f32, np.float32)
+        h, w = im.shape
+        pk, pa, pd, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+        nk = (C.c_int * max(noctaves, 64))()
+        self._check(self.L.pano_b200_sift_raw(self.h, _p(im), w, h, noctaves, nlevels, C.byref(pk), C.byref(pa), C.byref(pd),
+                                              C.byref(n), nk), "sift_raw")
+        n = n.value
+        keys = np.frombuffer(C.string_at(pk, n * KEY_DTYPE.itemsize), KEY_DTYPE).copy()
+        angles = np.frombuffer(C.string_at(pa, n * 8), np.float64).copy()
+        descr = np.frombuffer(C.string_at(pd, n * 512), np.float32).reshape(n, 128).copy()
+        for q in (pk, pa, pd):
+            self.L.pano_b200_free(q)
+        return dict(keys=keys, angles=angles, descr=descr, octave_nkeys=[nk[i] for i in range(noctaves)])
+
+    def sift_octave_dump(self, octave, nlevels=2):
+        ow, oh = C.c_int(), C.c_int()
+        self._check(self.L.pano_b200_sift_octave_dims(self.h, octave, C.byref(ow), C.byref(oh)), "octave_dims")
+        gss = np.empty((nlevels + 3, oh.value, ow.value), np.float32)
+        grad = np.empty((nlevels, oh.value, ow.value, 2), np.float32)
+        self._check(self.L.pano_b200_sift_octave_dump(self.h, octave, _p(gss), _p(grad)), "octave_dump")
+        return gss, grad
+
+    def match_idx(self, descA, descB):
+        dA = np.ascontiguousarray(descA, np.float32)
+        dB = np.ascontiguousarray(descB, np.float32)
+        idx = np.empty(len(dB), np.int32)
+        n = C.c_int()
+        self._check(self.L.pano_b200_match(self.h, _p(dA), len(dA), _p(dB), len(dB), _p(idx), C.byref(n)), "match")
+        return idx
+
+    def match(self, descA, keysA, descB, keysB):
+        """getImgPair: returns (A keypoints, B keypoints) of the matches in B's table order."""
+        idx = self.match_idx(descA, descB)
+        sel = idx >= 0
+        return np.ascontiguousarray(keysA, KEY_DTYPE)[idx[sel]].copy(), np.ascontiguousarray(keysB, KEY_DTYPE)[sel].copy()
+
+    def ransac(self, src, dst, debug=False):
+        pairs = np.empty(len(src), PAIR_DTYPE)
+        pairs["src"] = src
+        pairs["dst"] = dst
+        H = np.empty(8, np.float64)
+        counts = np.empty(72, np.int32)
+        hyps = np.empty((72, 8), np.float64)
+        inl = np.empty(len(src), np.int32)
+        ninl = C.c_int()
+        self._check(self.L.pano_b200_ransac(self.h, _p(pairs), len(pairs), _p(H), _p(counts), _p(hyps), _p(inl), C.byref(ninl)), "ransac")
+        if debug:
+            return H, counts, hyps, inl[: ninl.value].copy()
+        return H
+
+    def plan_canvas(self, dw, dh, fwdH, rw, rh):
+        H = np.ascontiguousarray(fwdH, np.float64)
+        b = np.empty(4, np.float32)
+        s = np.empty(2, np.int32)
+        self.L.pano_b200_plan_canvas(dw, dh, _p(H), rw, rh, _p(b), _p(s))
+        return b, s
+
+    def warp_shift(self, src, H8, offx, offy, prev, ioffx, ioffy, cw, ch):
+        H = np.ascontiguousarray(H8, np.float64) if H8 is not None else np.zeros(8)
+        a = b = None
+        sw = sh = pw = ph = 0
+        if src is not None:
+            src = _u8(src)
+            _, sh, sw = src.shape
+            a = np.empty((3, ch, cw), np.uint8)
+        if prev is not None:
+            prev = _u8(prev)
+            _, ph, pw = prev.shape
+            b = np.empty((3, ch, cw), np.uint8)
+        self._check(self.L.pano_b200_warp_shift(self.h, _p(src) if src is not None else None, sw, sh, _p(H), C.c_float(offx),
+                                                C.c_float(offy), _p(prev) if prev is not None else None, pw, ph, int(ioffx),
+                                                int(ioffy), cw, ch, _p(a) if a is not None else None,
+                                                _p(b) if b is not None else None), "warp_shift")
+        return a, b
+
+    def blend(self, a, b):
+        a, b = _u8(a), _u8(b)
+        _, h, w = a.shape
+        out = np.empty_like(a)
+        self._check(self.L.pano_b200_blend(self.h, _p(a), _p(b), w, h, _p(out)), "blend")
+        return out
+
+    def equalize_mix(self, img):
+        img = _u8(img)
+        _, h, w = img.shape
+        out = np.empty_like(img)
+        self._check(self.L.pano_b200_equalize_mix(self.h, _p(img), w, h, _p(out)), "equalize_mix")
+        return out
+
+    def cimg_blur2(self, planes):
+        p = np.ascontiguousarray(planes, np.float32)
+        c, h, w = p.shape
+        out = np.empty_like(p)
+        self._check(self.L.pano_b200_cimg_blur2(self.h, _p(p), w, h, c, _p(out)), "cimg_blur2")
+        return out
+
+    def cimg_resize3(self, planes, nw, nh):
+        p = np.ascontiguousarray(planes, np.float32)
+        c, h, w = p.shape
+        out = np.empty((c, nh, nw), np.float32)
+        self._check(self.L.pano_b200_cimg_resize3(self.h, _p(p), w, h, c, nw, nh, _p(out)), "cimg_resize3")
+        return out
+
+    # ---- pipeline -------------------------------------------------------------------------------------------------
+    def stitch(self, imgs):
+        """ImageProcess(dir, n) on in-memory planar RGB images -> (panorama [3][H][W] u8, info dict)."""
+        imgs = [_u8(i) for i in imgs]
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+        ws = (C.c_int * n)(*[i.shape[2] for i in imgs])
+        hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
+        out, ow, oh = C.c_void_p(), C.c_int(), C.c_int()
+        self._check(self.L.pano_b200_stitch(self.h, ptrs, ws, hs, n, C.byref(out), C.byref(ow), C.byref(oh)), "stitch")
+        pano = np.frombuffer(C.string_at(out, 3 * ow.value * oh.value), np.uint8).reshape(3, oh.value, ow.value).copy()
+        self.L.pano_b200_free(out)
+        buf = C.create_string_buffer(1 << 16)
+        self.L.pano_b200_stitch_log(self.h, buf, 1 << 16)
+        t = Times()
+        self.L.pano_b200_stitch_times(self.h, C.byref(t))
+        info = dict(log=buf.value.decode(), nfeat=[self.L.pano_b200_stitch_nfeatures(self.h, i) for i in range(n)],
+                    times={f[0]: getattr(t, f[0]) for f in Times._fields_})
+        return pano, info
+
+
+def fnv1a64(buf) -> str:
+    """FNV-1a 64 over the planar bytes (hash convention of SURVEY.md 8c)."""
+    data = np.ascontiguousarray(buf).tobytes()
+    h = 0xCBF29CE484222325
+    for b in data:
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"

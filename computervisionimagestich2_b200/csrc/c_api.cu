@@ -1,0 +1,246 @@
+// c_api.cu -- extern "C" entry points of libpano_b200.so (include/pano_b200.h).  Exceptions stop here.
+#include "../../include/pano_b200.h"
+#include "stitcher.h"
+#include "stitch_host.h"
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+using namespace pb;
+
+struct pano_b200_ctx {
+    std::unique_ptr<Stitcher> st;
+    std::string err;
+    RawFeatures last_raw;
+};
+
+static_assert(sizeof(pano_b200_keypoint) == sizeof(VlKey), "keypoint ABI");
+static_assert(sizeof(pano_b200_pair) == sizeof(KeyPair), "pair ABI");
+
+#define PB_API_BEGIN try {
+#define PB_API_END                                                     \
+    }                                                                  \
+    catch (const std::exception& e) {                                  \
+        if (ctx) ctx->err = e.what();                                  \
+        return -100;                                                   \
+    }                                                                  \
+    catch (...) {                                                      \
+        if (ctx) ctx->err = "unknown exception";                       \
+        return -101;                                                   \
+    }
+
+extern "C" {
+
+int pano_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pano_b200_create(int device, pano_b200_ctx** out) {
+    *out = nullptr;
+    pano_b200_ctx* ctx = new pano_b200_ctx();
+    try {
+        ctx->st.reset(new Stitcher(device));
+    } catch (const std::exception& e) {
+        fprintf(stderr, "pano_b200_create: %s\n", e.what());
+        delete ctx;
+        return -100;
+    }
+    *out = ctx;
+    return 0;
+}
+void pano_b200_destroy(pano_b200_ctx* ctx) { delete ctx; }
+const char* pano_b200_last_error(pano_b200_ctx* ctx) {
+    if (!ctx) return "no context";
+    if (ctx->err.empty() && ctx->st) return ctx->st->error().c_str();
+    return ctx->err.c_str();
+}
+void pano_b200_free(void* p) { free(p); }
+
+int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n, uint8_t** out,
+                     int* out_w, int* out_h) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    Stitcher& S = *ctx->st;
+    S.clear();
+    for (int i = 0; i < n; ++i) S.add_image(imgs[i], w[i], h[i]);
+    int rc = S.run();
+    if (rc) { ctx->err = S.error(); return rc; }
+    *out_w = S.result_width();
+    *out_h = S.result_height();
+    *out = (uint8_t*)malloc((size_t)3 * *out_w * *out_h);
+    S.copy_result(*out);
+    return 0;
+    PB_API_END
+}
+int pano_b200_stitch_log(pano_b200_ctx* ctx, char* dst, int cap) {
+    const std::string& s = ctx->st->log();
+    int n = (int)s.size();
+    if (n >= cap) n = cap - 1;
+    memcpy(dst, s.data(), n);
+    dst[n] = 0;
+    return n;
+}
+int pano_b200_stitch_times(pano_b200_ctx* ctx, pano_b200_times* t) {
+    const StageTimes& s = ctx->st->times();
+    t->project = s.project; t->sift = s.sift; t->table = s.table; t->match = s.match; t->ransac = s.ransac;
+    t->warp = s.warp; t->blend = s.blend; t->tail = s.tail; t->total = s.total;
+    t->match_pairs_evaluated = s.match_pairs_evaluated; t->sift_pixels = s.sift_pixels;
+    t->n_match_calls = s.n_match_calls; t->n_blends = s.n_blends;
+    return 0;
+}
+int pano_b200_stitch_nfeatures(pano_b200_ctx* ctx, int image) {
+    if (image < 0 || image >= ctx->st->num_images()) return -1;
+    return ctx->st->features(image).n;
+}
+
+int pano_b200_project(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* out_rgb, uint8_t* out_gray) {
+    PB_API_BEGIN
+    ctx->st->project(rgb, w, h, out_rgb, out_gray);
+    return 0;
+    PB_API_END
+}
+int pano_b200_gray(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* out_gray) {
+    PB_API_BEGIN
+    ctx->st->gray(rgb, w, h, out_gray);
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_sift_features(pano_b200_ctx* ctx, const uint8_t* gray, int w, int h, float** descr,
+                            pano_b200_keypoint** keys, int* n) {
+    PB_API_BEGIN
+    RawFeatures raw;
+    ctx->st->sift_raw_u8(gray, w, h, SiftParams(), raw);
+    FeatureTable t;
+    Stitcher::build_table(raw, t);
+    *n = t.n;
+    *descr = (float*)malloc(std::max<size_t>((size_t)t.n * 128 * sizeof(float), 4));
+    *keys = (pano_b200_keypoint*)malloc(std::max<size_t>((size_t)t.n * sizeof(VlKey), 4));
+    memcpy(*descr, t.descr.data(), (size_t)t.n * 128 * sizeof(float));
+    memcpy(*keys, t.keys.data(), (size_t)t.n * sizeof(VlKey));
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_sift_raw(pano_b200_ctx* ctx, const float* image, int w, int h, int noctaves, int nlevels,
+                       pano_b200_keypoint** keys, double** angles, float** descr, int* n, int* octave_nkeys) {
+    PB_API_BEGIN
+    SiftParams p;
+    p.O = noctaves;
+    p.S = nlevels;
+    RawFeatures& raw = ctx->last_raw;
+    ctx->st->sift_raw_f32(image, w, h, p, raw);
+    *n = raw.n;
+    *keys = (pano_b200_keypoint*)malloc(std::max<size_t>((size_t)raw.n * sizeof(VlKey), 4));
+    *angles = (double*)malloc(std::max<size_t>((size_t)raw.n * sizeof(double), 8));
+    *descr = (float*)malloc(std::max<size_t>((size_t)raw.n * 128 * sizeof(float), 4));
+    memcpy(*keys, raw.keys.data(), (size_t)raw.n * sizeof(VlKey));
+    memcpy(*angles, raw.angles.data(), (size_t)raw.n * sizeof(double));
+    memcpy(*descr, raw.descr.data(), (size_t)raw.n * 128 * sizeof(float));
+    if (octave_nkeys)
+        for (size_t i = 0; i < raw.noct_keys.size(); ++i) octave_nkeys[i] = raw.noct_keys[i];
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_sift_octave_dims(pano_b200_ctx* ctx, int octave, int* ow, int* oh) {
+    SiftEngine& E = ctx->st->sift_engine();
+    if (octave < 0 || octave >= E.noctaves()) return -1;
+    *ow = E.octave(octave).w;
+    *oh = E.octave(octave).h;
+    return 0;
+}
+int pano_b200_sift_octave_dump(pano_b200_ctx* ctx, int octave, float* gss, float* grad) {
+    PB_API_BEGIN
+    SiftEngine& E = ctx->st->sift_engine();
+    if (octave < 0 || octave >= E.noctaves()) return -1;
+    OctaveBuf& ob = E.octave(octave);
+    cudaStream_t st = E.stream();
+    const int nl = E.nlevels();
+    if (gss)
+        PB_CUDA(cudaMemcpy2DAsync(gss, (size_t)ob.w * 4, ob.gss.p, (size_t)ob.pitch * 4, (size_t)ob.w * 4,
+                                  (size_t)ob.h * nl, cudaMemcpyDeviceToHost, st));
+    if (grad)
+        PB_CUDA(cudaMemcpy2DAsync(grad, (size_t)ob.w * 8, ob.grad.p, (size_t)ob.pitch * 8, (size_t)ob.w * 8,
+                                  (size_t)ob.h * (nl - 3), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_match(pano_b200_ctx* ctx, const float* descrA, int nA, const float* descrB, int nB, int* match_idx,
+                    int* nmatches) {
+    PB_API_BEGIN
+    FeatureTable A, B;
+    A.n = nA; A.descr.assign(descrA, descrA + (size_t)nA * 128);
+    B.n = nB; B.descr.assign(descrB, descrB + (size_t)nB * 128);
+    std::vector<int> idx;
+    ctx->st->match_idx(A, B, idx);
+    int c = 0;
+    for (int b = 0; b < nB; ++b) { match_idx[b] = idx[b]; c += idx[b] >= 0; }
+    if (nmatches) *nmatches = c;
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_ransac(pano_b200_ctx* ctx, const pano_b200_pair* pairs, int npairs, double* H8, int* counts,
+                     double* hyps, int* inliers, int* ninliers) {
+    PB_API_BEGIN
+    std::vector<KeyPair> p((const KeyPair*)pairs, (const KeyPair*)pairs + npairs);
+    std::vector<int> c, inl;
+    std::vector<double> hy;
+    if (!ctx->st->ransac_debug(p, c, hy, inl, H8)) { ctx->err = "RANSAC failed (fewer than 4 pairs or no inliers)"; return -3; }
+    if (counts) memcpy(counts, c.data(), c.size() * sizeof(int));
+    if (hyps) memcpy(hyps, hy.data(), hy.size() * sizeof(double));
+    if (inliers) memcpy(inliers, inl.data(), inl.size() * sizeof(int));
+    if (ninliers) *ninliers = (int)inl.size();
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_plan_canvas(int dst_w, int dst_h, const double* forward_H8, int result_w, int result_h, float* bounds,
+                          int* size) {
+    stitch::CanvasPlan p = stitch::plan_canvas(dst_w, dst_h, forward_H8, result_w, result_h);
+    bounds[0] = p.min_x; bounds[1] = p.min_y; bounds[2] = p.max_x; bounds[3] = p.max_y;
+    size[0] = p.new_w; size[1] = p.new_h;
+    return 0;
+}
+
+int pano_b200_warp_shift(pano_b200_ctx* ctx, const uint8_t* src, int sw, int sh, const double* H8, float offx,
+                         float offy, const uint8_t* prev, int pw, int ph, int ioffx, int ioffy, int cw, int ch,
+                         uint8_t* a, uint8_t* b) {
+    PB_API_BEGIN
+    ctx->st->warp_shift(src, sw, sh, H8, offx, offy, prev, pw, ph, ioffx, ioffy, cw, ch, a, b);
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_blend(pano_b200_ctx* ctx, const uint8_t* a, const uint8_t* b, int w, int h, uint8_t* out) {
+    PB_API_BEGIN
+    int rc = ctx->st->blend(a, b, w, h, out);
+    if (rc) ctx->err = ctx->st->error();
+    return rc;
+    PB_API_END
+}
+int pano_b200_equalize_mix(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* out) {
+    PB_API_BEGIN
+    ctx->st->equalize_mix(rgb, w, h, out);
+    return 0;
+    PB_API_END
+}
+int pano_b200_cimg_blur2(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst) {
+    PB_API_BEGIN
+    ctx->st->cimg_blur2(src, w, h, c, dst);
+    return 0;
+    PB_API_END
+}
+int pano_b200_cimg_resize3(pano_b200_ctx* ctx, const float* src, int w, int h, int c, int nw, int nh, float* dst) {
+    PB_API_BEGIN
+    ctx->st->cimg_resize(src, w, h, c, nw, nh, dst);
+    return 0;
+    PB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// canvas_kernels.cu -- sm_100a kernels of the image-space stages: cylindrical projection (+gray), homography warp
+// + canvas shift, multiband blend (recursive Gaussian, reduce, expand/blend/collapse) and the equalisation tail.
+// All of them are HBM-bound byte/float streaming; arithmetic is in canvas_device.cuh (bit-exact bodies).
+#include "canvas_kernels.h"
+#include "common.h"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------------------------------------
+// projection + gray
+// ---------------------------------------------------------------------------------------------------------
+__global__ void project_gray_kernel(const u8* __restrict__ src, int w, int h, const float* __restrict__ ktab,
+                                    u8* __restrict__ dst, float* __restrict__ gray32, int gray_pitch,
+                                    u8* __restrict__ gray8) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t n = (size_t)w * h, o = (size_t)y * w + x;
+    float sx, sy;
+    u8 r = 0, g = 0, b = 0;
+    if (project_source(x, y, w, h, ktab, &sx, &sy)) {
+        r = bilinear_u8(src, w, h, sx, sy);
+        g = bilinear_u8(src + n, w, h, sx, sy);
+        b = bilinear_u8(src + 2 * n, w, h, sx, sy);
+    }
+    dst[o] = r; dst[n + o] = g; dst[2 * n + o] = b;
+    const u8 gr = gray_u8(r, g, b);
+    if (gray32) gray32[(size_t)y * gray_pitch + x] = (float)gr;
+    if (gray8) gray8[o] = gr;
+}
+void launch_project_gray(const u8* src, int w, int h, const float* ktab, u8* dst_rgb, float* gray_f32, int gray_pitch,
+                         u8* gray8, cudaStream_t st) {
+    dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
+    project_gray_kernel<<<g, b, 0, st>>>(src, w, h, ktab, dst_rgb, gray_f32, gray_pitch, gray8);
+    PB_KERNEL_CHECK();
+}
+
+__global__ void gray_kernel(const u8* __restrict__ rgb, int w, int h, float* __restrict__ gray32, int gray_pitch,
+                            u8* __restrict__ gray8) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t n = (size_t)w * h, o = (size_t)y * w + x;
+    const u8 gr = gray_u8(rgb[o], rgb[n + o], rgb[2 * n + o]);
+    if (gray32) gray32[(size_t)y * gray_pitch + x] = (float)gr;
+    if (gray8) gray8[o] = gr;
+}
+void launch_gray(const u8* rgb, int w, int h, float* gray_f32, int gray_pitch, u8* gray8, cudaStream_t st) {
+    dim3 b(128, 2), g(div_up(w, 128), div_up(h, 2));
+    gray_kernel<<<g, b, 0, st>>>(rgb, w, h, gray_f32, gray_pitch, gray8);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// warp + shift
+// ---------------------------------------------------------------------------------------------------------
+__global__ void warp_shift_kernel(const u8* __restrict__ src, int sw, int sh, const double* __restrict__ H8g,
+                                  float offx, float offy, const u8* __restrict__ prev, int pw, int ph, int ioffx,
+                                  int ioffy, u8* __restrict__ a, u8* __restrict__ b, int cw, int ch) {
+    __shared__ double H8[8];
+    if (threadIdx.x < 8 && threadIdx.y == 0) H8[threadIdx.x] = H8g ? H8g[threadIdx.x] : 0.0;
+    __syncthreads();
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cw || y >= ch) return;
+    const size_t cn = (size_t)cw * ch, o = (size_t)y * cw + x;
+    if (a) {
+        long s = warp_source(H8, x, y, offx, offy, sw, sh);
+        const size_t sn = (size_t)sw * sh;
+        u8 r = 0, g = 0, bb = 0;
+        if (s >= 0) { r = src[s]; g = src[sn + s]; bb = src[2 * sn + s]; }
+        a[o] = r; a[cn + o] = g; a[2 * cn + o] = bb;
+    }
+    if (b) {
+        int nx = x + ioffx, ny = y + ioffy;
+        u8 r = 0, g = 0, bb = 0;
+        if (nx >= 0 && nx < pw && ny >= 0 && ny < ph) {
+            const size_t pn = (size_t)pw * ph, s = (size_t)ny * pw + nx;
+            r = prev[s]; g = prev[pn + s]; bb = prev[2 * pn + s];
+        }
+        b[o] = r; b[cn + o] = g; b[2 * cn + o] = bb;
+    }
+}
+void launch_warp_shift(const u8* src, int sw, int sh, const double* H8, float offx, float offy, const u8* prev, int pw,
+                       int ph, int ioffx, int ioffy, u8* a, u8* b, int cw, int ch, cudaStream_t st) {
+    dim3 bl(64, 4), g(div_up(cw, 64), div_up(ch, 4));
+    warp_shift_kernel<<<g, bl, 0, st>>>(src, sw, sh, H8, offx, offy, prev, pw, ph, ioffx, ioffy, a, b, cw, ch);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// seam statistics + level 0 planes
+// ---------------------------------------------------------------------------------------------------------
+__global__ void seam_stats_kernel(const u8* __restrict__ a, const u8* __restrict__ b, int cw, int ch,
+                                  int* __restrict__ stats) {
+    __shared__ unsigned s[4];
+    if (threadIdx.x < 4) s[threadIdx.x] = 0;
+    __syncthreads();
+    const int mid_y = ch / 2;
+    unsigned sa = 0, na = 0, so = 0, no = 0;
+    for (int x = threadIdx.x; x < cw; x += blockDim.x) {
+        if (a[(size_t)mid_y * cw + x] != 0) {
+            sa += (unsigned)x; ++na;
+            if (b[(size_t)mid_y * cw + x] != 0) { so += (unsigned)x; ++no; }
+        }
+    }
+    atomicAdd(&s[0], sa); atomicAdd(&s[1], na); atomicAdd(&s[2], so); atomicAdd(&s[3], no);
+    __syncthreads();
+    if (threadIdx.x < 4) stats[threadIdx.x] = (int)s[threadIdx.x];
+}
+void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, cudaStream_t st) {
+    seam_stats_kernel<<<1, 1024, 0, st>>>(a, b, cw, ch, stats);
+    PB_KERNEL_CHECK();
+}
+
+__global__ void level0_kernel(const u8* __restrict__ a, const u8* __restrict__ b, int cw, int ch,
+                              const int* __restrict__ stats, float* __restrict__ G0, int* __restrict__ err_flag) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int sum_a_x = stats[0], width_mid_a = stats[1], sum_overlap_x = stats[2], width_mid_overlap = stats[3];
+    if (width_mid_a == 0 || width_mid_overlap == 0) {
+        if (x == 0 && y == 0) *err_flag = 1;
+        return;
+    }
+    if (x >= cw || y >= ch) return;
+    const float ratio = (float)(1.0 * (double)sum_a_x / (double)width_mid_a);
+    const float overlap_ratio = (float)(1.0 * (double)sum_overlap_x / (double)width_mid_overlap);
+    float m;
+    if (ratio < overlap_ratio) m = ((float)x < overlap_ratio) ? 1.0f : 0.0f;
+    else m = (x >= (int)(overlap_ratio + 1)) ? 1.0f : 0.0f;
+    const size_t n = (size_t)cw * ch, o = (size_t)y * cw + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        G0[c * n + o] = (float)a[c * n + o];
+        G0[(3 + c) * n + o] = (float)b[c * n + o];
+    }
+    G0[6 * n + o] = m;
+}
+void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
+                   cudaStream_t st) {
+    dim3 bl(128, 2), g(div_up(cw, 128), div_up(ch, 2));
+    level0_kernel<<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// recursive Gaussian (CImg vanvliet order 0, Neumann / Triggs boundary)
+// x pass: one warp owns 32 consecutive rows; 32x32 tiles are moved with coalesced accesses and transposed through
+// shared memory so that lane r walks row r sequentially with its 3 doubles of filter state in registers.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) iir_x_kernel(float* __restrict__ planes, int w, long nlines, IirCoef c) {
+    __shared__ float tile[4][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long line0 = ((long)blockIdx.x * 4 + warp) * 32;
+    if (line0 >= nlines) return;
+    float(*t)[33] = tile[warp];
+    const long myline = line0 + lane;
+    const bool active = myline < nlines;
+    const int nrows = (int)((nlines - line0) < 32 ? (nlines - line0) : 32);
+    float* base = planes + line0 * (long)w;
+    double v1 = 0, v2 = 0, v3 = 0, iplus = 0;
+    if (active) {
+        iplus = (double)planes[myline * (long)w + (w - 1)];
+        v1 = v2 = v3 = (double)planes[myline * (long)w] / c.sumsq;
+    }
+    // forward
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        const int nx = (w - x0) < 32 ? (w - x0) : 32;
+        if (lane < nx)
+            for (int r = 0; r < nrows; ++r) t[r][lane] = base[(long)r * w + x0 + lane];
+        __syncwarp();
+        if (active)
+            for (int i = 0; i < nx; ++i) {
+                double v0 = (double)t[lane][i];
+                v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+                t[lane][i] = (float)v0;
+                v3 = v2; v2 = v1; v1 = v0;
+            }
+        __syncwarp();
+        if (lane < nx)
+            for (int r = 0; r < nrows; ++r) base[(long)r * w + x0 + lane] = t[r][lane];
+        __syncwarp();
+    }
+    // backward
+    bool first = true;
+    for (int x0 = ((w - 1) / 32) * 32; x0 >= 0; x0 -= 32) {
+        const int nx = (w - x0) < 32 ? (w - x0) : 32;
+        if (lane < nx)
+            for (int r = 0; r < nrows; ++r) t[r][lane] = base[(long)r * w + x0 + lane];
+        __syncwarp();
+        if (active)
+            for (int i = nx - 1; i >= 0; --i) {
+                double v0;
+                if (first) {
+                    const double uplus = iplus / c.bnd, vplus = uplus / c.bnd;
+                    const double unp = v1 - uplus, unp1 = v2 - uplus, unp2 = v3 - uplus;
+                    v0 = (c.M[0] * unp + c.M[1] * unp1 + c.M[2] * unp2 + vplus) * c.sum;
+                    const double n1 = (c.M[3] * unp + c.M[4] * unp1 + c.M[5] * unp2 + vplus) * c.sum;
+                    const double n2 = (c.M[6] * unp + c.M[7] * unp1 + c.M[8] * unp2 + vplus) * c.sum;
+                    v3 = n2; v2 = n1; v1 = v0;
+                    first = false;
+                } else {
+                    v0 = (double)t[lane][i];
+                    v0 *= c.sum;
+                    v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+                    v3 = v2; v2 = v1; v1 = v0;
+                }
+                t[lane][i] = (float)v0;
+            }
+        first = false;
+        __syncwarp();
+        if (lane < nx)
+            for (int r = 0; r < nrows; ++r) base[(long)r * w + x0 + lane] = t[r][lane];
+        __syncwarp();
+    }
+}
+
+// y pass: one thread per column of a plane; neighbouring threads touch neighbouring addresses on every step.
+__global__ void iir_y_kernel(float* __restrict__ planes, int w, int h, int nplanes, IirCoef c) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)w * nplanes) return;
+    int p = (int)(i / w), x = (int)(i - (long)p * w);
+    iir_line(planes + (size_t)p * w * h + x, h, w, c);
+}
+
+void launch_iir_blur(float* planes, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st) {
+    if (w > 1) {
+        long nlines = (long)nplanes * h;
+        iir_x_kernel<<<div_up(nlines, 128), 128, 0, st>>>(planes, w, nlines, coef);
+        PB_KERNEL_CHECK();
+    }
+    if (h > 1) {
+        long n = (long)w * nplanes;
+        iir_y_kernel<<<div_up(n, 64), 64, 0, st>>>(planes, w, h, nplanes, coef);
+        PB_KERNEL_CHECK();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2:1 reduce (moving average, x pass rounded to float then y pass) and linear expand
+// ---------------------------------------------------------------------------------------------------------
+__global__ void reduce_kernel(const float* __restrict__ src, int w, int h, float* __restrict__ dst, int nw, int nh,
+                              DevMovAvg tx, DevMovAvg ty) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int p = blockIdx.z;
+    if (x >= nw || y >= nh) return;
+    const float* s = src + (size_t)p * w * h;
+    float acc = 0.0f;
+    for (int j = ty.start[y]; j < ty.start[y + 1]; ++j) {
+        const float rowavg = movavg_sample(s + (size_t)ty.src[j] * w, 1, tx.start, tx.src, tx.wgt, x, tx.div);
+        acc += rowavg * ty.wgt[j];
+    }
+    dst[((size_t)p * nh + y) * nw + x] = acc / ty.div;
+}
+void launch_reduce(const float* src, int w, int h, int nplanes, float* dst, int nw, int nh, DevMovAvg tx, DevMovAvg ty,
+                   cudaStream_t st) {
+    if (nw <= 0 || nh <= 0) return;
+    dim3 b(64, 4), g(div_up(nw, 64), div_up(nh, 4), nplanes);
+    reduce_kernel<<<g, b, 0, st>>>(src, w, h, dst, nw, nh, tx, ty);
+    PB_KERNEL_CHECK();
+}
+
+__device__ __forceinline__ float upsample_at(const float* __restrict__ src, int uw, int uh, const DevLinear& tx,
+                                             const DevLinear& ty, int x, int y) {
+    const int px = tx.pos[x], py = ty.pos[y];
+    const double ax = tx.alpha[x], ay = ty.alpha[y];
+    const float* r0 = src + (size_t)py * uw;
+    const float v0 = linear_sample(r0, 1, uw, px, ax);
+    const float v1 = (py < uh - 1) ? linear_sample(r0 + uw, 1, uw, px, ax) : v0;
+    return (float)((1 - ay) * (double)v0 + ay * (double)v1);
+}
+
+__global__ void expand_kernel(const float* __restrict__ src, int w, int h, float* __restrict__ dst, int nw, int nh,
+                              DevLinear tx, DevLinear ty) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int p = blockIdx.z;
+    if (x >= nw || y >= nh) return;
+    dst[((size_t)p * nh + y) * nw + x] = upsample_at(src + (size_t)p * w * h, w, h, tx, ty, x, y);
+}
+void launch_expand(const float* src, int w, int h, int nplanes, float* dst, int nw, int nh, DevLinear tx, DevLinear ty,
+                   cudaStream_t st) {
+    dim3 b(64, 4), g(div_up(nw, 64), div_up(nh, 4), nplanes);
+    expand_kernel<<<g, b, 0, st>>>(src, w, h, dst, nw, nh, tx, ty);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Laplacian blend + collapse of one level
+// ---------------------------------------------------------------------------------------------------------
+__global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const float* __restrict__ Gup,
+                                const float* __restrict__ Eup, int uw, int uh, DevLinear tx, DevLinear ty,
+                                float* __restrict__ E, u8* __restrict__ out8) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t n = (size_t)w * h, o = (size_t)y * w + x, un = (size_t)uw * uh;
+    const float m = G[6 * n + o];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float la = G[c * n + o], lb = G[(3 + c) * n + o];
+        float e;
+        if (Gup) {
+            la = la - upsample_at(Gup + c * un, uw, uh, tx, ty, x, y);
+            lb = lb - upsample_at(Gup + (3 + c) * un, uw, uh, tx, ty, x, y);
+            const float bl = blend_px(la, lb, m);
+            e = collapse_px(bl, upsample_at(Eup + c * un, uw, uh, tx, ty, x, y));
+        } else {
+            e = blend_px(la, lb, m);
+        }
+        if (out8) out8[c * n + o] = (u8)e;
+        else E[c * n + o] = e;
+    }
+}
+void launch_collapse(const float* G_i, int w, int h, const float* G_up, const float* E_up, int uw, int uh, DevLinear tx,
+                     DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st) {
+    dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
+    collapse_kernel<<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// equalisation tail
+// ---------------------------------------------------------------------------------------------------------
+__global__ void luma_hist_kernel(const u8* __restrict__ rgb, size_t n, int* __restrict__ hist) {
+    __shared__ int sh[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[luma_bin(rgb[i], rgb[n + i], rgb[2 * n + i])], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+void launch_luma_hist(const u8* rgb, int w, int h, int* hist256, cudaStream_t st) {
+    size_t n = (size_t)w * h;
+    PB_CUDA(cudaMemsetAsync(hist256, 0, 256 * sizeof(int), st));
+    int blocks = div_up((long)n, 256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    luma_hist_kernel<<<blocks, 256, 0, st>>>(rgb, n, hist256);
+    PB_KERNEL_CHECK();
+}
+
+__global__ void equalize_mix_kernel(const u8* __restrict__ rgb, size_t n, const int* __restrict__ lut,
+                                    u8* __restrict__ out) {
+    __shared__ int sl[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sl[i] = lut[i];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u8 r, g, b;
+        equalize_mix_px(rgb[i], rgb[n + i], rgb[2 * n + i], sl, &r, &g, &b);
+        out[i] = r; out[n + i] = g; out[2 * n + i] = b;
+    }
+}
+void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, cudaStream_t st) {
+    size_t n = (size_t)w * h;
+    int blocks = div_up((long)n, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    equalize_mix_kernel<<<blocks, 256, 0, st>>>(rgb, n, lut256, out);
+    PB_KERNEL_CHECK();
+}
+
+}  // namespace pb

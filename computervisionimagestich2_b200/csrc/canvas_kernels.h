@@ -1,0 +1,51 @@
+// canvas_kernels.h -- launch interface of the image-space kernels (canvas_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "canvas_device.cuh"
+
+namespace pb {
+
+// Cylindrical projection fused with grayscale + u8->f32 (Projection.cpp:20-73, ImageProcess.cpp:27-51).
+// src/dst_rgb: planar u8 [3][h][w]; gray_f32: pitched float image for the SIFT engine (may be null);
+// gray_u8 (optional, [h][w]).  ktab: device copy of hostnum::cylinder_table (length min(w, h)).
+void launch_project_gray(const u8* src, int w, int h, const float* ktab, u8* dst_rgb, float* gray_f32, int gray_pitch,
+                         u8* gray_u8, cudaStream_t st);
+void launch_gray(const u8* rgb, int w, int h, float* gray_f32, int gray_pitch, u8* gray_u8, cudaStream_t st);
+
+// a = warp(src image, H8, off) and b = shift(previous canvas, ioff) in one pass over the new canvas
+// (ImageProcess.cpp:596-620).  H8: device pointer to 8 doubles.  Either output may be null.
+void launch_warp_shift(const u8* src, int sw, int sh, const double* H8, float offx, float offy, const u8* prev, int pw,
+                       int ph, int ioffx, int ioffy, u8* a, u8* b, int cw, int ch, cudaStream_t st);
+
+// Seam statistics of the middle row (ImageProcess.cpp:659-671): stats[4] = {sum_a_x, width_mid_a, sum_overlap_x,
+// width_mid_overlap} (int32 wrap-around like the reference's int sums).
+void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, cudaStream_t st);
+// Level-0 float planes: G0[0..2] = a, G0[3..5] = b, G0[6] = seam mask (ImageProcess.cpp:678-698). err_flag set to 1
+// when the middle row is empty (the reference would loop forever / divide by zero).
+void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
+                   cudaStream_t st);
+
+// CImg get_blur(2, true, true) on `nplanes` planes [nplanes][h][w] in place (x pass then y pass).
+void launch_iir_blur(float* planes, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st);
+
+// Moving-average 2:1 reduce (CImg resize type 2 via type 3): src [n][h][w] -> dst [n][nh][nw]; tables on device.
+struct DevMovAvg { const int* start; const int* src; const float* wgt; float div; };  // div = source length (1 for identity)
+void launch_reduce(const float* src, int w, int h, int nplanes, float* dst, int nw, int nh, DevMovAvg tx, DevMovAvg ty,
+                   cudaStream_t st);
+// Linear up-resize (CImg resize type 3): src [n][h][w] -> dst [n][nh][nw]
+struct DevLinear { const int* pos; const double* alpha; };
+void launch_expand(const float* src, int w, int h, int nplanes, float* dst, int nw, int nh, DevLinear tx, DevLinear ty,
+                   cudaStream_t st);
+
+// One level of Laplacian blend + collapse (ImageProcess.cpp:727-771):
+//   E_i = clamp( blend(Ga_i - up(Ga_{i+1}), Gb_i - up(Gb_{i+1}), M_i) + up(E_{i+1}) )
+// G_i: 7 planes [7][h][w] (a rgb, b rgb, mask); G_up: 7 planes of level i+1 (uw x uh) or null for the top level;
+// E_up: 3 planes of level i+1 or null; E_out: 3 float planes, or out_u8 (level 0: truncating store, planar u8).
+void launch_collapse(const float* G_i, int w, int h, const float* G_up, const float* E_up, int uw, int uh, DevLinear tx,
+                     DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st);
+
+// Equalisation tail (equalization.cpp:74-131 + ImageProcess.cpp:237-268)
+void launch_luma_hist(const u8* rgb, int w, int h, int* hist256, cudaStream_t st);
+void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, cudaStream_t st);
+
+}  // namespace pb

@@ -34,6 +34,7 @@ struct DevBuf {
     size_t cap = 0;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { if (p) cudaFree(p); }
     T* ensure(size_t n) {

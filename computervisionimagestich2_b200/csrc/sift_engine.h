@@ -58,6 +58,10 @@ class SiftEngine {
 
     // Geometry + constants for an image; (re)allocates octave buffers.  Mirrors vl_sift_new (vl/sift.c:217-279).
     void configure(int w, int h, const SiftParams& p);
+    void set_thresholds(const SiftParams& p) {
+        p_.peak_thresh = p.peak_thresh; p_.edge_thresh = p.edge_thresh; p_.norm_thresh = p.norm_thresh;
+        p_.magnif = p.magnif; p_.window_size = p.window_size;
+    }
 
     // --- batched path ------------------------------------------------------------------------------------
     // d_img: device float image, rows img_pitch floats apart, values 0..255.

@@ -1,0 +1,652 @@
+// stitcher.cu -- see stitcher.h
+#include "stitcher.h"
+#include "stitch_host.h"
+#include "host_numerics.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <queue>
+#include <sstream>
+
+namespace pb {
+
+namespace {
+struct WallTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+IirCoef make_iir(float sigma) {
+    hostnum::VanVliet v = hostnum::vanvliet_coeffs(sigma);
+    IirCoef c;
+    c.f1 = v.filter[1]; c.f2 = v.filter[2]; c.f3 = v.filter[3];
+    c.sumsq = v.filter[0]; c.sum = v.sum; c.bnd = v.bnd;
+    for (int i = 0; i < 9; ++i) c.M[i] = v.M[i];
+    return c;
+}
+}  // namespace
+
+Stitcher::Stitcher(int device) : dev_(device) {
+    PB_CUDA(cudaSetDevice(device));
+    PB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    sift_.reset(new SiftEngine(st_));
+}
+Stitcher::~Stitcher() {
+    cudaSetDevice(dev_);
+    imgs_.clear();
+    sift_.reset();
+    if (st_) cudaStreamDestroy(st_);
+}
+
+void Stitcher::ensure_ktab(int short_side) {
+    if (ktab_n_ == short_side) return;
+    std::vector<float> k;
+    hostnum::cylinder_table(short_side, k);
+    ktab_.ensure(short_side);
+    PB_CUDA(cudaMemcpyAsync(ktab_.p, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    ktab_n_ = short_side;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stages
+// ------------------------------------------------------------------------------------------------------------
+void Stitcher::project(const u8* rgb, int w, int h, u8* out_rgb, u8* out_gray) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)w * h;
+    in_rgb_.ensure(3 * n);
+    a_.ensure(3 * n);
+    tmp8_.ensure(n);
+    ensure_ktab(std::min(w, h));
+    PB_CUDA(cudaMemcpyAsync(in_rgb_.p, rgb, 3 * n, cudaMemcpyHostToDevice, st_));
+    launch_project_gray(in_rgb_.p, w, h, ktab_.p, a_.p, nullptr, 0, tmp8_.p, st_);
+    if (out_rgb) PB_CUDA(cudaMemcpyAsync(out_rgb, a_.p, 3 * n, cudaMemcpyDeviceToHost, st_));
+    if (out_gray) PB_CUDA(cudaMemcpyAsync(out_gray, tmp8_.p, n, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Stitcher::gray(const u8* rgb, int w, int h, u8* out_gray) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)w * h;
+    in_rgb_.ensure(3 * n);
+    tmp8_.ensure(n);
+    PB_CUDA(cudaMemcpyAsync(in_rgb_.p, rgb, 3 * n, cudaMemcpyHostToDevice, st_));
+    launch_gray(in_rgb_.p, w, h, nullptr, 0, tmp8_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(out_gray, tmp8_.p, n, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Stitcher::sift_raw_u8(const u8* gray8, int w, int h, const SiftParams& p, RawFeatures& out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)w * h;
+    tmp8_.ensure(n);
+    int pitch = align_up(w, 32);
+    gray32_.ensure((size_t)pitch * h);
+    PB_CUDA(cudaMemcpyAsync(tmp8_.p, gray8, n, cudaMemcpyHostToDevice, st_));
+    launch_u8_to_f32(tmp8_.p, w, gray32_.p, w, h, pitch, st_);  // ImageProcess.cpp:47-51
+    sift_->configure(w, h, p);
+    sift_->extract(gray32_.p, pitch, out);
+}
+void Stitcher::sift_raw_f32(const float* img, int w, int h, const SiftParams& p, RawFeatures& out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    int pitch = align_up(w, 32);
+    gray32_.ensure((size_t)pitch * h);
+    PB_CUDA(cudaMemcpy2DAsync(gray32_.p, (size_t)pitch * 4, img, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice,
+                              st_));
+    sift_->configure(w, h, p);
+    sift_->extract(gray32_.p, pitch, out);
+}
+
+// std::map<std::vector<float>, VlSiftKeypoint>::insert semantics (ImageProcess.cpp:57, 80-86): ordered by
+// lexicographic descriptor comparison, an equal key keeps the FIRST inserted keypoint.
+void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t) {
+    const int n = raw.n;
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    const float* D = raw.descr.data();
+    auto less = [D](int a, int b) {
+        const float *pa = D + (size_t)a * 128, *pb_ = D + (size_t)b * 128;
+        for (int k = 0; k < 128; ++k) {
+            if (pa[k] < pb_[k]) return true;
+            if (pb_[k] < pa[k]) return false;
+        }
+        return false;
+    };
+    std::stable_sort(idx.begin(), idx.end(), less);
+    t.descr.clear();
+    t.keys.clear();
+    t.descr.reserve((size_t)n * 128);
+    t.keys.reserve(n);
+    for (int i = 0; i < n; ++i) {
+        if (i > 0 && !less(idx[i - 1], idx[i]) && !less(idx[i], idx[i - 1])) continue;  // duplicate key
+        const int s = idx[i];
+        t.descr.insert(t.descr.end(), D + (size_t)s * 128, D + (size_t)(s + 1) * 128);
+        VlKey k = raw.keys[s];
+        k.ix = (int)k.x;
+        k.iy = (int)k.y;
+        t.keys.push_back(k);
+    }
+    t.n = (int)t.keys.size();
+    t.on_device = false;
+}
+
+void Stitcher::upload_table(FeatureTable& t) {
+    if (t.on_device) return;
+    t.d_descr.ensure(std::max<size_t>((size_t)t.n * 128, 128));
+    if (t.n > 0)
+        PB_CUDA(cudaMemcpyAsync(t.d_descr.p, t.descr.data(), (size_t)t.n * 128 * sizeof(float), cudaMemcpyHostToDevice,
+                                st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    t.on_device = true;
+}
+
+void Stitcher::match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx) {
+    PB_CUDA(cudaSetDevice(dev_));
+    upload_table(A);
+    upload_table(B);
+    idx.assign(B.n, -1);
+    if (B.n == 0 || A.n < 2) return;  // the reference reads an unset second neighbour when NA < 2
+    int ns = match_num_splits(A.n, B.n);
+    partial_.ensure((size_t)ns * B.n);
+    midx_.ensure(B.n);
+    int* h = h_midx_.ensure(B.n);
+    launch_match_l1(A.d_descr.p, A.n, B.d_descr.p, B.n, partial_.p, ns, midx_.p, nullptr, st_);
+    PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * B.n, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    std::copy(h, h + B.n, idx.begin());
+    tm_.match_pairs_evaluated += (long)A.n * B.n;
+    tm_.n_match_calls++;
+}
+
+void Stitcher::match(FeatureTable& A, FeatureTable& B, std::vector<KeyPair>& pairs) {
+    std::vector<int> idx;
+    match_idx(A, B, idx);
+    pairs.clear();
+    for (int b = 0; b < B.n; ++b)
+        if (idx[b] >= 0) pairs.push_back(KeyPair{A.keys[idx[b]], B.keys[b]});
+}
+
+bool Stitcher::ransac(const std::vector<const std::vector<KeyPair>*>& problems, std::vector<double>& H8s) {
+    PB_CUDA(cudaSetDevice(dev_));
+    const int P = (int)problems.size();
+    const int iters = stitch::ransac_iterations();
+    H8s.assign((size_t)P * 8, 0.0);
+    std::vector<int> off(P + 1, 0), samples((size_t)P * iters * 4);
+    int maxn = 0;
+    for (int p = 0; p < P; ++p) {
+        const int n = (int)problems[p]->size();
+        off[p + 1] = off[p] + n;
+        maxn = std::max(maxn, n);
+        std::vector<int> s;
+        if (!stitch::draw_samples(n, s)) { err_ = "RANSAC needs at least 4 pairs"; return false; }
+        std::copy(s.begin(), s.end(), samples.begin() + (size_t)p * iters * 4);
+    }
+    std::vector<KeyPair> all(off[P]);
+    for (int p = 0; p < P; ++p) std::copy(problems[p]->begin(), problems[p]->end(), all.begin() + off[p]);
+    const int words = div_up(maxn, 32);
+    r_pairs_.ensure(all.size());
+    r_off_.ensure(P + 1);
+    r_samples_.ensure(samples.size());
+    r_counts_.ensure((size_t)P * iters);
+    r_masks_.ensure((size_t)P * iters * words);
+    PB_CUDA(cudaMemcpyAsync(r_pairs_.p, all.data(), all.size() * sizeof(KeyPair), cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(r_off_.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(r_samples_.p, samples.data(), samples.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    launch_ransac_score(r_pairs_.p, r_off_.p, P, r_samples_.p, iters, r_counts_.p, r_masks_.p, words, nullptr, st_);
+    std::vector<int> counts((size_t)P * iters);
+    std::vector<unsigned> masks((size_t)P * iters * words);
+    PB_CUDA(cudaMemcpyAsync(counts.data(), r_counts_.p, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaMemcpyAsync(masks.data(), r_masks_.p, masks.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    for (int p = 0; p < P; ++p) {
+        const int n = (int)problems[p]->size();
+        int best = stitch::select_hypothesis(counts.data() + (size_t)p * iters, iters);
+        if (best < 0) { err_ = "RANSAC found no inliers"; return false; }
+        const unsigned* m = masks.data() + ((size_t)p * iters + best) * words;
+        std::vector<int> inl;
+        for (int i = 0; i < n; ++i)
+            if (m[i >> 5] >> (i & 31) & 1u) inl.push_back(i);
+        if (!stitch::refit(problems[p]->data(), inl, H8s.data() + (size_t)p * 8)) return false;
+    }
+    return true;
+}
+
+bool Stitcher::ransac_debug(const std::vector<KeyPair>& pairs, std::vector<int>& counts, std::vector<double>& hyps,
+                            std::vector<int>& best_inliers, double* H8) {
+    PB_CUDA(cudaSetDevice(dev_));
+    const int iters = stitch::ransac_iterations();
+    const int n = (int)pairs.size();
+    std::vector<int> samples;
+    if (!stitch::draw_samples(n, samples)) return false;
+    int off[2] = {0, n};
+    const int words = div_up(n, 32);
+    r_pairs_.ensure(n); r_off_.ensure(2); r_samples_.ensure(samples.size()); r_counts_.ensure(iters);
+    r_masks_.ensure((size_t)iters * words); r_hyp_.ensure((size_t)iters * 8);
+    PB_CUDA(cudaMemcpyAsync(r_pairs_.p, pairs.data(), n * sizeof(KeyPair), cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(r_off_.p, off, sizeof off, cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(r_samples_.p, samples.data(), samples.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    launch_ransac_score(r_pairs_.p, r_off_.p, 1, r_samples_.p, iters, r_counts_.p, r_masks_.p, words, r_hyp_.p, st_);
+    counts.resize(iters);
+    hyps.resize((size_t)iters * 8);
+    std::vector<unsigned> masks((size_t)iters * words);
+    PB_CUDA(cudaMemcpyAsync(counts.data(), r_counts_.p, iters * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaMemcpyAsync(hyps.data(), r_hyp_.p, hyps.size() * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaMemcpyAsync(masks.data(), r_masks_.p, masks.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    int best = stitch::select_hypothesis(counts.data(), iters);
+    best_inliers.clear();
+    if (best < 0) return false;
+    const unsigned* m = masks.data() + (size_t)best * words;
+    for (int i = 0; i < n; ++i)
+        if (m[i >> 5] >> (i & 31) & 1u) best_inliers.push_back(i);
+    return stitch::refit(pairs.data(), best_inliers, H8);
+}
+
+void Stitcher::warp_shift(const u8* src, int sw, int sh, const double* H8, float offx, float offy, const u8* prev, int pw,
+                          int ph, int ioffx, int ioffy, int cw, int ch, u8* a_out, u8* b_out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t cn = (size_t)cw * ch;
+    a_.ensure(3 * cn);
+    b_.ensure(3 * cn);
+    H8_.ensure(8);
+    if (src) {
+        in_rgb_.ensure((size_t)3 * sw * sh);
+        PB_CUDA(cudaMemcpyAsync(in_rgb_.p, src, (size_t)3 * sw * sh, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaMemcpyAsync(H8_.p, H8, 8 * sizeof(double), cudaMemcpyHostToDevice, st_));
+    }
+    if (prev) {
+        res_[0].ensure((size_t)3 * pw * ph);
+        PB_CUDA(cudaMemcpyAsync(res_[0].p, prev, (size_t)3 * pw * ph, cudaMemcpyHostToDevice, st_));
+    }
+    launch_warp_shift(src ? in_rgb_.p : nullptr, sw, sh, H8_.p, offx, offy, prev ? res_[0].p : nullptr, pw, ph, ioffx,
+                      ioffy, src ? a_.p : nullptr, prev ? b_.p : nullptr, cw, ch, st_);
+    if (src && a_out) PB_CUDA(cudaMemcpyAsync(a_out, a_.p, 3 * cn, cudaMemcpyDeviceToHost, st_));
+    if (prev && b_out) PB_CUDA(cudaMemcpyAsync(b_out, b_.p, 3 * cn, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// multiband blend (ImageProcess.cpp:648-773) on device buffers
+// ------------------------------------------------------------------------------------------------------------
+int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out) {
+    std::vector<int> lw, lh;
+    const int L = stitch::blend_levels(cw, ch, lw, lh);
+    if (L < 1) { err_ = "blend: canvas too small"; return -2; }
+    // level storage: 7 planes per level
+    std::vector<size_t> goff(L + 1, 0);
+    for (int i = 0; i < L; ++i) goff[i + 1] = goff[i] + (size_t)7 * lw[i] * lh[i];
+    pyr_.ensure(goff[L]);
+    tmpf_.ensure((size_t)7 * lw[0] * lh[0]);
+    if (L > 1) {
+        E_[0].ensure((size_t)3 * lw[1] * lh[1]);
+        E_[1].ensure((size_t)3 * lw[1] * lh[1]);
+    }
+    // resampling tables for every level transition, packed and uploaded once
+    std::vector<int> ti;
+    std::vector<float> tf;
+    std::vector<double> td;
+    struct LevelTab { size_t mx_start, mx_src, mx_wgt, my_start, my_src, my_wgt, lx_pos, lx_alpha, ly_pos, ly_alpha; };
+    std::vector<LevelTab> lt(L);
+    auto push_mov = [&](int n, int m, size_t& s0, size_t& s1, size_t& s2) {
+        s0 = ti.size();
+        if (m == n) {  // identity (no resize along this axis)
+            for (int i = 0; i <= m; ++i) ti.push_back(i);
+            s1 = ti.size();
+            for (int i = 0; i < m; ++i) ti.push_back(i);
+            s2 = tf.size();
+            for (int i = 0; i < m; ++i) tf.push_back(1.0f);
+            return;
+        }
+        hostnum::MovAvgTable T = hostnum::movavg_table((unsigned)n, (unsigned)m);
+        ti.insert(ti.end(), T.start.begin(), T.start.end());
+        s1 = ti.size();
+        ti.insert(ti.end(), T.src.begin(), T.src.end());
+        s2 = tf.size();
+        tf.insert(tf.end(), T.wgt.begin(), T.wgt.end());
+    };
+    auto push_lin = [&](int n, int m, size_t& s0, size_t& s1) {
+        hostnum::LinearTable T;
+        if (n == 1) { T.pos.assign(m, 0); T.alpha.assign(m, 0.0); }
+        else if (n == m) { T.pos.resize(m); T.alpha.assign(m, 0.0); for (int i = 0; i < m; ++i) T.pos[i] = i; }
+        else T = hostnum::linear_table((unsigned)n, (unsigned)m);
+        s0 = ti.size();
+        ti.insert(ti.end(), T.pos.begin(), T.pos.end());
+        s1 = td.size();
+        td.insert(td.end(), T.alpha.begin(), T.alpha.end());
+    };
+    for (int i = 0; i + 1 < L; ++i) {
+        push_mov(lw[i], lw[i + 1], lt[i].mx_start, lt[i].mx_src, lt[i].mx_wgt);
+        push_mov(lh[i], lh[i + 1], lt[i].my_start, lt[i].my_src, lt[i].my_wgt);
+        push_lin(lw[i + 1], lw[i], lt[i].lx_pos, lt[i].lx_alpha);
+        push_lin(lh[i + 1], lh[i], lt[i].ly_pos, lt[i].ly_alpha);
+    }
+    tab_i_.ensure(std::max<size_t>(ti.size(), 1));
+    tab_f_.ensure(std::max<size_t>(tf.size(), 1));
+    tab_d_.ensure(std::max<size_t>(td.size(), 1));
+    stats_.ensure(8);
+    if (!ti.empty()) PB_CUDA(cudaMemcpyAsync(tab_i_.p, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    if (!tf.empty()) PB_CUDA(cudaMemcpyAsync(tab_f_.p, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice, st_));
+    if (!td.empty()) PB_CUDA(cudaMemcpyAsync(tab_d_.p, td.data(), td.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemsetAsync(stats_.p, 0, 8 * sizeof(int), st_));
+    PB_CUDA(cudaStreamSynchronize(st_));  // the packed tables are pageable temporaries
+
+    const IirCoef coef = make_iir(2.0f);
+    launch_seam_stats(d_a, d_b, cw, ch, stats_.p, st_);
+    launch_level0(d_a, d_b, cw, ch, stats_.p, pyr_.p, stats_.p + 4, st_);
+    // REDUCE chain (ImageProcess.cpp:705-715)
+    for (int i = 1; i < L; ++i) {
+        const size_t nprev = (size_t)7 * lw[i - 1] * lh[i - 1];
+        PB_CUDA(cudaMemcpyAsync(tmpf_.p, pyr_.p + goff[i - 1], nprev * sizeof(float), cudaMemcpyDeviceToDevice, st_));
+        launch_iir_blur(tmpf_.p, lw[i - 1], lh[i - 1], 7, coef, st_);
+        const LevelTab& t = lt[i - 1];
+        DevMovAvg mx{tab_i_.p + t.mx_start, tab_i_.p + t.mx_src, tab_f_.p + t.mx_wgt,
+                     lw[i] == lw[i - 1] ? 1.0f : (float)lw[i - 1]};
+        DevMovAvg my{tab_i_.p + t.my_start, tab_i_.p + t.my_src, tab_f_.p + t.my_wgt,
+                     lh[i] == lh[i - 1] ? 1.0f : (float)lh[i - 1]};
+        launch_reduce(tmpf_.p, lw[i - 1], lh[i - 1], 7, pyr_.p + goff[i], lw[i], lh[i], mx, my, st_);
+    }
+    // Laplacian + blend + collapse, top-down (ImageProcess.cpp:727-771)
+    const float* Eup = nullptr;
+    int eb = 0;
+    for (int i = L - 1; i >= 0; --i) {
+        const float* Gi = pyr_.p + goff[i];
+        DevLinear lx{nullptr, nullptr}, ly{nullptr, nullptr};
+        const float* Gup = nullptr;
+        int uw = 0, uh = 0;
+        if (i < L - 1) {
+            const LevelTab& t = lt[i];
+            lx = DevLinear{tab_i_.p + t.lx_pos, tab_d_.p + t.lx_alpha};
+            ly = DevLinear{tab_i_.p + t.ly_pos, tab_d_.p + t.ly_alpha};
+            Gup = pyr_.p + goff[i + 1];
+            uw = lw[i + 1]; uh = lh[i + 1];
+        }
+        if (i == 0) {
+            launch_collapse(Gi, lw[0], lh[0], Gup, Eup, uw, uh, lx, ly, nullptr, d_out, st_);
+        } else {
+            float* Eo = E_[eb].p;
+            launch_collapse(Gi, lw[i], lh[i], Gup, Eup, uw, uh, lx, ly, Eo, nullptr, st_);
+            Eup = Eo;
+            eb ^= 1;
+        }
+    }
+    int flag = 0;
+    PB_CUDA(cudaMemcpyAsync(&flag, stats_.p + 4, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    if (flag) { err_ = "blend: empty middle row (the reference does not terminate on this input)"; return -1; }
+    tm_.n_blends++;
+    return 0;
+}
+
+int Stitcher::blend(const u8* a, const u8* b, int cw, int ch, u8* out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t cn = (size_t)3 * cw * ch;
+    a_.ensure(cn); b_.ensure(cn); res_[0].ensure(cn);
+    PB_CUDA(cudaMemcpyAsync(a_.p, a, cn, cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(b_.p, b, cn, cudaMemcpyHostToDevice, st_));
+    int rc = blend_device(a_.p, b_.p, cw, ch, res_[0].p);
+    if (rc) return rc;
+    PB_CUDA(cudaMemcpyAsync(out, res_[0].p, cn, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    return 0;
+}
+
+void Stitcher::equalize_mix_device(const u8* d_rgb, int w, int h, u8* d_out) {
+    hist_.ensure(256);
+    lut_.ensure(256);
+    launch_luma_hist(d_rgb, w, h, hist_.p, st_);
+    int hist[256], lut[256];
+    PB_CUDA(cudaMemcpyAsync(hist, hist_.p, sizeof hist, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    {  // equalization.cpp:110-124
+        double prob[256], sum[256];
+        for (int i = 0; i < 256; ++i) prob[i] = (double)hist[i] / (double)(w * h);
+        sum[0] = prob[0];
+        lut[0] = (int)round(255.0 * sum[0]);
+        for (int i = 1; i < 256; ++i) { sum[i] = sum[i - 1] + prob[i]; lut[i] = (int)round(255.0 * sum[i]); }
+    }
+    PB_CUDA(cudaMemcpyAsync(lut_.p, lut, sizeof lut, cudaMemcpyHostToDevice, st_));
+    launch_equalize_mix(d_rgb, w, h, lut_.p, d_out, st_);
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Stitcher::equalize_mix(const u8* rgb, int w, int h, u8* out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)3 * w * h;
+    a_.ensure(n); b_.ensure(n);
+    PB_CUDA(cudaMemcpyAsync(a_.p, rgb, n, cudaMemcpyHostToDevice, st_));
+    equalize_mix_device(a_.p, w, h, b_.p);
+    PB_CUDA(cudaMemcpyAsync(out, b_.p, n, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Stitcher::cimg_blur2(const float* src, int w, int h, int c, float* dst) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)w * h * c;
+    tmpf_.ensure(n);
+    PB_CUDA(cudaMemcpyAsync(tmpf_.p, src, n * 4, cudaMemcpyHostToDevice, st_));
+    launch_iir_blur(tmpf_.p, w, h, c, make_iir(2.0f), st_);
+    PB_CUDA(cudaMemcpyAsync(dst, tmpf_.p, n * 4, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Stitcher::cimg_resize(const float* src, int w, int h, int c, int nw, int nh, float* dst) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)w * h * c, nn = (size_t)nw * nh * c;
+    tmpf_.ensure(n);
+    pyr_.ensure(nn);
+    PB_CUDA(cudaMemcpyAsync(tmpf_.p, src, n * 4, cudaMemcpyHostToDevice, st_));
+    std::vector<int> ti;
+    std::vector<float> tf;
+    std::vector<double> td;
+    if (nw <= w && nh <= h) {
+        size_t o[6];
+        auto push = [&](int a, int b, size_t& s0, size_t& s1, size_t& s2) {
+            s0 = ti.size();
+            if (a == b) {
+                for (int i = 0; i <= b; ++i) ti.push_back(i);
+                s1 = ti.size();
+                for (int i = 0; i < b; ++i) ti.push_back(i);
+                s2 = tf.size();
+                for (int i = 0; i < b; ++i) tf.push_back(1.0f);
+                return;
+            }
+            hostnum::MovAvgTable T = hostnum::movavg_table(a, b);
+            ti.insert(ti.end(), T.start.begin(), T.start.end());
+            s1 = ti.size();
+            ti.insert(ti.end(), T.src.begin(), T.src.end());
+            s2 = tf.size();
+            tf.insert(tf.end(), T.wgt.begin(), T.wgt.end());
+        };
+        push(w, nw, o[0], o[1], o[2]);
+        push(h, nh, o[3], o[4], o[5]);
+        tab_i_.ensure(ti.size()); tab_f_.ensure(tf.size());
+        PB_CUDA(cudaMemcpyAsync(tab_i_.p, ti.data(), ti.size() * 4, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaMemcpyAsync(tab_f_.p, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+        launch_reduce(tmpf_.p, w, h, c, pyr_.p, nw, nh, DevMovAvg{tab_i_.p + o[0], tab_i_.p + o[1], tab_f_.p + o[2], nw == w ? 1.0f : (float)w},
+                      DevMovAvg{tab_i_.p + o[3], tab_i_.p + o[4], tab_f_.p + o[5], nh == h ? 1.0f : (float)h}, st_);
+    } else if (nw >= w && nh >= h) {
+        size_t o[4];
+        auto push = [&](int a, int b, size_t& s0, size_t& s1) {
+            hostnum::LinearTable T;
+            if (a == 1) { T.pos.assign(b, 0); T.alpha.assign(b, 0.0); }
+            else if (a == b) { T.pos.resize(b); T.alpha.assign(b, 0.0); for (int i = 0; i < b; ++i) T.pos[i] = i; }
+            else T = hostnum::linear_table(a, b);
+            s0 = ti.size();
+            ti.insert(ti.end(), T.pos.begin(), T.pos.end());
+            s1 = td.size();
+            td.insert(td.end(), T.alpha.begin(), T.alpha.end());
+        };
+        push(w, nw, o[0], o[1]);
+        push(h, nh, o[2], o[3]);
+        tab_i_.ensure(ti.size()); tab_d_.ensure(td.size());
+        PB_CUDA(cudaMemcpyAsync(tab_i_.p, ti.data(), ti.size() * 4, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaMemcpyAsync(tab_d_.p, td.data(), td.size() * 8, cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaStreamSynchronize(st_));
+        launch_expand(tmpf_.p, w, h, c, pyr_.p, nw, nh, DevLinear{tab_i_.p + o[0], tab_d_.p + o[1]},
+                      DevLinear{tab_i_.p + o[2], tab_d_.p + o[3]}, st_);
+    } else {
+        throw std::runtime_error("cimg_resize: mixed shrink/grow is not on the stitching path");
+    }
+    PB_CUDA(cudaMemcpyAsync(dst, pyr_.p, nn * 4, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pipeline
+// ------------------------------------------------------------------------------------------------------------
+void Stitcher::clear() {
+    imgs_.clear();
+    log_.clear();
+    err_.clear();
+    tm_ = StageTimes();
+    rw_ = rh_ = 0;
+}
+
+// readFile body for one image (ImageProcess.cpp:12-23)
+void Stitcher::add_image(const u8* rgb, int w, int h) {
+    PB_CUDA(cudaSetDevice(dev_));
+    WallTimer t0;
+    std::unique_ptr<Image> im(new Image());
+    im->w = w; im->h = h;
+    size_t n = (size_t)w * h;
+    in_rgb_.ensure(3 * n);
+    im->proj.ensure(3 * n);
+    int pitch = align_up(w, 32);
+    gray32_.ensure((size_t)pitch * h);
+    ensure_ktab(std::min(w, h));
+    PB_CUDA(cudaMemcpyAsync(in_rgb_.p, rgb, 3 * n, cudaMemcpyHostToDevice, st_));
+    launch_project_gray(in_rgb_.p, w, h, ktab_.p, im->proj.p, gray32_.p, pitch, nullptr, st_);
+    PB_CUDA(cudaStreamSynchronize(st_));
+    tm_.project += t0.ms();
+    WallTimer t1;
+    SiftParams sp;
+    RawFeatures raw;
+    sift_->configure(w, h, sp);
+    sift_->extract(gray32_.p, pitch, raw);
+    tm_.sift += t1.ms();
+    tm_.sift_pixels += (long)n;
+    WallTimer t2;
+    build_table(raw, im->feat);
+    upload_table(im->feat);
+    tm_.table += t2.ms();
+    imgs_.push_back(std::move(im));
+}
+
+int Stitcher::run() {
+    PB_CUDA(cudaSetDevice(dev_));
+    WallTimer ttot;
+    const int n = (int)imgs_.size();
+    if (n == 0) { err_ = "no images"; return -1; }
+    std::ostringstream log;
+    std::vector<std::vector<char>> adj(n, std::vector<char>(n, 0));
+    std::vector<std::vector<int>> next(n);
+    std::vector<KeyPair> pairs;
+    // adjacency discovery (ImageProcess.cpp:117-137)
+    {
+        WallTimer t;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                if (i == j) continue;
+                if (adj[j][i]) { adj[i][j] = 1; next[i].push_back(j); continue; }
+                match(imgs_[i]->feat, imgs_[j]->feat, pairs);
+                if ((int)pairs.size() >= 20) { adj[i][j] = 1; next[i].push_back(j); }
+            }
+        tm_.match += t.ms();
+    }
+    const int start = stitch::middle_index(next, adj);
+    log << start << "\n";
+    int pre = start;
+    std::queue<int> wait;
+    wait.push(start);
+    // result = imgs[start].projectedSrc
+    {
+        Image& s = *imgs_[start];
+        rw_ = s.w; rh_ = s.h;
+        cur_ = 0;
+        res_[0].ensure((size_t)3 * rw_ * rh_);
+        PB_CUDA(cudaMemcpyAsync(res_[0].p, s.proj.p, (size_t)3 * rw_ * rh_, cudaMemcpyDeviceToDevice, st_));
+    }
+    H8_.ensure(8);
+    while (!wait.empty()) {
+        int src = wait.front();
+        wait.pop();
+        for (int i = (int)next[src].size() - 1; i >= 0; i--) {
+            int dst = next[src][i];
+            if (!adj[src][dst]) continue;
+            adj[src][dst] = adj[dst][src] = 0;
+            wait.push(dst);
+            std::vector<KeyPair> s2d, d2s;
+            {
+                WallTimer t;
+                match(imgs_[src]->feat, imgs_[dst]->feat, s2d);
+                match(imgs_[dst]->feat, imgs_[src]->feat, d2s);
+                tm_.match += t.ms();
+            }
+            log << src << " " << dst << "\n";
+            if (s2d.size() > d2s.size()) {
+                d2s.clear();
+                for (size_t q = 0; q < s2d.size(); ++q) d2s.push_back(KeyPair{s2d[q].dst, s2d[q].src});
+            } else {
+                s2d.clear();
+                for (size_t q = 0; q < d2s.size(); ++q) s2d.push_back(KeyPair{d2s[q].dst, d2s[q].src});
+            }
+            std::vector<double> H;
+            {
+                WallTimer t;
+                std::vector<const std::vector<KeyPair>*> probs{&d2s, &s2d};
+                if (!ransac(probs, H)) return -3;
+                tm_.ransac += t.ms();
+            }
+            const double* fwd = H.data();       // RANSAC(dstToSrcPair)
+            const double* bwd = H.data() + 8;   // RANSAC(srcToDstPair)
+            Image& D = *imgs_[dst];
+            stitch::CanvasPlan cp = stitch::plan_canvas(D.w, D.h, fwd, rw_, rh_);
+            if (cp.new_w <= 0 || cp.new_h <= 0 || (long)cp.new_w * cp.new_h > (1L << 31)) {
+                err_ = "degenerate canvas";
+                return -4;
+            }
+            const size_t cn = (size_t)3 * cp.new_w * cp.new_h;
+            {
+                WallTimer t;
+                a_.ensure(cn);
+                b_.ensure(cn);
+                PB_CUDA(cudaMemcpyAsync(H8_.p, bwd, 8 * sizeof(double), cudaMemcpyHostToDevice, st_));
+                launch_warp_shift(D.proj.p, D.w, D.h, H8_.p, cp.min_x, cp.min_y, res_[cur_].p, rw_, rh_, (int)cp.min_x,
+                                  (int)cp.min_y, a_.p, b_.p, cp.new_w, cp.new_h, st_);
+                PB_CUDA(cudaStreamSynchronize(st_));
+                tm_.warp += t.ms();
+            }
+            stitch::update_features_by_homography(D.feat.keys.data(), D.feat.n, fwd, cp.min_x, cp.min_y);
+            stitch::update_features_by_offset(imgs_[pre]->feat.keys.data(), imgs_[pre]->feat.n, (int)cp.min_x,
+                                              (int)cp.min_y);
+            {
+                WallTimer t;
+                res_[cur_ ^ 1].ensure(cn);
+                int rc = blend_device(a_.p, b_.p, cp.new_w, cp.new_h, res_[cur_ ^ 1].p);
+                if (rc) return rc;
+                cur_ ^= 1;
+                rw_ = cp.new_w; rh_ = cp.new_h;
+                tm_.blend += t.ms();
+            }
+            pre = dst;
+        }
+    }
+    {
+        WallTimer t;
+        res_[cur_ ^ 1].ensure((size_t)3 * rw_ * rh_);
+        equalize_mix_device(res_[cur_].p, rw_, rh_, res_[cur_ ^ 1].p);
+        cur_ ^= 1;
+        tm_.tail += t.ms();
+    }
+    log_ = log.str();
+    tm_.total += ttot.ms();
+    return 0;
+}
+
+void Stitcher::copy_result(u8* dst) {
+    PB_CUDA(cudaSetDevice(dev_));
+    PB_CUDA(cudaMemcpyAsync(dst, res_[cur_].p, (size_t)3 * rw_ * rh_, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+}  // namespace pb

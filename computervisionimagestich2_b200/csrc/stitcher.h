@@ -1,0 +1,109 @@
+// stitcher.h -- the host orchestrator of the GPU panorama path: the B200 counterpart of class ImageProcess
+// (ImageProcess.h:77-146).  One Stitcher = one CUDA device + one stream + grow-only HBM workspaces.
+//
+//   readFile()  (ImageProcess.cpp:11-24)   -> add_image(): H2D, projection+gray kernel, SIFT engine, feature table
+//   matching()  (ImageProcess.cpp:101-271) -> run(): all-pairs adjacency, middle image, BFS stitch loop, tail
+// Every stage is also reachable on its own (host buffers in / out) for the parity tests and stage benchmarks.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+#include "common.h"
+#include "types.h"
+#include "sift_engine.h"
+#include "match_kernels.h"
+#include "canvas_kernels.h"
+
+namespace pb {
+
+struct FeatureTable {   // == std::map<std::vector<float>, VlSiftKeypoint> flattened in key order (ImageProcess.h:54)
+    int n = 0;
+    std::vector<float> descr;   // [n][128], lexicographically sorted, duplicates removed (first insertion kept)
+    std::vector<VlKey> keys;    // ix, iy = (int)x, (int)y (ImageProcess.cpp:84-85); coordinates move during stitching
+    DevBuf<float> d_descr;      // device copy of descr
+    bool on_device = false;
+};
+
+struct StageTimes {  // milliseconds, CUDA events on the stitcher's stream (host work between kernels included)
+    double project = 0, sift = 0, table = 0, match = 0, ransac = 0, warp = 0, blend = 0, tail = 0, total = 0;
+    long match_pairs_evaluated = 0;   // sum of NA*NB over all getImgPair calls
+    long sift_pixels = 0;
+    int n_match_calls = 0, n_blends = 0;
+};
+
+class Stitcher {
+  public:
+    explicit Stitcher(int device);
+    ~Stitcher();
+    cudaStream_t stream() const { return st_; }
+    SiftEngine& sift_engine() { return *sift_; }
+
+    // ---- stages (host in / host out) ---------------------------------------------------------------------
+    void project(const u8* rgb, int w, int h, u8* out_rgb, u8* out_gray);
+    void gray(const u8* rgb, int w, int h, u8* out_gray);
+    void sift_raw_u8(const u8* gray8, int w, int h, const SiftParams& p, RawFeatures& out);
+    void sift_raw_f32(const float* img, int w, int h, const SiftParams& p, RawFeatures& out);
+    static void build_table(const RawFeatures& raw, FeatureTable& t);
+    void upload_table(FeatureTable& t);
+    // idx[b] = row of A matched by query row b of B, or -1 (ImageProcess.cpp:311-346)
+    void match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx);
+    void match(FeatureTable& A, FeatureTable& B, std::vector<KeyPair>& pairs);
+    // several RANSAC problems in one launch; returns false for a problem the reference cannot solve (<4 pairs ...)
+    bool ransac(const std::vector<const std::vector<KeyPair>*>& problems, std::vector<double>& H8s);
+    bool ransac_debug(const std::vector<KeyPair>& pairs, std::vector<int>& counts, std::vector<double>& hyps,
+                      std::vector<int>& best_inliers, double* H8);
+    void warp_shift(const u8* src, int sw, int sh, const double* H8, float offx, float offy, const u8* prev, int pw,
+                    int ph, int ioffx, int ioffy, int cw, int ch, u8* a_out, u8* b_out);
+    int blend(const u8* a, const u8* b, int cw, int ch, u8* out);          // host buffers
+    void equalize_mix(const u8* rgb, int w, int h, u8* out);               // host buffers
+    void cimg_blur2(const float* src, int w, int h, int c, float* dst);    // get_blur(2,true,true), host buffers
+    void cimg_resize(const float* src, int w, int h, int c, int nw, int nh, float* dst);
+
+    // ---- pipeline ---------------------------------------------------------------------------------------
+    void clear();
+    void add_image(const u8* rgb, int w, int h);     // planar RGB host buffer
+    int run();                                       // 0 ok; fills result
+    int result_width() const { return rw_; }
+    int result_height() const { return rh_; }
+    void copy_result(u8* dst);                        // planar RGB
+    const std::string& log() const { return log_; }
+    const StageTimes& times() const { return tm_; }
+    int num_images() const { return (int)imgs_.size(); }
+    const FeatureTable& features(int i) const { return imgs_[i]->feat; }
+    const std::string& error() const { return err_; }
+
+  private:
+    struct Image {
+        int w = 0, h = 0;
+        DevBuf<u8> proj;   // projected planar RGB
+        FeatureTable feat;
+    };
+    int blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out);
+    void equalize_mix_device(const u8* d_rgb, int w, int h, u8* d_out);
+    void ensure_ktab(int short_side);
+
+    int dev_;
+    cudaStream_t st_ = nullptr;
+    std::unique_ptr<SiftEngine> sift_;
+    std::vector<std::unique_ptr<Image>> imgs_;
+    // workspaces
+    DevBuf<u8> in_rgb_, a_, b_, res_[2], tmp8_;
+    DevBuf<float> gray32_, ktab_;
+    int ktab_n_ = 0;
+    DevBuf<Top2> partial_;
+    DevBuf<int> midx_;
+    PinBuf<int> h_midx_;
+    DevBuf<KeyPair> r_pairs_;
+    DevBuf<int> r_off_, r_samples_, r_counts_;
+    DevBuf<unsigned> r_masks_;
+    DevBuf<double> r_hyp_, H8_;
+    DevBuf<float> pyr_, tmpf_, E_[2];
+    DevBuf<int> tab_i_, stats_, hist_, lut_;
+    DevBuf<float> tab_f_;
+    DevBuf<double> tab_d_;
+    int cur_ = 0, rw_ = 0, rh_ = 0;
+    std::string log_, err_;
+    StageTimes tm_;
+};
+
+}  // namespace pb

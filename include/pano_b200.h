@@ -1,0 +1,114 @@
+/* pano_b200.h -- C ABI of libpano_b200.so, the B200 (sm_100a) implementation of the panorama-stitching hot path of
+ * chensh236/ComputerVisionImageStich2.  Plain pointers and sizes only; every buffer named here is HOST memory unless
+ * its name starts with d_.  All functions return 0 on success and a negative code on failure;
+ * pano_b200_last_error() gives the message.  A context is bound to one CUDA device and one stream and must not be
+ * used from two threads at once (distinct contexts may run concurrently).
+ *
+ * Image layout everywhere: CImg planar, data[x + y*W + c*W*H], c = 0,1,2 = R,G,B (CImg.h:48533-48546).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
+ */
+#ifndef PANO_B200_H
+#define PANO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pano_b200_ctx pano_b200_ctx;
+
+/* VlSiftKeypoint (vl/sift.h:19-31), 32 bytes */
+typedef struct pano_b200_keypoint {
+    int o, ix, iy, is;
+    float x, y, s, sigma;
+} pano_b200_keypoint;
+
+/* ImgPair (ImageProcess.h:43-47) */
+typedef struct pano_b200_pair {
+    pano_b200_keypoint src, dst;
+} pano_b200_pair;
+
+/* per-stage wall times of the last pano_b200_stitch call, milliseconds */
+typedef struct pano_b200_times {
+    double project, sift, table, match, ransac, warp, blend, tail, total;
+    int64_t match_pairs_evaluated, sift_pixels;
+    int n_match_calls, n_blends;
+} pano_b200_times;
+
+int pano_b200_create(int device, pano_b200_ctx** out);
+void pano_b200_destroy(pano_b200_ctx* ctx);
+const char* pano_b200_last_error(pano_b200_ctx* ctx);
+int pano_b200_device_count(void);
+void pano_b200_free(void* p); /* frees any buffer this library returned through an out-pointer */
+
+/* ---- whole pipeline: `ImageProcess ip(dir, n)` + private member `result` (main.cpp:9, ImageProcess.cpp:3-8,
+ *      ImageProcess.h:145).  imgs[i]: planar RGB of size w[i] x h[i].  *out is library-allocated (pano_b200_free). */
+int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n, uint8_t** out,
+                     int* out_w, int* out_h);
+/* the lines the reference prints to stdout: middle index, then "src dst" per stitched edge (ImageProcess.cpp:183,391) */
+int pano_b200_stitch_log(pano_b200_ctx* ctx, char* dst, int cap);
+int pano_b200_stitch_times(pano_b200_ctx* ctx, pano_b200_times* t);
+int pano_b200_stitch_nfeatures(pano_b200_ctx* ctx, int image); /* size of imgs[i].features after the run, -1 if none */
+
+/* ---- stages ---------------------------------------------------------------------------------------------------- */
+/* Projection::imageProjection (Projection.cpp:20-73) [+ ImageProcess::toGrayScale (ImageProcess.cpp:27-40) when
+ * out_gray != NULL].  Either output may be NULL. */
+int pano_b200_project(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* out_rgb, uint8_t* out_gray);
+/* ImageProcess::toGrayScale (ImageProcess.cpp:27-40) */
+int pano_b200_gray(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* out_gray);
+
+/* ImageProcess::siftAlgorithm (ImageProcess.cpp:44-99): gray u8 image -> feature table in std::map order (sorted by
+ * descriptor, duplicates dropped).  *descr [n][128] floats and *keys [n] are library-allocated. */
+int pano_b200_sift_features(pano_b200_ctx* ctx, const uint8_t* gray, int w, int h, float** descr,
+                            pano_b200_keypoint** keys, int* n);
+
+/* The raw vl_sift_* call sequence of siftAlgorithm (ImageProcess.cpp:55-92) on a float image with explicit
+ * (noctaves, nlevels): every (keypoint, angle) descriptor in call order, nothing sorted or de-duplicated.
+ * Out arrays are library-allocated: keys [n] (ix/iy as detected), angles [n], descr [n][128]; octave_nkeys[noctaves]
+ * (caller-provided, may be NULL) receives the refined keypoint count per octave. */
+int pano_b200_sift_raw(pano_b200_ctx* ctx, const float* image, int w, int h, int noctaves, int nlevels,
+                       pano_b200_keypoint** keys, double** angles, float** descr, int* n, int* octave_nkeys);
+
+/* Scale-space dump of one octave for parity tests: after pano_b200_sift_raw, copies the octave's GSS levels
+ * ([nlevels+3][oh][ow] floats) and gradient map ([nlevels][oh][ow][2]) to host buffers (either may be NULL). */
+int pano_b200_sift_octave_dims(pano_b200_ctx* ctx, int octave, int* ow, int* oh);
+int pano_b200_sift_octave_dump(pano_b200_ctx* ctx, int octave, float* gss, float* grad);
+
+/* ImageProcess::getImgPair (ImageProcess.cpp:273-351): A = database, B = queries, both feature tables in sorted order.
+ * match_idx[b] = row of A matched by row b of B, or -1.  Returns the number of matches through *nmatches. */
+int pano_b200_match(pano_b200_ctx* ctx, const float* descrA, int nA, const float* descrB, int nB, int* match_idx,
+                    int* nmatches);
+
+/* ImageProcess::RANSAC (ImageProcess.cpp:395-436): pairs (src -> dst) -> 8 bilinear coefficients in Homography
+ * constructor order (x' = H[0] x + H[1] y + H[2] x y + H[3]; y' = H[4] x + H[5] y + H[6] x y + H[7]).
+ * Optional outputs: counts[72] inlier count per hypothesis, hyps[72][8] fitted hypotheses (getHomographyMat,
+ * ImageProcess.cpp:439-462), inliers[npairs] / *ninliers the winning inlier set (getInlinerIndex, :473-497). */
+int pano_b200_ransac(pano_b200_ctx* ctx, const pano_b200_pair* pairs, int npairs, double* H8, int* counts,
+                     double* hyps, int* inliers, int* ninliers);
+
+/* Canvas sizing (ImageProcess.cpp:206-216, 532-594): bounds[4] = min_x, min_y, max_x, max_y (already merged with the
+ * current result size), size[2] = new_width, new_height.  Host arithmetic only. */
+int pano_b200_plan_canvas(int dst_w, int dst_h, const double* forward_H8, int result_w, int result_h, float* bounds,
+                          int* size);
+
+/* warpingImageByHomography + movingImageByOffset (ImageProcess.cpp:596-620) in one pass over the new canvas.
+ * src (sw x sh) is warped with H8 and float offsets into a; prev (pw x ph) is shifted by the int offsets into b.
+ * Pass src = NULL or prev = NULL to run only one of them. */
+int pano_b200_warp_shift(pano_b200_ctx* ctx, const uint8_t* src, int sw, int sh, const double* H8, float offx,
+                         float offy, const uint8_t* prev, int pw, int ph, int ioffx, int ioffy, int cw, int ch,
+                         uint8_t* a, uint8_t* b);
+
+/* ImageProcess::blendTwoImages (ImageProcess.cpp:648-773) */
+int pano_b200_blend(pano_b200_ctx* ctx, const uint8_t* a, const uint8_t* b, int w, int h, uint8_t* out);
+/* equalization(tmp, 1) + the Y mix that closes ImageProcess::matching (equalization.cpp:74-131, ImageProcess.cpp:237-268) */
+int pano_b200_equalize_mix(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* out);
+/* CImg<float>::get_blur(2, true, true) (CImg.h:35111-35147, vanvliet) and get_resize(nw, nh, 1, c, 3)
+ * (CImg.h:29321-29700) on float planes [c][h][w]; the two CImg primitives blendTwoImages is made of. */
+int pano_b200_cimg_blur2(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst);
+int pano_b200_cimg_resize3(pano_b200_ctx* ctx, const float* src, int w, int h, int c, int nw, int nh, float* dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
