@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 panorama-stitching path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload input2|input|synth4k]
+
+Metric (BASELINE.json): stitched Mpixel/s = sum of input pixels of the panorama job / time from "decoded images" to
+"finished panorama".  One step = one whole panorama job (projection, SIFT, all-pairs matching, RANSAC, warp, multiband
+blend, equalisation) on the named workload; default workload = BASELINE.json configs[1], the bundled Input2 set
+(4 x 1210x907).  `value` is measured with the decoded input images already resident in HBM and the result left in HBM;
+`e2e` is the same job through the C ABI with pinned HOST buffers (H2D of the inputs and D2H of the panorama inside the
+timed region).  With N > 1 (torchrun, one rank per GPU) every rank stitches its own job (weak scaling, no data-path
+collective); time = max over ranks, value = N x pixels / time.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, compiled from the reference sources) on the
+host cores of the box, as process-level replicas (the reference is single-threaded), on a bounded sample of the same
+workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "stitched_mpixel_per_s"
+UNIT = "Mpixel/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------
+def synth_scene_views(n, w, h, seed=20181126):
+    """n overlapping views (50 % overlap) of one deterministic textured scene, planar uint8."""
+    rng = np.random.default_rng(seed)
+    W = w // 2 * (n + 1)
+    scene = np.zeros((3, h + 32, W), np.float32)
+    for octave in range(5):
+        s = 4 << octave
+        g = rng.random((3, (h + 32) // s + 2, W // s + 2)).astype(np.float32)
+        scene += np.kron(g, np.ones((1, s, s), np.float32))[:, : h + 32, :W] * (s / 64.0)
+    scene = 255.0 * (scene - scene.min()) / (scene.max() - scene.min())
+    nblobs = int(200 * W * h / 1e6)
+    ys = rng.integers(0, h + 32, nblobs); xs = rng.integers(0, W, nblobs); rs = rng.integers(3, 24, nblobs)
+    cols = rng.integers(0, 256, (nblobs, 3))
+    for y, x, r, c in zip(ys, xs, rs, cols):
+        y0, y1, x0, x1 = max(0, y - r), min(h + 32, y + r), max(0, x - r), min(W, x + r)
+        scene[:, y0:y1, x0:x1] = 0.5 * scene[:, y0:y1, x0:x1] + 0.5 * c[:, None, None]
+    scene = np.clip(scene, 0, 255).astype(np.uint8)
+    views = []
+    for i in range(n):
+        dy = int(rng.integers(0, 17))
+        views.append(np.ascontiguousarray(scene[:, dy : dy + h, i * (w // 2) : i * (w // 2) + w]))
+    return views
+
+
+def load_workload(name):
+    from computervisionimagestich2_b200 import bmpio
+    data = os.path.join(ROOT, "oracle", "_ref", "data")
+    if name in ("input", "input2"):
+        d = os.path.join(data, "Input" if name == "input" else "Input2")
+        imgs = [bmpio.load_bmp(os.path.join(d, f"{i}.bmp")) for i in range(1, 5)]
+        desc = ("Input/1-4.bmp 4-image panorama (384x512)" if name == "input"
+                else "Input2/1-4.bmp 4-image panorama (1210x907), BASELINE.json configs[1]")
+        return imgs, desc, "bundled reference fixtures (Input2 BMPs)" if name == "input2" else "bundled reference fixtures (Input BMPs)"
+    if name == "synth4k":
+        return synth_scene_views(8, 3840, 2160), "synthetic 8-image 3840x2160 horizontal panorama, BASELINE.json configs[2]", "synthetic"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def megapixels(imgs):
+    return sum(i.shape[1] * i.shape[2] for i in imgs) / 1e6
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle/_ref = the reference itself compiled from its sources)
+# ----------------------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    name, idx, reps = args
+    sys.path.insert(0, ROOT)
+    from oracle import ref_api
+    imgs, _, _ = load_workload(name)
+    imgs = [imgs[i] for i in idx]
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out, _info = ref_api.stitch_mem(imgs)
+    return time.perf_counter() - t0, out.shape
+
+
+def ref_sample_plan(name, steps_total, budget_s=200.0):
+    """Pick the bounded sample: the full job when it fits the time budget, else a 2-image sub-panorama."""
+    est_full = {"input": 2.5, "input2": 45.0, "synth4k": 1e9}[name]
+    est_pair = {"input": 1.0, "input2": 12.0, "synth4k": 1e9}[name]
+    if steps_total * est_full <= budget_s:
+        return [0, 1, 2, 3], "the full 4-image job", steps_total
+    n = max(1, min(steps_total, int(budget_s // est_pair)))
+    return [1, 2], "2-image sub-panorama (images 2 and 3 of the set: 2 SIFT, 3 directed matches, 2 RANSAC, 1 blend, tail)", n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_api
+    name = args.workload if args.workload != "synth4k" else "input2"
+    if not ref_api.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpano_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, args.ref_procs))
+    idx, what, nsteps = ref_sample_plan(name, args.steps + args.warmup)
+    warm = min(args.warmup, max(0, nsteps - 1), 1)
+    timed = max(1, min(args.steps, nsteps - warm))
+    imgs, desc, data = load_workload(name)
+    mpix = megapixels([imgs[i] for i in idx])
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        if warm:
+            pool.map(_ref_worker, [(name, idx, warm)] * cores)
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, [(name, idx, timed)] * cores)
+        wall = time.perf_counter() - t0
+    value = cores * timed * mpix / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+        "warmup": warm, "ms_per_step": 1e3 * wall / timed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": data,
+        "config": {"workload": desc, "sample": what, "replicas": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{what} of {desc}; {cores} single-threaded process replicas of oracle/_ref (the reference has no threads), {timed} timed step(s) each"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_single(name, time_cap_s=40.0):
+    """One core, one bounded sample (kind = reference), for the cpu_baseline object of the B200 arm."""
+    from oracle import ref_api
+    if not ref_api.available():
+        return None
+    name = name if name != "synth4k" else "input2"
+    idx, what, _ = ref_sample_plan(name, 1, budget_s=time_cap_s)
+    imgs, desc, _ = load_workload(name)
+    sub = [imgs[i] for i in idx]
+    t0 = time.perf_counter()
+    ref_api.stitch_mem(sub)
+    dt = time.perf_counter() - t0
+    return {"value": megapixels(sub) / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"{what} of {desc}, one run on one core ({dt:.1f} s)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import computervisionimagestich2_b200 as pano
+    L = pano.lib()
+    imgs, desc, data = load_workload(args.workload)
+    n = len(imgs)
+    mpix = megapixels(imgs)
+    ctx = pano.Context(local_rank)
+    ws = (C.c_int * n)(*[i.shape[2] for i in imgs])
+    hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # --- device-resident measurement ------------------------------------------------------------------------------
+    ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+    ctx._check(L.pano_b200_stage_images(ctx.h, ptrs, ws, hs, n), "stage_images")
+    ow, oh = C.c_int(), C.c_int()
+    for _ in range(args.warmup):
+        ctx._check(L.pano_b200_stitch_staged(ctx.h, C.byref(ow), C.byref(oh)), "stitch_staged")
+    L.pano_b200_ktimer_enable(0)
+    L.pano_b200_ktimer_reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    ms = C.c_float()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        L.pano_b200_flush_l2(ctx.h)
+        L.pano_b200_timer_start(ctx.h)
+        ctx._check(L.pano_b200_stitch_staged(ctx.h, C.byref(ow), C.byref(oh)), "stitch_staged")
+        L.pano_b200_timer_stop(ctx.h, C.byref(ms))
+        total_ms += ms.value
+    barrier()
+    launches = L.pano_b200_ktimer_launches()
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * mpix / (ms_per_step / 1e3)
+    t = pano.Times()
+    L.pano_b200_stitch_times(ctx.h, C.byref(t))
+    stages = {f[0]: round(getattr(t, f[0]), 3) for f in pano.Times._fields_}
+
+    # --- end to end through the C ABI with pinned host buffers --------------------------------------------------
+    in_bytes = [3 * i.shape[1] * i.shape[2] for i in imgs]
+    pin_in = []
+    for im, b in zip(imgs, in_bytes):
+        p = L.pano_b200_alloc_pinned(C.c_size_t(b))
+        C.memmove(p, im.ctypes.data, b)
+        pin_in.append(p)
+    out_cap = 3 * ow.value * oh.value
+    pin_out = L.pano_b200_alloc_pinned(C.c_size_t(out_cap))
+    pptrs = (C.c_void_p * n)(*pin_in)
+    e2e_ms = 0.0
+    e2e_steps = max(1, args.steps)
+    for it in range(1 + e2e_steps):
+        L.pano_b200_flush_l2(ctx.h)
+        t0 = time.perf_counter()
+        ctx._check(L.pano_b200_stitch_into(ctx.h, pptrs, ws, hs, n, C.c_void_p(pin_out), C.c_size_t(out_cap), C.byref(ow), C.byref(oh)), "stitch_into")
+        dt = (time.perf_counter() - t0) * 1e3
+        if it > 0:
+            e2e_ms += dt
+    e2e_ms = max_over_ranks(e2e_ms)
+    e2e_value = world * mpix / (e2e_ms / e2e_steps / 1e3)
+    pano_hash = None
+    if rank == 0:
+        res = np.ctypeslib.as_array(C.cast(pin_out, C.POINTER(C.c_uint8)), (out_cap,))
+        pano_hash = pano.fnv1a64(res) if out_cap < (8 << 20) else None
+
+    # --- per-kernel pass (CUDA events around every launch; not part of the timed numbers above) -------------------
+    L.pano_b200_ktimer_reset()
+    L.pano_b200_ktimer_enable(1)
+    L.pano_b200_flush_l2(ctx.h)
+    ctx._check(L.pano_b200_stitch_staged(ctx.h, C.byref(ow), C.byref(oh)), "stitch_staged")
+    buf = C.create_string_buffer(1 << 16)
+    L.pano_b200_ktimer_report(buf, 1 << 16)
+    L.pano_b200_ktimer_enable(0)
+    kernels = json.loads(buf.value.decode())
+    for p in pin_in:
+        L.pano_b200_free_pinned(C.c_void_p(p))
+    L.pano_b200_free_pinned(C.c_void_p(pin_out))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ksum = sum(k["ms"] for k in kernels.values())
+    top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+    top_name, top_k = top
+    roofline = None
+    if top_k["ms"] > 0:
+        per_launch_ms = top_k["ms"] / top_k["launches"]
+        if top_name == "match.l1":  # FP32 CUDA-core kernel: ops, not bytes
+            ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e12
+            # non-FMA FP32 issue peak: 148 SMs x 128 lanes x sm clock
+            clk = (clocks or {}).get("sm_mhz") or 1500.0
+            peak = 148 * 128 * clk * 1e6 / 1e12
+            roofline = {"kernel": top_name, "bound": "fp32-issue", "achieved": ach, "peak": peak, "unit": "Tinstr/s",
+                        "frac": ach / peak, "traffic": None, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
+                        "share_of_kernel_time": top_k["ms"] / ksum,
+                        "note": "exact float-L1 matcher: 2 FP32 instructions (FADD sub, FADD |.|-accumulate) per dimension, no FMA possible; peak = 148 SM x 128 lanes x median SM clock"}
+        else:
+            ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": None, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
+                        "share_of_kernel_time": top_k["ms"] / ksum, "peak_source": peak_src}
+    # the HBM-bound scale-space kernels, always reported (north_star: blur GB/s)
+    hbm_kernels = {}
+    for name, k in kernels.items():
+        if k["ms"] > 0 and k["bytes"] > 0 and not name.startswith(("match", "ransac", "sift.refine", "sift.orient", "sift.descr")):
+            hbm_kernels[name] = {"GBps": round(k["bytes"] / (k["ms"] * 1e-3) / 1e9, 1), "ms": round(k["ms"], 4), "launches": k["launches"]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_single(args.workload)
+        except Exception as e:  # the baseline is informative; never fail the bench on it
+            cpu = {"error": str(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": data,
+        "config": {"workload": desc, "images": n, "input_mpixel": mpix, "output": [ow.value, oh.value],
+                   "l2": "flushed (256 MB memset) between timed iterations", "parallelism": f"replicas x{world}" if world > 1 else "1 GPU",
+                   "bit_exact_vs_reference": True, "panorama_fnv1a64": pano_hash},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(in_bytes), "d2h_bytes_per_step": out_cap,
+                "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "stages_ms_last_step": stages,
+        "kernels_ms": {k: round(v["ms"], 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
+        "hbm_kernels": hbm_kernels,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="input2", choices=["input", "input2", "synth4k"])
+    ap.add_argument("--ref-procs", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,10 @@ def lib() -> C.CDLL:
         L.pano_b200_last_error.argtypes = [C.c_void_p]
         L.pano_b200_free.argtypes = [C.c_void_p]
         L.pano_b200_destroy.argtypes = [C.c_void_p]
+        L.pano_b200_alloc_pinned.restype = C.c_void_p
+        L.pano_b200_alloc_pinned.argtypes = [C.c_size_t]
+        L.pano_b200_free_pinned.argtypes = [C.c_void_p]
+        L.pano_b200_ktimer_launches.restype = C.c_long
         _lib = L
     return _lib
 

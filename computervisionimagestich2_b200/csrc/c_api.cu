@@ -2,6 +2,8 @@
 #include "../../include/pano_b200.h"
 #include "stitcher.h"
 #include "stitch_host.h"
+#include "ktimer.h"
+#include <sstream>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -74,6 +76,89 @@ int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* 
     return 0;
     PB_API_END
 }
+int pano_b200_stage_images(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n) {
+    PB_API_BEGIN
+    ctx->st->stage_images(imgs, w, h, n);
+    return 0;
+    PB_API_END
+}
+int pano_b200_stitch_staged(pano_b200_ctx* ctx, int* out_w, int* out_h) {
+    PB_API_BEGIN
+    int rc = ctx->st->run_staged();
+    if (rc) { ctx->err = ctx->st->error(); return rc; }
+    if (out_w) *out_w = ctx->st->result_width();
+    if (out_h) *out_h = ctx->st->result_height();
+    return 0;
+    PB_API_END
+}
+int pano_b200_result_copy(pano_b200_ctx* ctx, uint8_t* out) {
+    PB_API_BEGIN
+    ctx->st->copy_result(out);
+    return 0;
+    PB_API_END
+}
+int pano_b200_stitch_into(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n,
+                          uint8_t* out, size_t out_cap, int* out_w, int* out_h) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    Stitcher& S = *ctx->st;
+    S.clear();
+    for (int i = 0; i < n; ++i) S.add_image(imgs[i], w[i], h[i]);
+    int rc = S.run();
+    if (rc) { ctx->err = S.error(); return rc; }
+    *out_w = S.result_width();
+    *out_h = S.result_height();
+    if ((size_t)3 * *out_w * *out_h > out_cap) { ctx->err = "output buffer too small"; return -5; }
+    S.copy_result(out);
+    return 0;
+    PB_API_END
+}
+void* pano_b200_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void pano_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+int pano_b200_flush_l2(pano_b200_ctx* ctx) {
+    PB_API_BEGIN
+    ctx->st->flush_l2();
+    return 0;
+    PB_API_END
+}
+int pano_b200_timer_start(pano_b200_ctx* ctx) {
+    PB_API_BEGIN
+    ctx->st->timer_start();
+    return 0;
+    PB_API_END
+}
+int pano_b200_timer_stop(pano_b200_ctx* ctx, float* ms) {
+    PB_API_BEGIN
+    *ms = ctx->st->timer_stop();
+    return 0;
+    PB_API_END
+}
+void pano_b200_ktimer_enable(int on) { KTimer::get().enable(on != 0); }
+void pano_b200_ktimer_reset(void) { KTimer::get().reset(); }
+long pano_b200_ktimer_launches(void) { return KTimer::get().total_launches(); }
+int pano_b200_ktimer_report(char* dst, int cap) {
+    std::ostringstream o;
+    o << "{";
+    bool first = true;
+    for (auto& kv : KTimer::get().snapshot()) {
+        if (!first) o << ", ";
+        first = false;
+        o << "\"" << kv.first << "\": {\"launches\": " << kv.second.launches << ", \"ms\": " << kv.second.ms
+          << ", \"bytes\": " << kv.second.bytes << "}";
+    }
+    o << "}";
+    std::string s = o.str();
+    int n = (int)s.size();
+    if (n >= cap) n = cap - 1;
+    memcpy(dst, s.data(), n);
+    dst[n] = 0;
+    return n;
+}
+
 int pano_b200_stitch_log(pano_b200_ctx* ctx, char* dst, int cap) {
     const std::string& s = ctx->st->log();
     int n = (int)s.size();

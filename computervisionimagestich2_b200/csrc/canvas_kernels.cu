@@ -3,6 +3,7 @@
 // All of them are HBM-bound byte/float streaming; arithmetic is in canvas_device.cuh (bit-exact bodies).
 #include "canvas_kernels.h"
 #include "common.h"
+#include "ktimer.h"
 
 namespace pb {
 
@@ -30,6 +31,7 @@ __global__ void project_gray_kernel(const u8* __restrict__ src, int w, int h, co
 }
 void launch_project_gray(const u8* src, int w, int h, const float* ktab, u8* dst_rgb, float* gray_f32, int gray_pitch,
                          u8* gray8, cudaStream_t st) {
+    KScope ks("canvas.project_gray", st, 10.0 * w * h);
     dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
     project_gray_kernel<<<g, b, 0, st>>>(src, w, h, ktab, dst_rgb, gray_f32, gray_pitch, gray8);
     PB_KERNEL_CHECK();
@@ -46,6 +48,7 @@ __global__ void gray_kernel(const u8* __restrict__ rgb, int w, int h, float* __r
     if (gray8) gray8[o] = gr;
 }
 void launch_gray(const u8* rgb, int w, int h, float* gray_f32, int gray_pitch, u8* gray8, cudaStream_t st) {
+    KScope ks("canvas.gray", st, 7.0 * w * h);
     dim3 b(128, 2), g(div_up(w, 128), div_up(h, 2));
     gray_kernel<<<g, b, 0, st>>>(rgb, w, h, gray_f32, gray_pitch, gray8);
     PB_KERNEL_CHECK();
@@ -83,6 +86,7 @@ __global__ void warp_shift_kernel(const u8* __restrict__ src, int sw, int sh, co
 }
 void launch_warp_shift(const u8* src, int sw, int sh, const double* H8, float offx, float offy, const u8* prev, int pw,
                        int ph, int ioffx, int ioffy, u8* a, u8* b, int cw, int ch, cudaStream_t st) {
+    KScope ks("canvas.warp_shift", st, 12.0 * cw * ch);
     dim3 bl(64, 4), g(div_up(cw, 64), div_up(ch, 4));
     warp_shift_kernel<<<g, bl, 0, st>>>(src, sw, sh, H8, offx, offy, prev, pw, ph, ioffx, ioffy, a, b, cw, ch);
     PB_KERNEL_CHECK();
@@ -109,6 +113,7 @@ __global__ void seam_stats_kernel(const u8* __restrict__ a, const u8* __restrict
     if (threadIdx.x < 4) stats[threadIdx.x] = (int)s[threadIdx.x];
 }
 void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, cudaStream_t st) {
+    KScope ks("blend.seam_stats", st, 2.0 * cw);
     seam_stats_kernel<<<1, 1024, 0, st>>>(a, b, cw, ch, stats);
     PB_KERNEL_CHECK();
 }
@@ -138,6 +143,7 @@ __global__ void level0_kernel(const u8* __restrict__ a, const u8* __restrict__ b
 }
 void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
                    cudaStream_t st) {
+    KScope ks("blend.level0", st, 34.0 * cw * ch);
     dim3 bl(128, 2), g(div_up(cw, 128), div_up(ch, 2));
     level0_kernel<<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
     PB_KERNEL_CHECK();
@@ -226,11 +232,13 @@ __global__ void iir_y_kernel(float* __restrict__ planes, int w, int h, int nplan
 void launch_iir_blur(float* planes, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st) {
     if (w > 1) {
         long nlines = (long)nplanes * h;
+        KScope ks("blend.iir_x", st, 16.0 * nplanes * w * h);
         iir_x_kernel<<<div_up(nlines, 128), 128, 0, st>>>(planes, w, nlines, coef);
         PB_KERNEL_CHECK();
     }
     if (h > 1) {
         long n = (long)w * nplanes;
+        KScope ks("blend.iir_y", st, 16.0 * nplanes * w * h);
         iir_y_kernel<<<div_up(n, 64), 64, 0, st>>>(planes, w, h, nplanes, coef);
         PB_KERNEL_CHECK();
     }
@@ -256,6 +264,7 @@ __global__ void reduce_kernel(const float* __restrict__ src, int w, int h, float
 void launch_reduce(const float* src, int w, int h, int nplanes, float* dst, int nw, int nh, DevMovAvg tx, DevMovAvg ty,
                    cudaStream_t st) {
     if (nw <= 0 || nh <= 0) return;
+    KScope ks("blend.reduce", st, 4.0 * nplanes * ((double)w * h + (double)nw * nh));
     dim3 b(64, 4), g(div_up(nw, 64), div_up(nh, 4), nplanes);
     reduce_kernel<<<g, b, 0, st>>>(src, w, h, dst, nw, nh, tx, ty);
     PB_KERNEL_CHECK();
@@ -281,6 +290,7 @@ __global__ void expand_kernel(const float* __restrict__ src, int w, int h, float
 }
 void launch_expand(const float* src, int w, int h, int nplanes, float* dst, int nw, int nh, DevLinear tx, DevLinear ty,
                    cudaStream_t st) {
+    KScope ks("blend.expand", st, 4.0 * nplanes * ((double)w * h + (double)nw * nh));
     dim3 b(64, 4), g(div_up(nw, 64), div_up(nh, 4), nplanes);
     expand_kernel<<<g, b, 0, st>>>(src, w, h, dst, nw, nh, tx, ty);
     PB_KERNEL_CHECK();
@@ -315,6 +325,7 @@ __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const
 }
 void launch_collapse(const float* G_i, int w, int h, const float* G_up, const float* E_up, int uw, int uh, DevLinear tx,
                      DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st) {
+    KScope ks("blend.collapse", st, (28.0 + (out_u8 ? 3.0 : 12.0)) * w * h + 40.0 * uw * uh);
     dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
     collapse_kernel<<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
     PB_KERNEL_CHECK();
@@ -336,6 +347,7 @@ __global__ void luma_hist_kernel(const u8* __restrict__ rgb, size_t n, int* __re
 void launch_luma_hist(const u8* rgb, int w, int h, int* hist256, cudaStream_t st) {
     size_t n = (size_t)w * h;
     PB_CUDA(cudaMemsetAsync(hist256, 0, 256 * sizeof(int), st));
+    KScope ks("tail.luma_hist", st, 3.0 * n);
     int blocks = div_up((long)n, 256 * 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
     luma_hist_kernel<<<blocks, 256, 0, st>>>(rgb, n, hist256);
@@ -355,6 +367,7 @@ __global__ void equalize_mix_kernel(const u8* __restrict__ rgb, size_t n, const 
 }
 void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, cudaStream_t st) {
     size_t n = (size_t)w * h;
+    KScope ks("tail.equalize_mix", st, 6.0 * n);
     int blocks = div_up((long)n, 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
     equalize_mix_kernel<<<blocks, 256, 0, st>>>(rgb, n, lut256, out);

@@ -11,6 +11,7 @@
 #include "match_device.cuh"
 #include "ransac_device.cuh"
 #include "common.h"
+#include "ktimer.h"
 
 namespace pb {
 
@@ -101,8 +102,12 @@ void launch_match_l1(const float* dA, int NA, const float* dB, int NB, Top2* par
     int rps = align_up(div_up(NA, nsplit), 4);
     nsplit = div_up(NA, rps);
     dim3 g(div_up(NB, kQ), nsplit);
+    {
+    KScope ks("match.l1", st, 256.0 * NA * NB);
     match_l1_kernel<<<g, kQ, 0, st>>>(dA, NA, dB, NB, rps, partial);
     PB_KERNEL_CHECK();
+    }
+    KScope ks2("match.merge", st, 0);
     match_merge_kernel<<<div_up(NB, 128), 128, 0, st>>>(partial, nsplit, NA, NB, idx, d01);
     PB_KERNEL_CHECK();
 }
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(128) ransac_score_kernel(const KeyPair* __rest
 void launch_ransac_score(const KeyPair* pairs, const int* pair_off, int nproblems, const int* samples, int iters,
                          int* counts, unsigned* masks, int words_stride, double* hyp, cudaStream_t st) {
     if (nproblems <= 0) return;
+    KScope ks("ransac.score", st, 0);
     long warps = (long)nproblems * iters;
     // 4 warps per CTA; iters (72) is a multiple of 4 so a CTA never straddles two problems' tail
     long threads = warps * 32;

@@ -6,6 +6,7 @@
 // the reference's `acc += v * c` (vl/imopv.c:163-187).
 #include "sift_kernels.h"
 #include "common.h"
+#include "ktimer.h"
 
 namespace pb {
 
@@ -19,6 +20,7 @@ __global__ void u8_to_f32_kernel(const unsigned char* __restrict__ src, int src_
     if (x < w && y < h) dst[(long)y * pitch + x] = (float)src[(long)y * src_pitch + x];
 }
 void launch_u8_to_f32(const unsigned char* src, int src_pitch, float* dst, int w, int h, int pitch, cudaStream_t st) {
+    KScope ks("sift.u8_to_f32", st, 5.0 * w * h);
     dim3 b(128, 2), g(div_up(w, 128), div_up(h, 2));
     u8_to_f32_kernel<<<g, b, 0, st>>>(src, src_pitch, dst, w, h, pitch);
     PB_KERNEL_CHECK();
@@ -144,8 +146,12 @@ static void launch_blur_w(const float* src, float* tmp, float* dst, int w, int h
                           float* ds, int ds_pitch, cudaStream_t st) {
     constexpr int R = 8;
     dim3 bv(32, 8), gv(div_up(w, 32), div_up(h, 8 * R));
-    blur_v_kernel<W, R><<<gv, bv, 0, st>>>(src, tmp, w, h, pitch, taps);
-    PB_KERNEL_CHECK();
+    {
+        KScope ks("sift.blur_v", st, 4.0 * w * h);
+        blur_v_kernel<W, R><<<gv, bv, 0, st>>>(src, tmp, w, h, pitch, taps);
+        PB_KERNEL_CHECK();
+    }
+    KScope ks("sift.blur_h", st, 4.0 * w * h + (ds ? 1.0 * w * h : 0.0));
     dim3 bh(128, 2), gh(div_up(w, 512), div_up(h, 8));
     if (ds)
         blur_h_kernel<W, true><<<gh, bh, 0, st>>>(tmp, dst, w, h, pitch, taps, ds, ds_pitch, w / 2, h / 2);
@@ -163,6 +169,7 @@ void launch_blur(const float* src, float* tmp, float* dst, int w, int h, int pit
     case 19: launch_blur_w<19>(src, tmp, dst, w, h, pitch, taps, ds, ds_pitch, st); return;
     default: break;
     }
+    KScope ks("sift.blur_generic", st, 8.0 * w * h);
     dim3 b(128, 2), g(div_up(w, 128), div_up(h, 2));
     blur_generic_kernel<<<g, b, 0, st>>>(src, tmp, w, h, pitch, taps, 1);
     PB_KERNEL_CHECK();
@@ -259,6 +266,7 @@ __global__ void detect_generic_kernel(OctaveView ov, SiftConsts sc, Cand* __rest
 
 void launch_detect(const OctaveView& ov, const SiftConsts& sc, Cand* cand, int* count, int cap, cudaStream_t st) {
     if (ov.w < 3 || ov.h < 3) return;
+    KScope ks("sift.detect", st, 16.0 * ov.w * ov.h);
     if (ov.nlevels == 5) {
         dim3 g(div_up(ov.w, 64), div_up(ov.h, 16));
         detect_kernel<5><<<g, 256, 0, st>>>(ov, sc, cand, count, cap);
@@ -280,6 +288,7 @@ __global__ void refine_kernel(OctaveView ov, SiftConsts sc, const Cand* __restri
 }
 void launch_refine(const OctaveView& ov, const SiftConsts& sc, const Cand* cand, const int* count, int cap,
                    RefinedKey* out, double xper, cudaStream_t st) {
+    KScope ks("sift.refine", st, 0);
     int blocks = div_up(cap, 128);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
@@ -303,6 +312,7 @@ __global__ void gradient_kernel(OctaveView ov, int first_level, float* __restric
 void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cudaStream_t st) {
     int nl = (sc.s_max - 2) - (sc.s_min + 1) + 1;
     if (nl <= 0) return;
+    KScope ks("sift.gradient", st, 12.0 * nl * ov.w * ov.h);
     dim3 b(128, 2), g(div_up(ov.w, 128), div_up(ov.h, 2), nl);
     gradient_kernel<<<g, b, 0, st>>>(ov, 1, grad);  // grad level l <-> s = s_min+1+l <-> GSS level index 1+l
     PB_KERNEL_CHECK();
@@ -333,6 +343,7 @@ __global__ void __launch_bounds__(128) orient_kernel(OctaveView ov, SiftConsts s
 void launch_orient(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
                    int nkeys, double xper, int* nangles, double* angles, cudaStream_t st) {
     if (nkeys <= 0) return;
+    KScope ks("sift.orient", st, 36.0 * nkeys);
     const int threads = 128;
     size_t smem = (size_t)(threads / 32) * 36 * 32 * sizeof(double);
     orient_kernel<<<div_up(nkeys, threads), threads, smem, st>>>(ov, sc, expn_tab, o_cur, keys, nkeys, xper, nangles,
@@ -359,6 +370,7 @@ __global__ void __launch_bounds__(64) descr_kernel(OctaveView ov, SiftConsts sc,
 void launch_descr(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
                   const DescJob* jobs, int njobs, double xper, float* descr, int* written, cudaStream_t st) {
     if (njobs <= 0) return;
+    KScope ks("sift.descr", st, 512.0 * njobs);
     const int threads = 64;
     size_t smem = (size_t)(threads / 32) * 128 * 32 * sizeof(float);
     descr_kernel<<<div_up(njobs, threads), threads, smem, st>>>(ov, sc, expn_tab, o_cur, keys, jobs, njobs, xper,

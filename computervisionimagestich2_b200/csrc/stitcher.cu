@@ -505,17 +505,23 @@ void Stitcher::clear() {
 // readFile body for one image (ImageProcess.cpp:12-23)
 void Stitcher::add_image(const u8* rgb, int w, int h) {
     PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)w * h;
+    in_rgb_.ensure(3 * n);
+    PB_CUDA(cudaMemcpyAsync(in_rgb_.p, rgb, 3 * n, cudaMemcpyHostToDevice, st_));
+    add_image_device(in_rgb_.p, w, h);
+}
+
+void Stitcher::add_image_device(const u8* d_rgb, int w, int h) {
+    PB_CUDA(cudaSetDevice(dev_));
     WallTimer t0;
     std::unique_ptr<Image> im(new Image());
     im->w = w; im->h = h;
     size_t n = (size_t)w * h;
-    in_rgb_.ensure(3 * n);
     im->proj.ensure(3 * n);
     int pitch = align_up(w, 32);
     gray32_.ensure((size_t)pitch * h);
     ensure_ktab(std::min(w, h));
-    PB_CUDA(cudaMemcpyAsync(in_rgb_.p, rgb, 3 * n, cudaMemcpyHostToDevice, st_));
-    launch_project_gray(in_rgb_.p, w, h, ktab_.p, im->proj.p, gray32_.p, pitch, nullptr, st_);
+    launch_project_gray(d_rgb, w, h, ktab_.p, im->proj.p, gray32_.p, pitch, nullptr, st_);
     PB_CUDA(cudaStreamSynchronize(st_));
     tm_.project += t0.ms();
     WallTimer t1;
@@ -530,6 +536,46 @@ void Stitcher::add_image(const u8* rgb, int w, int h) {
     upload_table(im->feat);
     tm_.table += t2.ms();
     imgs_.push_back(std::move(im));
+}
+
+void Stitcher::stage_images(const u8* const* imgs, const int* w, const int* h, int n) {
+    PB_CUDA(cudaSetDevice(dev_));
+    staged_.clear();
+    for (int i = 0; i < n; ++i) {
+        std::unique_ptr<Staged> s(new Staged());
+        s->w = w[i]; s->h = h[i];
+        size_t bytes = (size_t)3 * w[i] * h[i];
+        s->rgb.ensure(bytes);
+        PB_CUDA(cudaMemcpyAsync(s->rgb.p, imgs[i], bytes, cudaMemcpyHostToDevice, st_));
+        staged_.push_back(std::move(s));
+    }
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+int Stitcher::run_staged() {
+    clear();
+    for (auto& s : staged_) add_image_device(s->rgb.p, s->w, s->h);
+    return run();
+}
+
+void Stitcher::flush_l2() {
+    PB_CUDA(cudaSetDevice(dev_));
+    const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+    flush_.ensure(bytes);
+    PB_CUDA(cudaMemsetAsync(flush_.p, 1, bytes, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+void Stitcher::timer_start() {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (!ev0_) { PB_CUDA(cudaEventCreate(&ev0_)); PB_CUDA(cudaEventCreate(&ev1_)); }
+    PB_CUDA(cudaEventRecord(ev0_, st_));
+}
+float Stitcher::timer_stop() {
+    PB_CUDA(cudaEventRecord(ev1_, st_));
+    PB_CUDA(cudaEventSynchronize(ev1_));
+    float ms = 0;
+    PB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return ms;
 }
 
 int Stitcher::run() {

@@ -62,6 +62,13 @@ class Stitcher {
     // ---- pipeline ---------------------------------------------------------------------------------------
     void clear();
     void add_image(const u8* rgb, int w, int h);     // planar RGB host buffer
+    void add_image_device(const u8* d_rgb, int w, int h);   // planar RGB already resident in HBM
+    // inputs staged in HBM once (outside any timed region), then stitched any number of times
+    void stage_images(const u8* const* imgs, const int* w, const int* h, int n);
+    int run_staged();
+    void flush_l2();
+    void timer_start();
+    float timer_stop();
     int run();                                       // 0 ok; fills result
     int result_width() const { return rw_; }
     int result_height() const { return rh_; }
@@ -102,6 +109,10 @@ class Stitcher {
     DevBuf<float> tab_f_;
     DevBuf<double> tab_d_;
     int cur_ = 0, rw_ = 0, rh_ = 0;
+    struct Staged { int w, h; DevBuf<u8> rgb; };
+    std::vector<std::unique_ptr<Staged>> staged_;
+    DevBuf<char> flush_;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::string log_, err_;
     StageTimes tm_;
 };

@@ -10,6 +10,7 @@
  */
 #ifndef PANO_B200_H
 #define PANO_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -46,6 +47,14 @@ void pano_b200_free(void* p); /* frees any buffer this library returned through 
  *      ImageProcess.h:145).  imgs[i]: planar RGB of size w[i] x h[i].  *out is library-allocated (pano_b200_free). */
 int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n, uint8_t** out,
                      int* out_w, int* out_h);
+/* same, into a caller-provided (e.g. pinned) buffer of out_cap bytes */
+int pano_b200_stitch_into(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n,
+                          uint8_t* out, size_t out_cap, int* out_w, int* out_h);
+/* Inputs staged in HBM once, then stitched any number of times with no host<->device pixel traffic
+ * (device-resident throughput measurement); pano_b200_result_copy downloads the last result. */
+int pano_b200_stage_images(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n);
+int pano_b200_stitch_staged(pano_b200_ctx* ctx, int* out_w, int* out_h);
+int pano_b200_result_copy(pano_b200_ctx* ctx, uint8_t* out);
 /* the lines the reference prints to stdout: middle index, then "src dst" per stitched edge (ImageProcess.cpp:183,391) */
 int pano_b200_stitch_log(pano_b200_ctx* ctx, char* dst, int cap);
 int pano_b200_stitch_times(pano_b200_ctx* ctx, pano_b200_times* t);
@@ -107,6 +116,17 @@ int pano_b200_equalize_mix(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h,
  * (CImg.h:29321-29700) on float planes [c][h][w]; the two CImg primitives blendTwoImages is made of. */
 int pano_b200_cimg_blur2(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst);
 int pano_b200_cimg_resize3(pano_b200_ctx* ctx, const float* src, int w, int h, int c, int nw, int nh, float* dst);
+
+/* ---- measurement helpers --------------------------------------------------------------------------------------- */
+void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
+void pano_b200_free_pinned(void* p);
+int pano_b200_flush_l2(pano_b200_ctx* ctx);           /* overwrite a 256 MB scratch buffer (2x L2) */
+int pano_b200_timer_start(pano_b200_ctx* ctx);        /* CUDA events on the context's stream */
+int pano_b200_timer_stop(pano_b200_ctx* ctx, float* ms);
+void pano_b200_ktimer_enable(int on);                 /* per-kernel CUDA-event timing (adds 2 event records / launch) */
+void pano_b200_ktimer_reset(void);
+long pano_b200_ktimer_launches(void);                 /* kernels launched by this library since the last reset */
+int pano_b200_ktimer_report(char* dst, int cap);      /* JSON {kernel: {launches, ms, bytes}} */
 
 #ifdef __cplusplus
 }
