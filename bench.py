@@ -85,49 +85,59 @@ def megapixels(imgs):
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region by an in-process NVML thread (a spawned
+    `nvidia-smi -lms` loop takes driver locks that stall a launch/sync-heavy host pipeline)."""
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, gpu_index, period_s=0.05):
+        import threading
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self.ok = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    idx = gpu_index
+            self.h = N.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        N = self.N
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                r = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        if not self.ok:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+        self._stop.set()
+        self.t.join(timeout=2)
+        if self.sm:
+            out["sm_mhz"] = statistics.median(self.sm)
+            out["sm_max_mhz"] = self.max_sm
+        out["reasons"] = sorted(self.reasons)
+        out["samples"] = len(self.sm)
         return out
 
 

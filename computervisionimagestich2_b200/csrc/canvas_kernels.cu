@@ -154,7 +154,8 @@ void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, f
 // x pass: one warp owns 32 consecutive rows; 32x32 tiles are moved with coalesced accesses and transposed through
 // shared memory so that lane r walks row r sequentially with its 3 doubles of filter state in registers.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) iir_x_kernel(float* __restrict__ planes, int w, long nlines, IirCoef c) {
+__global__ void __launch_bounds__(128) iir_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int w,
+                                                    long nlines, IirCoef c) {
     __shared__ float tile[4][32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long line0 = ((long)blockIdx.x * 4 + warp) * 32;
@@ -163,18 +164,27 @@ __global__ void __launch_bounds__(128) iir_x_kernel(float* __restrict__ planes, 
     const long myline = line0 + lane;
     const bool active = myline < nlines;
     const int nrows = (int)((nlines - line0) < 32 ? (nlines - line0) : 32);
-    float* base = planes + line0 * (long)w;
+    const float* sbase = src + line0 * (long)w;
+    float* dbase = dst + line0 * (long)w;
     double v1 = 0, v2 = 0, v3 = 0, iplus = 0;
     if (active) {
-        iplus = (double)planes[myline * (long)w + (w - 1)];
-        v1 = v2 = v3 = (double)planes[myline * (long)w] / c.sumsq;
+        iplus = (double)src[myline * (long)w + (w - 1)];
+        v1 = v2 = v3 = (double)src[myline * (long)w] / c.sumsq;
     }
-    // forward
+    float pre[32];
+    // forward (reads src, writes dst); the next tile is prefetched into registers while this one is filtered
+#pragma unroll
+    for (int r = 0; r < 32; ++r) pre[r] = (r < nrows && lane < w) ? sbase[(long)r * w + lane] : 0.0f;
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int nx = (w - x0) < 32 ? (w - x0) : 32;
-        if (lane < nx)
-            for (int r = 0; r < nrows; ++r) t[r][lane] = base[(long)r * w + x0 + lane];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) t[r][lane] = pre[r];
         __syncwarp();
+        const int xn = x0 + 32;
+        if (xn < w) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) pre[r] = (r < nrows && xn + lane < w) ? sbase[(long)r * w + xn + lane] : 0.0f;
+        }
         if (active)
             for (int i = 0; i < nx; ++i) {
                 double v0 = (double)t[lane][i];
@@ -183,17 +193,28 @@ __global__ void __launch_bounds__(128) iir_x_kernel(float* __restrict__ planes, 
                 v3 = v2; v2 = v1; v1 = v0;
             }
         __syncwarp();
-        if (lane < nx)
-            for (int r = 0; r < nrows; ++r) base[(long)r * w + x0 + lane] = t[r][lane];
+        if (lane < nx) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+                if (r < nrows) dbase[(long)r * w + x0 + lane] = t[r][lane];
+        }
         __syncwarp();
     }
-    // backward
+    // backward (in place on dst)
     bool first = true;
-    for (int x0 = ((w - 1) / 32) * 32; x0 >= 0; x0 -= 32) {
+    const int xlast = ((w - 1) / 32) * 32;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) pre[r] = (r < nrows && xlast + lane < w) ? dbase[(long)r * w + xlast + lane] : 0.0f;
+    for (int x0 = xlast; x0 >= 0; x0 -= 32) {
         const int nx = (w - x0) < 32 ? (w - x0) : 32;
-        if (lane < nx)
-            for (int r = 0; r < nrows; ++r) t[r][lane] = base[(long)r * w + x0 + lane];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) t[r][lane] = pre[r];
         __syncwarp();
+        const int xn = x0 - 32;
+        if (xn >= 0) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) pre[r] = (r < nrows) ? dbase[(long)r * w + xn + lane] : 0.0f;
+        }
         if (active)
             for (int i = nx - 1; i >= 0; --i) {
                 double v0;
@@ -215,31 +236,81 @@ __global__ void __launch_bounds__(128) iir_x_kernel(float* __restrict__ planes, 
             }
         first = false;
         __syncwarp();
-        if (lane < nx)
-            for (int r = 0; r < nrows; ++r) base[(long)r * w + x0 + lane] = t[r][lane];
+        if (lane < nx) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+                if (r < nrows) dbase[(long)r * w + x0 + lane] = t[r][lane];
+        }
         __syncwarp();
     }
 }
 
 // y pass: one thread per column of a plane; neighbouring threads touch neighbouring addresses on every step.
-__global__ void iir_y_kernel(float* __restrict__ planes, int w, int h, int nplanes, IirCoef c) {
+// Rows are processed in batches of 8: the 8 loads are independent of the recurrence and issue back to back.
+__global__ void __launch_bounds__(64) iir_y_kernel(float* __restrict__ planes, int w, int h, int nplanes, IirCoef c) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)w * nplanes) return;
-    int p = (int)(i / w), x = (int)(i - (long)p * w);
-    iir_line(planes + (size_t)p * w * h + x, h, w, c);
+    const int p = (int)(i / w), x = (int)(i - (long)p * w);
+    float* data = planes + (size_t)p * w * h + x;
+    const long off = w;
+    const int N = h;
+    constexpr int B = 8;
+    double v1, v2, v3;
+    const double iplus = (double)data[(long)(N - 1) * off];
+    v1 = v2 = v3 = (double)data[0] / c.sumsq;
+    for (int n0 = 0; n0 < N; n0 += B) {
+        float in[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) in[j] = (n0 + j < N) ? data[(long)(n0 + j) * off] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+            if (n0 + j < N) {
+                double v0 = (double)in[j];
+                v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+                data[(long)(n0 + j) * off] = (float)v0;
+                v3 = v2; v2 = v1; v1 = v0;
+            }
+    }
+    {
+        const double uplus = iplus / c.bnd, vplus = uplus / c.bnd;
+        const double unp = v1 - uplus, unp1 = v2 - uplus, unp2 = v3 - uplus;
+        const double v0 = (c.M[0] * unp + c.M[1] * unp1 + c.M[2] * unp2 + vplus) * c.sum;
+        const double n1 = (c.M[3] * unp + c.M[4] * unp1 + c.M[5] * unp2 + vplus) * c.sum;
+        const double n2 = (c.M[6] * unp + c.M[7] * unp1 + c.M[8] * unp2 + vplus) * c.sum;
+        data[(long)(N - 1) * off] = (float)v0;
+        v3 = n2; v2 = n1; v1 = v0;
+    }
+    for (int n0 = N - 2; n0 >= 0; n0 -= B) {
+        float in[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) in[j] = (n0 - j >= 0) ? data[(long)(n0 - j) * off] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+            if (n0 - j >= 0) {
+                double v0 = (double)in[j];
+                v0 *= c.sum;
+                v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+                data[(long)(n0 - j) * off] = (float)v0;
+                v3 = v2; v2 = v1; v1 = v0;
+            }
+    }
 }
 
-void launch_iir_blur(float* planes, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st) {
+void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st) {
+    const float* ysrc = src;
     if (w > 1) {
         long nlines = (long)nplanes * h;
         KScope ks("blend.iir_x", st, 16.0 * nplanes * w * h);
-        iir_x_kernel<<<div_up(nlines, 128), 128, 0, st>>>(planes, w, nlines, coef);
+        iir_x_kernel<<<div_up(nlines, 128), 128, 0, st>>>(src, dst, w, nlines, coef);
         PB_KERNEL_CHECK();
+        ysrc = dst;
     }
+    if (ysrc != dst)
+        PB_CUDA(cudaMemcpyAsync(dst, src, (size_t)nplanes * w * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (h > 1) {
         long n = (long)w * nplanes;
         KScope ks("blend.iir_y", st, 16.0 * nplanes * w * h);
-        iir_y_kernel<<<div_up(n, 64), 64, 0, st>>>(planes, w, h, nplanes, coef);
+        iir_y_kernel<<<div_up(n, 64), 64, 0, st>>>(dst, w, h, nplanes, coef);
         PB_KERNEL_CHECK();
     }
 }

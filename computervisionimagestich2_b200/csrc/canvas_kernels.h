@@ -25,8 +25,9 @@ void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, cud
 void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
                    cudaStream_t st);
 
-// CImg get_blur(2, true, true) on `nplanes` planes [nplanes][h][w] in place (x pass then y pass).
-void launch_iir_blur(float* planes, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st);
+// CImg get_blur(2, true, true) on `nplanes` planes [nplanes][h][w]: dst = blur(src) (x pass src->dst, y pass in place
+// on dst; src may equal dst).
+void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st);
 
 // Moving-average 2:1 reduce (CImg resize type 2 via type 3): src [n][h][w] -> dst [n][nh][nw]; tables on device.
 struct DevMovAvg { const int* start; const int* src; const float* wgt; float div; };  // div = source length (1 for identity)

@@ -332,4 +332,136 @@ PB_HD int descriptor_of(const OctaveView& ov, const SiftConsts& sc, const double
     return 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Descriptor, cell-parallel formulation (what the CUDA kernel runs).
+//
+// The reference scans the (2W+1)^2 window in raster order and scatters every sample into 2x2 spatial cells x 2
+// orientation bins.  Floating-point addition order matters only WITHIN a bin, and a bin belongs to exactly one
+// spatial cell, so the 16 cells can be accumulated independently: a worker that owns cell (cx, cy) visits, in raster
+// order, only the samples that can reach its cell (a rotated square of side 2*SBP in the patch; it scans a
+// conservative superset and applies the reference's exact bin test to every sample), and adds them to its own 8
+// orientation bins.  Every bin therefore receives exactly the reference's addends in the reference's order.
+// ---------------------------------------------------------------------------------------------------------
+struct DescFrame {
+    double x, y, SBP, st0, ct0, angle0, wden;
+    int xi, yi, W, dx0, dx1, dy0, dy1;
+    const float* pt;   // gradient plane of the keypoint's level
+    int pitch;
+    int valid;
+};
+
+PB_HD DescFrame descriptor_frame(const OctaveView& ov, const SiftConsts& sc, int o_cur, int ko, int kis, float kx,
+                                 float ky, float ksigma, double xper, double angle0, double st0, double ct0) {
+    enum { NBP = 4 };
+    DescFrame F;
+    const int w = ov.w, h = ov.h;
+    F.x = (double)kx / xper;
+    F.y = (double)ky / xper;
+    const double sigma = (double)ksigma / xper;
+    F.xi = (int)(F.x + 0.5);
+    F.yi = (int)(F.y + 0.5);
+    F.SBP = sc.magnif * sigma + kEpsD;
+    F.W = (int)floor(1.4142135623730951 * F.SBP * (NBP + 1) / 2.0 + 0.5);
+    F.st0 = st0; F.ct0 = ct0; F.angle0 = angle0;
+    const float wsigma = (float)sc.window_size;
+    F.wden = 2.0 * wsigma * wsigma;
+    F.valid = !(ko != o_cur || F.xi < 0 || F.xi >= w || F.yi < 0 || F.yi >= h - 1 || kis < sc.s_min + 1 ||
+                kis > sc.s_max - 2);
+    F.pt = ov.grad + 2 * ((long)(kis - sc.s_min - 1) * ov.h * ov.pitch);
+    F.pitch = ov.pitch;
+    F.dy0 = (-F.W > 1 - F.yi) ? -F.W : 1 - F.yi;
+    F.dy1 = (F.W < h - F.yi - 2) ? F.W : h - F.yi - 2;
+    F.dx0 = (-F.W > 1 - F.xi) ? -F.W : 1 - F.xi;
+    F.dx1 = (F.W < w - F.xi - 2) ? F.W : w - F.xi - 2;
+    return F;
+}
+
+// Accumulates cell (cx, cy), cx, cy in -2..1, into hist8[t * hstride], t = 0..7 (must be zeroed by the caller).
+PB_HD void descriptor_cell(const DescFrame& F, const double* __restrict__ expn_tab, int cx, int cy, float* hist8,
+                           int hstride) {
+    enum { NBO = 8 };
+    const double ucx = cx + 0.5, ucy = cy + 0.5;
+    // centre and half extent (bounding box) of the cell's footprint, in pixel offsets from the keypoint
+    const double pcx = F.SBP * (F.ct0 * ucx - F.st0 * ucy);
+    const double pcy = F.SBP * (F.st0 * ucx + F.ct0 * ucy);
+    const double act = abs_d(F.ct0), ast = abs_d(F.st0);
+    const double e = F.SBP * (act + ast) + 1.5;
+    const double offx = (double)F.xi - F.x, offy = (double)F.yi - F.y;   // sample offset = d?i + off?
+    int ry0 = (int)floor(pcy - e - offy), ry1 = (int)floor(pcy + e - offy) + 1;
+    if (ry0 < F.dy0) ry0 = F.dy0;
+    if (ry1 > F.dy1) ry1 = F.dy1;
+    const int bx0 = (int)floor(pcx - e - offx), bx1 = (int)floor(pcx + e - offx) + 1;
+    for (int dyi = ry0; dyi <= ry1; ++dyi) {
+        const double dyr = (double)dyi + offy;
+        // x range where both rotated-strip constraints can hold (+1.5 px slack), clipped to the bounding box
+        double lo = (double)bx0, hi = (double)bx1;
+        if (act > 1e-3) {  // |ct0*dx + st0*dy - SBP*ucx| <= SBP
+            const double c = F.SBP * ucx - F.st0 * dyr;
+            double a = (c - F.SBP) / F.ct0, b = (c + F.SBP) / F.ct0;
+            if (a > b) { double t = a; a = b; b = t; }
+            a = a - offx - 1.5; b = b - offx + 1.5;
+            if (a > lo) lo = a;
+            if (b < hi) hi = b;
+        }
+        if (ast > 1e-3) {  // |-st0*dx + ct0*dy - SBP*ucy| <= SBP
+            const double c = F.ct0 * dyr - F.SBP * ucy;
+            double a = (c - F.SBP) / F.st0, b = (c + F.SBP) / F.st0;
+            if (a > b) { double t = a; a = b; b = t; }
+            a = a - offx - 1.5; b = b - offx + 1.5;
+            if (a > lo) lo = a;
+            if (b < hi) hi = b;
+        }
+        if (lo > hi) continue;
+        int x0 = (int)floor(lo), x1 = (int)floor(hi) + 1;
+        if (x0 < F.dx0) x0 = F.dx0;
+        if (x1 > F.dx1) x1 = F.dx1;
+        const float* row = F.pt + 2 * ((long)(F.yi + dyi) * F.pitch);
+        const float dy = (float)((double)(F.yi + dyi) - F.y);
+        const double sdy = F.st0 * (double)dy, cdy = F.ct0 * (double)dy;
+        for (int dxi = x0; dxi <= x1; ++dxi) {
+            const float dx = (float)((double)(F.xi + dxi) - F.x);
+            const float nx = (float)((F.ct0 * (double)dx + sdy) / F.SBP);
+            const int binx = floor_f((float)((double)nx - 0.5));
+            const int dbx = cx - binx;
+            if (dbx != 0 && dbx != 1) continue;
+            const float ny = (float)((-F.st0 * (double)dx + cdy) / F.SBP);
+            const int biny = floor_f((float)((double)ny - 0.5));
+            const int dby = cy - biny;
+            if (dby != 0 && dby != 1) continue;
+            const float mod = row[2 * (F.xi + dxi)];
+            const float angle = row[2 * (F.xi + dxi) + 1];
+            const float theta = mod_2pi_f((float)((double)angle - F.angle0));
+            const float nt = (float)((double)((float)NBO * theta) / (2 * kPi));
+            const float win = (float)fast_expn(expn_tab, (double)(nx * nx + ny * ny) / F.wden);
+            const int bint = floor_f(nt);
+            const float rbinx = (float)((double)nx - ((double)binx + 0.5));
+            const float rbiny = (float)((double)ny - ((double)biny + 0.5));
+            const float rbint = nt - (float)bint;
+            const float wxy = win * mod * fabs_f((float)(1 - dbx) - rbinx) * fabs_f((float)(1 - dby) - rbiny);
+            hist8[((bint + 0) % NBO) * hstride] += wxy * fabs_f((float)(1 - 0) - rbint);
+            hist8[((bint + 1) % NBO) * hstride] += wxy * fabs_f((float)(1 - 1) - rbint);
+        }
+    }
+}
+
+// normalise -> clamp 0.2 -> normalise over the 128 bins in index order (vl/sift.c:1048-1063, 1415-1436);
+// hist: bin b at hist[b * hstride]; writes out[0..127]
+PB_HD void descriptor_finish(const SiftConsts& sc, float* hist, int hstride, float* __restrict__ out) {
+    const int n = 128;
+    float norm = 0.0f;
+    for (int i = 0; i < n; ++i) norm += hist[i * hstride] * hist[i * hstride];
+    norm = fast_sqrt_f(norm) + kEpsF;
+    for (int i = 0; i < n; ++i) hist[i * hstride] /= norm;
+    if (sc.norm_thresh != 0 && (double)norm < sc.norm_thresh) {
+        for (int i = 0; i < n; ++i) out[i] = 0;
+        return;
+    }
+    for (int i = 0; i < n; ++i)
+        if ((double)hist[i * hstride] > 0.2) hist[i * hstride] = (float)0.2;
+    norm = 0.0f;
+    for (int i = 0; i < n; ++i) norm += hist[i * hstride] * hist[i * hstride];
+    norm = fast_sqrt_f(norm) + kEpsF;
+    for (int i = 0; i < n; ++i) out[i] = hist[i * hstride] / norm;
+}
+
 }  // namespace pb

@@ -324,57 +324,181 @@ void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cu
 // The histograms of a warp's 32 items are interleaved in shared memory (bin b of lane l at [b * 32 + l]):
 // conflict-free whatever bins the lanes touch.
 // ---------------------------------------------------------------------------------------------------------
+// Orientation: one warp per keypoint.  The lanes evaluate 32 consecutive samples of the patch (raster order) in
+// parallel; the two histogram contributions of every sample are then handed, in sample order, to the lane that owns
+// the bin (lane b owns bins b and b + 32), so each bin sees the reference's addends in the reference's order.
+// Smoothing and peak picking are 36-element serial recurrences, done redundantly by every lane from shared memory.
 __global__ void __launch_bounds__(128) orient_kernel(OctaveView ov, SiftConsts sc, const double* __restrict__ expn_tab,
                                                      int o_cur, const KeyIn* __restrict__ keys, int nkeys, double xper,
                                                      int* __restrict__ nangles, double* __restrict__ angles) {
-    extern __shared__ double hsm[];
     __shared__ double tab[257];
+    __shared__ double hsm[4][36];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
     __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nkeys) return;
-    double* hist = hsm + (threadIdx.x >> 5) * 36 * 32 + (threadIdx.x & 31);
-    KeyIn k = keys[i];
-    double a[4] = {0, 0, 0, 0};
-    int n = orientations_of(ov, sc, tab, o_cur, o_cur, k.is, k.x, k.y, k.sigma, xper, hist, 32, a);
-    nangles[i] = n;
-    for (int j = 0; j < 4; ++j) angles[i * 4 + j] = a[j];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ki = blockIdx.x * 4 + wid;
+    if (ki >= nkeys) return;
+    const KeyIn k = keys[ki];
+    enum { nbins = 36 };
+    const int w = ov.w, h = ov.h;
+    const double x = (double)k.x / xper, y = (double)k.y / xper, sigma = (double)k.sigma / xper;
+    const int xi = (int)(x + 0.5), yi = (int)(y + 0.5), si = k.is;
+    const double sigmaw = 1.5 * sigma;
+    const double Wd = floor(3.0 * sigmaw);
+    const int W = (int)(Wd > 1 ? Wd : 1);
+    if (xi < 0 || xi > w - 1 || yi < 0 || yi > h - 1 || si < sc.s_min + 1 || si > sc.s_max - 2) {
+        if (lane == 0) { nangles[ki] = 0; for (int j = 0; j < 4; ++j) angles[ki * 4 + j] = 0; }
+        return;
+    }
+    const float* pt = ov.grad + 2 * ((long)(si - sc.s_min - 1) * ov.h * ov.pitch);
+    const int ys0 = (-W > -yi) ? -W : -yi, ys1 = (W < h - 1 - yi) ? W : h - 1 - yi;
+    const int xs0 = (-W > -xi) ? -W : -xi, xs1 = (W < w - 1 - xi) ? W : w - 1 - xi;
+    const int nxw = xs1 - xs0 + 1, total = nxw * (ys1 - ys0 + 1);
+    const double r2max = W * W + 0.6, den = 2 * sigmaw * sigmaw;
+    double h0 = 0.0, h1 = 0.0;  // bins lane and lane + 32
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        int bin = -1000;
+        double v0 = 0.0, v1 = 0.0;
+        if (i < total) {
+            const int ry = i / nxw, ys = ys0 + ry, xs = xs0 + (i - ry * nxw);
+            const double dx = (double)(xi + xs) - x, dy = (double)(yi + ys) - y;
+            const double r2 = dx * dx + dy * dy;
+            if (!(r2 >= r2max)) {
+                const float2 g = reinterpret_cast<const float2*>(pt)[(long)(yi + ys) * ov.pitch + (xi + xs)];
+                const double wgt = fast_expn(tab, r2 / den);
+                const double mod = g.x, ang = g.y;
+                const double fbin = nbins * ang / (2 * kPi);
+                bin = floor_d(fbin - 0.5);
+                const double rbin = fbin - bin - 0.5;
+                v0 = (1 - rbin) * mod * wgt;
+                v1 = (rbin)*mod * wgt;
+            }
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, bin != -1000);
+        for (unsigned m = any; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const int bj = __shfl_sync(0xffffffffu, bin, j);
+            const double a0 = __shfl_sync(0xffffffffu, v0, j);
+            const double a1 = __shfl_sync(0xffffffffu, v1, j);
+            const int b0 = (bj + nbins) % nbins, b1 = (bj + 1) % nbins;
+            if (b0 == lane) h0 += a0; else if (b0 == lane + 32) h1 += a0;
+            if (b1 == lane) h0 += a1; else if (b1 == lane + 32) h1 += a1;
+        }
+    }
+    double* hist = hsm[wid];
+    hist[lane] = h0;
+    if (lane < 4) hist[lane + 32] = h1;
+    __syncwarp();
+    // vl/sift.c:1000-1036 on a private copy (every lane computes the same thing; lane 0 stores)
+    double hh[nbins];
+#pragma unroll
+    for (int i = 0; i < nbins; ++i) hh[i] = hist[i];
+    for (int iter = 0; iter < 6; iter++) {
+        double prev = hh[nbins - 1];
+        const double first = hh[0];
+#pragma unroll
+        for (int i = 0; i < nbins - 1; i++) {
+            const double newh = (prev + hh[i] + hh[i + 1]) / 3.0;
+            prev = hh[i];
+            hh[i] = newh;
+        }
+        hh[nbins - 1] = (prev + hh[nbins - 1] + first) / 3.0;
+    }
+    double maxh = 0;
+#pragma unroll
+    for (int i = 0; i < nbins; ++i) maxh = (maxh > hh[i]) ? maxh : hh[i];
+    int na = 0;
+    double out[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < nbins; ++i) {
+        const double c0 = hh[i], hm = hh[(i - 1 + nbins) % nbins], hp = hh[(i + 1) % nbins];
+        if (na < 4 && c0 > 0.8 * maxh && c0 > hm && c0 > hp) {
+            const double di = -0.5 * (hp - hm) / (hp + hm - 2 * c0);
+            out[na++] = 2 * kPi * (i + di + 0.5) / nbins;
+        }
+    }
+    if (lane == 0) {
+        nangles[ki] = na;
+        for (int j = 0; j < 4; ++j) angles[ki * 4 + j] = out[j];
+    }
 }
 void launch_orient(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
                    int nkeys, double xper, int* nangles, double* angles, cudaStream_t st) {
     if (nkeys <= 0) return;
     KScope ks("sift.orient", st, 36.0 * nkeys);
-    const int threads = 128;
-    size_t smem = (size_t)(threads / 32) * 36 * 32 * sizeof(double);
-    orient_kernel<<<div_up(nkeys, threads), threads, smem, st>>>(ov, sc, expn_tab, o_cur, keys, nkeys, xper, nangles,
-                                                                 angles);
+    orient_kernel<<<div_up(nkeys, 4), 128, 0, st>>>(ov, sc, expn_tab, o_cur, keys, nkeys, xper, nangles, angles);
     PB_KERNEL_CHECK();
 }
 
-__global__ void __launch_bounds__(64) descr_kernel(OctaveView ov, SiftConsts sc, const double* __restrict__ expn_tab,
-                                                   int o_cur, const KeyIn* __restrict__ keys,
-                                                   const DescJob* __restrict__ jobs, int njobs, double xper,
-                                                   float* __restrict__ descr, int* __restrict__ written) {
-    extern __shared__ float fsm[];
+// Descriptor: 16 lanes (half a warp) per (keypoint, angle), one lane per spatial cell of the 4x4 grid.  Each lane
+// walks -- in raster order -- only the part of the patch that can reach its cell and keeps its 8 orientation bins
+// privately, so every bin receives the reference's addends in the reference's order (see descriptor_cell in
+// sift_device.cuh) while 16 lanes share the work of one descriptor.  The 128 bins are then gathered in shared
+// memory for the two sequential L2 normalisations and written as one 512-byte row.
+__global__ void __launch_bounds__(128) descr_kernel(OctaveView ov, SiftConsts sc, const double* __restrict__ expn_tab,
+                                                    int o_cur, const KeyIn* __restrict__ keys,
+                                                    const DescJob* __restrict__ jobs, int njobs, double xper,
+                                                    float* __restrict__ descr, int* __restrict__ written) {
     __shared__ double tab[257];
+    __shared__ float hs[8][128];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
     __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= njobs) return;
-    float* hist = fsm + (threadIdx.x >> 5) * 128 * 32 + (threadIdx.x & 31);
-    DescJob j = jobs[i];
-    KeyIn k = keys[j.key];
-    written[i] = descriptor_of(ov, sc, tab, o_cur, o_cur, k.is, k.x, k.y, k.sigma, xper, j.angle, j.st0, j.ct0, hist,
-                               32, descr + (long)i * 128);
+    const int slot = threadIdx.x >> 4, cell = threadIdx.x & 15;
+    const int job = blockIdx.x * 8 + slot;
+    const bool act = job < njobs;
+    const unsigned halfmask = 0xFFFFu << (16 * (slot & 1));
+    float h[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) h[t] = 0.0f;
+    int valid = 0;
+    if (act) {
+        const DescJob j = jobs[job];
+        const KeyIn k = keys[j.key];
+        const DescFrame F = descriptor_frame(ov, sc, o_cur, o_cur, k.is, k.x, k.y, k.sigma, xper, j.angle, j.st0, j.ct0);
+        valid = F.valid;
+        if (valid) descriptor_cell(F, tab, (cell & 3) - 2, (cell >> 2) - 2, h, 1);
+    }
+    float* my = &hs[slot][0];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) my[cell * 8 + t] = h[t];
+    __syncwarp();
+    if (act && valid) {
+        float norm = 0.0f;
+        for (int i = 0; i < 128; ++i) norm += my[i] * my[i];
+        norm = fast_sqrt_f(norm) + kEpsF;
+        const bool zero = sc.norm_thresh != 0 && (double)norm < sc.norm_thresh;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            float v = h[t] / norm;
+            if ((double)v > 0.2) v = (float)0.2;
+            h[t] = v;
+        }
+        __syncwarp(halfmask);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) my[cell * 8 + t] = h[t];
+        __syncwarp(halfmask);
+        float norm2 = 0.0f;
+        for (int i = 0; i < 128; ++i) norm2 += my[i] * my[i];
+        norm2 = fast_sqrt_f(norm2) + kEpsF;
+        float4 o0, o1;
+        if (zero) {
+            o0 = o1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            o0 = make_float4(h[0] / norm2, h[1] / norm2, h[2] / norm2, h[3] / norm2);
+            o1 = make_float4(h[4] / norm2, h[5] / norm2, h[6] / norm2, h[7] / norm2);
+        }
+        float4* dst = reinterpret_cast<float4*>(descr + (size_t)job * 128 + cell * 8);
+        dst[0] = o0;
+        dst[1] = o1;
+    }
+    if (act && cell == 0) written[job] = valid;
 }
 void launch_descr(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
                   const DescJob* jobs, int njobs, double xper, float* descr, int* written, cudaStream_t st) {
     if (njobs <= 0) return;
     KScope ks("sift.descr", st, 512.0 * njobs);
-    const int threads = 64;
-    size_t smem = (size_t)(threads / 32) * 128 * 32 * sizeof(float);
-    descr_kernel<<<div_up(njobs, threads), threads, smem, st>>>(ov, sc, expn_tab, o_cur, keys, jobs, njobs, xper,
-                                                                descr, written);
+    descr_kernel<<<div_up(njobs, 8), 128, 0, st>>>(ov, sc, expn_tab, o_cur, keys, jobs, njobs, xper, descr, written);
     PB_KERNEL_CHECK();
 }
 

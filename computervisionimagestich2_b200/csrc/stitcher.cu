@@ -33,6 +33,7 @@ Stitcher::Stitcher(int device) : dev_(device) {
 Stitcher::~Stitcher() {
     cudaSetDevice(dev_);
     imgs_.clear();
+    pool_.clear();
     sift_.reset();
     if (st_) cudaStreamDestroy(st_);
 }
@@ -335,8 +336,8 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
     // REDUCE chain (ImageProcess.cpp:705-715)
     for (int i = 1; i < L; ++i) {
         const size_t nprev = (size_t)7 * lw[i - 1] * lh[i - 1];
-        PB_CUDA(cudaMemcpyAsync(tmpf_.p, pyr_.p + goff[i - 1], nprev * sizeof(float), cudaMemcpyDeviceToDevice, st_));
-        launch_iir_blur(tmpf_.p, lw[i - 1], lh[i - 1], 7, coef, st_);
+        (void)nprev;
+        launch_iir_blur(pyr_.p + goff[i - 1], tmpf_.p, lw[i - 1], lh[i - 1], 7, coef, st_);
         const LevelTab& t = lt[i - 1];
         DevMovAvg mx{tab_i_.p + t.mx_start, tab_i_.p + t.mx_src, tab_f_.p + t.mx_wgt,
                      lw[i] == lw[i - 1] ? 1.0f : (float)lw[i - 1]};
@@ -423,7 +424,7 @@ void Stitcher::cimg_blur2(const float* src, int w, int h, int c, float* dst) {
     size_t n = (size_t)w * h * c;
     tmpf_.ensure(n);
     PB_CUDA(cudaMemcpyAsync(tmpf_.p, src, n * 4, cudaMemcpyHostToDevice, st_));
-    launch_iir_blur(tmpf_.p, w, h, c, make_iir(2.0f), st_);
+    launch_iir_blur(tmpf_.p, tmpf_.p, w, h, c, make_iir(2.0f), st_);
     PB_CUDA(cudaMemcpyAsync(dst, tmpf_.p, n * 4, cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
 }
@@ -495,6 +496,9 @@ void Stitcher::cimg_resize(const float* src, int w, int h, int c, int nw, int nh
 // pipeline
 // ------------------------------------------------------------------------------------------------------------
 void Stitcher::clear() {
+    // keep the per-image HBM buffers (projected image, descriptor table) for the next job: cudaMalloc / cudaFree
+    // cost milliseconds each and synchronise the device
+    for (auto& im : imgs_) pool_.push_back(std::move(im));
     imgs_.clear();
     log_.clear();
     err_.clear();
@@ -514,7 +518,9 @@ void Stitcher::add_image(const u8* rgb, int w, int h) {
 void Stitcher::add_image_device(const u8* d_rgb, int w, int h) {
     PB_CUDA(cudaSetDevice(dev_));
     WallTimer t0;
-    std::unique_ptr<Image> im(new Image());
+    std::unique_ptr<Image> im;
+    if (!pool_.empty()) { im = std::move(pool_.back()); pool_.pop_back(); }
+    else im.reset(new Image());
     im->w = w; im->h = h;
     size_t n = (size_t)w * h;
     im->proj.ensure(3 * n);

@@ -93,6 +93,7 @@ class Stitcher {
     cudaStream_t st_ = nullptr;
     std::unique_ptr<SiftEngine> sift_;
     std::vector<std::unique_ptr<Image>> imgs_;
+    std::vector<std::unique_ptr<Image>> pool_;   // recycled Image objects (their HBM buffers stay allocated)
     // workspaces
     DevBuf<u8> in_rgb_, a_, b_, res_[2], tmp8_;
     DevBuf<float> gray32_, ktab_;

@@ -27,6 +27,8 @@ struct EmulOct {
     std::vector<int> descr_key, descr_written;
 };
 struct EmulSift { std::vector<EmulOct> oct; };
+static int g_check_serial = 1;
+static int g_serial_mismatch = 0;
 
 static void blur_plane(const float* src, float* tmp, float* dst, int w, int h, int pitch, double sigma) {
     float c[129];
@@ -100,8 +102,21 @@ EmulSift* emul_sift_run(const float* im, int w, int h, int O, int S) {
             for (int j = 0; j < na; ++j) {
                 float fh[128], d[128];
                 for (int q = 0; q < 128; ++q) d[q] = -1.0f;
-                int wr = descriptor_of(ov, sc, tab, o, k.o, k.is, k.x, k.y, k.sigma, xper, ang[j], sin(ang[j]), cos(ang[j]),
-                                       fh, 1, d);
+                // the cell-parallel formulation the CUDA kernel runs (16 independent cell workers)
+                DescFrame F = descriptor_frame(ov, sc, o, k.o, k.is, k.x, k.y, k.sigma, xper, ang[j], sin(ang[j]), cos(ang[j]));
+                int wr = F.valid;
+                if (wr) {
+                    for (int q = 0; q < 128; ++q) fh[q] = 0.f;
+                    for (int cy = -2; cy < 2; ++cy)
+                        for (int cx = -2; cx < 2; ++cx) descriptor_cell(F, tab, cx, cy, fh + (cy + 2) * 32 + (cx + 2) * 8, 1);
+                    descriptor_finish(sc, fh, 1, d);
+                }
+                if (g_check_serial) {  // cross-check against the serial restatement
+                    float fh2[128], d2[128];
+                    for (int q = 0; q < 128; ++q) d2[q] = -1.0f;
+                    int wr2 = descriptor_of(ov, sc, tab, o, k.o, k.is, k.x, k.y, k.sigma, xper, ang[j], sin(ang[j]), cos(ang[j]), fh2, 1, d2);
+                    if (wr2 != wr || memcmp(d, d2, sizeof d) != 0) g_serial_mismatch++;
+                }
                 ob.descr.insert(ob.descr.end(), d, d + 128);
                 ob.descr_key.push_back((int)i);
                 ob.descr_written.push_back(wr);
@@ -110,6 +125,7 @@ EmulSift* emul_sift_run(const float* im, int w, int h, int O, int S) {
     }
     return E;
 }
+int emul_serial_mismatches() { return g_serial_mismatch; }
 int emul_sift_noctaves(EmulSift* E) { return (int)E->oct.size(); }
 void emul_sift_info(EmulSift* E, int o, int* w, int* h, int* pitch, int* nkeys, int* ndesc) {
     EmulOct& O = E->oct[o];
