@@ -333,14 +333,18 @@ PB_HD int descriptor_of(const OctaveView& ov, const SiftConsts& sc, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Descriptor, cell-parallel formulation (what the CUDA kernel runs).
+// Descriptor, sample-parallel formulation (what the CUDA kernel runs).
 //
 // The reference scans the (2W+1)^2 window in raster order and scatters every sample into 2x2 spatial cells x 2
-// orientation bins.  Floating-point addition order matters only WITHIN a bin, and a bin belongs to exactly one
-// spatial cell, so the 16 cells can be accumulated independently: a worker that owns cell (cx, cy) visits, in raster
-// order, only the samples that can reach its cell (a rotated square of side 2*SBP in the patch; it scans a
-// conservative superset and applies the reference's exact bin test to every sample), and adds them to its own 8
-// orientation bins.  Every bin therefore receives exactly the reference's addends in the reference's order.
+// orientation bins.  Floating-point addition order matters only WITHIN a bin, and the 8 bins one sample touches are
+// all different.  The kernel therefore splits the work in two:
+//   phase A (parallel over samples)  descriptor_sample(): everything that depends on one sample alone -- the bin
+//            coordinates and the partial weight products, in the reference's evaluation order;
+//   phase B (parallel over bins)     every bin owner adds, in raster order of the samples, the contributions that
+//            land in its bin.  Each bin receives exactly the reference's addends in the reference's order.
+// Samples that cannot reach the 4x4 grid (|nx| or |ny| beyond 2.5 cells) are skipped: descriptor_rows() /
+// descriptor_row_range() give a conservative superset of the contributing samples and descriptor_sample() applies
+// the reference's exact bin test to every sample of that superset.
 // ---------------------------------------------------------------------------------------------------------
 struct DescFrame {
     double x, y, SBP, st0, ct0, angle0, wden;
@@ -376,72 +380,91 @@ PB_HD DescFrame descriptor_frame(const OctaveView& ov, const SiftConsts& sc, int
     return F;
 }
 
-// Accumulates cell (cx, cy), cx, cy in -2..1, into hist8[t * hstride], t = 0..7 (must be zeroed by the caller).
-PB_HD void descriptor_cell(const DescFrame& F, const double* __restrict__ expn_tab, int cx, int cy, float* hist8,
-                           int hstride) {
-    enum { NBO = 8 };
-    const double ucx = cx + 0.5, ucy = cy + 0.5;
-    // centre and half extent (bounding box) of the cell's footprint, in pixel offsets from the keypoint
-    const double pcx = F.SBP * (F.ct0 * ucx - F.st0 * ucy);
-    const double pcy = F.SBP * (F.st0 * ucx + F.ct0 * ucy);
+// Rows (dyi) that can hold contributing samples: |dy| <= 2.5 SBP (|cos| + |sin|) + slack, inside the window.
+PB_HD void descriptor_rows(const DescFrame& F, int* ry0, int* ry1) {
     const double act = abs_d(F.ct0), ast = abs_d(F.st0);
-    const double e = F.SBP * (act + ast) + 1.5;
+    const double e = 2.5 * F.SBP * (act + ast) + 1.5;
+    const double offy = (double)F.yi - F.y;
+    int a = (int)floor(-e - offy), b = (int)floor(e - offy) + 1;
+    if (a < F.dy0) a = F.dy0;
+    if (b > F.dy1) b = F.dy1;
+    *ry0 = a;
+    *ry1 = b;
+}
+
+// Columns [x0, x1] (dxi) of row dyi that can hold contributing samples (empty when x0 > x1): both rotated-strip
+// constraints |ct0 dx + st0 dy| <= 2.5 SBP and |-st0 dx + ct0 dy| <= 2.5 SBP, each widened by 1.5 px.
+PB_HD void descriptor_row_range(const DescFrame& F, int dyi, int* px0, int* px1) {
+    const double act = abs_d(F.ct0), ast = abs_d(F.st0);
     const double offx = (double)F.xi - F.x, offy = (double)F.yi - F.y;   // sample offset = d?i + off?
-    int ry0 = (int)floor(pcy - e - offy), ry1 = (int)floor(pcy + e - offy) + 1;
-    if (ry0 < F.dy0) ry0 = F.dy0;
-    if (ry1 > F.dy1) ry1 = F.dy1;
-    const int bx0 = (int)floor(pcx - e - offx), bx1 = (int)floor(pcx + e - offx) + 1;
-    for (int dyi = ry0; dyi <= ry1; ++dyi) {
-        const double dyr = (double)dyi + offy;
-        // x range where both rotated-strip constraints can hold (+1.5 px slack), clipped to the bounding box
-        double lo = (double)bx0, hi = (double)bx1;
-        if (act > 1e-3) {  // |ct0*dx + st0*dy - SBP*ucx| <= SBP
-            const double c = F.SBP * ucx - F.st0 * dyr;
-            double a = (c - F.SBP) / F.ct0, b = (c + F.SBP) / F.ct0;
-            if (a > b) { double t = a; a = b; b = t; }
-            a = a - offx - 1.5; b = b - offx + 1.5;
-            if (a > lo) lo = a;
-            if (b < hi) hi = b;
-        }
-        if (ast > 1e-3) {  // |-st0*dx + ct0*dy - SBP*ucy| <= SBP
-            const double c = F.ct0 * dyr - F.SBP * ucy;
-            double a = (c - F.SBP) / F.st0, b = (c + F.SBP) / F.st0;
-            if (a > b) { double t = a; a = b; b = t; }
-            a = a - offx - 1.5; b = b - offx + 1.5;
-            if (a > lo) lo = a;
-            if (b < hi) hi = b;
-        }
-        if (lo > hi) continue;
-        int x0 = (int)floor(lo), x1 = (int)floor(hi) + 1;
-        if (x0 < F.dx0) x0 = F.dx0;
-        if (x1 > F.dx1) x1 = F.dx1;
-        const float* row = F.pt + 2 * ((long)(F.yi + dyi) * F.pitch);
-        const float dy = (float)((double)(F.yi + dyi) - F.y);
-        const double sdy = F.st0 * (double)dy, cdy = F.ct0 * (double)dy;
-        for (int dxi = x0; dxi <= x1; ++dxi) {
-            const float dx = (float)((double)(F.xi + dxi) - F.x);
-            const float nx = (float)((F.ct0 * (double)dx + sdy) / F.SBP);
-            const int binx = floor_f((float)((double)nx - 0.5));
-            const int dbx = cx - binx;
-            if (dbx != 0 && dbx != 1) continue;
-            const float ny = (float)((-F.st0 * (double)dx + cdy) / F.SBP);
-            const int biny = floor_f((float)((double)ny - 0.5));
-            const int dby = cy - biny;
-            if (dby != 0 && dby != 1) continue;
-            const float mod = row[2 * (F.xi + dxi)];
-            const float angle = row[2 * (F.xi + dxi) + 1];
-            const float theta = mod_2pi_f((float)((double)angle - F.angle0));
-            const float nt = (float)((double)((float)NBO * theta) / (2 * kPi));
-            const float win = (float)fast_expn(expn_tab, (double)(nx * nx + ny * ny) / F.wden);
-            const int bint = floor_f(nt);
-            const float rbinx = (float)((double)nx - ((double)binx + 0.5));
-            const float rbiny = (float)((double)ny - ((double)biny + 0.5));
-            const float rbint = nt - (float)bint;
-            const float wxy = win * mod * fabs_f((float)(1 - dbx) - rbinx) * fabs_f((float)(1 - dby) - rbiny);
-            hist8[((bint + 0) % NBO) * hstride] += wxy * fabs_f((float)(1 - 0) - rbint);
-            hist8[((bint + 1) % NBO) * hstride] += wxy * fabs_f((float)(1 - 1) - rbint);
-        }
+    const double half = 2.5 * F.SBP;
+    const double dyr = (double)dyi + offy;
+    double lo = (double)F.dx0, hi = (double)F.dx1;
+    if (act > 1e-3) {
+        const double c = -F.st0 * dyr;
+        double a = (c - half) / F.ct0, b = (c + half) / F.ct0;
+        if (a > b) { double t = a; a = b; b = t; }
+        a = a - offx - 1.5; b = b - offx + 1.5;
+        if (a > lo) lo = a;
+        if (b < hi) hi = b;
     }
+    if (ast > 1e-3) {
+        const double c = F.ct0 * dyr;
+        double a = (c - half) / F.st0, b = (c + half) / F.st0;
+        if (a > b) { double t = a; a = b; b = t; }
+        a = a - offx - 1.5; b = b - offx + 1.5;
+        if (a > lo) lo = a;
+        if (b < hi) hi = b;
+    }
+    if (lo > hi) { *px0 = 0; *px1 = -1; return; }
+    int x0 = (int)floor(lo), x1 = (int)floor(hi) + 1;
+    if (x0 < F.dx0) x0 = F.dx0;
+    if (x1 > F.dx1) x1 = F.dx1;
+    *px0 = x0;
+    *px1 = x1;
+}
+
+// Everything one sample contributes (vl/sift.c:1351-1413).  A sample reaches cells (binx + {0,1}, biny + {0,1})
+// that lie inside the 4x4 grid and orientation bins (bint + {0,1}) % 8 with
+//   weight = (((win * mod) * |1 - dbx - rbinx|) * |1 - dby - rbiny|) * |1 - dbt - rbint|
+// wxy[dbx][dby] holds the first three factors, at[dbt] the last.
+struct DescSample {
+    int active;            // 0: the sample reaches no cell of the grid
+    int binx, biny, bint;  // binx, biny in -3..1, bint in 0..8
+    float wxy[2][2];
+    float at[2];
+};
+
+PB_HD DescSample descriptor_sample(const DescFrame& F, const double* __restrict__ expn_tab, int dxi, int dyi, float mod,
+                                   float angle) {
+    enum { NBO = 8 };
+    DescSample S;
+    S.active = 0;
+    const float dy = (float)((double)(F.yi + dyi) - F.y);
+    const float dx = (float)((double)(F.xi + dxi) - F.x);
+    const float nx = (float)((F.ct0 * (double)dx + F.st0 * (double)dy) / F.SBP);
+    const int binx = floor_f((float)((double)nx - 0.5));
+    if (binx < -3 || binx > 1) return S;
+    const float ny = (float)((-F.st0 * (double)dx + F.ct0 * (double)dy) / F.SBP);
+    const int biny = floor_f((float)((double)ny - 0.5));
+    if (biny < -3 || biny > 1) return S;
+    const float theta = mod_2pi_f((float)((double)angle - F.angle0));
+    const float nt = (float)((double)((float)NBO * theta) / (2 * kPi));
+    const float win = (float)fast_expn(expn_tab, (double)(nx * nx + ny * ny) / F.wden);
+    const int bint = floor_f(nt);
+    const float rbinx = (float)((double)nx - ((double)binx + 0.5));
+    const float rbiny = (float)((double)ny - ((double)biny + 0.5));
+    const float rbint = nt - (float)bint;
+    const float base = win * mod;
+    const float bx0 = base * fabs_f((float)(1 - 0) - rbinx), bx1 = base * fabs_f((float)(1 - 1) - rbinx);
+    const float ay0 = fabs_f((float)(1 - 0) - rbiny), ay1 = fabs_f((float)(1 - 1) - rbiny);
+    S.wxy[0][0] = bx0 * ay0; S.wxy[0][1] = bx0 * ay1;
+    S.wxy[1][0] = bx1 * ay0; S.wxy[1][1] = bx1 * ay1;
+    S.at[0] = fabs_f((float)(1 - 0) - rbint);
+    S.at[1] = fabs_f((float)(1 - 1) - rbint);
+    S.binx = binx; S.biny = biny; S.bint = bint;
+    S.active = 1;
+    return S;
 }
 
 // normalise -> clamp 0.2 -> normalise over the 128 bins in index order (vl/sift.c:1048-1063, 1415-1436);

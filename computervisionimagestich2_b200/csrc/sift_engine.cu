@@ -174,9 +174,14 @@ void SiftEngine::detect_octave(int oi) {
     finish_keys(hr, n, o, sigma0_, p_.S, ob.keys);
 }
 
-static void upload_keyin(OctaveBuf& ob, const std::vector<KeyIn>& ki, cudaStream_t st) {
-    ob.keyin.ensure(ki.size());
-    PB_CUDA(cudaMemcpyAsync(ob.keyin.p, ki.data(), ki.size() * sizeof(KeyIn), cudaMemcpyHostToDevice, st));
+OctaveSet SiftEngine::octave_set(int first, int count) const {
+    OctaveSet os;
+    memset(&os, 0, sizeof os);
+    for (int i = 0; i < count && i < kMaxOctaveSet; ++i) {
+        os.ov[i] = oct_[first + i].view(nlev_);
+        os.xper[i] = pow(2.0, p_.o_min + first + i);
+    }
+    return os;
 }
 
 void SiftEngine::orient_custom(int oi, const std::vector<KeyIn>& keys, std::vector<int>& nang,
@@ -186,20 +191,23 @@ void SiftEngine::orient_custom(int oi, const std::vector<KeyIn>& keys, std::vect
     nang.assign(n, 0);
     ang.assign((size_t)n * 4, 0.0);
     if (n == 0 || ob.w < 2 || ob.h < 2) return;
-    upload_keyin(ob, keys, st_);
-    ob.nangles.ensure(n);
-    ob.angles.ensure((size_t)n * 4);
-    int o = p_.o_min + oi;
-    launch_orient(ob.view(nlev_), consts(), expn_tab_.p, o, ob.keyin.p, n, pow(2.0, o), ob.nangles.p, ob.angles.p, st_);
-    PB_CUDA(cudaMemcpyAsync(nang.data(), ob.nangles.p, n * sizeof(int), cudaMemcpyDeviceToHost, st_));
-    PB_CUDA(cudaMemcpyAsync(ang.data(), ob.angles.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    std::vector<KeyIn> ki(keys);
+    for (auto& k : ki) k.oct = 0;
+    keyin_.ensure(n);
+    nangles_.ensure(n);
+    angles_.ensure((size_t)n * 4);
+    PB_CUDA(cudaMemcpyAsync(keyin_.p, ki.data(), ki.size() * sizeof(KeyIn), cudaMemcpyHostToDevice, st_));
+    launch_orient(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, n, nangles_.p, angles_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(nang.data(), nangles_.p, n * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaMemcpyAsync(ang.data(), angles_.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
 }
 
 void SiftEngine::orient_octave(int oi) {
     OctaveBuf& ob = oct_[oi];
     std::vector<KeyIn> ki(ob.keys.size());
-    for (size_t i = 0; i < ki.size(); ++i) ki[i] = KeyIn{ob.keys[i].x, ob.keys[i].y, ob.keys[i].sigma, ob.keys[i].is};
+    for (size_t i = 0; i < ki.size(); ++i)
+        ki[i] = KeyIn{ob.keys[i].x, ob.keys[i].y, ob.keys[i].sigma, (short)ob.keys[i].is, 0};
     orient_custom(oi, ki, ob.h_nangles, ob.h_angles);
 }
 
@@ -212,7 +220,16 @@ void SiftEngine::describe_octave(int oi, const std::vector<int>& key_idx, const 
         for (int i = 0; i < nj; ++i) out_written[i] = 0;
         return;
     }
-    if (custom_keys) upload_keyin(ob, *custom_keys, st_);
+    std::vector<KeyIn> ki;
+    if (custom_keys) ki = *custom_keys;
+    else {
+        ki.resize(ob.keys.size());
+        for (size_t i = 0; i < ki.size(); ++i)
+            ki[i] = KeyIn{ob.keys[i].x, ob.keys[i].y, ob.keys[i].sigma, (short)ob.keys[i].is, 0};
+    }
+    for (auto& k : ki) k.oct = 0;
+    keyin_.ensure(ki.size());
+    PB_CUDA(cudaMemcpyAsync(keyin_.p, ki.data(), ki.size() * sizeof(KeyIn), cudaMemcpyHostToDevice, st_));
     std::vector<DescJob> jobs(nj);
     for (int i = 0; i < nj; ++i) {
         jobs[i].key = key_idx[i];
@@ -221,15 +238,13 @@ void SiftEngine::describe_octave(int oi, const std::vector<int>& key_idx, const 
         jobs[i].st0 = sin(ang[i]);  // vl/sift.c:1308-1309, glibc
         jobs[i].ct0 = cos(ang[i]);
     }
-    ob.jobs.ensure(nj);
-    ob.descr.ensure((size_t)nj * 128);
-    ob.written.ensure(nj);
-    PB_CUDA(cudaMemcpyAsync(ob.jobs.p, jobs.data(), nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
-    int o = p_.o_min + oi;
-    launch_descr(ob.view(nlev_), consts(), expn_tab_.p, o, ob.keyin.p, ob.jobs.p, nj, pow(2.0, o), ob.descr.p,
-                 ob.written.p, st_);
-    PB_CUDA(cudaMemcpyAsync(out_descr, ob.descr.p, (size_t)nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
-    PB_CUDA(cudaMemcpyAsync(out_written, ob.written.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    jobs_.ensure(nj);
+    descr_.ensure((size_t)nj * 128);
+    written_.ensure(nj);
+    PB_CUDA(cudaMemcpyAsync(jobs_.p, jobs.data(), nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
+    launch_descr(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, jobs_.p, nj, descr_.p, written_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(out_descr, descr_.p, (size_t)nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaMemcpyAsync(out_written, written_.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
 }
 
@@ -237,6 +252,7 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     out = RawFeatures();
     const int O = (int)oct_.size();
     if (O == 0) return;
+    if (O > kMaxOctaveSet) throw std::runtime_error("more than 8 octaves per image are not supported by the batched path");
     SiftConsts sc = consts();
     // 1. whole pyramid + detection + refinement + gradient maps, no host round trip
     load_base_from_device(d_img, img_pitch);
@@ -280,74 +296,75 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
             finish_keys(hr + off, cnt[oi], p_.o_min + oi, sigma0_, p_.S, oct_[oi].keys);
             off += cnt[oi];
         }
-    // 3. orientations of every octave, one round trip
-    size_t nk_total = 0;
+    // 3. orientations of the keypoints of all octaves: one launch, one round trip
+    std::vector<int> kfirst(O + 1, 0);
     for (int oi = 0; oi < O; ++oi) {
-        OctaveBuf& ob = oct_[oi];
-        int n = (int)ob.keys.size();
-        out.noct_keys.push_back(n);
-        ob.h_nangles.assign(n, 0);
-        ob.h_angles.assign((size_t)n * 4, 0.0);
-        if (n == 0) continue;
-        nk_total += n;
-        std::vector<KeyIn> ki(n);
-        for (int i = 0; i < n; ++i) ki[i] = KeyIn{ob.keys[i].x, ob.keys[i].y, ob.keys[i].sigma, ob.keys[i].is};
-        upload_keyin(ob, ki, st_);
-        PB_CUDA(cudaStreamSynchronize(st_));  // ki is a pageable temporary
-        ob.nangles.ensure(n);
-        ob.angles.ensure((size_t)n * 4);
-        int o = p_.o_min + oi;
-        launch_orient(ob.view(nlev_), sc, expn_tab_.p, o, ob.keyin.p, n, pow(2.0, o), ob.nangles.p, ob.angles.p, st_);
-        PB_CUDA(cudaMemcpyAsync(ob.h_nangles.data(), ob.nangles.p, n * sizeof(int), cudaMemcpyDeviceToHost, st_));
-        PB_CUDA(cudaMemcpyAsync(ob.h_angles.data(), ob.angles.p, (size_t)n * 4 * sizeof(double),
-                                cudaMemcpyDeviceToHost, st_));
+        out.noct_keys.push_back((int)oct_[oi].keys.size());
+        kfirst[oi + 1] = kfirst[oi] + (int)oct_[oi].keys.size();
     }
+    const int nk = kfirst[O];
+    if (nk == 0) return;
+    const OctaveSet os = octave_set(0, O);
+    KeyIn* hk = (KeyIn*)h_keyin_.ensure((size_t)nk * sizeof(KeyIn));
+    for (int oi = 0; oi < O; ++oi) {
+        const OctaveBuf& ob = oct_[oi];
+        for (size_t i = 0; i < ob.keys.size(); ++i)
+            hk[kfirst[oi] + i] = KeyIn{ob.keys[i].x, ob.keys[i].y, ob.keys[i].sigma, (short)ob.keys[i].is, (short)oi};
+    }
+    keyin_.ensure(nk);
+    nangles_.ensure(nk);
+    angles_.ensure((size_t)nk * 4);
+    int* h_na = (int*)h_nang_.ensure((size_t)nk * sizeof(int));
+    double* h_an = (double*)h_ang_.ensure((size_t)nk * 4 * sizeof(double));
+    PB_CUDA(cudaMemcpyAsync(keyin_.p, hk, (size_t)nk * sizeof(KeyIn), cudaMemcpyHostToDevice, st_));
+    launch_orient(os, sc, expn_tab_.p, keyin_.p, nk, nangles_.p, angles_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(h_na, nangles_.p, (size_t)nk * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaMemcpyAsync(h_an, angles_.p, (size_t)nk * 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
-    if (nk_total == 0) return;
-    // 4. descriptors of every octave, one round trip (sin/cos on the host)
-    std::vector<std::vector<DescJob>> jobs(O);
-    size_t nj_total = 0;
     for (int oi = 0; oi < O; ++oi) {
         OctaveBuf& ob = oct_[oi];
-        for (int i = 0; i < (int)ob.keys.size(); ++i)
-            for (int j = 0; j < ob.h_nangles[i]; ++j) {
-                double a = ob.h_angles[(size_t)i * 4 + j];
-                jobs[oi].push_back(DescJob{i, 0, a, sin(a), cos(a)});
+        const int n = (int)ob.keys.size();
+        ob.h_nangles.assign(h_na + kfirst[oi], h_na + kfirst[oi] + n);
+        ob.h_angles.assign(h_an + (size_t)kfirst[oi] * 4, h_an + (size_t)(kfirst[oi] + n) * 4);
+    }
+    // 4. descriptors of all octaves: one launch, one round trip (sin/cos on the host)
+    size_t nj = 0;
+    for (int i = 0; i < nk; ++i) nj += h_na[i];
+    if (nj == 0) return;
+    DescJob* hj = (DescJob*)h_jobs_.ensure(nj * sizeof(DescJob));
+    {
+        size_t q = 0;
+        for (int i = 0; i < nk; ++i)
+            for (int j = 0; j < h_na[i]; ++j) {
+                const double a = h_an[(size_t)i * 4 + j];
+                hj[q++] = DescJob{i, 0, a, sin(a), cos(a)};
             }
-        nj_total += jobs[oi].size();
     }
-    std::vector<float> hd(nj_total * 128);
-    std::vector<int> hw(nj_total);
-    off = 0;
-    for (int oi = 0; oi < O; ++oi) {
-        OctaveBuf& ob = oct_[oi];
-        int nj = (int)jobs[oi].size();
-        if (nj == 0) continue;
-        ob.jobs.ensure(nj);
-        ob.descr.ensure((size_t)nj * 128);
-        ob.written.ensure(nj);
-        PB_CUDA(cudaMemcpyAsync(ob.jobs.p, jobs[oi].data(), nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
-        int o = p_.o_min + oi;
-        launch_descr(ob.view(nlev_), sc, expn_tab_.p, o, ob.keyin.p, ob.jobs.p, nj, pow(2.0, o), ob.descr.p,
-                     ob.written.p, st_);
-        PB_CUDA(cudaMemcpyAsync(hd.data() + off * 128, ob.descr.p, (size_t)nj * 128 * sizeof(float),
-                                cudaMemcpyDeviceToHost, st_));
-        PB_CUDA(cudaMemcpyAsync(hw.data() + off, ob.written.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
-        off += nj;
-    }
+    jobs_.ensure(nj);
+    descr_.ensure(nj * 128);
+    written_.ensure(nj);
+    float* hd = (float*)h_descr_.ensure(nj * 128 * sizeof(float));
+    int* hw = (int*)h_written_.ensure(nj * sizeof(int));
+    PB_CUDA(cudaMemcpyAsync(jobs_.p, hj, nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
+    launch_descr(os, sc, expn_tab_.p, keyin_.p, jobs_.p, (int)nj, descr_.p, written_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(hd, descr_.p, nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaMemcpyAsync(hw, written_.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
-    // 5. assemble in the reference's insertion order, dropping descriptors the reference leaves unwritten
-    out.descr.reserve(nj_total * 128);
-    off = 0;
-    for (int oi = 0; oi < O; ++oi) {
-        OctaveBuf& ob = oct_[oi];
-        for (size_t j = 0; j < jobs[oi].size(); ++j, ++off) {
-            if (!hw[off]) { out.dropped_unwritten++; continue; }
-            out.keys.push_back(ob.keys[jobs[oi][j].key]);
-            out.angles.push_back(jobs[oi][j].angle);
-            out.key_index.push_back(jobs[oi][j].key);
-            out.descr.insert(out.descr.end(), hd.begin() + off * 128, hd.begin() + (off + 1) * 128);
-        }
+    // 5. assemble in the reference's insertion order (octave, keypoint, angle), dropping descriptors the reference
+    //    leaves unwritten
+    out.descr.reserve(nj * 128);
+    out.keys.reserve(nj);
+    out.angles.reserve(nj);
+    out.key_index.reserve(nj);
+    int oi = 0;
+    for (size_t q = 0; q < nj; ++q) {
+        if (!hw[q]) { out.dropped_unwritten++; continue; }
+        const int gk = hj[q].key;
+        while (gk >= kfirst[oi + 1]) ++oi;
+        out.keys.push_back(oct_[oi].keys[gk - kfirst[oi]]);
+        out.angles.push_back(hj[q].angle);
+        out.key_index.push_back(gk - kfirst[oi]);
+        out.descr.insert(out.descr.end(), hd + q * 128, hd + (q + 1) * 128);
     }
     out.n = (int)out.keys.size();
 }

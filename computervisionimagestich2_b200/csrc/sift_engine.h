@@ -36,12 +36,6 @@ struct OctaveBuf {
     DevBuf<float> gss, grad;
     DevBuf<Cand> cand;
     DevBuf<RefinedKey> refined;
-    DevBuf<KeyIn> keyin;
-    DevBuf<int> nangles;
-    DevBuf<double> angles;
-    DevBuf<DescJob> jobs;
-    DevBuf<float> descr;
-    DevBuf<int> written;
     int cand_cap = 0;
     // host mirrors of the per-octave results
     std::vector<VlKey> keys;
@@ -104,6 +98,14 @@ class SiftEngine {
     DevBuf<int> counts_;
     PinBuf<int> h_counts_;
     PinBuf<char> h_stage_;
+    // keypoints / jobs / results of all octaves of the current image (one launch per stage)
+    DevBuf<KeyIn> keyin_;
+    DevBuf<int> nangles_, written_;
+    DevBuf<double> angles_;
+    DevBuf<DescJob> jobs_;
+    DevBuf<float> descr_;
+    PinBuf<char> h_keyin_, h_nang_, h_ang_, h_jobs_, h_descr_, h_written_;
+    OctaveSet octave_set(int first, int count) const;
     bool tab_ready_ = false;
 };
 

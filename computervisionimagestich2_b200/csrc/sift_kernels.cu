@@ -319,27 +319,30 @@ void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cu
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// orientation + descriptor: one thread per keypoint / per (keypoint, angle); the accumulation order inside a
-// histogram bin is the raster order of the patch, exactly as in the reference, so results are bit-identical.
-// The histograms of a warp's 32 items are interleaved in shared memory (bin b of lane l at [b * 32 + l]):
-// conflict-free whatever bins the lanes touch.
+// orientation + descriptor: ONE WARP per keypoint / per (keypoint, angle), items of all octaves of an image in one
+// launch.  Both kernels run in two phases per chunk of 32 patch samples (raster order):
+//   phase A  the 32 lanes evaluate 32 samples in parallel (the expensive double-precision part) and park the
+//            per-sample contributions in shared memory;
+//   phase B  the lanes switch roles and become BIN OWNERS: each owner adds, in sample order, the contributions that
+//            land in its bins.  Every histogram bin therefore receives the reference's addends in the reference's
+//            order (bit-exact), yet no lane ever walks the whole patch serially.
 // ---------------------------------------------------------------------------------------------------------
-// Orientation: one warp per keypoint.  The lanes evaluate 32 consecutive samples of the patch (raster order) in
-// parallel; the two histogram contributions of every sample are then handed, in sample order, to the lane that owns
-// the bin (lane b owns bins b and b + 32), so each bin sees the reference's addends in the reference's order.
-// Smoothing and peak picking are 36-element serial recurrences, done redundantly by every lane from shared memory.
-__global__ void __launch_bounds__(128) orient_kernel(OctaveView ov, SiftConsts sc, const double* __restrict__ expn_tab,
-                                                     int o_cur, const KeyIn* __restrict__ keys, int nkeys, double xper,
+__global__ void __launch_bounds__(128) orient_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
+                                                     const KeyIn* __restrict__ keys, int nkeys,
                                                      int* __restrict__ nangles, double* __restrict__ angles) {
+    enum { nbins = 36 };
     __shared__ double tab[257];
-    __shared__ double hsm[4][36];
+    __shared__ double hsm[4][nbins];
+    __shared__ double sv0[4][32], sv1[4][32];
+    __shared__ unsigned binmask[4][nbins];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ki = blockIdx.x * 4 + wid;
     if (ki >= nkeys) return;
     const KeyIn k = keys[ki];
-    enum { nbins = 36 };
+    const OctaveView ov = os.ov[k.oct];
+    const double xper = os.xper[k.oct];
     const int w = ov.w, h = ov.h;
     const double x = (double)k.x / xper, y = (double)k.y / xper, sigma = (double)k.sigma / xper;
     const int xi = (int)(x + 0.5), yi = (int)(y + 0.5), si = k.is;
@@ -350,45 +353,59 @@ __global__ void __launch_bounds__(128) orient_kernel(OctaveView ov, SiftConsts s
         if (lane == 0) { nangles[ki] = 0; for (int j = 0; j < 4; ++j) angles[ki * 4 + j] = 0; }
         return;
     }
-    const float* pt = ov.grad + 2 * ((long)(si - sc.s_min - 1) * ov.h * ov.pitch);
+    const float2* pt = reinterpret_cast<const float2*>(ov.grad) + (long)(si - sc.s_min - 1) * ov.h * ov.pitch;
     const int ys0 = (-W > -yi) ? -W : -yi, ys1 = (W < h - 1 - yi) ? W : h - 1 - yi;
     const int xs0 = (-W > -xi) ? -W : -xi, xs1 = (W < w - 1 - xi) ? W : w - 1 - xi;
     const int nxw = xs1 - xs0 + 1, total = nxw * (ys1 - ys0 + 1);
     const double r2max = W * W + 0.6, den = 2 * sigmaw * sigmaw;
     double h0 = 0.0, h1 = 0.0;  // bins lane and lane + 32
+    unsigned* bm = binmask[wid];
     for (int base = 0; base < total; base += 32) {
+        // ---- phase A: one sample per lane ----
         const int i = base + lane;
-        int bin = -1000;
-        double v0 = 0.0, v1 = 0.0;
+        int b0 = 99;  // 99 = no contribution
         if (i < total) {
             const int ry = i / nxw, ys = ys0 + ry, xs = xs0 + (i - ry * nxw);
             const double dx = (double)(xi + xs) - x, dy = (double)(yi + ys) - y;
             const double r2 = dx * dx + dy * dy;
             if (!(r2 >= r2max)) {
-                const float2 g = reinterpret_cast<const float2*>(pt)[(long)(yi + ys) * ov.pitch + (xi + xs)];
+                const float2 g = pt[(long)(yi + ys) * ov.pitch + (xi + xs)];
                 const double wgt = fast_expn(tab, r2 / den);
                 const double mod = g.x, ang = g.y;
                 const double fbin = nbins * ang / (2 * kPi);
-                bin = floor_d(fbin - 0.5);
+                const int bin = floor_d(fbin - 0.5);
                 const double rbin = fbin - bin - 0.5;
-                v0 = (1 - rbin) * mod * wgt;
-                v1 = (rbin)*mod * wgt;
+                sv0[wid][lane] = (1 - rbin) * mod * wgt;
+                sv1[wid][lane] = (rbin)*mod * wgt;
+                b0 = (bin + nbins) % nbins;
             }
         }
-        const unsigned any = __ballot_sync(0xffffffffu, bin != -1000);
-        for (unsigned m = any; m; m &= m - 1) {
-            const int j = __ffs(m) - 1;
-            const int bj = __shfl_sync(0xffffffffu, bin, j);
-            const double a0 = __shfl_sync(0xffffffffu, v0, j);
-            const double a1 = __shfl_sync(0xffffffffu, v1, j);
-            const int b0 = (bj + nbins) % nbins, b1 = (bj + 1) % nbins;
-            if (b0 == lane) h0 += a0; else if (b0 == lane + 32) h1 += a0;
-            if (b1 == lane) h0 += a1; else if (b1 == lane + 32) h1 += a1;
+        bm[lane] = 0;
+        if (lane < nbins - 32) bm[lane + 32] = 0;
+        __syncwarp();
+        const unsigned grp = __match_any_sync(0xffffffffu, b0);
+        if (b0 != 99) bm[b0] = grp;  // all members of a group write the same value
+        __syncwarp();
+        // ---- phase B: lane owns bins lane and lane + 32; sample j adds v0 to bin b0_j and v1 to bin b0_j + 1 ----
+        {
+            const unsigned m0 = bm[lane], m1 = bm[(lane + nbins - 1) % nbins];
+            for (unsigned m = m0 | m1; m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                h0 += ((m0 >> j) & 1u) ? sv0[wid][j] : sv1[wid][j];
+            }
         }
+        if (lane < nbins - 32) {
+            const unsigned m0 = bm[lane + 32], m1 = bm[lane + 31];
+            for (unsigned m = m0 | m1; m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                h1 += ((m0 >> j) & 1u) ? sv0[wid][j] : sv1[wid][j];
+            }
+        }
+        __syncwarp();
     }
     double* hist = hsm[wid];
     hist[lane] = h0;
-    if (lane < 4) hist[lane + 32] = h1;
+    if (lane < nbins - 32) hist[lane + 32] = h1;
     __syncwarp();
     // vl/sift.c:1000-1036 on a private copy (every lane computes the same thing; lane 0 stores)
     double hh[nbins];
@@ -423,82 +440,153 @@ __global__ void __launch_bounds__(128) orient_kernel(OctaveView ov, SiftConsts s
         for (int j = 0; j < 4; ++j) angles[ki * 4 + j] = out[j];
     }
 }
-void launch_orient(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
-                   int nkeys, double xper, int* nangles, double* angles, cudaStream_t st) {
+void launch_orient(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys, int nkeys,
+                   int* nangles, double* angles, cudaStream_t st) {
     if (nkeys <= 0) return;
     KScope ks("sift.orient", st, 36.0 * nkeys);
-    orient_kernel<<<div_up(nkeys, 4), 128, 0, st>>>(ov, sc, expn_tab, o_cur, keys, nkeys, xper, nangles, angles);
+    orient_kernel<<<div_up(nkeys, 4), 128, 0, st>>>(os, sc, expn_tab, keys, nkeys, nangles, angles);
     PB_KERNEL_CHECK();
 }
 
-// Descriptor: 16 lanes (half a warp) per (keypoint, angle), one lane per spatial cell of the 4x4 grid.  Each lane
-// walks -- in raster order -- only the part of the patch that can reach its cell and keeps its 8 orientation bins
-// privately, so every bin receives the reference's addends in the reference's order (see descriptor_cell in
-// sift_device.cuh) while 16 lanes share the work of one descriptor.  The 128 bins are then gathered in shared
-// memory for the two sequential L2 normalisations and written as one 512-byte row.
-__global__ void __launch_bounds__(128) descr_kernel(OctaveView ov, SiftConsts sc, const double* __restrict__ expn_tab,
-                                                    int o_cur, const KeyIn* __restrict__ keys,
-                                                    const DescJob* __restrict__ jobs, int njobs, double xper,
-                                                    float* __restrict__ descr, int* __restrict__ written) {
+// Descriptor.  Phase A: lane = sample (descriptor_sample, sift_device.cuh); the samples of the conservative
+// per-row ranges are flattened so that all 32 lanes stay busy whatever the patch geometry.  Phase B: lane = (cell,
+// orientation parity): lane 2c + p owns the four orientation bins p, p+2, p+4, p+6 of cell c; a sample touches one
+// even and one odd orientation bin, so both lanes of a cell consume every sample that reaches the cell, in order.
+constexpr int kDescRows = 192;   // rows of the patch handled per pass (taller patches take several passes)
+struct DescWarpSmem {
+    int rowstart[kDescRows + 1];
+    int rowx0[kDescRows];
+    int packed[32];
+    float at[2][32];
+    float wxy[4][32];
+    float hist[128];
+};
+__global__ void __launch_bounds__(128) descr_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
+                                                    const KeyIn* __restrict__ keys, const DescJob* __restrict__ jobs,
+                                                    int njobs, float* __restrict__ descr, int* __restrict__ written) {
     __shared__ double tab[257];
-    __shared__ float hs[8][128];
+    __shared__ DescWarpSmem wsm[4];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
     __syncthreads();
-    const int slot = threadIdx.x >> 4, cell = threadIdx.x & 15;
-    const int job = blockIdx.x * 8 + slot;
-    const bool act = job < njobs;
-    const unsigned halfmask = 0xFFFFu << (16 * (slot & 1));
-    float h[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) h[t] = 0.0f;
-    int valid = 0;
-    if (act) {
-        const DescJob j = jobs[job];
-        const KeyIn k = keys[j.key];
-        const DescFrame F = descriptor_frame(ov, sc, o_cur, o_cur, k.is, k.x, k.y, k.sigma, xper, j.angle, j.st0, j.ct0);
-        valid = F.valid;
-        if (valid) descriptor_cell(F, tab, (cell & 3) - 2, (cell >> 2) - 2, h, 1);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.x * 4 + wid;
+    if (job >= njobs) return;
+    DescWarpSmem& S = wsm[wid];
+    const DescJob j = jobs[job];
+    const KeyIn k = keys[j.key];
+    const DescFrame F = descriptor_frame(os.ov[k.oct], sc, 0, 0, k.is, k.x, k.y, k.sigma, os.xper[k.oct], j.angle, j.st0,
+                                         j.ct0);
+    if (!F.valid) {
+        if (lane == 0) written[job] = 0;
+        return;
     }
-    float* my = &hs[slot][0];
+    const int cell = lane >> 1, par = lane & 1;
+    const int cx = (cell & 3) - 2, cy = (cell >> 2) - 2;
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;   // orientation bins par, par+2, par+4, par+6 of my cell
+    int ry0, ry1;
+    descriptor_rows(F, &ry0, &ry1);
+    const float2* gp = reinterpret_cast<const float2*>(F.pt);
+    for (int rg = ry0; rg <= ry1; rg += kDescRows) {
+        const int nr = (ry1 - rg + 1) < kDescRows ? (ry1 - rg + 1) : kDescRows;
+        // conservative column range of every row (lanes = rows) + exclusive prefix of the row lengths
+        int running = 0;
+        for (int r0 = 0; r0 < nr; r0 += 32) {
+            const int r = r0 + lane;
+            int cnt = 0;
+            if (r < nr) {
+                int x0, x1;
+                descriptor_row_range(F, rg + r, &x0, &x1);
+                cnt = x1 >= x0 ? x1 - x0 + 1 : 0;
+                S.rowx0[r] = x0;
+            }
+            int incl = cnt;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) my[cell * 8 + t] = h[t];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (r < nr) S.rowstart[r + 1] = running + incl;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) S.rowstart[0] = 0;
+        __syncwarp();
+        const int total = running;
+        int r = 0;
+        for (int base = 0; base < total; base += 32) {
+            // ---- phase A ----
+            const int i = base + lane;
+            unsigned cellmask = 0;
+            if (i < total) {
+                while (i >= S.rowstart[r + 1]) ++r;
+                const int dxi = S.rowx0[r] + (i - S.rowstart[r]), dyi = rg + r;
+                const float2 g = gp[(long)(F.yi + dyi) * F.pitch + (F.xi + dxi)];
+                const DescSample sm = descriptor_sample(F, tab, dxi, dyi, g.x, g.y);
+                if (sm.active) {
+                    S.packed[lane] = (sm.binx + 8) | ((sm.biny + 8) << 8) | (sm.bint << 16);
+                    S.at[0][lane] = sm.at[0]; S.at[1][lane] = sm.at[1];
+                    S.wxy[0][lane] = sm.wxy[0][0]; S.wxy[1][lane] = sm.wxy[0][1];
+                    S.wxy[2][lane] = sm.wxy[1][0]; S.wxy[3][lane] = sm.wxy[1][1];
+                    // cells (binx + {0,1}, biny + {0,1}) inside the grid, as a 4x4 bit mask (bit = (cy+2)*4 + cx+2)
+                    const unsigned mx = ((3u << (sm.binx + 3)) >> 1) & 0xFu;
+                    const unsigned my = ((3u << (sm.biny + 3)) >> 1) & 0xFu;
+                    cellmask = ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 4 : 0u) | ((my & 4u) ? mx << 8 : 0u) |
+                               ((my & 8u) ? mx << 12 : 0u);
+                }
+            }
+            __syncwarp();
+            unsigned mine = 0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const unsigned m = __ballot_sync(0xffffffffu, (cellmask >> c) & 1u);
+                if (c == cell) mine = m;
+            }
+            // ---- phase B ----
+            for (; mine; mine &= mine - 1) {
+                const int q = __ffs(mine) - 1;
+                const int pk = S.packed[q];
+                const int dbx = cx - ((pk & 0xff) - 8), dby = cy - (((pk >> 8) & 0xff) - 8), bt = pk >> 16;
+                const int sel = ((bt & 1) == par) ? 0 : 1;
+                const float v = S.wxy[dbx * 2 + dby][q] * S.at[sel][q];
+                const int kk = ((bt + sel) & 7) >> 1;
+                if (kk == 0) h0 += v;
+                else if (kk == 1) h1 += v;
+                else if (kk == 2) h2 += v;
+                else h3 += v;
+            }
+            __syncwarp();
+        }
+    }
+    // 128 bins to shared memory in descriptor order, then the two sequential L2 normalisations (vl/sift.c:1415-1436)
+    float* hs = S.hist;
+    hs[cell * 8 + par] = h0; hs[cell * 8 + par + 2] = h1; hs[cell * 8 + par + 4] = h2; hs[cell * 8 + par + 6] = h3;
     __syncwarp();
-    if (act && valid) {
-        float norm = 0.0f;
-        for (int i = 0; i < 128; ++i) norm += my[i] * my[i];
-        norm = fast_sqrt_f(norm) + kEpsF;
-        const bool zero = sc.norm_thresh != 0 && (double)norm < sc.norm_thresh;
+    float norm = 0.0f;
+    for (int i = 0; i < 128; ++i) norm += hs[i] * hs[i];
+    norm = fast_sqrt_f(norm) + kEpsF;
+    const bool zero = sc.norm_thresh != 0 && (double)norm < sc.norm_thresh;
+    float v[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            float v = h[t] / norm;
-            if ((double)v > 0.2) v = (float)0.2;
-            h[t] = v;
-        }
-        __syncwarp(halfmask);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) my[cell * 8 + t] = h[t];
-        __syncwarp(halfmask);
-        float norm2 = 0.0f;
-        for (int i = 0; i < 128; ++i) norm2 += my[i] * my[i];
-        norm2 = fast_sqrt_f(norm2) + kEpsF;
-        float4 o0, o1;
-        if (zero) {
-            o0 = o1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            o0 = make_float4(h[0] / norm2, h[1] / norm2, h[2] / norm2, h[3] / norm2);
-            o1 = make_float4(h[4] / norm2, h[5] / norm2, h[6] / norm2, h[7] / norm2);
-        }
-        float4* dst = reinterpret_cast<float4*>(descr + (size_t)job * 128 + cell * 8);
-        dst[0] = o0;
-        dst[1] = o1;
+    for (int t = 0; t < 4; ++t) {
+        float q = hs[lane * 4 + t] / norm;
+        if ((double)q > 0.2) q = (float)0.2;
+        v[t] = q;
     }
-    if (act && cell == 0) written[job] = valid;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) hs[lane * 4 + t] = v[t];
+    __syncwarp();
+    float norm2 = 0.0f;
+    for (int i = 0; i < 128; ++i) norm2 += hs[i] * hs[i];
+    norm2 = fast_sqrt_f(norm2) + kEpsF;
+    float4 o = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(v[0] / norm2, v[1] / norm2, v[2] / norm2, v[3] / norm2);
+    reinterpret_cast<float4*>(descr + (size_t)job * 128)[lane] = o;
+    if (lane == 0) written[job] = 1;
 }
-void launch_descr(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
-                  const DescJob* jobs, int njobs, double xper, float* descr, int* written, cudaStream_t st) {
+void launch_descr(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys,
+                  const DescJob* jobs, int njobs, float* descr, int* written, cudaStream_t st) {
     if (njobs <= 0) return;
     KScope ks("sift.descr", st, 512.0 * njobs);
-    descr_kernel<<<div_up(njobs, 8), 128, 0, st>>>(ov, sc, expn_tab, o_cur, keys, jobs, njobs, xper, descr, written);
+    descr_kernel<<<div_up(njobs, 4), 128, 0, st>>>(os, sc, expn_tab, keys, jobs, njobs, descr, written);
     PB_KERNEL_CHECK();
 }
 

@@ -16,13 +16,19 @@ struct Cand { int x, y, s; };
 
 struct KeyIn {       // what the orientation / descriptor kernels need of a VlSiftKeypoint
     float x, y, sigma;
-    int is;
+    short is, oct;   // level index; slot of the keypoint's octave in the OctaveSet
 };
 
 struct DescJob {     // one (keypoint, angle) pair; sin/cos evaluated on the host
-    int key;
+    int key;         // index into the KeyIn array
     int pad;
     double angle, st0, ct0;
+};
+
+constexpr int kMaxOctaveSet = 8;
+struct OctaveSet {   // the octaves of one image, so that one launch serves the keypoints of all of them
+    OctaveView ov[kMaxOctaveSet];
+    double xper[kMaxOctaveSet];   // 2^o
 };
 
 void launch_u8_to_f32(const unsigned char* src, int src_pitch, float* dst, int w, int h, int pitch, cudaStream_t st);
@@ -42,9 +48,9 @@ void launch_detect(const OctaveView& ov, const SiftConsts& sc, Cand* cand, int* 
 void launch_refine(const OctaveView& ov, const SiftConsts& sc, const Cand* cand, const int* count, int cap,
                    RefinedKey* out, double xper, cudaStream_t st);
 void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cudaStream_t st);
-void launch_orient(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
-                   int nkeys, double xper, int* nangles, double* angles, cudaStream_t st);
-void launch_descr(const OctaveView& ov, const SiftConsts& sc, const double* expn_tab, int o_cur, const KeyIn* keys,
-                  const DescJob* jobs, int njobs, double xper, float* descr, int* written, cudaStream_t st);
+void launch_orient(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys, int nkeys,
+                   int* nangles, double* angles, cudaStream_t st);
+void launch_descr(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys,
+                  const DescJob* jobs, int njobs, float* descr, int* written, cudaStream_t st);
 
 }  // namespace pb

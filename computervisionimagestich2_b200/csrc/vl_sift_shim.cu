@@ -246,7 +246,7 @@ int vl_sift_calc_keypoint_orientations(VlSiftFilt* f, double angles[4], VlSiftKe
     }
     try {
         PB_CUDA(cudaSetDevice(I->device));
-        std::vector<KeyIn> ki{KeyIn{k->x, k->y, k->sigma, k->is}};
+        std::vector<KeyIn> ki{KeyIn{k->x, k->y, k->sigma, (short)k->is, 0}};
         std::vector<int> na;
         std::vector<double> an;
         I->eng->orient_custom(I->oi, ki, na, an);
@@ -275,7 +275,7 @@ void vl_sift_calc_keypoint_descriptor(VlSiftFilt* f, vl_sift_pix* descr, VlSiftK
     }
     try {
         PB_CUDA(cudaSetDevice(I->device));
-        std::vector<KeyIn> ki{KeyIn{k->x, k->y, k->sigma, k->is}};
+        std::vector<KeyIn> ki{KeyIn{k->x, k->y, k->sigma, (short)k->is, 0}};
         std::vector<int> jk{0};
         std::vector<double> ja{angle};
         float d[128];

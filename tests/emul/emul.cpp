@@ -102,13 +102,31 @@ EmulSift* emul_sift_run(const float* im, int w, int h, int O, int S) {
             for (int j = 0; j < na; ++j) {
                 float fh[128], d[128];
                 for (int q = 0; q < 128; ++q) d[q] = -1.0f;
-                // the cell-parallel formulation the CUDA kernel runs (16 independent cell workers)
+                // the sample-parallel formulation the CUDA kernel runs: conservative row / column ranges, per-sample
+                // records (phase A), bin owners adding their contributions in sample order (phase B)
                 DescFrame F = descriptor_frame(ov, sc, o, k.o, k.is, k.x, k.y, k.sigma, xper, ang[j], sin(ang[j]), cos(ang[j]));
                 int wr = F.valid;
                 if (wr) {
                     for (int q = 0; q < 128; ++q) fh[q] = 0.f;
-                    for (int cy = -2; cy < 2; ++cy)
-                        for (int cx = -2; cx < 2; ++cx) descriptor_cell(F, tab, cx, cy, fh + (cy + 2) * 32 + (cx + 2) * 8, 1);
+                    int ry0, ry1;
+                    descriptor_rows(F, &ry0, &ry1);
+                    for (int dyi = ry0; dyi <= ry1; ++dyi) {
+                        int x0, x1;
+                        descriptor_row_range(F, dyi, &x0, &x1);
+                        const float* row = F.pt + 2 * ((long)(F.yi + dyi) * F.pitch);
+                        for (int dxi = x0; dxi <= x1; ++dxi) {
+                            DescSample S = descriptor_sample(F, tab, dxi, dyi, row[2 * (F.xi + dxi)], row[2 * (F.xi + dxi) + 1]);
+                            if (!S.active) continue;
+                            for (int cell = 0; cell < 16; ++cell) {
+                                const int dbx = (cell & 3) - 2 - S.binx, dby = (cell >> 2) - 2 - S.biny;
+                                if (dbx < 0 || dbx > 1 || dby < 0 || dby > 1) continue;
+                                for (int par = 0; par < 2; ++par) {
+                                    const int sel = ((S.bint & 1) == par) ? 0 : 1;
+                                    fh[cell * 8 + ((S.bint + sel) & 7)] += S.wxy[dbx][dby] * S.at[sel];
+                                }
+                            }
+                        }
+                    }
                     descriptor_finish(sc, fh, 1, d);
                 }
                 if (g_check_serial) {  // cross-check against the serial restatement
