@@ -66,7 +66,7 @@ int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* 
     ctx->err.clear();
     Stitcher& S = *ctx->st;
     S.clear();
-    for (int i = 0; i < n; ++i) S.add_image(imgs[i], w[i], h[i]);
+    S.add_images(imgs, w, h, n, false);
     int rc = S.run();
     if (rc) { ctx->err = S.error(); return rc; }
     *out_w = S.result_width();
@@ -103,7 +103,7 @@ int pano_b200_stitch_into(pano_b200_ctx* ctx, const uint8_t* const* imgs, const 
     ctx->err.clear();
     Stitcher& S = *ctx->st;
     S.clear();
-    for (int i = 0; i < n; ++i) S.add_image(imgs[i], w[i], h[i]);
+    S.add_images(imgs, w, h, n, false);
     int rc = S.run();
     if (rc) { ctx->err = S.error(); return rc; }
     *out_w = S.result_width();

@@ -150,169 +150,240 @@ void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// recursive Gaussian (CImg vanvliet order 0, Neumann / Triggs boundary)
-// x pass: one warp owns 32 consecutive rows; 32x32 tiles are moved with coalesced accesses and transposed through
-// shared memory so that lane r walks row r sequentially with its 3 doubles of filter state in registers.
+// recursive Gaussian (CImg vanvliet order 0, Neumann / Triggs boundary; CImg.h:34905-34932)
+//
+// A line (image row for the x pass, image column for the y pass) is a strictly serial third-order recurrence in
+// double precision: out[n] = ((in[n] + f1 out[n-1]) + f2 out[n-2]) + f3 out[n-3], rounded to float on store, then the
+// same backwards.  The rounding order is the reference's, so the dependent chain per sample (DMUL + 3 DADD) cannot
+// be shortened; what CAN be removed is everything else on the critical path -- global-memory latency and the
+// transposition the x pass needs.  One CTA = two warps that share 32 lines:
+//   * the CONSUMER warp (lane = line) runs nothing but the recurrence, in place on 32x32 tiles in shared memory;
+//   * the PRODUCER warp streams the tiles: cp.async (LDGSTS) global -> shared, completion signalled on an mbarrier
+//     (cp.async.mbarrier.arrive), NS tiles in flight, and copies finished tiles back to HBM with coalesced stores.
+// Tile layout in shared memory is [element][line] with a 33-float pitch: conflict-free for the consumer (lanes =
+// consecutive lines), for the x-pass producer (lanes = consecutive elements of one line, i.e. a transposing copy)
+// and for the y-pass producer (lanes = consecutive lines of one element).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) iir_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int w,
-                                                    long nlines, IirCoef c) {
-    __shared__ float tile[4][32][33];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long line0 = ((long)blockIdx.x * 4 + warp) * 32;
-    if (line0 >= nlines) return;
-    float(*t)[33] = tile[warp];
-    const long myline = line0 + lane;
-    const bool active = myline < nlines;
-    const int nrows = (int)((nlines - line0) < 32 ? (nlines - line0) : 32);
-    const float* sbase = src + line0 * (long)w;
-    float* dbase = dst + line0 * (long)w;
-    double v1 = 0, v2 = 0, v3 = 0, iplus = 0;
-    if (active) {
-        iplus = (double)src[myline * (long)w + (w - 1)];
-        v1 = v2 = v3 = (double)src[myline * (long)w] / c.sumsq;
-    }
-    float pre[32];
-    // forward (reads src, writes dst); the next tile is prefetched into registers while this one is filtered
+namespace {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// float -> double, exact, on the integer pipe.  F2F.F64.F32 costs ~19 cycles of latency and ~11 issue cycles per warp
+// on sm_100a (tools/ubench/f2f_lat.cu); on the IIR's serial chain that is more than the four FP64 operations of a
+// step.  Normal numbers and zero are re-biased with integer instructions; denormals / inf / nan take the real cvt.
+__device__ __forceinline__ double f2d_exact(float f) {
+    const unsigned u = __float_as_uint(f);
+    const unsigned a = u & 0x7fffffffu;
+    const unsigned sign = u & 0x80000000u;
+    unsigned hi = ((a >> 3) + 0x38000000u) | sign;
+    if (a == 0u) hi = sign;
+    double d = __hiloint2double((int)hi, (int)(a << 29));
+    if (a != 0u && ((a >> 23) - 1u) >= 254u) asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(f));
+    return d;
+}
+constexpr int kIirNS = 4;          // tiles in flight per CTA
+constexpr int kIirPitch = 33;      // floats between consecutive elements of a tile
+}  // namespace
+
+// One full 32-sample tile of one line, in place in shared memory (t = the lane's column of the tile).  Measured in
+// isolation (tools/ubench/iir_tile.cu) this plain form runs at 38 cycles per sample against 32 for the bare
+// DMUL + 3 DADD chain; hand software-pipelined variants were slower (ptxas re-schedules them anyway).
+template <bool FWD>
+__device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, double& v3, const IirCoef& c) {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) pre[r] = (r < nrows && lane < w) ? sbase[(long)r * w + lane] : 0.0f;
-    for (int x0 = 0; x0 < w; x0 += 32) {
-        const int nx = (w - x0) < 32 ? (w - x0) : 32;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) t[r][lane] = pre[r];
-        __syncwarp();
-        const int xn = x0 + 32;
-        if (xn < w) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) pre[r] = (r < nrows && xn + lane < w) ? sbase[(long)r * w + xn + lane] : 0.0f;
-        }
-        if (active)
-            for (int i = 0; i < nx; ++i) {
-                double v0 = (double)t[lane][i];
-                v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
-                t[lane][i] = (float)v0;
-                v3 = v2; v2 = v1; v1 = v0;
-            }
-        __syncwarp();
-        if (lane < nx) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-                if (r < nrows) dbase[(long)r * w + x0 + lane] = t[r][lane];
-        }
-        __syncwarp();
-    }
-    // backward (in place on dst)
-    bool first = true;
-    const int xlast = ((w - 1) / 32) * 32;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) pre[r] = (r < nrows && xlast + lane < w) ? dbase[(long)r * w + xlast + lane] : 0.0f;
-    for (int x0 = xlast; x0 >= 0; x0 -= 32) {
-        const int nx = (w - x0) < 32 ? (w - x0) : 32;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) t[r][lane] = pre[r];
-        __syncwarp();
-        const int xn = x0 - 32;
-        if (xn >= 0) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) pre[r] = (r < nrows) ? dbase[(long)r * w + xn + lane] : 0.0f;
-        }
-        if (active)
-            for (int i = nx - 1; i >= 0; --i) {
-                double v0;
-                if (first) {
-                    const double uplus = iplus / c.bnd, vplus = uplus / c.bnd;
-                    const double unp = v1 - uplus, unp1 = v2 - uplus, unp2 = v3 - uplus;
-                    v0 = (c.M[0] * unp + c.M[1] * unp1 + c.M[2] * unp2 + vplus) * c.sum;
-                    const double n1 = (c.M[3] * unp + c.M[4] * unp1 + c.M[5] * unp2 + vplus) * c.sum;
-                    const double n2 = (c.M[6] * unp + c.M[7] * unp1 + c.M[8] * unp2 + vplus) * c.sum;
-                    v3 = n2; v2 = n1; v1 = v0;
-                    first = false;
-                } else {
-                    v0 = (double)t[lane][i];
-                    v0 *= c.sum;
-                    v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
-                    v3 = v2; v2 = v1; v1 = v0;
-                }
-                t[lane][i] = (float)v0;
-            }
-        first = false;
-        __syncwarp();
-        if (lane < nx) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-                if (r < nrows) dbase[(long)r * w + x0 + lane] = t[r][lane];
-        }
-        __syncwarp();
+    for (int e = 0; e < 32; ++e) {
+        float* p = t + (FWD ? e : 31 - e) * kIirPitch;
+        double v0 = (double)(*p);
+        if (!FWD) v0 *= c.sum;
+        v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+        *p = (float)v0;
+        v3 = v2; v2 = v1; v1 = v0;
     }
 }
 
-// y pass: one thread per column of a plane; neighbouring threads touch neighbouring addresses on every step.
-// Rows are processed in batches of 8: the 8 loads are independent of the recurrence and issue back to back.
-__global__ void __launch_bounds__(64) iir_y_kernel(float* __restrict__ planes, int w, int h, int nplanes, IirCoef c) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long)w * nplanes) return;
-    const int p = (int)(i / w), x = (int)(i - (long)p * w);
-    float* data = planes + (size_t)p * w * h + x;
-    const long off = w;
-    const int N = h;
-    constexpr int B = 8;
-    double v1, v2, v3;
-    const double iplus = (double)data[(long)(N - 1) * off];
-    v1 = v2 = v3 = (double)data[0] / c.sumsq;
-    for (int n0 = 0; n0 < N; n0 += B) {
-        float in[B];
-#pragma unroll
-        for (int j = 0; j < B; ++j) in[j] = (n0 + j < N) ? data[(long)(n0 + j) * off] : 0.0f;
-#pragma unroll
-        for (int j = 0; j < B; ++j)
-            if (n0 + j < N) {
-                double v0 = (double)in[j];
-                v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
-                data[(long)(n0 + j) * off] = (float)v0;
-                v3 = v2; v2 = v1; v1 = v0;
-            }
+// kElemContig: true  = x pass (the 32 elements of a tile are contiguous in HBM; planes are contiguous, so line l
+//                      starts at l * N)
+//              false = y pass (the 32 lines of a tile are contiguous in HBM, elements are `elem_stride` apart; line l
+//                      of plane p = l / lines_per_plane starts at p * plane_stride + l % lines_per_plane)
+// Three warps per CTA: 0 = consumer (recurrence), 1 = loader (HBM -> tile), 2 = storer (tile -> HBM).
+// Barriers per stage: full (loader -> consumer), done (consumer -> storer), vacant (storer -> loader).
+template <bool kElemContig>
+__global__ void __launch_bounds__(96) iir_pipe_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
+                                                      long nlines, int lines_per_plane, long plane_stride,
+                                                      long elem_stride, IirCoef c) {
+    __shared__ float tiles[kIirNS][32 * kIirPitch];
+    __shared__ unsigned long long full[kIirNS], done[kIirNS], vacant[kIirNS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long line0 = (long)blockIdx.x * 32;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kIirNS; ++s) { mbar_init(&full[s], 32); mbar_init(&done[s], 1); mbar_init(&vacant[s], 1); }
     }
-    {
-        const double uplus = iplus / c.bnd, vplus = uplus / c.bnd;
-        const double unp = v1 - uplus, unp1 = v2 - uplus, unp2 = v3 - uplus;
-        const double v0 = (c.M[0] * unp + c.M[1] * unp1 + c.M[2] * unp2 + vplus) * c.sum;
-        const double n1 = (c.M[3] * unp + c.M[4] * unp1 + c.M[5] * unp2 + vplus) * c.sum;
-        const double n2 = (c.M[6] * unp + c.M[7] * unp1 + c.M[8] * unp2 + vplus) * c.sum;
-        data[(long)(N - 1) * off] = (float)v0;
-        v3 = n2; v2 = n1; v1 = v0;
-    }
-    for (int n0 = N - 2; n0 >= 0; n0 -= B) {
-        float in[B];
-#pragma unroll
-        for (int j = 0; j < B; ++j) in[j] = (n0 - j >= 0) ? data[(long)(n0 - j) * off] : 0.0f;
-#pragma unroll
-        for (int j = 0; j < B; ++j)
-            if (n0 - j >= 0) {
-                double v0 = (double)in[j];
-                v0 *= c.sum;
-                v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
-                data[(long)(n0 - j) * off] = (float)v0;
-                v3 = v2; v2 = v1; v1 = v0;
+    __syncthreads();
+    const int T = (N + 31) >> 5;   // tiles per line
+    // job q of the CTA: q < T forward over tile q; q >= T backward over tile 2T-1-q.  Stage = q % NS; the k-th use
+    // of a stage (k = q / NS) completes phase k of each of its barriers.
+    if (warp == 0) {
+        // ------------------------------------------ consumer ------------------------------------------
+        double v1 = 0, v2 = 0, v3 = 0, iplus = 0;
+        for (int q = 0; q < 2 * T; ++q) {
+            const int s = q % kIirNS;
+            mbar_wait(&full[s], (unsigned)((q / kIirNS) & 1));
+            float* t = &tiles[s][lane];
+            const bool fwd = q < T;
+            const int tile = fwd ? q : 2 * T - 1 - q;
+            const int ne = (N - tile * 32) < 32 ? (N - tile * 32) : 32;
+            if (fwd) {
+                if (q == 0) v1 = v2 = v3 = (double)t[0] / c.sumsq;
+                if (tile == T - 1) iplus = (double)t[(ne - 1) * kIirPitch];
+                if (ne == 32) {
+                    iir_tile32<true>(t, v1, v2, v3, c);
+                } else {
+                    for (int e = 0; e < ne; ++e) {
+                        double v0 = (double)t[e * kIirPitch];
+                        v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+                        t[e * kIirPitch] = (float)v0;
+                        v3 = v2; v2 = v1; v1 = v0;
+                    }
+                }
+            } else {
+                int e = ne - 1;
+                if (q == T) {  // Triggs boundary on the last sample of the line
+                    const double uplus = iplus / c.bnd, vplus = uplus / c.bnd;
+                    const double unp = v1 - uplus, unp1 = v2 - uplus, unp2 = v3 - uplus;
+                    const double v0 = (c.M[0] * unp + c.M[1] * unp1 + c.M[2] * unp2 + vplus) * c.sum;
+                    const double n1 = (c.M[3] * unp + c.M[4] * unp1 + c.M[5] * unp2 + vplus) * c.sum;
+                    const double n2 = (c.M[6] * unp + c.M[7] * unp1 + c.M[8] * unp2 + vplus) * c.sum;
+                    t[e * kIirPitch] = (float)v0;
+                    v3 = n2; v2 = n1; v1 = v0;
+                    --e;
+                }
+                if (e == 31) {
+                    iir_tile32<false>(t, v1, v2, v3, c);
+                } else {
+                    for (; e >= 0; --e) {
+                        double v0 = (double)t[e * kIirPitch];
+                        v0 *= c.sum;
+                        v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+                        t[e * kIirPitch] = (float)v0;
+                        v3 = v2; v2 = v1; v1 = v0;
+                    }
+                }
             }
+            __syncwarp();                       // one arrival per warp: 32 arrivals on one mbarrier serialise
+            if (lane == 0) mbar_arrive(&done[s]);
+        }
+        return;
+    }
+    // ------------------------------------------ loader / storer ------------------------------------------
+    // x pass: lane = element, loop over the CTA's lines; y pass: lane = line, loop over the tile's elements
+    const int nl = (int)((nlines - line0) < 32 ? (nlines - line0) : 32);
+    long mybase = 0;
+    bool line_ok = true;
+    if (kElemContig) {
+        mybase = line0 * (long)N + lane;
+    } else {
+        const long l = line0 + lane;
+        line_ok = l < nlines;
+        const long p = (line_ok ? l : 0) / lines_per_plane;
+        mybase = p * plane_stride + ((line_ok ? l : 0) - p * lines_per_plane);
+    }
+    if (warp == 1) {
+        for (int q = 0; q < 2 * T; ++q) {
+            const int s = q % kIirNS;
+            if (q >= kIirNS) mbar_wait(&vacant[s], (unsigned)(((q - kIirNS) / kIirNS) & 1));
+            if (q == T) {
+                // the backward run reads the forward output: every forward tile must have reached HBM
+                for (int j = (T - kIirNS > 0 ? T - kIirNS : 0); j < T; ++j)
+                    mbar_wait(&vacant[j % kIirNS], (unsigned)((j / kIirNS) & 1));
+            }
+            const bool fwd = q < T;
+            const int tile = fwd ? q : 2 * T - 1 - q;
+            const float* from = fwd ? src : dst;
+            const int e0 = tile * 32;
+            float* t = tiles[s];
+            if (kElemContig) {
+                if (e0 + lane < N) {
+                    const float* g = from + mybase + e0;
+#pragma unroll 8
+                    for (int r = 0; r < nl; ++r) cp_async4(&t[lane * kIirPitch + r], g + (long)r * N);
+                }
+            } else {
+                if (line_ok) {
+                    const int ne = (N - e0) < 32 ? (N - e0) : 32;
+                    const float* g = from + mybase + (long)e0 * elem_stride;
+#pragma unroll 8
+                    for (int e = 0; e < ne; ++e) cp_async4(&t[e * kIirPitch + lane], g + (long)e * elem_stride);
+                }
+            }
+            cp_async_arrive(&full[s]);
+        }
+    } else {
+        for (int q = 0; q < 2 * T; ++q) {
+            const int s = q % kIirNS;
+            mbar_wait(&done[s], (unsigned)((q / kIirNS) & 1));
+            const bool fwd = q < T;
+            const int tile = fwd ? q : 2 * T - 1 - q;
+            const int e0 = tile * 32;
+            const float* t = tiles[s];
+            if (kElemContig) {
+                if (e0 + lane < N) {
+                    float* g = dst + mybase + e0;
+#pragma unroll 8
+                    for (int r = 0; r < nl; ++r) g[(long)r * N] = t[lane * kIirPitch + r];
+                }
+            } else {
+                if (line_ok) {
+                    const int ne = (N - e0) < 32 ? (N - e0) : 32;
+                    float* g = dst + mybase + (long)e0 * elem_stride;
+#pragma unroll 8
+                    for (int e = 0; e < ne; ++e) g[(long)e * elem_stride] = t[e * kIirPitch + lane];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&vacant[s]);   // release: the loader (same CTA) re-reads forward tiles after acquiring this
+        }
     }
 }
 
 void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st) {
     const float* ysrc = src;
+    const long plane = (long)w * h;
     if (w > 1) {
-        long nlines = (long)nplanes * h;
+        const long nlines = (long)nplanes * h;
         KScope ks("blend.iir_x", st, 16.0 * nplanes * w * h);
-        iir_x_kernel<<<div_up(nlines, 128), 128, 0, st>>>(src, dst, w, nlines, coef);
+        iir_pipe_kernel<true><<<div_up(nlines, 32), 96, 0, st>>>(src, dst, w, nlines, h, plane, 1L, coef);
+        PB_KERNEL_CHECK();
+        ysrc = dst;
+    }
+    if (h > 1) {
+        const long nlines = (long)nplanes * w;
+        KScope ks("blend.iir_y", st, 16.0 * nplanes * w * h);
+        iir_pipe_kernel<false><<<div_up(nlines, 32), 96, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
     if (ysrc != dst)
         PB_CUDA(cudaMemcpyAsync(dst, src, (size_t)nplanes * w * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (h > 1) {
-        long n = (long)w * nplanes;
-        KScope ks("blend.iir_y", st, 16.0 * nplanes * w * h);
-        iir_y_kernel<<<div_up(n, 64), 64, 0, st>>>(dst, w, h, nplanes, coef);
-        PB_KERNEL_CHECK();
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

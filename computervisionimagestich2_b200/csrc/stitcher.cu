@@ -7,6 +7,7 @@
 #include <cmath>
 #include <queue>
 #include <sstream>
+#include <thread>
 
 namespace pb {
 
@@ -35,6 +36,12 @@ Stitcher::~Stitcher() {
     imgs_.clear();
     pool_.clear();
     sift_.reset();
+    for (auto& L : lanes_) {
+        L->eng.reset();
+        if (L->st) cudaStreamDestroy(L->st);
+        L->st = nullptr;
+    }
+    lanes_.clear();
     if (st_) cudaStreamDestroy(st_);
 }
 
@@ -130,15 +137,16 @@ void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t) {
     t.on_device = false;
 }
 
-void Stitcher::upload_table(FeatureTable& t) {
+void Stitcher::upload_table_on(FeatureTable& t, cudaStream_t st) {
     if (t.on_device) return;
     t.d_descr.ensure(std::max<size_t>((size_t)t.n * 128, 128));
     if (t.n > 0)
         PB_CUDA(cudaMemcpyAsync(t.d_descr.p, t.descr.data(), (size_t)t.n * 128 * sizeof(float), cudaMemcpyHostToDevice,
-                                st_));
-    PB_CUDA(cudaStreamSynchronize(st_));
+                                st));
+    PB_CUDA(cudaStreamSynchronize(st));
     t.on_device = true;
 }
+void Stitcher::upload_table(FeatureTable& t) { upload_table_on(t, st_); }
 
 void Stitcher::match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx) {
     PB_CUDA(cudaSetDevice(dev_));
@@ -544,6 +552,90 @@ void Stitcher::add_image_device(const u8* d_rgb, int w, int h) {
     imgs_.push_back(std::move(im));
 }
 
+// One lane's share of readFile(): images first, first + step, ...  Runs on its own host thread.
+void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, const int* w, const int* h, int n,
+                         bool on_device) {
+    try {
+        PB_CUDA(cudaSetDevice(dev_));
+        for (int i = first; i < n; i += step) {
+            Image& im = *imgs_[i];
+            const int iw = w[i], ih = h[i];
+            im.w = iw; im.h = ih;
+            const size_t np = (size_t)iw * ih;
+            WallTimer t0;
+            const u8* d_rgb = imgs[i];
+            if (!on_device) {
+                L.in_rgb.ensure(3 * np);
+                PB_CUDA(cudaMemcpyAsync(L.in_rgb.p, imgs[i], 3 * np, cudaMemcpyHostToDevice, L.st));
+                d_rgb = L.in_rgb.p;
+            }
+            im.proj.ensure(3 * np);
+            const int pitch = align_up(iw, 32);
+            L.gray32.ensure((size_t)pitch * ih);
+            const int shortside = std::min(iw, ih);
+            if (L.ktab_n != shortside) {
+                std::vector<float> k;
+                hostnum::cylinder_table(shortside, k);
+                L.ktab.ensure(shortside);
+                PB_CUDA(cudaMemcpyAsync(L.ktab.p, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice, L.st));
+                PB_CUDA(cudaStreamSynchronize(L.st));
+                L.ktab_n = shortside;
+            }
+            launch_project_gray(d_rgb, iw, ih, L.ktab.p, im.proj.p, L.gray32.p, pitch, nullptr, L.st);
+            L.t_project += t0.ms();
+            WallTimer t1;
+            SiftParams sp;
+            RawFeatures raw;
+            L.eng->configure(iw, ih, sp);
+            L.eng->extract(L.gray32.p, pitch, raw);
+            L.t_sift += t1.ms();
+            WallTimer t2;
+            build_table(raw, im.feat);
+            upload_table_on(im.feat, L.st);
+            L.t_table += t2.ms();
+        }
+    } catch (const std::exception& e) {
+        L.err = e.what();
+    }
+}
+
+void Stitcher::add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device) {
+    PB_CUDA(cudaSetDevice(dev_));
+    WallTimer tw;
+    const int nl = std::max(1, std::min(want_lanes_, n));
+    while ((int)lanes_.size() < nl) {
+        std::unique_ptr<Lane> L(new Lane());
+        PB_CUDA(cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking));
+        L->eng.reset(new SiftEngine(L->st));
+        lanes_.push_back(std::move(L));
+    }
+    const int base = (int)imgs_.size();
+    (void)base;
+    for (int i = 0; i < n; ++i) {
+        std::unique_ptr<Image> im;
+        if (!pool_.empty()) { im = std::move(pool_.back()); pool_.pop_back(); }
+        else im.reset(new Image());
+        imgs_.push_back(std::move(im));
+    }
+    // the lanes index imgs_ from 0: add_images is the only producer of a job's image list
+    for (int k = 0; k < nl; ++k) { lanes_[k]->err.clear(); lanes_[k]->t_project = lanes_[k]->t_sift = lanes_[k]->t_table = 0; }
+    if (nl == 1) {
+        lane_work(*lanes_[0], 0, 1, imgs, w, h, n, on_device);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nl; ++k)
+            th.emplace_back([this, k, nl, imgs, w, h, n, on_device] { lane_work(*lanes_[k], k, nl, imgs, w, h, n, on_device); });
+        for (auto& t : th) t.join();
+    }
+    for (int k = 0; k < nl; ++k) {
+        if (!lanes_[k]->err.empty()) throw std::runtime_error(lanes_[k]->err);
+        tm_.project += lanes_[k]->t_project;   // per-lane times overlap; `features` is the wall time of the stage
+        tm_.table += lanes_[k]->t_table;
+    }
+    for (int i = 0; i < n; ++i) tm_.sift_pixels += (long)w[i] * h[i];
+    tm_.sift += tw.ms();
+}
+
 void Stitcher::stage_images(const u8* const* imgs, const int* w, const int* h, int n) {
     PB_CUDA(cudaSetDevice(dev_));
     staged_.clear();
@@ -560,7 +652,11 @@ void Stitcher::stage_images(const u8* const* imgs, const int* w, const int* h, i
 
 int Stitcher::run_staged() {
     clear();
-    for (auto& s : staged_) add_image_device(s->rgb.p, s->w, s->h);
+    const int n = (int)staged_.size();
+    std::vector<const u8*> p(n);
+    std::vector<int> w(n), h(n);
+    for (int i = 0; i < n; ++i) { p[i] = staged_[i]->rgb.p; w[i] = staged_[i]->w; h[i] = staged_[i]->h; }
+    add_images(p.data(), w.data(), h.data(), n, true);
     return run();
 }
 

@@ -63,6 +63,11 @@ class Stitcher {
     void clear();
     void add_image(const u8* rgb, int w, int h);     // planar RGB host buffer
     void add_image_device(const u8* d_rgb, int w, int h);   // planar RGB already resident in HBM
+    // readFile() for all images at once (ImageProcess.cpp:12-23): images are independent until matching, so they
+    // are processed concurrently, image i on lane i % nlanes (one CUDA stream + SIFT engine + host thread per lane).
+    // on_device: imgs[i] are HBM pointers (staged inputs) instead of host buffers.
+    void add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
+    void set_lanes(int n) { want_lanes_ = n < 1 ? 1 : n; }
     // inputs staged in HBM once (outside any timed region), then stitched any number of times
     void stage_images(const u8* const* imgs, const int* w, const int* h, int n);
     int run_staged();
@@ -110,6 +115,19 @@ class Stitcher {
     DevBuf<float> tab_f_;
     DevBuf<double> tab_d_;
     int cur_ = 0, rw_ = 0, rh_ = 0;
+    struct Lane {   // per-worker resources for concurrent feature extraction
+        cudaStream_t st = nullptr;
+        std::unique_ptr<SiftEngine> eng;
+        DevBuf<u8> in_rgb;
+        DevBuf<float> gray32, ktab;
+        int ktab_n = 0;
+        double t_project = 0, t_sift = 0, t_table = 0;
+        std::string err;
+    };
+    void lane_work(Lane& L, int first, int step, const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
+    void upload_table_on(FeatureTable& t, cudaStream_t st);
+    std::vector<std::unique_ptr<Lane>> lanes_;
+    int want_lanes_ = 4;
     struct Staged { int w, h; DevBuf<u8> rgb; };
     std::vector<std::unique_ptr<Staged>> staged_;
     DevBuf<char> flush_;
