@@ -116,3 +116,43 @@ def test_repeated_stitch_is_deterministic(ctx, anchors):
     imgs = _load_set("Input")
     h = {sha(ctx.stitch(imgs)[0]) for _ in range(3)}
     assert h == {anchors["Input"]["pano_sha256"]}
+
+
+# ---- the reference-side bindings: C++ host programs linked against libpano_b200.so -----------------
+def _fnv(b):
+    h = 0xCBF29CE484222325
+    for x in b:
+        h = ((h ^ x) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+def _example(name):
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(ROOT, "examples", name)
+
+
+def test_vl_sift_shim_runs_the_reference_call_sequence(small, tmp_path):
+    """examples/sift_features.cpp is ImageProcess::siftAlgorithm compiled against include/vl_b200/sift.h."""
+    import subprocess
+    exe = _example("sift_features")
+    for tag in ("s160x120", "s97x61"):
+        g = small[f"{tag}_gray"]
+        raw = tmp_path / f"{tag}.raw"
+        raw.write_bytes(np.ascontiguousarray(g).tobytes())
+        out = subprocess.run([exe, str(raw), str(g.shape[1]), str(g.shape[0])], capture_output=True, text=True, check=True).stdout.split()
+        d, k = small[f"{tag}_descr"], small[f"{tag}_keys"]
+        assert int(out[0]) == len(k)
+        assert out[1] == _fnv(d.tobytes()) and out[2] == _fnv(k.tobytes())
+
+
+def test_imageprocess_drop_in_main(anchors):
+    """examples/main.cpp is the reference's main.cpp on include/pano_b200/ImageProcess.h."""
+    import subprocess
+    d = os.path.join(ROOT, "oracle", "_ref", "data", "Input")
+    if not os.path.isdir(d):
+        pytest.skip("bundled inputs not staged")
+    out = subprocess.run([_example("pano_main"), d + "/", "4"], capture_output=True, text=True, check=True).stdout
+    A = anchors["Input"]
+    assert out.splitlines()[:-1] == A["log"].splitlines()
+    assert out.splitlines()[-1] == f"panorama {A['pano_shape'][2]}x{A['pano_shape'][1]} fnv1a64 {A['pano_fnv1a64']}"
