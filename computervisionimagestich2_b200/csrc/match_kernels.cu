@@ -12,15 +12,21 @@
 #include "ransac_device.cuh"
 #include "common.h"
 #include "ktimer.h"
+#include <algorithm>
 
 namespace pb {
 
 constexpr int kQ = 128;   // queries per CTA (one per thread)
 constexpr int kTA = 32;   // database rows per shared-memory tile
 
-__global__ void __launch_bounds__(kQ) match_l1_kernel(const float* __restrict__ A, int NA, const float* __restrict__ B,
-                                                      int NB, int rows_per_split, Top2* __restrict__ partial) {
+__global__ void __launch_bounds__(kQ) match_l1_kernel(const MatchJob* __restrict__ jobs) {
     __shared__ __align__(16) float tile[kTA][128];
+    const MatchJob J = jobs[blockIdx.z];
+    const float* __restrict__ A = J.A;
+    const float* __restrict__ B = J.B;
+    const int NA = J.NA, NB = J.NB, rows_per_split = J.rows_per_split;
+    Top2* __restrict__ partial = J.partial;
+    if (blockIdx.x * kQ >= NB || blockIdx.y >= J.nsplit) return;   // grid is sized for the largest job of the batch
     const int b = blockIdx.x * kQ + threadIdx.x;
     const int a_begin = blockIdx.y * rows_per_split;
     const int a_end = min(NA, a_begin + rows_per_split);
@@ -73,8 +79,12 @@ __global__ void __launch_bounds__(kQ) match_l1_kernel(const float* __restrict__ 
     if (b < NB) partial[(size_t)blockIdx.y * NB + b] = best;
 }
 
-__global__ void match_merge_kernel(const Top2* __restrict__ partial, int nsplit, int NA, int NB, int* __restrict__ idx,
-                                   float* __restrict__ d01) {
+__global__ void match_merge_kernel(const MatchJob* __restrict__ jobs) {
+    const MatchJob J = jobs[blockIdx.y];
+    const Top2* __restrict__ partial = J.partial;
+    const int nsplit = J.nsplit, NA = J.NA, NB = J.NB;
+    int* __restrict__ idx = J.idx;
+    float* __restrict__ d01 = J.d01;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= NB) return;
     Top2 t = partial[b];
@@ -92,23 +102,32 @@ int match_num_splits(int NA, int NB) {
     return s < 1 ? 1 : s;
 }
 
-void launch_match_l1(const float* dA, int NA, const float* dB, int NB, Top2* partial, int nsplit, int* idx, float* d01,
-                     cudaStream_t st) {
-    if (NB <= 0) return;
-    if (NA <= 0) {
-        PB_CUDA(cudaMemsetAsync(idx, 0xff, sizeof(int) * NB, st));
-        return;
+MatchJob make_match_job(const float* dA, int NA, const float* dB, int NB, Top2* partial, int nsplit, int* idx,
+                        float* d01) {
+    MatchJob J;
+    J.A = dA; J.B = dB; J.NA = NA; J.NB = NB;
+    J.rows_per_split = align_up(div_up(NA > 0 ? NA : 1, nsplit > 0 ? nsplit : 1), 4);
+    J.nsplit = div_up(NA > 0 ? NA : 1, J.rows_per_split);
+    J.partial = partial; J.idx = idx; J.d01 = d01;
+    return J;
+}
+
+void launch_match_batch(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, cudaStream_t st) {
+    if (njobs <= 0) return;
+    int gx = 1, gy = 1;
+    double work = 0;
+    for (int i = 0; i < njobs; ++i) {
+        gx = std::max(gx, div_up(h_jobs[i].NB, kQ));
+        gy = std::max(gy, h_jobs[i].nsplit);
+        work += 256.0 * h_jobs[i].NA * h_jobs[i].NB;
     }
-    int rps = align_up(div_up(NA, nsplit), 4);
-    nsplit = div_up(NA, rps);
-    dim3 g(div_up(NB, kQ), nsplit);
     {
-    KScope ks("match.l1", st, 256.0 * NA * NB);
-    match_l1_kernel<<<g, kQ, 0, st>>>(dA, NA, dB, NB, rps, partial);
-    PB_KERNEL_CHECK();
+        KScope ks("match.l1", st, work);
+        match_l1_kernel<<<dim3(gx, gy, njobs), kQ, 0, st>>>(d_jobs);
+        PB_KERNEL_CHECK();
     }
     KScope ks2("match.merge", st, 0);
-    match_merge_kernel<<<div_up(NB, 128), 128, 0, st>>>(partial, nsplit, NA, NB, idx, d01);
+    match_merge_kernel<<<dim3(div_up(gx * kQ, 128), njobs), 128, 0, st>>>(d_jobs);
     PB_KERNEL_CHECK();
 }
 

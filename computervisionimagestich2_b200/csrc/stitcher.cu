@@ -148,22 +148,64 @@ void Stitcher::upload_table_on(FeatureTable& t, cudaStream_t st) {
 }
 void Stitcher::upload_table(FeatureTable& t) { upload_table_on(t, st_); }
 
-void Stitcher::match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx) {
+// Several directed matching problems (A = database, B = queries) in ONE launch.  out[k][b] = row of A matched by
+// query row b, or -1 (ImageProcess.cpp:311-346).
+void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTable*>>& probs,
+                           std::vector<std::vector<int>>& out) {
     PB_CUDA(cudaSetDevice(dev_));
-    upload_table(A);
-    upload_table(B);
-    idx.assign(B.n, -1);
-    if (B.n == 0 || A.n < 2) return;  // the reference reads an unset second neighbour when NA < 2
-    int ns = match_num_splits(A.n, B.n);
-    partial_.ensure((size_t)ns * B.n);
-    midx_.ensure(B.n);
-    int* h = h_midx_.ensure(B.n);
-    launch_match_l1(A.d_descr.p, A.n, B.d_descr.p, B.n, partial_.p, ns, midx_.p, nullptr, st_);
-    PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * B.n, cudaMemcpyDeviceToHost, st_));
+    const int P = (int)probs.size();
+    out.assign(P, std::vector<int>());
+    std::vector<MatchJob> jobs;
+    std::vector<int> job_of(P, -1);
+    size_t npart = 0, nidx = 0;
+    std::vector<size_t> poff, ioff;
+    std::vector<int> nsplits;
+    for (int k = 0; k < P; ++k) {
+        FeatureTable &A = *probs[k].first, &B = *probs[k].second;
+        upload_table(A);
+        upload_table(B);
+        out[k].assign(B.n, -1);
+        if (B.n == 0 || A.n < 2) continue;  // the reference reads an unset second neighbour when NA < 2
+        const int ns = match_num_splits(A.n, B.n);
+        job_of[k] = (int)nsplits.size();
+        nsplits.push_back(ns);
+        poff.push_back(npart);
+        ioff.push_back(nidx);
+        npart += (size_t)ns * B.n;
+        nidx += B.n;
+        tm_.match_pairs_evaluated += (long)A.n * B.n;
+        tm_.n_match_calls++;
+    }
+    if (nsplits.empty()) return;
+    partial_.ensure(npart);
+    midx_.ensure(nidx);
+    int* h = h_midx_.ensure(nidx);
+    for (int k = 0; k < P; ++k) {
+        if (job_of[k] < 0) continue;
+        const int q = job_of[k];
+        FeatureTable &A = *probs[k].first, &B = *probs[k].second;
+        jobs.push_back(make_match_job(A.d_descr.p, A.n, B.d_descr.p, B.n, partial_.p + poff[q], nsplits[q],
+                                      midx_.p + ioff[q], nullptr));
+    }
+    MatchJob* hj = (MatchJob*)h_mjobs_.ensure(jobs.size() * sizeof(MatchJob));
+    memcpy(hj, jobs.data(), jobs.size() * sizeof(MatchJob));
+    mjobs_.ensure(jobs.size());
+    PB_CUDA(cudaMemcpyAsync(mjobs_.p, hj, jobs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st_));
+    launch_match_batch(mjobs_.p, hj, (int)jobs.size(), st_);
+    PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * nidx, cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
-    std::copy(h, h + B.n, idx.begin());
-    tm_.match_pairs_evaluated += (long)A.n * B.n;
-    tm_.n_match_calls++;
+    for (int k = 0; k < P; ++k) {
+        if (job_of[k] < 0) continue;
+        const int q = job_of[k];
+        std::copy(h + ioff[q], h + ioff[q] + out[k].size(), out[k].begin());
+    }
+}
+
+void Stitcher::match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx) {
+    std::vector<std::pair<FeatureTable*, FeatureTable*>> probs{{&A, &B}};
+    std::vector<std::vector<int>> out;
+    match_batch(probs, out);
+    idx.swap(out[0]);
 }
 
 void Stitcher::match(FeatureTable& A, FeatureTable& B, std::vector<KeyPair>& pairs) {
@@ -689,15 +731,41 @@ int Stitcher::run() {
     std::vector<std::vector<char>> adj(n, std::vector<char>(n, 0));
     std::vector<std::vector<int>> next(n);
     std::vector<KeyPair> pairs;
-    // adjacency discovery (ImageProcess.cpp:117-137)
+    // adjacency discovery (ImageProcess.cpp:117-137).  The reference evaluates getImgPair(i, j) for i < j always and
+    // for i > j only when (j, i) turned out not adjacent; the same set of directed problems is evaluated here, as two
+    // batched launches.  Match INDICES depend only on the descriptor tables, so they are cached per directed pair
+    // and reused by the stitching loop (which the reference re-evaluates, ImageProcess.cpp:177-178).
+    std::vector<std::vector<std::vector<int>>> midx(n, std::vector<std::vector<int>>(n));
+    std::vector<std::vector<char>> have(n, std::vector<char>(n, 0));
+    auto run_wave = [&](const std::vector<std::pair<int, int>>& w) {
+        if (w.empty()) return;
+        std::vector<std::pair<FeatureTable*, FeatureTable*>> probs;
+        for (auto& ij : w) probs.push_back({&imgs_[ij.first]->feat, &imgs_[ij.second]->feat});
+        std::vector<std::vector<int>> out;
+        match_batch(probs, out);
+        for (size_t k = 0; k < w.size(); ++k) { midx[w[k].first][w[k].second].swap(out[k]); have[w[k].first][w[k].second] = 1; }
+    };
+    auto count_matches = [&](int i, int j) {
+        int c = 0;
+        for (int v : midx[i][j]) c += v >= 0;
+        return c;
+    };
     {
         WallTimer t;
+        std::vector<std::pair<int, int>> wave;
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) wave.push_back({i, j});
+        run_wave(wave);
+        wave.clear();
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < i; ++j)
+                if (count_matches(j, i) < 20) wave.push_back({i, j});
+        run_wave(wave);
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) {
                 if (i == j) continue;
                 if (adj[j][i]) { adj[i][j] = 1; next[i].push_back(j); continue; }
-                match(imgs_[i]->feat, imgs_[j]->feat, pairs);
-                if ((int)pairs.size() >= 20) { adj[i][j] = 1; next[i].push_back(j); }
+                if (count_matches(i, j) >= 20) { adj[i][j] = 1; next[i].push_back(j); }
             }
         tm_.match += t.ms();
     }
@@ -715,6 +783,35 @@ int Stitcher::run() {
         PB_CUDA(cudaMemcpyAsync(res_[0].p, s.proj.p, (size_t)3 * rw_ * rh_, cudaMemcpyDeviceToDevice, st_));
     }
     H8_.ensure(8);
+    {   // the stitching order depends on the adjacency alone: plan it now and evaluate, in one launch, the directed
+        // problems of the tree edges that the discovery stage skipped
+        WallTimer t;
+        std::vector<std::vector<char>> a2 = adj;
+        std::queue<int> q2;
+        q2.push(start);
+        std::vector<std::pair<int, int>> wave;
+        while (!q2.empty()) {
+            int src = q2.front();
+            q2.pop();
+            for (int i = (int)next[src].size() - 1; i >= 0; i--) {
+                int dst = next[src][i];
+                if (!a2[src][dst]) continue;
+                a2[src][dst] = a2[dst][src] = 0;
+                q2.push(dst);
+                if (!have[src][dst]) wave.push_back({src, dst});
+                if (!have[dst][src]) wave.push_back({dst, src});
+            }
+        }
+        run_wave(wave);
+        tm_.match += t.ms();
+    }
+    auto pairs_of = [&](int a, int b, std::vector<KeyPair>& out) {   // getImgPair(imgs[a], imgs[b]) with the current keys
+        out.clear();
+        const FeatureTable &A = imgs_[a]->feat, &B = imgs_[b]->feat;
+        const std::vector<int>& idx = midx[a][b];
+        for (int q = 0; q < B.n; ++q)
+            if (idx[q] >= 0) out.push_back(KeyPair{A.keys[idx[q]], B.keys[q]});
+    };
     while (!wait.empty()) {
         int src = wait.front();
         wait.pop();
@@ -726,8 +823,8 @@ int Stitcher::run() {
             std::vector<KeyPair> s2d, d2s;
             {
                 WallTimer t;
-                match(imgs_[src]->feat, imgs_[dst]->feat, s2d);
-                match(imgs_[dst]->feat, imgs_[src]->feat, d2s);
+                pairs_of(src, dst, s2d);
+                pairs_of(dst, src, d2s);
                 tm_.match += t.ms();
             }
             log << src << " " << dst << "\n";

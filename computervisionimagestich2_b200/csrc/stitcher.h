@@ -47,6 +47,7 @@ class Stitcher {
     void upload_table(FeatureTable& t);
     // idx[b] = row of A matched by query row b of B, or -1 (ImageProcess.cpp:311-346)
     void match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx);
+    void match_batch(const std::vector<std::pair<FeatureTable*, FeatureTable*>>& probs, std::vector<std::vector<int>>& out);
     void match(FeatureTable& A, FeatureTable& B, std::vector<KeyPair>& pairs);
     // several RANSAC problems in one launch; returns false for a problem the reference cannot solve (<4 pairs ...)
     bool ransac(const std::vector<const std::vector<KeyPair>*>& problems, std::vector<double>& H8s);
@@ -106,6 +107,8 @@ class Stitcher {
     DevBuf<Top2> partial_;
     DevBuf<int> midx_;
     PinBuf<int> h_midx_;
+    DevBuf<MatchJob> mjobs_;
+    PinBuf<char> h_mjobs_;
     DevBuf<KeyPair> r_pairs_;
     DevBuf<int> r_off_, r_samples_, r_counts_;
     DevBuf<unsigned> r_masks_;
