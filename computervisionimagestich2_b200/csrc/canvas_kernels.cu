@@ -181,6 +181,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                      : "memory");
     } while (!ok);
 }
+// wait with back-off: a warp that polls an mbarrier competes with the consumer's LDS / STS for the shared-memory pipe
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    for (;;) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (ok) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -188,26 +200,15 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
 __device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// float -> double, exact, on the integer pipe.  F2F.F64.F32 costs ~19 cycles of latency and ~11 issue cycles per warp
-// on sm_100a (tools/ubench/f2f_lat.cu); on the IIR's serial chain that is more than the four FP64 operations of a
-// step.  Normal numbers and zero are re-biased with integer instructions; denormals / inf / nan take the real cvt.
-__device__ __forceinline__ double f2d_exact(float f) {
-    const unsigned u = __float_as_uint(f);
-    const unsigned a = u & 0x7fffffffu;
-    const unsigned sign = u & 0x80000000u;
-    unsigned hi = ((a >> 3) + 0x38000000u) | sign;
-    if (a == 0u) hi = sign;
-    double d = __hiloint2double((int)hi, (int)(a << 29));
-    if (a != 0u && ((a >> 23) - 1u) >= 254u) asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(f));
-    return d;
-}
 constexpr int kIirNS = 4;          // tiles in flight per CTA
 constexpr int kIirPitch = 33;      // floats between consecutive elements of a tile
 }  // namespace
 
-// One full 32-sample tile of one line, in place in shared memory (t = the lane's column of the tile).  Measured in
-// isolation (tools/ubench/iir_tile.cu) this plain form runs at 38 cycles per sample against 32 for the bare
-// DMUL + 3 DADD chain; hand software-pipelined variants were slower (ptxas re-schedules them anyway).
+// One full 32-sample tile of one line, in place in shared memory (t = the lane's column of the tile).  The bare
+// DMUL + 3 DADD chain is 32 cycles per sample (tools/ubench/iir_step.cu); with the two float<->double conversions
+// (F2F: ~19 cycles latency, ~10 issue cycles per warp on a unit shared by the SM, tools/ubench/f2f_lat.cu) this plain
+// form measures 38 cycles in isolation and 62 in the kernel.  Integer-pipe conversions and hand software pipelining
+// were both tried and were slower (87 and 51 cycles).
 template <bool FWD>
 __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, double& v3, const IirCoef& c) {
 #pragma unroll
@@ -225,20 +226,25 @@ __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, dou
 //                      starts at l * N)
 //              false = y pass (the 32 lines of a tile are contiguous in HBM, elements are `elem_stride` apart; line l
 //                      of plane p = l / lines_per_plane starts at p * plane_stride + l % lines_per_plane)
-// Three warps per CTA: 0 = consumer (recurrence), 1 = loader (HBM -> tile), 2 = storer (tile -> HBM).
+// Roles: consumer (recurrence), loader (HBM -> tile), storer (tile -> HBM).  A CTA has four warps, one per SM
+// sub-partition; the role of a warp rotates with blockIdx.x so that the consumers of the CTAs resident on an SM
+// spread over all four sub-partitions (with fixed roles every consumer lands on sub-partition 0 and they serialise
+// on its FP64 pipe: measured 62 -> 153 cycles per sample going from 1 to 8 CTAs per SM).  The fourth warp exits.
 // Barriers per stage: full (loader -> consumer), done (consumer -> storer), vacant (storer -> loader).
 template <bool kElemContig>
-__global__ void __launch_bounds__(96) iir_pipe_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
+__global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
                                                       long nlines, int lines_per_plane, long plane_stride,
                                                       long elem_stride, IirCoef c) {
     __shared__ float tiles[kIirNS][32 * kIirPitch];
     __shared__ unsigned long long full[kIirNS], done[kIirNS], vacant[kIirNS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int warp = ((threadIdx.x >> 5) + 4 - (blockIdx.x & 3)) & 3;   // role: 0 consumer, 1 loader, 2 storer, 3 idle
     const long line0 = (long)blockIdx.x * 32;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kIirNS; ++s) { mbar_init(&full[s], 32); mbar_init(&done[s], 1); mbar_init(&vacant[s], 1); }
     }
     __syncthreads();
+    if (warp == 3) return;
     const int T = (N + 31) >> 5;   // tiles per line
     // job q of the CTA: q < T forward over tile q; q >= T backward over tile 2T-1-q.  Stage = q % NS; the k-th use
     // of a stage (k = q / NS) completes phase k of each of its barriers.
@@ -307,61 +313,62 @@ __global__ void __launch_bounds__(96) iir_pipe_kernel(const float* __restrict__ 
         const long p = (line_ok ? l : 0) / lines_per_plane;
         mybase = p * plane_stride + ((line_ok ? l : 0) - p * lines_per_plane);
     }
+    // smem offset (floats) of this lane's first tile element and the stride between the elements it touches
+    const int s_off = kElemContig ? lane * kIirPitch : lane;
+    const int s_step = kElemContig ? 1 : kIirPitch;
+    const long g_step = kElemContig ? (long)N : elem_stride;   // HBM stride between those elements
     if (warp == 1) {
-        for (int q = 0; q < 2 * T; ++q) {
-            const int s = q % kIirNS;
-            if (q >= kIirNS) mbar_wait(&vacant[s], (unsigned)(((q - kIirNS) / kIirNS) & 1));
-            if (q == T) {
-                // the backward run reads the forward output: every forward tile must have reached HBM
+        for (int pass = 0; pass < 2; ++pass) {
+            const float* from = pass == 0 ? src : dst;
+            if (pass == 1)   // the backward run reads the forward output: every forward tile must have reached HBM
                 for (int j = (T - kIirNS > 0 ? T - kIirNS : 0); j < T; ++j)
-                    mbar_wait(&vacant[j % kIirNS], (unsigned)((j / kIirNS) & 1));
-            }
-            const bool fwd = q < T;
-            const int tile = fwd ? q : 2 * T - 1 - q;
-            const float* from = fwd ? src : dst;
-            const int e0 = tile * 32;
-            float* t = tiles[s];
-            if (kElemContig) {
-                if (e0 + lane < N) {
-                    const float* g = from + mybase + e0;
+                    mbar_wait_relaxed(&vacant[j % kIirNS], (unsigned)((j / kIirNS) & 1));
+            for (int i = 0; i < T; ++i) {
+                const int q = pass * T + i;
+                const int s = q % kIirNS;
+                if (q >= kIirNS) mbar_wait_relaxed(&vacant[s], (unsigned)(((q - kIirNS) / kIirNS) & 1));
+                const int tile = pass == 0 ? i : T - 1 - i;
+                const int e0 = tile * 32;
+                float* sp = &tiles[s][s_off];
+                if (kElemContig) {
+                    if (e0 + lane < N) {
+                        const float* g = from + mybase + e0;
 #pragma unroll 8
-                    for (int r = 0; r < nl; ++r) cp_async4(&t[lane * kIirPitch + r], g + (long)r * N);
-                }
-            } else {
-                if (line_ok) {
+                        for (int r = 0; r < nl; ++r) { cp_async4(sp, g); sp += s_step; g += g_step; }
+                    }
+                } else if (line_ok) {
                     const int ne = (N - e0) < 32 ? (N - e0) : 32;
                     const float* g = from + mybase + (long)e0 * elem_stride;
 #pragma unroll 8
-                    for (int e = 0; e < ne; ++e) cp_async4(&t[e * kIirPitch + lane], g + (long)e * elem_stride);
+                    for (int e = 0; e < ne; ++e) { cp_async4(sp, g); sp += s_step; g += g_step; }
                 }
+                cp_async_arrive(&full[s]);
             }
-            cp_async_arrive(&full[s]);
         }
     } else {
-        for (int q = 0; q < 2 * T; ++q) {
-            const int s = q % kIirNS;
-            mbar_wait(&done[s], (unsigned)((q / kIirNS) & 1));
-            const bool fwd = q < T;
-            const int tile = fwd ? q : 2 * T - 1 - q;
-            const int e0 = tile * 32;
-            const float* t = tiles[s];
-            if (kElemContig) {
-                if (e0 + lane < N) {
-                    float* g = dst + mybase + e0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int i = 0; i < T; ++i) {
+                const int q = pass * T + i;
+                const int s = q % kIirNS;
+                mbar_wait_relaxed(&done[s], (unsigned)((q / kIirNS) & 1));
+                const int tile = pass == 0 ? i : T - 1 - i;
+                const int e0 = tile * 32;
+                const float* sp = &tiles[s][s_off];
+                if (kElemContig) {
+                    if (e0 + lane < N) {
+                        float* g = dst + mybase + e0;
 #pragma unroll 8
-                    for (int r = 0; r < nl; ++r) g[(long)r * N] = t[lane * kIirPitch + r];
-                }
-            } else {
-                if (line_ok) {
+                        for (int r = 0; r < nl; ++r) { *g = *sp; sp += s_step; g += g_step; }
+                    }
+                } else if (line_ok) {
                     const int ne = (N - e0) < 32 ? (N - e0) : 32;
                     float* g = dst + mybase + (long)e0 * elem_stride;
 #pragma unroll 8
-                    for (int e = 0; e < ne; ++e) g[(long)e * elem_stride] = t[e * kIirPitch + lane];
+                    for (int e = 0; e < ne; ++e) { *g = *sp; sp += s_step; g += g_step; }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&vacant[s]);   // release: the loader (same CTA) re-reads forward tiles after acquiring this
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&vacant[s]);   // release: the loader (same CTA) re-reads forward tiles after acquiring this
-        }
     }
 }
 
@@ -371,14 +378,14 @@ void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, co
     if (w > 1) {
         const long nlines = (long)nplanes * h;
         KScope ks("blend.iir_x", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<true><<<div_up(nlines, 32), 96, 0, st>>>(src, dst, w, nlines, h, plane, 1L, coef);
+        iir_pipe_kernel<true><<<div_up(nlines, 32), 128, 0, st>>>(src, dst, w, nlines, h, plane, 1L, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
     if (h > 1) {
         const long nlines = (long)nplanes * w;
         KScope ks("blend.iir_y", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<false><<<div_up(nlines, 32), 96, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
+        iir_pipe_kernel<false><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
