@@ -227,6 +227,28 @@ class Context:
         self._check(self.L.pano_b200_cimg_resize3(self.h, _p(p), w, h, c, nw, nh, _p(out)), "cimg_resize3")
         return out
 
+    # ---- uint8 / tcgen05 matcher (north-star stage 3; not on the reference-parity path) ---------------------------
+    def quantize_u8(self, descr):
+        d = np.ascontiguousarray(descr, np.float32)
+        out = np.empty(d.shape, np.uint8)
+        self._check(self.L.pano_b200_quantize_u8(self.h, _p(d), len(d), _p(out)), "quantize_u8")
+        return out
+
+    def match_u8(self, A, B):
+        """-> (idx [NB] (-1 = rejected by the ratio rule), d0, d1, nearest)"""
+        A = np.ascontiguousarray(A, np.uint8)
+        B = np.ascontiguousarray(B, np.uint8)
+        idx = np.empty(len(B), np.int32)
+        d01 = np.empty((len(B), 3), np.int32)
+        n = C.c_int()
+        self._check(self.L.pano_b200_match_u8(self.h, _p(A), len(A), _p(B), len(B), _p(idx), _p(d01), C.byref(n)), "match_u8")
+        return idx, d01[:, 0].copy(), d01[:, 1].copy(), d01[:, 2].copy()
+
+    def bench_match_u8(self, nA, nB, reps=5):
+        ms = C.c_float()
+        self._check(self.L.pano_b200_bench_match_u8(self.h, nA, nB, reps, C.byref(ms)), "bench_match_u8")
+        return ms.value
+
     # ---- pipeline -------------------------------------------------------------------------------------------------
     def stitch(self, imgs):
         """ImageProcess(dir, n) on in-memory planar RGB images -> (panorama [3][H][W] u8, info dict)."""

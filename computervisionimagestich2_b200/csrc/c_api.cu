@@ -180,6 +180,29 @@ int pano_b200_stitch_nfeatures(pano_b200_ctx* ctx, int image) {
     return ctx->st->features(image).n;
 }
 
+int pano_b200_quantize_u8(pano_b200_ctx* ctx, const float* descr, int n, uint8_t* out) {
+    PB_API_BEGIN
+    ctx->st->quantize_u8(descr, n, out);
+    return 0;
+    PB_API_END
+}
+int pano_b200_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const uint8_t* descrB, int nB, int* match_idx,
+                       int* d01, int* nmatches) {
+    PB_API_BEGIN
+    ctx->st->match_u8(descrA, nA, descrB, nB, match_idx, d01);
+    int c = 0;
+    for (int b = 0; b < nB; ++b) c += match_idx[b] >= 0;
+    if (nmatches) *nmatches = c;
+    return 0;
+    PB_API_END
+}
+int pano_b200_bench_match_u8(pano_b200_ctx* ctx, int nA, int nB, int reps, float* ms_per_rep) {
+    PB_API_BEGIN
+    *ms_per_rep = ctx->st->bench_match_u8(nA, nB, reps);
+    return 0;
+    PB_API_END
+}
+
 int pano_b200_project(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* out_rgb, uint8_t* out_gray) {
     PB_API_BEGIN
     ctx->st->project(rgb, w, h, out_rgb, out_gray);

@@ -1,0 +1,353 @@
+// match_i8_kernels.cu -- north-star stage (3): brute-force 2-NN on uint8-quantised descriptors as a dense integer
+// contraction on the 5th-generation tensor cores (tcgen05.mma.kind::i8, accumulators in TMEM), with the top-2
+// selection fused into the epilogue.
+//
+// This matcher has NO counterpart in the reference, which matches float descriptors under L1 (ImageProcess.cpp:
+// 273-351); the exact matcher of the stitching pipeline is match_kernels.cu.  Here descriptors are
+// quantised with VLFeat's own convention q = (uint8) min(512 x, 255) (the one its CLI / MATLAB drivers use) and
+// compared under squared L2:  d2(q, a) = |q|^2 + |a|^2 - 2 q.a,  ratio rule 4 d0 < d1  (<=> sqrt(d0)/sqrt(d1) < 0.5).
+// Everything is integer arithmetic (u8 x u8 -> s32), so distances and indices are exact; the oracle is
+// oracle/match_u8_oracle.py.
+//
+// Kernel shape (one CTA = 128 queries x one slice of the database, 256 threads):
+//   warp 0      producer: streams 256-row database tiles HBM -> shared memory with 16-byte cp.async into the
+//               canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), 4 stages
+//   warp 1      lane 0 issues 4 x tcgen05.mma (M128 x N256 x K32) per tile into one of two 256-column TMEM
+//               accumulators; tcgen05.commit releases the shared-memory stage and publishes the accumulator
+//   warps 4-7   epilogue: thread = query row (TMEM lane); tcgen05.ld 32 columns at a time, key = (|a|^2 - 2 q.a)
+//               * 256 + column with ONE integer multiply-add per element, running (min, 2nd min) on the packed keys;
+//               groups of 4 keys that cannot beat the current 2nd best are skipped after one 3-instruction test
+// Queries sit on the MMA's M side so that a thread owns a query and scans database columns: the top-2 needs no
+// cross-thread reduction.  Ties between equal distances cannot change an accepted match (a tie of the two best
+// fails the ratio rule), so the column packed in the key is only a payload.
+#include "match_i8_kernels.h"
+#include "common.h"
+#include "ktimer.h"
+#include <algorithm>
+#include <climits>
+
+namespace pb {
+
+namespace {
+
+constexpr int kMQ = 128;       // queries per CTA  (UMMA M)
+constexpr int kND = 256;       // database rows per MMA (UMMA N)
+constexpr int kStages = 4;     // shared-memory stages of database tiles
+constexpr int kLag = 2;        // cp.async groups in flight
+constexpr int kRowBytes = 128; // one descriptor
+constexpr int kGroupBytes = 8 * kRowBytes;   // an 8-row group: 8 K-chunks x (8 rows x 16 B)
+constexpr int kPadNorm = 0x7fffff;           // |a|^2 of a padding row: its key exceeds every real key
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+// 16-byte global -> shared copy; src_bytes = 0 zero-fills (rows past the end of a table)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// generic-proxy writes (cp.async / st.shared) -> visible to the async proxy that tcgen05.mma reads through
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes, contiguous (128 B);
+// LBO = distance between the two 16-byte K chunks of one K=32 step, SBO = distance between 8-row groups.
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= 1ull << 46;   // descriptor version for sm_100
+    return d;          // base_offset = 0, lbo_mode = 0, layout_type = 0 (no swizzle)
+}
+// instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = 256, M = 128
+constexpr unsigned kIdesc = (2u << 4) | (0u << 7) | (0u << 10) | ((unsigned)(kND >> 3) << 17) | ((unsigned)(kMQ >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct __align__(16) SmemLayout {
+    unsigned char q[kMQ * kRowBytes];                 // 16 KB: the CTA's queries (operand A)
+    unsigned char db[kStages][kND * kRowBytes];       // 4 x 32 KB: database tiles (operand B)
+    int cst[2][kND];                                  // per accumulator buffer: |a|^2 * 256 + column
+    unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+    unsigned tmem_base;
+};
+
+// canonical layout: row r, 16-byte chunk c of a tile -> byte offset
+__device__ __forceinline__ int canon_off(int r, int c) { return (r >> 3) * kGroupBytes + c * 128 + (r & 7) * 16; }
+
+}  // namespace
+
+__global__ void __launch_bounds__(256, 1)
+match_u8_kernel(const unsigned char* __restrict__ A, const int* __restrict__ normA, int NA,
+                const unsigned char* __restrict__ B, const int* __restrict__ normB, int NB, int rows_per_split,
+                U8Top2* __restrict__ partial) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kMQ;
+    const int a_begin = blockIdx.y * rows_per_split;
+    const int a_end = min(NA, a_begin + rows_per_split);
+    const int ntiles = (a_end - a_begin + kND - 1) / kND;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // one warp allocates all 512 TMEM columns (two 256-column accumulators) and later frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the queries: 128 rows x 8 chunks, rows past NB zero-filled
+    for (int i = threadIdx.x; i < kMQ * 8; i += 256) {
+        const int c = i >> 7, r = i & 127;   // consecutive threads -> consecutive rows: conflict-free shared stores
+        const int row = q0 + r;
+        cp_async16(S.q + canon_off(r, c), B + (size_t)min(row, NB - 1) * kRowBytes + c * 16, row < NB ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = S.tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer ------------------------------------------------
+        for (int t = 0; t < ntiles + kLag; ++t) {
+            if (t < ntiles) {
+                const int s = t % kStages;
+                if (t >= kStages) mbar_wait(&S.empty[s], (unsigned)(((t / kStages) - 1) & 1));
+                const int row0 = a_begin + t * kND;
+                unsigned char* dst = S.db[s];
+#pragma unroll 4
+                for (int i = lane; i < kND * 8; i += 32) {
+                    const int c = i >> 8, r = i & 255;
+                    const int row = row0 + r;
+                    cp_async16(dst + canon_off(r, c), A + (size_t)min(row, NA - 1) * kRowBytes + c * 16, row < a_end ? 16 : 0);
+                }
+            }
+            cp_async_commit();   // (an empty group when t >= ntiles keeps the wait_group arithmetic uniform)
+            if (t >= kLag) {
+                cp_async_wait<kLag>();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.full[(t - kLag) % kStages]);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer ------------------------------------------------
+        if (lane == 0) {
+            const unsigned qa = smem_u32(S.q);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kStages, b = t & 1;
+                mbar_wait(&S.full[s], (unsigned)((t / kStages) & 1));
+                if (t >= 2) mbar_wait(&S.tmem_empty[b], (unsigned)(((t >> 1) - 1) & 1));
+                tc_fence_after();
+                const unsigned ba = smem_u32(S.db[s]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)   // K = 128 = 4 steps of 32 bytes = chunks 2j, 2j+1
+                    umma_i8(tmem + (unsigned)(b * kND), umma_desc(qa + j * 256, 128, kGroupBytes),
+                            umma_desc(ba + j * 256, 128, kGroupBytes), j > 0 ? 1u : 0u);
+                umma_commit(&S.empty[s]);        // the stage may be refilled once these MMAs have read it
+                umma_commit(&S.tmem_full[b]);    // the accumulator is complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------ epilogue ------------------------------------------------
+        const int ew = warp - 4;                       // == warp % 4: the TMEM lanes this warp may read
+        const int et = threadIdx.x - 128;              // 0..127 = query row within the CTA = TMEM lane
+        int m1 = INT_MAX, m2 = INT_MAX, besttile = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int b = t & 1;
+            // per-column constants of this tile: |a|^2 * 256 + column (padding rows get a key above every real key)
+            {
+                const int row0 = a_begin + t * kND;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int col = et + k * 128, row = row0 + col;
+                    const int nrm = row < a_end ? normA[row] : kPadNorm;
+                    S.cst[b][col] = nrm * 256 + col;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&S.tmem_full[b], (unsigned)((t >> 1) & 1));
+            tc_fence_after();
+            const int m1_before = m1;
+            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kND; c0 += 32) {
+                int v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + (unsigned)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 32; g += 4) {
+                    const int4 cc = *reinterpret_cast<const int4*>(&S.cst[b][c0 + g]);
+                    const int k0 = v[g] * -512 + cc.x, k1 = v[g + 1] * -512 + cc.y, k2 = v[g + 2] * -512 + cc.z,
+                              k3 = v[g + 3] * -512 + cc.w;
+                    const int mn = min(min(k0, k1), min(k2, k3));
+                    if (mn < m2) {
+                        m2 = min(m2, max(k0, m1)); m1 = min(m1, k0);
+                        m2 = min(m2, max(k1, m1)); m1 = min(m1, k1);
+                        m2 = min(m2, max(k2, m1)); m1 = min(m1, k2);
+                        m2 = min(m2, max(k3, m1)); m1 = min(m1, k3);
+                    }
+                }
+            }
+            if (m1 != m1_before) besttile = t;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.tmem_empty[b]);
+        }
+        const int q = q0 + et;
+        if (q < NB) {
+            const int nq = normB[q];
+            U8Top2 r;
+            r.d0 = m1 == INT_MAX ? INT_MAX : (m1 >> 8) + nq;
+            r.d1 = m2 == INT_MAX ? INT_MAX : (m2 >> 8) + nq;
+            r.i0 = m1 == INT_MAX ? -1 : a_begin + besttile * kND + (m1 & 255);
+            partial[(size_t)blockIdx.y * NB + q] = r;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+__global__ void match_u8_merge_kernel(const U8Top2* __restrict__ partial, int nsplit, int NA, int NB, int* __restrict__ idx,
+                                      int* __restrict__ d01) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    int d0 = INT_MAX, d1 = INT_MAX, i0 = -1;
+    for (int s = 0; s < nsplit; ++s) {
+        const U8Top2 p = partial[(size_t)s * NB + b];
+        if (p.i0 < 0) continue;
+        if (p.d0 < d0) { d1 = min(d0, p.d1); d0 = p.d0; i0 = p.i0; }
+        else d1 = min(d1, p.d0);
+    }
+    // ratio rule sqrt(d0) / sqrt(d1) < 0.5  <=>  4 d0 < d1 (exact in integers)
+    const bool ok = NA >= 2 && i0 >= 0 && d1 != INT_MAX && 4ll * d0 < (long long)d1;
+    idx[b] = ok ? i0 : -1;
+    if (d01) { d01[3 * b] = d0; d01[3 * b + 1] = d1; d01[3 * b + 2] = i0; }
+}
+
+// VLFeat's uint8 descriptor convention: q = (uint8) min(512 x, 255); also |q|^2
+__global__ void quantize_u8_kernel(const float* __restrict__ src, int n, unsigned char* __restrict__ dst, int* __restrict__ norm) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float4 v = reinterpret_cast<const float4*>(src + (size_t)row * 128)[lane];
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    unsigned packed = 0;
+    int nrm = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float x = 512.0f * f[k];
+        x = (x < 255.0f) ? x : 255.0f;
+        const unsigned q = (unsigned)(unsigned char)x;
+        packed |= q << (8 * k);
+        nrm += (int)(q * q);
+    }
+    reinterpret_cast<unsigned*>(dst + (size_t)row * 128)[lane] = packed;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) norm[row] = nrm;
+}
+__global__ void norm_u8_kernel(const unsigned char* __restrict__ src, int n, int* __restrict__ norm) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const unsigned p = reinterpret_cast<const unsigned*>(src + (size_t)row * 128)[lane];
+    int nrm = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int q = (p >> (8 * k)) & 255; nrm += q * q; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) norm[row] = nrm;
+}
+
+void launch_quantize_u8(const float* src, int n, unsigned char* dst, int* norm, cudaStream_t st) {
+    if (n <= 0) return;
+    KScope ks("match_u8.quantize", st, 644.0 * n);
+    quantize_u8_kernel<<<div_up(n, 8), 256, 0, st>>>(src, n, dst, norm);
+    PB_KERNEL_CHECK();
+}
+void launch_norm_u8(const unsigned char* src, int n, int* norm, cudaStream_t st) {
+    if (n <= 0) return;
+    norm_u8_kernel<<<div_up(n, 8), 256, 0, st>>>(src, n, norm);
+    PB_KERNEL_CHECK();
+}
+
+int match_u8_num_splits(int NA, int NB) {
+    const int qtiles = div_up(NB, kMQ);
+    int want = div_up(148, qtiles);                    // one CTA per SM (each CTA owns all 512 TMEM columns)
+    const int maxs = std::max(1, div_up(NA, 4 * kND)); // at least four database tiles per split
+    want = std::min(want, maxs);
+    return std::max(1, want);
+}
+
+void launch_match_u8(const unsigned char* dA, const int* normA, int NA, const unsigned char* dB, const int* normB, int NB,
+                     U8Top2* partial, int nsplit, int* idx, int* d01, cudaStream_t st) {
+    if (NB <= 0) return;
+    if (NA <= 0) {
+        PB_CUDA(cudaMemsetAsync(idx, 0xff, sizeof(int) * NB, st));
+        return;
+    }
+    static bool attr_set = false;
+    const int smem = (int)sizeof(SmemLayout) + 1024;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(match_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    int rps = align_up(div_up(NA, nsplit), kND);
+    nsplit = div_up(NA, rps);
+    {
+        KScope ks("match_u8.mma", st, 2.0 * 128.0 * (double)NA * (double)NB);
+        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 256, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
+        PB_KERNEL_CHECK();
+    }
+    KScope ks2("match_u8.merge", st, 0);
+    match_u8_merge_kernel<<<div_up(NB, 128), 128, 0, st>>>(partial, nsplit, NA, NB, idx, d01);
+    PB_KERNEL_CHECK();
+}
+
+}  // namespace pb

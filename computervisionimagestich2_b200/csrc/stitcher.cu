@@ -216,6 +216,57 @@ void Stitcher::match(FeatureTable& A, FeatureTable& B, std::vector<KeyPair>& pai
         if (idx[b] >= 0) pairs.push_back(KeyPair{A.keys[idx[b]], B.keys[b]});
 }
 
+void Stitcher::quantize_u8(const float* descr, int n, u8* out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (n <= 0) return;
+    u8f_.ensure((size_t)n * 128);
+    u8a_.ensure((size_t)n * 128);
+    u8na_.ensure(n);
+    PB_CUDA(cudaMemcpyAsync(u8f_.p, descr, (size_t)n * 512, cudaMemcpyHostToDevice, st_));
+    launch_quantize_u8(u8f_.p, n, u8a_.p, u8na_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(out, u8a_.p, (size_t)n * 128, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Stitcher::match_u8(const u8* A, int nA, const u8* B, int nB, int* idx, int* d01) {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (nB <= 0) return;
+    if (nA <= 0) { for (int i = 0; i < nB; ++i) idx[i] = -1; return; }
+    u8a_.ensure((size_t)nA * 128); u8b_.ensure((size_t)nB * 128);
+    u8na_.ensure(nA); u8nb_.ensure(nB); u8idx_.ensure(nB); u8d01_.ensure((size_t)nB * 3);
+    const int ns = match_u8_num_splits(nA, nB);
+    u8part_.ensure((size_t)ns * nB);
+    PB_CUDA(cudaMemcpyAsync(u8a_.p, A, (size_t)nA * 128, cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(u8b_.p, B, (size_t)nB * 128, cudaMemcpyHostToDevice, st_));
+    launch_norm_u8(u8a_.p, nA, u8na_.p, st_);
+    launch_norm_u8(u8b_.p, nB, u8nb_.p, st_);
+    launch_match_u8(u8a_.p, u8na_.p, nA, u8b_.p, u8nb_.p, nB, u8part_.p, ns, u8idx_.p, u8d01_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(idx, u8idx_.p, sizeof(int) * nB, cudaMemcpyDeviceToHost, st_));
+    if (d01) PB_CUDA(cudaMemcpyAsync(d01, u8d01_.p, sizeof(int) * 3 * nB, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+float Stitcher::bench_match_u8(int nA, int nB, int reps) {
+    PB_CUDA(cudaSetDevice(dev_));
+    std::vector<u8> h((size_t)std::max(nA, nB) * 128);
+    unsigned x = 12345u;
+    for (auto& v : h) { x = x * 1664525u + 1013904223u; v = (u8)((x >> 24) & 63); }
+    u8a_.ensure((size_t)nA * 128); u8b_.ensure((size_t)nB * 128);
+    u8na_.ensure(nA); u8nb_.ensure(nB); u8idx_.ensure(nB);
+    const int ns = match_u8_num_splits(nA, nB);
+    u8part_.ensure((size_t)ns * nB);
+    PB_CUDA(cudaMemcpyAsync(u8a_.p, h.data(), (size_t)nA * 128, cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(u8b_.p, h.data() + 64, (size_t)nB * 128 - 64, cudaMemcpyHostToDevice, st_));
+    launch_norm_u8(u8a_.p, nA, u8na_.p, st_);
+    launch_norm_u8(u8b_.p, nB, u8nb_.p, st_);
+    launch_match_u8(u8a_.p, u8na_.p, nA, u8b_.p, u8nb_.p, nB, u8part_.p, ns, u8idx_.p, nullptr, st_);   // warm-up
+    PB_CUDA(cudaStreamSynchronize(st_));
+    timer_start();
+    for (int r = 0; r < reps; ++r)
+        launch_match_u8(u8a_.p, u8na_.p, nA, u8b_.p, u8nb_.p, nB, u8part_.p, ns, u8idx_.p, nullptr, st_);
+    return timer_stop() / reps;
+}
+
 bool Stitcher::ransac(const std::vector<const std::vector<KeyPair>*>& problems, std::vector<double>& H8s) {
     PB_CUDA(cudaSetDevice(dev_));
     const int P = (int)problems.size();

@@ -12,6 +12,7 @@
 #include "types.h"
 #include "sift_engine.h"
 #include "match_kernels.h"
+#include "match_i8_kernels.h"
 #include "canvas_kernels.h"
 
 namespace pb {
@@ -57,6 +58,10 @@ class Stitcher {
                     int ph, int ioffx, int ioffy, int cw, int ch, u8* a_out, u8* b_out);
     int blend(const u8* a, const u8* b, int cw, int ch, u8* out);          // host buffers
     void equalize_mix(const u8* rgb, int w, int h, u8* out);               // host buffers
+    // uint8 / tcgen05 matcher (north-star stage 3; not on the reference-parity path): host tables in, host results out
+    void quantize_u8(const float* descr, int n, u8* out);
+    void match_u8(const u8* A, int nA, const u8* B, int nB, int* idx, int* d01);
+    float bench_match_u8(int nA, int nB, int reps);   // ms per repetition on resident synthetic tables
     void cimg_blur2(const float* src, int w, int h, int c, float* dst);    // get_blur(2,true,true), host buffers
     void cimg_resize(const float* src, int w, int h, int c, int nw, int nh, float* dst);
 
@@ -108,6 +113,10 @@ class Stitcher {
     DevBuf<int> midx_;
     PinBuf<int> h_midx_;
     DevBuf<MatchJob> mjobs_;
+    DevBuf<u8> u8a_, u8b_;
+    DevBuf<int> u8na_, u8nb_, u8idx_, u8d01_;
+    DevBuf<U8Top2> u8part_;
+    DevBuf<float> u8f_;
     PinBuf<char> h_mjobs_;
     DevBuf<KeyPair> r_pairs_;
     DevBuf<int> r_off_, r_samples_, r_counts_;

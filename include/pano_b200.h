@@ -117,6 +117,16 @@ int pano_b200_equalize_mix(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h,
 int pano_b200_cimg_blur2(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst);
 int pano_b200_cimg_resize3(pano_b200_ctx* ctx, const float* src, int w, int h, int c, int nw, int nh, float* dst);
 
+/* ---- uint8 / tensor-core matcher (north-star stage 3).  NOT part of the reference-parity path: the reference matches
+ *      float descriptors under L1 (ImageProcess.cpp:273-351).  Descriptors are quantised with VLFeat's convention
+ *      q = (uint8) min(512 x, 255) and compared under squared L2 with int32 accumulation on tcgen05 tensor cores;
+ *      match_idx[b] = row of A with 4 d0 < d1, else -1; d01 (optional, [nB][3]) = d0, d1, nearest row. */
+int pano_b200_quantize_u8(pano_b200_ctx* ctx, const float* descr, int n, uint8_t* out);
+int pano_b200_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const uint8_t* descrB, int nB, int* match_idx,
+                       int* d01, int* nmatches);
+/* times the matcher kernel alone on resident synthetic tables (CUDA events), milliseconds per repetition */
+int pano_b200_bench_match_u8(pano_b200_ctx* ctx, int nA, int nB, int reps, float* ms_per_rep);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
 void pano_b200_free_pinned(void* p);
