@@ -9,14 +9,17 @@
 // Everything is integer arithmetic (u8 x u8 -> s32), so distances and indices are exact; the oracle is
 // oracle/match_u8_oracle.py.
 //
-// Kernel shape (one CTA = 128 queries x one slice of the database, 256 threads):
-//   warp 0      producer: streams 256-row database tiles HBM -> shared memory with 16-byte cp.async into the
-//               canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), 4 stages
+// Kernel shape (one CTA = 128 queries x one slice of the database, 384 threads):
+//   warp 0      producer: one lane streams 256-row database tiles HBM -> shared memory with TMA, eight
+//               cp.async.bulk.tensor boxes of {16 bytes, 256 rows} per tile (one per 16-byte K chunk), which lands
+//               the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices) directly; 4 stages,
+//               completion by mbarrier transaction bytes; rows past the end of a table are zero-filled by the TMA
 //   warp 1      lane 0 issues 4 x tcgen05.mma (M128 x N256 x K32) per tile into one of two 256-column TMEM
 //               accumulators; tcgen05.commit releases the shared-memory stage and publishes the accumulator
-//   warps 4-7   epilogue: thread = query row (TMEM lane); tcgen05.ld 32 columns at a time, key = (|a|^2 - 2 q.a)
-//               * 256 + column with ONE integer multiply-add per element, running (min, 2nd min) on the packed keys;
-//               groups of 4 keys that cannot beat the current 2nd best are skipped after one 3-instruction test
+//   warps 4-11  epilogue: thread = (query row = TMEM lane, half of the tile's columns); tcgen05.ld 32 columns at a
+//               time, two loads in flight; key = (|a|^2 - 2 q.a) * 256 + column with ONE integer multiply-add per
+//               element, running (min, 2nd min) on the packed keys; groups of 4 keys that cannot beat the current
+//               2nd best are skipped after one 3-instruction test
 // Queries sit on the MMA's M side so that a thread owns a query and scans database columns: the top-2 needs no
 // cross-thread reduction.  Ties between equal distances cannot change an accepted match (a tie of the two best
 // fails the ratio rule), so the column packed in the key is only a payload.
@@ -25,6 +28,7 @@
 #include "ktimer.h"
 #include <algorithm>
 #include <climits>
+#include <cuda.h>
 
 namespace pb {
 
@@ -33,9 +37,11 @@ namespace {
 constexpr int kMQ = 128;       // queries per CTA  (UMMA M)
 constexpr int kND = 256;       // database rows per MMA (UMMA N)
 constexpr int kStages = 4;     // shared-memory stages of database tiles
-constexpr int kLag = 2;        // cp.async groups in flight
 constexpr int kRowBytes = 128; // one descriptor
-constexpr int kGroupBytes = 8 * kRowBytes;   // an 8-row group: 8 K-chunks x (8 rows x 16 B)
+// shared-memory layout of a tile of R rows: chunk c (16 bytes of K) of row r at c * (R * 16) + r * 16, i.e. for every
+// chunk the rows are contiguous: 8 rows x 16 B = one UMMA core matrix, 8-row groups 128 B apart (SBO), chunks R*16 B
+// apart (LBO).  That is exactly what one TMA box {16 bytes, R rows} writes.
+constexpr int kSbo = 128;
 constexpr int kPadNorm = 0x7fffff;           // |a|^2 of a padding row: its key exceeds every real key
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -54,16 +60,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                      : "memory");
     } while (!ok);
 }
-// 16-byte global -> shared copy; src_bytes = 0 zero-fills (rows past the end of a table)
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: one box of the 2-D tensor map (dim 0 = byte within the descriptor, dim 1 = row) -> shared memory
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// generic-proxy writes (cp.async / st.shared) -> visible to the async proxy that tcgen05.mma reads through
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -99,18 +105,16 @@ struct __align__(16) SmemLayout {
     unsigned char q[kMQ * kRowBytes];                 // 16 KB: the CTA's queries (operand A)
     unsigned char db[kStages][kND * kRowBytes];       // 4 x 32 KB: database tiles (operand B)
     int cst[2][kND];                                  // per accumulator buffer: |a|^2 * 256 + column
-    unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+    unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], qfull;
     unsigned tmem_base;
+    int mrg[kMQ][3];                                  // merge of the two column halves of the epilogue
 };
-
-// canonical layout: row r, 16-byte chunk c of a tile -> byte offset
-__device__ __forceinline__ int canon_off(int r, int c) { return (r >> 3) * kGroupBytes + c * 128 + (r & 7) * 16; }
 
 }  // namespace
 
-__global__ void __launch_bounds__(256, 1)
-match_u8_kernel(const unsigned char* __restrict__ A, const int* __restrict__ normA, int NA,
-                const unsigned char* __restrict__ B, const int* __restrict__ normB, int NB, int rows_per_split,
+__global__ void __launch_bounds__(384, 1)
+match_u8_kernel(const __grid_constant__ CUtensorMap tmapA, const int* __restrict__ normA, int NA,
+                const __grid_constant__ CUtensorMap tmapB, const int* __restrict__ normB, int NB, int rows_per_split,
                 U8Top2* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -122,22 +126,14 @@ match_u8_kernel(const unsigned char* __restrict__ A, const int* __restrict__ nor
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 8); }
+        mbar_init(&S.qfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // one warp allocates all 512 TMEM columns (two 256-column accumulators) and later frees them
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // the queries: 128 rows x 8 chunks, rows past NB zero-filled
-    for (int i = threadIdx.x; i < kMQ * 8; i += 256) {
-        const int c = i >> 7, r = i & 127;   // consecutive threads -> consecutive rows: conflict-free shared stores
-        const int row = q0 + r;
-        cp_async16(S.q + canon_off(r, c), B + (size_t)min(row, NB - 1) * kRowBytes + c * 16, row < NB ? 16 : 0);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -145,31 +141,25 @@ match_u8_kernel(const unsigned char* __restrict__ A, const int* __restrict__ nor
 
     if (warp == 0) {
         // ------------------------------------------------ producer ------------------------------------------------
-        for (int t = 0; t < ntiles + kLag; ++t) {
-            if (t < ntiles) {
+        if (lane == 0) {
+            // the CTA's queries (operand A of the MMA): 8 boxes of {16 B, 128 rows}
+            mbar_expect_tx(&S.qfull, kMQ * kRowBytes);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) tma_load_2d(S.q + c * (kMQ * 16), &tmapB, c * 16, q0, &S.qfull);
+            for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages;
                 if (t >= kStages) mbar_wait(&S.empty[s], (unsigned)(((t / kStages) - 1) & 1));
+                mbar_expect_tx(&S.full[s], kND * kRowBytes);
                 const int row0 = a_begin + t * kND;
-                unsigned char* dst = S.db[s];
-#pragma unroll 4
-                for (int i = lane; i < kND * 8; i += 32) {
-                    const int c = i >> 8, r = i & 255;
-                    const int row = row0 + r;
-                    cp_async16(dst + canon_off(r, c), A + (size_t)min(row, NA - 1) * kRowBytes + c * 16, row < a_end ? 16 : 0);
-                }
-            }
-            cp_async_commit();   // (an empty group when t >= ntiles keeps the wait_group arithmetic uniform)
-            if (t >= kLag) {
-                cp_async_wait<kLag>();
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.full[(t - kLag) % kStages]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) tma_load_2d(S.db[s] + c * (kND * 16), &tmapA, c * 16, row0, &S.full[s]);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer ------------------------------------------------
         if (lane == 0) {
             const unsigned qa = smem_u32(S.q);
+            mbar_wait(&S.qfull, 0);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages, b = t & 1;
                 mbar_wait(&S.full[s], (unsigned)((t / kStages) & 1));
@@ -178,73 +168,93 @@ match_u8_kernel(const unsigned char* __restrict__ A, const int* __restrict__ nor
                 const unsigned ba = smem_u32(S.db[s]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)   // K = 128 = 4 steps of 32 bytes = chunks 2j, 2j+1
-                    umma_i8(tmem + (unsigned)(b * kND), umma_desc(qa + j * 256, 128, kGroupBytes),
-                            umma_desc(ba + j * 256, 128, kGroupBytes), j > 0 ? 1u : 0u);
+                    umma_i8(tmem + (unsigned)(b * kND), umma_desc(qa + j * 2 * (kMQ * 16), kMQ * 16, kSbo),
+                            umma_desc(ba + j * 2 * (kND * 16), kND * 16, kSbo), j > 0 ? 1u : 0u);
                 umma_commit(&S.empty[s]);        // the stage may be refilled once these MMAs have read it
                 umma_commit(&S.tmem_full[b]);    // the accumulator is complete
             }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------ epilogue ------------------------------------------------
-        const int ew = warp - 4;                       // == warp % 4: the TMEM lanes this warp may read
-        const int et = threadIdx.x - 128;              // 0..127 = query row within the CTA = TMEM lane
+        // 8 warps: warp w reads TMEM lanes 32 * (w % 4) .. +31 (its hardware lane quarter); warps 4-7 scan columns
+        // 0..127 of every tile, warps 8-11 columns 128..255, two tcgen05.ld in flight per thread.
+        const int ew = warp & 3;
+        const int half = (warp - 4) >> 2;              // which 128-column half of the tile
+        const int et = threadIdx.x - 128;              // 0..255
+        const int qrow = ew * 32 + lane;               // query row within the CTA = TMEM lane
         int m1 = INT_MAX, m2 = INT_MAX, besttile = 0;
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1;
-            // per-column constants of this tile: |a|^2 * 256 + column (padding rows get a key above every real key)
-            {
-                const int row0 = a_begin + t * kND;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int col = et + k * 128, row = row0 + col;
-                    const int nrm = row < a_end ? normA[row] : kPadNorm;
-                    S.cst[b][col] = nrm * 256 + col;
-                }
+            {   // per-column constants of this tile: |a|^2 * 256 + column (padding rows: a key above every real key)
+                const int row = a_begin + t * kND + et;
+                const int nrm = row < a_end ? normA[row] : kPadNorm;
+                S.cst[b][et] = nrm * 256 + et;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&S.tmem_full[b], (unsigned)((t >> 1) & 1));
             tc_fence_after();
             const int m1_before = m1;
-            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND);
-#pragma unroll 1
-            for (int c0 = 0; c0 < kND; c0 += 32) {
-                int v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + (unsigned)c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int g = 0; g < 32; g += 4) {
-                    const int4 cc = *reinterpret_cast<const int4*>(&S.cst[b][c0 + g]);
-                    const int k0 = v[g] * -512 + cc.x, k1 = v[g + 1] * -512 + cc.y, k2 = v[g + 2] * -512 + cc.z,
-                              k3 = v[g + 3] * -512 + cc.w;
-                    const int mn = min(min(k0, k1), min(k2, k3));
-                    if (mn < m2) {
-                        m2 = min(m2, max(k0, m1)); m1 = min(m1, k0);
-                        m2 = min(m2, max(k1, m1)); m1 = min(m1, k1);
-                        m2 = min(m2, max(k2, m1)); m1 = min(m1, k2);
-                        m2 = min(m2, max(k3, m1)); m1 = min(m1, k3);
-                    }
-                }
-            }
+            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND + half * 128);
+            const int* cst = &S.cst[b][half * 128];
+            int va[32], vb[32];
+#define PB_LDTM(v, col)                                                                                                      \
+    asm volatile(                                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "    \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                            \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),       \
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),           \
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),          \
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                        \
+        : "r"(taddr + (unsigned)(col)))
+#define PB_SCAN(v, col)                                                                                                      \
+    _Pragma("unroll") for (int g = 0; g < 32; g += 4) {                                                                      \
+        const int4 cc = *reinterpret_cast<const int4*>(&cst[(col) + g]);                                                     \
+        const int k0 = v[g] * -512 + cc.x, k1 = v[g + 1] * -512 + cc.y, k2 = v[g + 2] * -512 + cc.z,                       \
+                  k3 = v[g + 3] * -512 + cc.w;                                                                               \
+        const int mn = min(min(k0, k1), min(k2, k3));                                                                        \
+        if (mn < m2) {                                                                                                       \
+            m2 = min(m2, max(k0, m1)); m1 = min(m1, k0);                                                                     \
+            m2 = min(m2, max(k1, m1)); m1 = min(m1, k1);                                                                     \
+            m2 = min(m2, max(k2, m1)); m1 = min(m1, k2);                                                                     \
+            m2 = min(m2, max(k3, m1)); m1 = min(m1, k3);                                                                     \
+        }                                                                                                                    \
+    }
+            PB_LDTM(va, 0);
+            PB_LDTM(vb, 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            PB_SCAN(va, 0);
+            PB_LDTM(va, 64);
+            PB_SCAN(vb, 32);
+            PB_LDTM(vb, 96);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            PB_SCAN(va, 64);
+            PB_SCAN(vb, 96);
+#undef PB_LDTM
+#undef PB_SCAN
             if (m1 != m1_before) besttile = t;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.tmem_empty[b]);
         }
-        const int q = q0 + et;
-        if (q < NB) {
-            const int nq = normB[q];
-            U8Top2 r;
-            r.d0 = m1 == INT_MAX ? INT_MAX : (m1 >> 8) + nq;
-            r.d1 = m2 == INT_MAX ? INT_MAX : (m2 >> 8) + nq;
-            r.i0 = m1 == INT_MAX ? -1 : a_begin + besttile * kND + (m1 & 255);
-            partial[(size_t)blockIdx.y * NB + q] = r;
+        // merge the two column halves of every query row (the keys carry the column within the tile) and write
+        if (half == 1) { S.mrg[qrow][0] = m1; S.mrg[qrow][1] = m2; S.mrg[qrow][2] = besttile; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+            const int o1 = S.mrg[qrow][0], o2 = S.mrg[qrow][1], ot = S.mrg[qrow][2];
+            // order keys by (distance, tile, column) so that equal distances keep the lower database row
+            int d_a = m1 == INT_MAX ? INT_MAX : (m1 >> 8), d_b = o1 == INT_MAX ? INT_MAX : (o1 >> 8);
+            const bool take_b = d_b < d_a || (d_b == d_a && d_b != INT_MAX && (ot < besttile));
+            int best = take_b ? o1 : m1, bt = take_b ? ot : besttile;
+            int second = take_b ? min(m1, o2) : min(o1, m2);
+            const int q = q0 + qrow;
+            if (q < NB) {
+                const int nq = normB[q];
+                U8Top2 r;
+                r.d0 = best == INT_MAX ? INT_MAX : (best >> 8) + nq;
+                r.d1 = second == INT_MAX ? INT_MAX : (second >> 8) + nq;
+                r.i0 = best == INT_MAX ? -1 : a_begin + bt * kND + (best & 255);
+                partial[(size_t)blockIdx.y * NB + q] = r;
+            }
         }
     }
     tc_fence_before();
@@ -317,6 +327,20 @@ void launch_norm_u8(const unsigned char* src, int n, int* norm, cudaStream_t st)
     PB_KERNEL_CHECK();
 }
 
+// 2-D tensor map over a descriptor table [n][128] u8: dim 0 = the 128 bytes of a row, dim 1 = rows; box = {16 B, rows}
+static CUtensorMap make_table_map(const unsigned char* table, int n, int box_rows) {
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {128, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)table, dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
 int match_u8_num_splits(int NA, int NB) {
     const int qtiles = div_up(NB, kMQ);
     int want = div_up(148, qtiles);                    // one CTA per SM (each CTA owns all 512 TMEM columns)
@@ -340,9 +364,10 @@ void launch_match_u8(const unsigned char* dA, const int* normA, int NA, const un
     }
     int rps = align_up(div_up(NA, nsplit), kND);
     nsplit = div_up(NA, rps);
+    const CUtensorMap mapA = make_table_map(dA, NA, kND), mapB = make_table_map(dB, NB, kMQ);
     {
         KScope ks("match_u8.mma", st, 2.0 * 128.0 * (double)NA * (double)NB);
-        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 256, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
+        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 384, smem, st>>>(mapA, normA, NA, mapB, normB, NB, rps, partial);
         PB_KERNEL_CHECK();
     }
     KScope ks2("match_u8.merge", st, 0);
