@@ -244,9 +244,15 @@ class Context:
         self._check(self.L.pano_b200_match_u8(self.h, _p(A), len(A), _p(B), len(B), _p(idx), _p(d01), C.byref(n)), "match_u8")
         return idx, d01[:, 0].copy(), d01[:, 1].copy(), d01[:, 2].copy()
 
-    def bench_match_u8(self, nA, nB, reps=5):
+    def bench_match_u8(self, nA, nB, reps=5, A=None, B=None):
+        """ms per repetition of the matcher kernels on resident tables (A, B: row-major u8 tables, or uniform bytes)"""
         ms = C.c_float()
-        self._check(self.L.pano_b200_bench_match_u8(self.h, nA, nB, reps, C.byref(ms)), "bench_match_u8")
+        if A is not None:
+            A = np.ascontiguousarray(A, np.uint8)
+            B = np.ascontiguousarray(B, np.uint8)
+            nA, nB = len(A), len(B)
+        self._check(self.L.pano_b200_bench_match_u8(self.h, _p(A) if A is not None else None, nA,
+                                                    _p(B) if B is not None else None, nB, reps, C.byref(ms)), "bench_match_u8")
         return ms.value
 
     # ---- pipeline -------------------------------------------------------------------------------------------------

@@ -196,9 +196,10 @@ int pano_b200_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const 
     return 0;
     PB_API_END
 }
-int pano_b200_bench_match_u8(pano_b200_ctx* ctx, int nA, int nB, int reps, float* ms_per_rep) {
+int pano_b200_bench_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const uint8_t* descrB, int nB, int reps,
+                             float* ms_per_rep) {
     PB_API_BEGIN
-    *ms_per_rep = ctx->st->bench_match_u8(nA, nB, reps);
+    *ms_per_rep = ctx->st->bench_match_u8(descrA, nA, descrB, nB, reps);
     return 0;
     PB_API_END
 }

@@ -10,16 +10,21 @@
 // oracle/match_u8_oracle.py.
 //
 // Kernel shape (one CTA = 128 queries x one slice of the database, 384 threads):
-//   warp 0      producer: one lane streams 256-row database tiles HBM -> shared memory with TMA, eight
-//               cp.async.bulk.tensor boxes of {16 bytes, 256 rows} per tile (one per 16-byte K chunk), which lands
-//               the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices) directly; 4 stages,
-//               completion by mbarrier transaction bytes; rows past the end of a table are zero-filled by the TMA
+//   warp 0      producer: one lane streams 256-row database tiles HBM -> shared memory with ONE 32 KB TMA bulk copy
+//               (cp.async.bulk) per tile, 4 stages, completion by mbarrier transaction bytes.  The quantised tables
+//               are kept in HBM in the UMMA operand layout already ("blocked256": per block of 256 rows, chunk c
+//               (16 bytes of K) of row r at c * 4096 + r * 16), so a tile is one contiguous 32 KB run and lands as
+//               the canonical K-major no-swizzle layout (8-row x 16-byte core matrices) without any address math.
+//               (A first version gathered row-major tables with 8 TMA tensor boxes of {16 B, 256 rows} per tile:
+//               2048 16-byte requests per tile kept the TMA unit, not the tensor core, busy.)
 //   warp 1      lane 0 issues 4 x tcgen05.mma (M128 x N256 x K32) per tile into one of two 256-column TMEM
 //               accumulators; tcgen05.commit releases the shared-memory stage and publishes the accumulator
 //   warps 4-11  epilogue: thread = (query row = TMEM lane, half of the tile's columns); tcgen05.ld 32 columns at a
 //               time, two loads in flight; key = (|a|^2 - 2 q.a) * 256 + column with ONE integer multiply-add per
-//               element, running (min, 2nd min) on the packed keys; groups of 4 keys that cannot beat the current
-//               2nd best are skipped after one 3-instruction test
+//               element, running (min, 2nd min) on the packed keys.  Two levels of pruning keep the common path
+//               short: a 32-column chunk is skipped when (smallest constant of the chunk) - 512 * (largest dot
+//               product of the chunk, a 3-input max tree) cannot beat the thread's 2nd best; inside a chunk that
+//               survives, groups of 4 keys are tested the same way
 // Queries sit on the MMA's M side so that a thread owns a query and scans database columns: the top-2 needs no
 // cross-thread reduction.  Ties between equal distances cannot change an accepted match (a tie of the two best
 // fails the ratio rule), so the column packed in the key is only a payload.
@@ -28,7 +33,6 @@
 #include "ktimer.h"
 #include <algorithm>
 #include <climits>
-#include <cuda.h>
 
 namespace pb {
 
@@ -63,11 +67,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// TMA: one box of the 2-D tensor map (dim 0 = byte within the descriptor, dim 1 = row) -> shared memory
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+// TMA bulk copy: `bytes` contiguous bytes HBM -> shared memory, completion counted on the mbarrier
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
-                 "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -105,6 +109,7 @@ struct __align__(16) SmemLayout {
     unsigned char q[kMQ * kRowBytes];                 // 16 KB: the CTA's queries (operand A)
     unsigned char db[kStages][kND * kRowBytes];       // 4 x 32 KB: database tiles (operand B)
     int cst[2][kND];                                  // per accumulator buffer: |a|^2 * 256 + column
+    int cmin[2][kND / 32];                            // minimum of cst over each 32-column chunk
     unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], qfull;
     unsigned tmem_base;
     int mrg[kMQ][3];                                  // merge of the two column halves of the epilogue
@@ -113,8 +118,8 @@ struct __align__(16) SmemLayout {
 }  // namespace
 
 __global__ void __launch_bounds__(384, 1)
-match_u8_kernel(const __grid_constant__ CUtensorMap tmapA, const int* __restrict__ normA, int NA,
-                const __grid_constant__ CUtensorMap tmapB, const int* __restrict__ normB, int NB, int rows_per_split,
+match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ normA, int NA,
+                const unsigned char* __restrict__ Bblk, const int* __restrict__ normB, int NB, int rows_per_split,
                 U8Top2* __restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -144,15 +149,14 @@ match_u8_kernel(const __grid_constant__ CUtensorMap tmapA, const int* __restrict
         if (lane == 0) {
             // the CTA's queries (operand A of the MMA): 8 boxes of {16 B, 128 rows}
             mbar_expect_tx(&S.qfull, kMQ * kRowBytes);
+            const unsigned char* qsrc = Bblk + (size_t)(q0 / kND) * (kND * kRowBytes) + (size_t)(q0 % kND) * 16;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) tma_load_2d(S.q + c * (kMQ * 16), &tmapB, c * 16, q0, &S.qfull);
+            for (int c = 0; c < 8; ++c) tma_bulk_load(S.q + c * (kMQ * 16), qsrc + c * (kND * 16), kMQ * 16, &S.qfull);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages;
                 if (t >= kStages) mbar_wait(&S.empty[s], (unsigned)(((t / kStages) - 1) & 1));
                 mbar_expect_tx(&S.full[s], kND * kRowBytes);
-                const int row0 = a_begin + t * kND;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) tma_load_2d(S.db[s] + c * (kND * 16), &tmapA, c * 16, row0, &S.full[s]);
+                tma_bulk_load(S.db[s], Ablk + (size_t)(a_begin / kND + t) * (kND * kRowBytes), kND * kRowBytes, &S.full[s]);
             }
         }
     } else if (warp == 1) {
@@ -183,12 +187,20 @@ match_u8_kernel(const __grid_constant__ CUtensorMap tmapA, const int* __restrict
         const int et = threadIdx.x - 128;              // 0..255
         const int qrow = ew * 32 + lane;               // query row within the CTA = TMEM lane
         int m1 = INT_MAX, m2 = INT_MAX, besttile = 0;
+        int nrm_next = (a_begin + et) < a_end ? normA[a_begin + et] : kPadNorm;   // |a|^2 of my column of tile 0
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1;
-            {   // per-column constants of this tile: |a|^2 * 256 + column (padding rows: a key above every real key)
-                const int row = a_begin + t * kND + et;
-                const int nrm = row < a_end ? normA[row] : kPadNorm;
-                S.cst[b][et] = nrm * 256 + et;
+            {   // per-column constants of this tile: |a|^2 * 256 + column (padding rows: a key above every real key),
+                // and their minimum over every 32-column chunk (the chunk-level pruning bound below); the norm of
+                // the next tile's column is fetched now so that its latency hides behind this tile's scan
+                const int nrm = nrm_next;
+                const int rown = a_begin + (t + 1) * kND + et;
+                nrm_next = (t + 1 < ntiles && rown < a_end) ? normA[rown] : kPadNorm;
+                int cv = nrm * 256 + et;
+                S.cst[b][et] = cv;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cv = min(cv, __shfl_xor_sync(0xffffffffu, cv, o));
+                if (lane == 0) S.cmin[b][et >> 5] = cv;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&S.tmem_full[b], (unsigned)((t >> 1) & 1));
@@ -196,6 +208,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap tmapA, const int* __restrict
             const int m1_before = m1;
             const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND + half * 128);
             const int* cst = &S.cst[b][half * 128];
+            const int* cmin = &S.cmin[b][half * 4];
             int va[32], vb[32];
 #define PB_LDTM(v, col)                                                                                                      \
     asm volatile(                                                                                                            \
@@ -207,6 +220,12 @@ match_u8_kernel(const __grid_constant__ CUtensorMap tmapA, const int* __restrict
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                        \
         : "r"(taddr + (unsigned)(col)))
 #define PB_SCAN(v, col)                                                                                                      \
+    {                                                                                                                        \
+        /* a key is cst - 512 * dot: no key of this chunk can be below cmin - 512 * (largest dot of the chunk) */            \
+        int mx = __vimax3_s32(v[0], v[1], v[2]);                                                                             \
+        _Pragma("unroll") for (int g = 3; g + 1 < 32; g += 2) mx = __vimax3_s32(mx, v[g], v[g + 1]);                         \
+        mx = max(mx, v[31]);                                                                                                 \
+        if (cmin[(col) >> 5] - 512 * mx < m2)                                                                                \
     _Pragma("unroll") for (int g = 0; g < 32; g += 4) {                                                                      \
         const int4 cc = *reinterpret_cast<const int4*>(&cst[(col) + g]);                                                     \
         const int k0 = v[g] * -512 + cc.x, k1 = v[g + 1] * -512 + cc.y, k2 = v[g + 2] * -512 + cc.z,                       \
@@ -218,6 +237,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap tmapA, const int* __restrict
             m2 = min(m2, max(k2, m1)); m1 = min(m1, k2);                                                                     \
             m2 = min(m2, max(k3, m1)); m1 = min(m1, k3);                                                                     \
         }                                                                                                                    \
+    }                                                                                                                        \
     }
             PB_LDTM(va, 0);
             PB_LDTM(vb, 32);
@@ -298,7 +318,8 @@ __global__ void quantize_u8_kernel(const float* __restrict__ src, int n, unsigne
         packed |= q << (8 * k);
         nrm += (int)(q * q);
     }
-    reinterpret_cast<unsigned*>(dst + (size_t)row * 128)[lane] = packed;
+    // blocked256 layout: block = row / 256, chunk = lane / 4 (16 bytes of K), 4 bytes at (lane % 4) * 4 inside the chunk
+    *reinterpret_cast<unsigned*>(dst + (size_t)(row >> 8) * 32768 + (lane >> 2) * 4096 + (row & 255) * 16 + (lane & 3) * 4) = packed;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     if (lane == 0) norm[row] = nrm;
@@ -306,13 +327,28 @@ __global__ void quantize_u8_kernel(const float* __restrict__ src, int n, unsigne
 __global__ void norm_u8_kernel(const unsigned char* __restrict__ src, int n, int* __restrict__ norm) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= n) return;
-    const unsigned p = reinterpret_cast<const unsigned*>(src + (size_t)row * 128)[lane];
+    const unsigned p = *reinterpret_cast<const unsigned*>(src + (size_t)(row >> 8) * 32768 + (lane >> 2) * 4096 + (row & 255) * 16 + (lane & 3) * 4);
     int nrm = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const int q = (p >> (8 * k)) & 255; nrm += q * q; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     if (lane == 0) norm[row] = nrm;
+}
+
+// row-major [n][128] u8 <-> blocked256 (rows padded to a multiple of 256 must have been zeroed by the caller)
+__global__ void relayout_u8_kernel(const unsigned char* __restrict__ src, int n, unsigned char* __restrict__ dst, int to_blocked) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte chunk per thread
+    if (i >= (long)n * 8) return;
+    const int row = (int)(i >> 3), c = (int)(i & 7);
+    const size_t rm = (size_t)row * 128 + c * 16, bl = (size_t)(row >> 8) * 32768 + c * 4096 + (row & 255) * 16;
+    if (to_blocked) *reinterpret_cast<uint4*>(dst + bl) = *reinterpret_cast<const uint4*>(src + rm);
+    else *reinterpret_cast<uint4*>(dst + rm) = *reinterpret_cast<const uint4*>(src + bl);
+}
+void launch_relayout_u8(const unsigned char* src, int n, unsigned char* dst, bool to_blocked, cudaStream_t st) {
+    if (n <= 0) return;
+    relayout_u8_kernel<<<div_up((long)n * 8, 256), 256, 0, st>>>(src, n, dst, to_blocked ? 1 : 0);
+    PB_KERNEL_CHECK();
 }
 
 void launch_quantize_u8(const float* src, int n, unsigned char* dst, int* norm, cudaStream_t st) {
@@ -325,20 +361,6 @@ void launch_norm_u8(const unsigned char* src, int n, int* norm, cudaStream_t st)
     if (n <= 0) return;
     norm_u8_kernel<<<div_up(n, 8), 256, 0, st>>>(src, n, norm);
     PB_KERNEL_CHECK();
-}
-
-// 2-D tensor map over a descriptor table [n][128] u8: dim 0 = the 128 bytes of a row, dim 1 = rows; box = {16 B, rows}
-static CUtensorMap make_table_map(const unsigned char* table, int n, int box_rows) {
-    CUtensorMap m;
-    const cuuint64_t dims[2] = {128, (cuuint64_t)n};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)table, dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-    return m;
 }
 
 int match_u8_num_splits(int NA, int NB) {
@@ -364,10 +386,9 @@ void launch_match_u8(const unsigned char* dA, const int* normA, int NA, const un
     }
     int rps = align_up(div_up(NA, nsplit), kND);
     nsplit = div_up(NA, rps);
-    const CUtensorMap mapA = make_table_map(dA, NA, kND), mapB = make_table_map(dB, NB, kMQ);
     {
         KScope ks("match_u8.mma", st, 2.0 * 128.0 * (double)NA * (double)NB);
-        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 384, smem, st>>>(mapA, normA, NA, mapB, normB, NB, rps, partial);
+        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 384, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
         PB_KERNEL_CHECK();
     }
     KScope ks2("match_u8.merge", st, 0);

@@ -61,7 +61,8 @@ class Stitcher {
     // uint8 / tcgen05 matcher (north-star stage 3; not on the reference-parity path): host tables in, host results out
     void quantize_u8(const float* descr, int n, u8* out);
     void match_u8(const u8* A, int nA, const u8* B, int nB, int* idx, int* d01);
-    float bench_match_u8(int nA, int nB, int reps);   // ms per repetition on resident synthetic tables
+    // ms per repetition of the matcher kernels on resident tables (A, B row-major host tables, or NULL = uniform bytes)
+    float bench_match_u8(const u8* A, int nA, const u8* B, int nB, int reps);
     void cimg_blur2(const float* src, int w, int h, int c, float* dst);    // get_blur(2,true,true), host buffers
     void cimg_resize(const float* src, int w, int h, int c, int nw, int nh, float* dst);
 
@@ -113,7 +114,7 @@ class Stitcher {
     DevBuf<int> midx_;
     PinBuf<int> h_midx_;
     DevBuf<MatchJob> mjobs_;
-    DevBuf<u8> u8a_, u8b_;
+    DevBuf<u8> u8a_, u8b_, u8raw_;
     DevBuf<int> u8na_, u8nb_, u8idx_, u8d01_;
     DevBuf<U8Top2> u8part_;
     DevBuf<float> u8f_;

@@ -124,8 +124,10 @@ int pano_b200_cimg_resize3(pano_b200_ctx* ctx, const float* src, int w, int h, i
 int pano_b200_quantize_u8(pano_b200_ctx* ctx, const float* descr, int n, uint8_t* out);
 int pano_b200_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const uint8_t* descrB, int nB, int* match_idx,
                        int* d01, int* nmatches);
-/* times the matcher kernel alone on resident synthetic tables (CUDA events), milliseconds per repetition */
-int pano_b200_bench_match_u8(pano_b200_ctx* ctx, int nA, int nB, int reps, float* ms_per_rep);
+/* times the matcher kernels alone on resident tables (CUDA events), milliseconds per repetition; descrA / descrB are
+ * row-major host tables, or both NULL for uniform pseudo-random bytes */
+int pano_b200_bench_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const uint8_t* descrB, int nB, int reps,
+                             float* ms_per_rep);
 
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
