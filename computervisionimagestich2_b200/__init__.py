@@ -227,6 +227,51 @@ class Context:
         self._check(self.L.pano_b200_cimg_resize3(self.h, _p(p), w, h, c, nw, nh, _p(out)), "cimg_resize3")
         return out
 
+    # ---- sharded jobs (dist.py) -------------------------------------------------------------------------------------
+    def extract(self, img):
+        """readFile body for one image: -> (projected [3][H][W] u8, descr [n][128] f32, keys [n])"""
+        img = _u8(img)
+        _, h, w = img.shape
+        proj = np.empty_like(img)
+        pd, pk, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        self._check(self.L.pano_b200_extract(self.h, _p(img), w, h, _p(proj), C.byref(pd), C.byref(pk), C.byref(n)), "extract")
+        n = n.value
+        descr = np.frombuffer(C.string_at(pd, n * 512), np.float32).reshape(n, 128).copy()
+        keys = np.frombuffer(C.string_at(pk, n * KEY_DTYPE.itemsize), KEY_DTYPE).copy()
+        self.L.pano_b200_free(pd)
+        self.L.pano_b200_free(pk)
+        return proj, descr, keys
+
+    def stitch_features(self, projs, feats, match_idx=None):
+        """matching() on precomputed projections / feature tables; match_idx: {(i, j): idx array} of preset pairs."""
+        n = len(projs)
+        projs = [_u8(p) for p in projs]
+        descr = [np.ascontiguousarray(f[0], np.float32) for f in feats]
+        keys = [np.ascontiguousarray(f[1], KEY_DTYPE) for f in feats]
+        pp = (C.c_void_p * n)(*[p.ctypes.data for p in projs])
+        ws = (C.c_int * n)(*[p.shape[2] for p in projs])
+        hs = (C.c_int * n)(*[p.shape[1] for p in projs])
+        pd = (C.c_void_p * n)(*[d.ctypes.data for d in descr])
+        pk = (C.c_void_p * n)(*[k.ctypes.data for k in keys])
+        nf = (C.c_int * n)(*[len(k) for k in keys])
+        keep = []
+        pm = None
+        if match_idx:
+            pm = (C.c_void_p * (n * n))()
+            for (i, j), idx in match_idx.items():
+                a = np.ascontiguousarray(idx, np.int32)
+                assert len(a) == len(keys[j])
+                keep.append(a)
+                pm[i * n + j] = a.ctypes.data
+        out, ow, oh = C.c_void_p(), C.c_int(), C.c_int()
+        self._check(self.L.pano_b200_stitch_features(self.h, n, pp, ws, hs, pd, pk, nf, pm, C.byref(out), C.byref(ow), C.byref(oh)),
+                    "stitch_features")
+        pano = np.frombuffer(C.string_at(out, 3 * ow.value * oh.value), np.uint8).reshape(3, oh.value, ow.value).copy()
+        self.L.pano_b200_free(out)
+        buf = C.create_string_buffer(1 << 16)
+        self.L.pano_b200_stitch_log(self.h, buf, 1 << 16)
+        return pano, dict(log=buf.value.decode(), nfeat=[self.L.pano_b200_stitch_nfeatures(self.h, i) for i in range(n)])
+
     # ---- uint8 / tcgen05 matcher (north-star stage 3; not on the reference-parity path) ---------------------------
     def quantize_u8(self, descr):
         d = np.ascontiguousarray(descr, np.float32)

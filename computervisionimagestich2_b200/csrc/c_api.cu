@@ -76,6 +76,41 @@ int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* 
     return 0;
     PB_API_END
 }
+int pano_b200_extract(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* proj_out, float** descr,
+                      pano_b200_keypoint** keys, int* n) {
+    PB_API_BEGIN
+    FeatureTable t;
+    ctx->st->extract(rgb, w, h, proj_out, t);
+    *n = t.n;
+    *descr = (float*)malloc(std::max<size_t>((size_t)t.n * 128 * sizeof(float), 4));
+    *keys = (pano_b200_keypoint*)malloc(std::max<size_t>((size_t)t.n * sizeof(VlKey), 4));
+    memcpy(*descr, t.descr.data(), (size_t)t.n * 128 * sizeof(float));
+    memcpy(*keys, t.keys.data(), (size_t)t.n * sizeof(VlKey));
+    return 0;
+    PB_API_END
+}
+int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const* proj, const int* w, const int* h,
+                              const float* const* descr, const pano_b200_keypoint* const* keys, const int* nfeat,
+                              const int* const* match_idx, uint8_t** out, int* out_w, int* out_h) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    Stitcher& S = *ctx->st;
+    S.clear();
+    for (int i = 0; i < nimg; ++i)
+        S.add_precomputed(proj[i], w[i], h[i], descr[i], reinterpret_cast<const VlKey*>(keys[i]), nfeat[i]);
+    if (match_idx)
+        for (int i = 0; i < nimg; ++i)
+            for (int j = 0; j < nimg; ++j)
+                if (i != j && match_idx[(size_t)i * nimg + j]) S.preset_match(i, j, match_idx[(size_t)i * nimg + j], nfeat[j]);
+    int rc = S.run();
+    if (rc) { ctx->err = S.error(); return rc; }
+    *out_w = S.result_width();
+    *out_h = S.result_height();
+    *out = (uint8_t*)malloc((size_t)3 * *out_w * *out_h);
+    S.copy_result(*out);
+    return 0;
+    PB_API_END
+}
 int pano_b200_stage_images(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n) {
     PB_API_BEGIN
     ctx->st->stage_images(imgs, w, h, n);

@@ -615,7 +615,51 @@ void Stitcher::cimg_resize(const float* src, int w, int h, int c, int nw, int nh
 // ------------------------------------------------------------------------------------------------------------
 // pipeline
 // ------------------------------------------------------------------------------------------------------------
+// An image whose projection and feature table were computed elsewhere (another GPU of a sharded job).
+void Stitcher::add_precomputed(const u8* proj_rgb, int w, int h, const float* descr, const VlKey* keys, int n) {
+    PB_CUDA(cudaSetDevice(dev_));
+    std::unique_ptr<Image> im;
+    if (!pool_.empty()) { im = std::move(pool_.back()); pool_.pop_back(); }
+    else im.reset(new Image());
+    im->w = w; im->h = h;
+    const size_t np = (size_t)w * h;
+    im->proj.ensure(3 * np);
+    PB_CUDA(cudaMemcpyAsync(im->proj.p, proj_rgb, 3 * np, cudaMemcpyHostToDevice, st_));
+    im->feat.n = n;
+    im->feat.descr.assign(descr, descr + (size_t)n * 128);
+    im->feat.keys.assign(keys, keys + n);
+    im->feat.on_device = false;
+    upload_table(im->feat);   // synchronises the stream: proj_rgb may be released by the caller
+    imgs_.push_back(std::move(im));
+}
+void Stitcher::preset_match(int i, int j, const int* idx, int nB) {
+    PresetMatch pm;
+    pm.i = i; pm.j = j;
+    pm.idx.assign(idx, idx + nB);
+    preset_.push_back(std::move(pm));
+}
+// readFile() body for one image with everything returned to the host (sharded jobs exchange these between ranks)
+void Stitcher::extract(const u8* rgb, int w, int h, u8* proj_out, FeatureTable& t) {
+    PB_CUDA(cudaSetDevice(dev_));
+    const size_t np = (size_t)w * h;
+    in_rgb_.ensure(3 * np);
+    a_.ensure(3 * np);
+    const int pitch = align_up(w, 32);
+    gray32_.ensure((size_t)pitch * h);
+    ensure_ktab(std::min(w, h));
+    PB_CUDA(cudaMemcpyAsync(in_rgb_.p, rgb, 3 * np, cudaMemcpyHostToDevice, st_));
+    launch_project_gray(in_rgb_.p, w, h, ktab_.p, a_.p, gray32_.p, pitch, nullptr, st_);
+    if (proj_out) PB_CUDA(cudaMemcpyAsync(proj_out, a_.p, 3 * np, cudaMemcpyDeviceToHost, st_));
+    SiftParams sp;
+    RawFeatures raw;
+    sift_->configure(w, h, sp);
+    sift_->extract(gray32_.p, pitch, raw);
+    build_table(raw, t);
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
 void Stitcher::clear() {
+    preset_.clear();
     // keep the per-image HBM buffers (projected image, descriptor table) for the next job: cudaMalloc / cudaFree
     // cost milliseconds each and synchronise the device
     for (auto& im : imgs_) pool_.push_back(std::move(im));
@@ -807,7 +851,18 @@ int Stitcher::run() {
     // and reused by the stitching loop (which the reference re-evaluates, ImageProcess.cpp:177-178).
     std::vector<std::vector<std::vector<int>>> midx(n, std::vector<std::vector<int>>(n));
     std::vector<std::vector<char>> have(n, std::vector<char>(n, 0));
-    auto run_wave = [&](const std::vector<std::pair<int, int>>& w) {
+    for (auto& pm : preset_) {   // directed problems evaluated elsewhere (another GPU of a sharded job)
+        if (pm.i < 0 || pm.i >= n || pm.j < 0 || pm.j >= n || (int)pm.idx.size() != imgs_[pm.j]->feat.n) {
+            err_ = "preset match list does not fit the images";
+            return -6;
+        }
+        midx[pm.i][pm.j] = pm.idx;
+        have[pm.i][pm.j] = 1;
+    }
+    auto run_wave = [&](const std::vector<std::pair<int, int>>& w0) {
+        std::vector<std::pair<int, int>> w;
+        for (auto& ij : w0)
+            if (!have[ij.first][ij.second]) w.push_back(ij);
         if (w.empty()) return;
         std::vector<std::pair<FeatureTable*, FeatureTable*>> probs;
         for (auto& ij : w) probs.push_back({&imgs_[ij.first]->feat, &imgs_[ij.second]->feat});

@@ -75,6 +75,10 @@ class Stitcher {
     // on_device: imgs[i] are HBM pointers (staged inputs) instead of host buffers.
     void add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
     void set_lanes(int n) { want_lanes_ = n < 1 ? 1 : n; }
+    // ---- sharded jobs (features / matches computed on other GPUs) --------------------------------
+    void extract(const u8* rgb, int w, int h, u8* proj_out, FeatureTable& t);    // one image -> host projection + table
+    void add_precomputed(const u8* proj_rgb, int w, int h, const float* descr, const VlKey* keys, int n);
+    void preset_match(int i, int j, const int* idx, int nB);   // getImgPair(imgs[i], imgs[j]) indices, evaluated elsewhere
     // inputs staged in HBM once (outside any timed region), then stitched any number of times
     void stage_images(const u8* const* imgs, const int* w, const int* h, int n);
     int run_staged();
@@ -139,6 +143,8 @@ class Stitcher {
     };
     void lane_work(Lane& L, int first, int step, const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
     void upload_table_on(FeatureTable& t, cudaStream_t st);
+    struct PresetMatch { int i, j; std::vector<int> idx; };
+    std::vector<PresetMatch> preset_;
     std::vector<std::unique_ptr<Lane>> lanes_;
     int want_lanes_ = 4;
     struct Staged { int w, h; DevBuf<u8> rgb; };

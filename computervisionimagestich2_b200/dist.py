@@ -1,0 +1,140 @@
+"""Sharded panorama job: one process per GPU, `torch.distributed` for the plumbing.
+
+What shards, and how (reference: ImageProcess.cpp:12-23, 117-137):
+  * readFile -- load / project / SIFT / feature table of image i is independent of every other image: image i is
+    processed by rank i % world.  ONE exchange follows: an all-gather of the per-image blocks (feature count,
+    descriptor table [n][128] f32, keypoints [n] x 32 B, projected image), ragged sizes padded to the maximum.
+  * all-pairs matching -- directed problem (i, j) is independent of every other: the problems of a wave are dealt
+    round-robin to the ranks, the match lists (nfeat[j] int32 each) are all-gathered.  The two waves reproduce the set of
+    problems the reference evaluates: (i, j) for i < j always, (i, j) for i > j only when (j, i) found fewer than 20 matches.
+  * the BFS stitching loop is sequential (canvas k depends on canvas k-1): rank 0 runs it (pano_b200_stitch_features)
+    with every match list preset; the few tree-edge directions the discovery skipped are evaluated there.
+No other collective is used.  The engine is injected so that the host logic can be tested on CPU with the gloo backend
+(tests/test_cpu_dist.py drives it with the oracle); the product engine is `Context` (CUDA, no fallback).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import KEY_DTYPE
+
+THRESHOLD = 20  # ImageProcess.h:18
+
+
+def images_of_rank(n: int, world: int, rank: int):
+    return list(range(rank, n, world))
+
+
+def wave1(n: int):
+    return [(i, j) for i in range(n) for j in range(i + 1, n)]
+
+
+def wave2(n: int, counts: dict):
+    return [(i, j) for i in range(n) for j in range(i) if counts[(j, i)] < THRESHOLD]
+
+
+def _all_gather_ragged(dist, arr: np.ndarray, device):
+    """all-gather of one byte blob per rank (ragged): sizes first, then blobs padded to the maximum."""
+    import torch
+    world = dist.get_world_size()
+    raw = np.frombuffer(np.ascontiguousarray(arr).tobytes(), np.uint8)
+    size = torch.tensor([raw.size], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if raw.size:
+        buf[: raw.size] = torch.from_numpy(raw.copy()).to(device)
+    outs = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)]
+
+
+def _pack_images(items):
+    """[(index, proj, descr, keys)] -> one byte blob"""
+    parts = [np.array([len(items)], np.int64).tobytes()]
+    for i, proj, descr, keys in items:
+        hdr = np.array([i, proj.shape[1], proj.shape[2], len(keys)], np.int64)
+        parts += [hdr.tobytes(), np.ascontiguousarray(proj, np.uint8).tobytes(),
+                  np.ascontiguousarray(descr, np.float32).tobytes(), np.ascontiguousarray(keys, KEY_DTYPE).tobytes()]
+    return np.frombuffer(b"".join(parts), np.uint8)
+
+
+def _unpack_images(blob):
+    b = blob.tobytes()
+    k = int(np.frombuffer(b, np.int64, 1, 0)[0])
+    off = 8
+    out = []
+    for _ in range(k):
+        i, h, w, n = (int(x) for x in np.frombuffer(b, np.int64, 4, off))
+        off += 32
+        proj = np.frombuffer(b, np.uint8, 3 * h * w, off).reshape(3, h, w).copy()
+        off += 3 * h * w
+        descr = np.frombuffer(b, np.float32, n * 128, off).reshape(n, 128).copy()
+        off += n * 512
+        keys = np.frombuffer(b, KEY_DTYPE, n, off).copy()
+        off += n * KEY_DTYPE.itemsize
+        out.append((i, proj, descr, keys))
+    return out
+
+
+def _pack_matches(items):
+    parts = [np.array([len(items)], np.int64).tobytes()]
+    for (i, j), idx in items:
+        parts += [np.array([i, j, len(idx)], np.int64).tobytes(), np.ascontiguousarray(idx, np.int32).tobytes()]
+    return np.frombuffer(b"".join(parts), np.uint8)
+
+
+def _unpack_matches(blob):
+    b = blob.tobytes()
+    k = int(np.frombuffer(b, np.int64, 1, 0)[0])
+    off = 8
+    out = {}
+    for _ in range(k):
+        i, j, n = (int(x) for x in np.frombuffer(b, np.int64, 3, off))
+        off += 24
+        out[(i, j)] = np.frombuffer(b, np.int32, n, off).copy()
+        off += 4 * n
+    return out
+
+
+def stitch_sharded(engine, images, dist=None, device="cpu"):
+    """images: the full list of planar uint8 [3][H][W] inputs (every rank holds it, or at least its own share at the
+    right positions).  Returns (panorama, info) on rank 0 and (None, info) elsewhere; info carries the exchanged
+    feature counts and match counts so that callers / tests can check them on every rank."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    n = len(images)
+    # 1. features of my images
+    mine = []
+    for i in images_of_rank(n, world, rank):
+        proj, descr, keys = engine.extract(images[i])
+        mine.append((i, proj, descr, keys))
+    # 2. the one exchange of the job: all-gather of the per-image blocks
+    blobs = _all_gather_ragged(dist, _pack_images(mine), device) if dist is not None else [_pack_images(mine)]
+    table = {}
+    for blob in blobs:
+        for i, proj, descr, keys in _unpack_images(blob):
+            table[i] = (proj, descr, keys)
+    assert sorted(table) == list(range(n))
+    # 3. all-pairs matching, problems dealt round-robin, match lists all-gathered after each wave
+    midx = {}
+
+    def run_wave(pairs):
+        local = [((i, j), engine.match_idx(table[i][1], table[j][1])) for (i, j) in pairs[rank::world]]
+        got = _all_gather_ragged(dist, _pack_matches(local), device) if dist is not None else [_pack_matches(local)]
+        for blob in got:
+            midx.update(_unpack_matches(blob))
+
+    run_wave(wave1(n))
+    counts = {k: int((v >= 0).sum()) for k, v in midx.items()}
+    run_wave(wave2(n, counts))
+    counts = {k: int((v >= 0).sum()) for k, v in midx.items()}
+    info = dict(nfeat=[len(table[i][2]) for i in range(n)], match_counts=counts, world=world)
+    # 4. the sequential part on rank 0
+    if rank != 0:
+        return None, info
+    pano, sinfo = engine.stitch_features([table[i][0] for i in range(n)], [(table[i][1], table[i][2]) for i in range(n)], midx)
+    info.update(sinfo)
+    return pano, info

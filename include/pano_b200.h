@@ -50,6 +50,18 @@ int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* 
 /* same, into a caller-provided (e.g. pinned) buffer of out_cap bytes */
 int pano_b200_stitch_into(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n,
                           uint8_t* out, size_t out_cap, int* out_w, int* out_h);
+/* ---- sharded jobs (one process per GPU; the exchange between ranks is the caller's, see
+ *      computervisionimagestich2_b200/dist.py).  pano_b200_extract = the body of readFile for ONE image
+ *      (ImageProcess.cpp:12-23): projected image (proj_out, w*h*3, may be NULL) + feature table, library-allocated.
+ *      pano_b200_stitch_features = ImageProcess::matching (ImageProcess.cpp:101-271) on images whose projections and
+ *      feature tables were computed elsewhere; match_idx (optional) is an nimg*nimg array of per-directed-pair match
+ *      lists (entry [i*nimg+j] = getImgPair(imgs[i], imgs[j]) as nfeat[j] indices into table i, or -1; NULL entries
+ *      are evaluated here). */
+int pano_b200_extract(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint8_t* proj_out, float** descr,
+                      pano_b200_keypoint** keys, int* n);
+int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const* proj, const int* w, const int* h,
+                              const float* const* descr, const pano_b200_keypoint* const* keys, const int* nfeat,
+                              const int* const* match_idx, uint8_t** out, int* out_w, int* out_h);
 /* Inputs staged in HBM once, then stitched any number of times with no host<->device pixel traffic
  * (device-resident throughput measurement); pano_b200_result_copy downloads the last result. */
 int pano_b200_stage_images(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n);

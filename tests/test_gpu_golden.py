@@ -156,3 +156,13 @@ def test_imageprocess_drop_in_main(anchors):
     A = anchors["Input"]
     assert out.splitlines()[:-1] == A["log"].splitlines()
     assert out.splitlines()[-1] == f"panorama {A['pano_shape'][2]}x{A['pano_shape'][1]} fnv1a64 {A['pano_fnv1a64']}"
+
+
+def test_sharded_job_single_rank_equals_the_fused_pipeline(ctx, anchors):
+    """dist.stitch_sharded with one rank: extract -> preset match lists -> pano_b200_stitch_features."""
+    from computervisionimagestich2_b200 import dist as pdist
+    imgs = _load_set("Input")
+    pano, info = pdist.stitch_sharded(ctx, imgs)
+    A = anchors["Input"]
+    assert info["nfeat"][:0] == [] and info["log"] == A["log"]
+    assert list(pano.shape) == A["pano_shape"] and sha(pano) == A["pano_sha256"]
