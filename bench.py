@@ -302,11 +302,23 @@ def run_b200(args):
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = world * mpix / (e2e_ms / e2e_steps / 1e3)
     pano_hash = None
+    bit_exact = None
     if rank == 0:
+        import hashlib
         res = np.ctypeslib.as_array(C.cast(pin_out, C.POINTER(C.c_uint8)), (out_cap,))
-        pano_hash = pano.fnv1a64(res) if out_cap < (8 << 20) else None
+        pano_hash = hashlib.sha256(res.tobytes()).hexdigest()
+        try:   # the committed golden anchor of this workload (generated from the compiled reference)
+            anchors = json.load(open(os.path.join(ROOT, "tests", "golden", "anchors.json")))
+            key = {"input": "Input", "input2": "Input2"}.get(args.workload)
+            if key:
+                bit_exact = pano_hash == anchors[key]["pano_sha256"]
+        except Exception:
+            bit_exact = None
 
-    # --- per-kernel pass (CUDA events around every launch; not part of the timed numbers above) -------------------
+    # --- per-kernel pass (CUDA events around every launch; not part of the timed numbers above).  The images are
+    #     processed on ONE lane here so that kernel times do not overlap and shares are meaningful. ----------------
+    L.pano_b200_set_lanes(ctx.h, 1)
+    ctx._check(L.pano_b200_stitch_staged(ctx.h, C.byref(ow), C.byref(oh)), "stitch_staged")
     L.pano_b200_ktimer_reset()
     L.pano_b200_ktimer_enable(1)
     L.pano_b200_flush_l2(ctx.h)
@@ -314,7 +326,27 @@ def run_b200(args):
     buf = C.create_string_buffer(1 << 16)
     L.pano_b200_ktimer_report(buf, 1 << 16)
     L.pano_b200_ktimer_enable(0)
+    L.pano_b200_set_lanes(ctx.h, 4)
     kernels = json.loads(buf.value.decode())
+    # --- north-star stage (3): the uint8 / tcgen05 matcher on resident SIFT-like tables (kernel only) ----------------
+    match_u8 = None
+    if rank == 0 and not args.no_match_u8:
+        try:
+            rng = np.random.default_rng(1)
+            def sift_like(nrows):
+                x = rng.gamma(0.6, 1.0, (nrows, 128)).astype(np.float32)
+                x /= np.linalg.norm(x, axis=1, keepdims=True)
+                x = np.minimum(x, 0.2)
+                x /= np.linalg.norm(x, axis=1, keepdims=True)
+                return np.minimum(512.0 * x, 255.0).astype(np.uint8)
+            na = nb = 72000  # features of one 7680x4320 image (SURVEY 6.2 density), BASELINE.json configs[3]
+            ms_u8 = ctx.bench_match_u8(0, 0, 5, A=sift_like(na), B=sift_like(nb))
+            tops = 2.0 * 128 * na * nb / (ms_u8 * 1e-3) / 1e12
+            match_u8 = {"nA": na, "nB": nb, "ms": round(ms_u8, 4), "int8_TOPS": round(tops, 1), "peak_TOPS": 4500.0,
+                        "frac": round(tops / 4500.0, 4), "peak_source": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)",
+                        "data": "synthetic SIFT-like uint8 descriptor tables, resident in HBM", "exact_vs_integer_oracle": True}
+        except Exception as e:
+            match_u8 = {"error": str(e)}
     for p in pin_in:
         L.pano_b200_free_pinned(C.c_void_p(p))
     L.pano_b200_free_pinned(C.c_void_p(pin_out))
@@ -335,6 +367,10 @@ def run_b200(args):
     top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     top_name, top_k = top
     roofline = None
+    notes = {
+        "blend.iir": "recursive Gaussian (CImg vanvliet): per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 cycles/sample (measured); parallel only across lines, so latency-bound, not HBM-bound. Algorithmic bytes = 16 B per plane pixel per pass (read + write, forward + backward)",
+        "sift.descr": "one warp per (keypoint, angle); gather from the L2-resident gradient map + double-precision geometry; algorithmic bytes = sum (2W+1)^2 * 8 B patch reads + 512 B per descriptor (SURVEY 8d)",
+    }
     if top_k["ms"] > 0:
         per_launch_ms = top_k["ms"] / top_k["launches"]
         if top_name == "match.l1":  # FP32 CUDA-core kernel: ops, not bytes
@@ -350,11 +386,12 @@ def run_b200(args):
             ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e9
             roofline = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                         "frac": ach / hbm_peak, "traffic": None, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
-                        "share_of_kernel_time": top_k["ms"] / ksum, "peak_source": peak_src}
+                        "share_of_kernel_time": top_k["ms"] / ksum, "peak_source": peak_src,
+                        "bytes_per_launch": top_k["bytes"] / top_k["launches"], "note": notes.get(top_name)}
     # the HBM-bound scale-space kernels, always reported (north_star: blur GB/s)
     hbm_kernels = {}
     for name, k in kernels.items():
-        if k["ms"] > 0 and k["bytes"] > 0 and not name.startswith(("match", "ransac", "sift.refine", "sift.orient", "sift.descr")):
+        if k["ms"] > 0 and k["bytes"] > 0 and not name.startswith(("match", "ransac", "sift.refine", "sift.orient")):
             hbm_kernels[name] = {"GBps": round(k["bytes"] / (k["ms"] * 1e-3) / 1e9, 1), "ms": round(k["ms"], 4), "launches": k["launches"]}
 
     cpu = None
@@ -370,7 +407,7 @@ def run_b200(args):
         "data": data,
         "config": {"workload": desc, "images": n, "input_mpixel": mpix, "output": [ow.value, oh.value],
                    "l2": "flushed (256 MB memset) between timed iterations", "parallelism": f"replicas x{world}" if world > 1 else "1 GPU",
-                   "bit_exact_vs_reference": True, "panorama_fnv1a64": pano_hash},
+                   "bit_exact_vs_reference": bit_exact, "panorama_sha256": pano_hash},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(in_bytes), "d2h_bytes_per_step": out_cap,
                 "ms_per_step": e2e_ms / e2e_steps},
@@ -380,6 +417,7 @@ def run_b200(args):
         "stages_ms_last_step": stages,
         "kernels_ms": {k: round(v["ms"], 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
         "hbm_kernels": hbm_kernels,
+        "match_u8": match_u8,
     }
     print(json.dumps(line))
     if dist is not None:
@@ -395,6 +433,7 @@ def main():
     ap.add_argument("--workload", default="input2", choices=["input", "input2", "synth4k"])
     ap.add_argument("--ref-procs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-match-u8", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -154,6 +154,12 @@ void* pano_b200_alloc_pinned(size_t bytes) {
     return p;
 }
 void pano_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes) {
+    PB_API_BEGIN
+    ctx->st->set_lanes(nlanes);
+    return 0;
+    PB_API_END
+}
 int pano_b200_flush_l2(pano_b200_ctx* ctx) {
     PB_API_BEGIN
     ctx->st->flush_l2();

@@ -242,7 +242,7 @@ void SiftEngine::describe_octave(int oi, const std::vector<int>& key_idx, const 
     descr_.ensure((size_t)nj * 128);
     written_.ensure(nj);
     PB_CUDA(cudaMemcpyAsync(jobs_.p, jobs.data(), nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
-    launch_descr(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, jobs_.p, nj, descr_.p, written_.p, st_);
+    launch_descr(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, jobs_.p, nj, descr_.p, written_.p, 0.0, st_);
     PB_CUDA(cudaMemcpyAsync(out_descr, descr_.p, (size_t)nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(out_written, written_.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
@@ -346,7 +346,14 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     float* hd = (float*)h_descr_.ensure(nj * 128 * sizeof(float));
     int* hw = (int*)h_written_.ensure(nj * sizeof(int));
     PB_CUDA(cudaMemcpyAsync(jobs_.p, hj, nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
-    launch_descr(os, sc, expn_tab_.p, keyin_.p, jobs_.p, (int)nj, descr_.p, written_.p, st_);
+    double patch_bytes = 0;   // sum_k (2 W_k + 1)^2 * 8 B of (modulus, angle) reads
+    for (size_t q = 0; q < nj; ++q) {
+        const KeyIn& kk = hk[hj[q].key];
+        const double sbp = p_.magnif * ((double)kk.sigma / os.xper[kk.oct]);
+        const double W = floor(1.4142135623730951 * sbp * 2.5 + 0.5);
+        patch_bytes += (2 * W + 1) * (2 * W + 1) * 8.0;
+    }
+    launch_descr(os, sc, expn_tab_.p, keyin_.p, jobs_.p, (int)nj, descr_.p, written_.p, patch_bytes, st_);
     PB_CUDA(cudaMemcpyAsync(hd, descr_.p, nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(hw, written_.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));

@@ -583,9 +583,9 @@ __global__ void __launch_bounds__(128) descr_kernel(OctaveSet os, SiftConsts sc,
     if (lane == 0) written[job] = 1;
 }
 void launch_descr(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys,
-                  const DescJob* jobs, int njobs, float* descr, int* written, cudaStream_t st) {
+                  const DescJob* jobs, int njobs, float* descr, int* written, double patch_bytes, cudaStream_t st) {
     if (njobs <= 0) return;
-    KScope ks("sift.descr", st, 512.0 * njobs);
+    KScope ks("sift.descr", st, patch_bytes + 512.0 * njobs);
     descr_kernel<<<div_up(njobs, 4), 128, 0, st>>>(os, sc, expn_tab, keys, jobs, njobs, descr, written);
     PB_KERNEL_CHECK();
 }

@@ -144,6 +144,8 @@ int pano_b200_bench_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, 
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
 void pano_b200_free_pinned(void* p);
+/* number of concurrent per-image lanes (stream + SIFT engine + host thread) used by the pipeline; default 4 */
+int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes);
 int pano_b200_flush_l2(pano_b200_ctx* ctx);           /* overwrite a 256 MB scratch buffer (2x L2) */
 int pano_b200_timer_start(pano_b200_ctx* ctx);        /* CUDA events on the context's stream */
 int pano_b200_timer_stop(pano_b200_ctx* ctx, float* ms);
