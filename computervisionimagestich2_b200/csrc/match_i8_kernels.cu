@@ -21,10 +21,8 @@
 //               accumulators; tcgen05.commit releases the shared-memory stage and publishes the accumulator
 //   warps 4-11  epilogue: thread = (query row = TMEM lane, half of the tile's columns); tcgen05.ld 32 columns at a
 //               time, two loads in flight; key = (|a|^2 - 2 q.a) * 256 + column with ONE integer multiply-add per
-//               element, running (min, 2nd min) on the packed keys.  Two levels of pruning keep the common path
-//               short: a 32-column chunk is skipped when (smallest constant of the chunk) - 512 * (largest dot
-//               product of the chunk, a 3-input max tree) cannot beat the thread's 2nd best; inside a chunk that
-//               survives, groups of 4 keys are tested the same way
+//               element and a branch-free 3-input min tree per 128-row unit (see the comment in the epilogue);
+//               the second-nearest row inside the winning unit is recomputed by match_u8_finish_kernel
 // Queries sit on the MMA's M side so that a thread owns a query and scans database columns: the top-2 needs no
 // cross-thread reduction.  Ties between equal distances cannot change an accepted match (a tie of the two best
 // fails the ratio rule), so the column packed in the key is only a payload.
@@ -108,8 +106,7 @@ __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
 struct __align__(16) SmemLayout {
     unsigned char q[kMQ * kRowBytes];                 // 16 KB: the CTA's queries (operand A)
     unsigned char db[kStages][kND * kRowBytes];       // 4 x 32 KB: database tiles (operand B)
-    int cst[2][kND];                                  // per accumulator buffer: |a|^2 * 256 + column
-    int cmin[2][kND / 32];                            // minimum of cst over each 32-column chunk
+    int cstw[8][2][128];                              // per epilogue warp, per accumulator buffer: |a|^2 * 256 + column
     unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], qfull;
     unsigned tmem_base;
     int mrg[kMQ][3];                                  // merge of the two column halves of the epilogue
@@ -181,34 +178,40 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
     } else if (warp >= 4) {
         // ------------------------------------------------ epilogue ------------------------------------------------
         // 8 warps: warp w reads TMEM lanes 32 * (w % 4) .. +31 (its hardware lane quarter); warps 4-7 scan columns
-        // 0..127 of every tile, warps 8-11 columns 128..255, two tcgen05.ld in flight per thread.
+        // 0..127 of every tile, warps 8-11 columns 128..255.  A (tile, half) of 128 database rows is a UNIT.  Per unit
+        // and query the thread computes only the unit MINIMUM of the packed keys (128 IMAD + a 3-input min tree, no
+        // branches) and keeps, over its units, the best key, the unit it came from, and the second smallest unit
+        // minimum.  The overall second-nearest row is either another unit's minimum (tracked here) or the second
+        // smallest row INSIDE the best unit, which match_u8_finish_kernel recomputes exactly for that one unit.
         const int ew = warp & 3;
-        const int half = (warp - 4) >> 2;              // which 128-column half of the tile
-        const int et = threadIdx.x - 128;              // 0..255
+        const int half = (warp - 4) >> 2;
         const int qrow = ew * 32 + lane;               // query row within the CTA = TMEM lane
-        int m1 = INT_MAX, m2 = INT_MAX, besttile = 0;
-        int nrm_next = (a_begin + et) < a_end ? normA[a_begin + et] : kPadNorm;   // |a|^2 of my column of tile 0
+        int* cw = S.cstw[warp - 4][0];                 // this warp's private constants, double-buffered per tile
+        int m1 = INT_MAX, s2 = INT_MAX, bestunit = 0;
+        // |a|^2 of the 4 columns this lane prepares for the warp (columns lane*4 .. +3 of the warp's half)
+        int4 nrm_next;
+        {
+            const int r0 = a_begin + half * 128 + lane * 4;
+            nrm_next.x = r0 + 0 < a_end ? normA[r0 + 0] : kPadNorm; nrm_next.y = r0 + 1 < a_end ? normA[r0 + 1] : kPadNorm;
+            nrm_next.z = r0 + 2 < a_end ? normA[r0 + 2] : kPadNorm; nrm_next.w = r0 + 3 < a_end ? normA[r0 + 3] : kPadNorm;
+        }
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1;
-            {   // per-column constants of this tile: |a|^2 * 256 + column (padding rows: a key above every real key),
-                // and their minimum over every 32-column chunk (the chunk-level pruning bound below); the norm of
-                // the next tile's column is fetched now so that its latency hides behind this tile's scan
-                const int nrm = nrm_next;
-                const int rown = a_begin + (t + 1) * kND + et;
-                nrm_next = (t + 1 < ntiles && rown < a_end) ? normA[rown] : kPadNorm;
-                int cv = nrm * 256 + et;
-                S.cst[b][et] = cv;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cv = min(cv, __shfl_xor_sync(0xffffffffu, cv, o));
-                if (lane == 0) S.cmin[b][et >> 5] = cv;
+            int* cst = cw + b * 128;
+            {   // constants of this unit: |a|^2 * 256 + column-in-tile (padding rows: a key above every real key);
+                // the norms of the next tile are fetched now so that their latency hides behind this tile's scan
+                const int c0 = half * 128 + lane * 4;
+                *reinterpret_cast<int4*>(&cst[lane * 4]) =
+                    make_int4(nrm_next.x * 256 + c0, nrm_next.y * 256 + c0 + 1, nrm_next.z * 256 + c0 + 2, nrm_next.w * 256 + c0 + 3);
+                const int r0 = a_begin + (t + 1) * kND + c0;
+                const bool more = t + 1 < ntiles;
+                nrm_next.x = more && r0 + 0 < a_end ? normA[r0 + 0] : kPadNorm; nrm_next.y = more && r0 + 1 < a_end ? normA[r0 + 1] : kPadNorm;
+                nrm_next.z = more && r0 + 2 < a_end ? normA[r0 + 2] : kPadNorm; nrm_next.w = more && r0 + 3 < a_end ? normA[r0 + 3] : kPadNorm;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            __syncwarp();
             mbar_wait(&S.tmem_full[b], (unsigned)((t >> 1) & 1));
             tc_fence_after();
-            const int m1_before = m1;
             const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND + half * 128);
-            const int* cst = &S.cst[b][half * 128];
-            const int* cmin = &S.cmin[b][half * 4];
             int va[32], vb[32];
 #define PB_LDTM(v, col)                                                                                                      \
     asm volatile(                                                                                                            \
@@ -219,26 +222,16 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),          \
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                        \
         : "r"(taddr + (unsigned)(col)))
+// unit minimum of key = cst - 512 * dot over 32 columns: 32 IMAD + 16 VIMNMX3
 #define PB_SCAN(v, col)                                                                                                      \
-    {                                                                                                                        \
-        /* a key is cst - 512 * dot: no key of this chunk can be below cmin - 512 * (largest dot of the chunk) */            \
-        int mx = __vimax3_s32(v[0], v[1], v[2]);                                                                             \
-        _Pragma("unroll") for (int g = 3; g + 1 < 32; g += 2) mx = __vimax3_s32(mx, v[g], v[g + 1]);                         \
-        mx = max(mx, v[31]);                                                                                                 \
-        if (cmin[(col) >> 5] - 512 * mx < m2)                                                                                \
     _Pragma("unroll") for (int g = 0; g < 32; g += 4) {                                                                      \
         const int4 cc = *reinterpret_cast<const int4*>(&cst[(col) + g]);                                                     \
         const int k0 = v[g] * -512 + cc.x, k1 = v[g + 1] * -512 + cc.y, k2 = v[g + 2] * -512 + cc.z,                       \
                   k3 = v[g + 3] * -512 + cc.w;                                                                               \
-        const int mn = min(min(k0, k1), min(k2, k3));                                                                        \
-        if (mn < m2) {                                                                                                       \
-            m2 = min(m2, max(k0, m1)); m1 = min(m1, k0);                                                                     \
-            m2 = min(m2, max(k1, m1)); m1 = min(m1, k1);                                                                     \
-            m2 = min(m2, max(k2, m1)); m1 = min(m1, k2);                                                                     \
-            m2 = min(m2, max(k3, m1)); m1 = min(m1, k3);                                                                     \
-        }                                                                                                                    \
-    }                                                                                                                        \
+        umin = __vimin3_s32(umin, k0, k1);                                                                                   \
+        umin = __vimin3_s32(umin, k2, k3);                                                                                   \
     }
+            int umin = INT_MAX;
             PB_LDTM(va, 0);
             PB_LDTM(vb, 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -251,28 +244,30 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
             PB_SCAN(vb, 96);
 #undef PB_LDTM
 #undef PB_SCAN
-            if (m1 != m1_before) besttile = t;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.tmem_empty[b]);
+            s2 = min(s2, max(umin, m1));
+            if (umin < m1) { m1 = umin; bestunit = t * 2 + half; }
         }
-        // merge the two column halves of every query row (the keys carry the column within the tile) and write
-        if (half == 1) { S.mrg[qrow][0] = m1; S.mrg[qrow][1] = m2; S.mrg[qrow][2] = besttile; }
+        // merge the two halves of every query row and write (best distance, its row, second smallest unit minimum)
+        if (half == 1) { S.mrg[qrow][0] = m1; S.mrg[qrow][1] = s2; S.mrg[qrow][2] = bestunit; }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (half == 0) {
-            const int o1 = S.mrg[qrow][0], o2 = S.mrg[qrow][1], ot = S.mrg[qrow][2];
-            // order keys by (distance, tile, column) so that equal distances keep the lower database row
-            int d_a = m1 == INT_MAX ? INT_MAX : (m1 >> 8), d_b = o1 == INT_MAX ? INT_MAX : (o1 >> 8);
-            const bool take_b = d_b < d_a || (d_b == d_a && d_b != INT_MAX && (ot < besttile));
-            int best = take_b ? o1 : m1, bt = take_b ? ot : besttile;
-            int second = take_b ? min(m1, o2) : min(o1, m2);
+            const int o1 = S.mrg[qrow][0], o2 = S.mrg[qrow][1], ou = S.mrg[qrow][2];
+            const int da = m1 == INT_MAX ? INT_MAX : (m1 >> 8), db2 = o1 == INT_MAX ? INT_MAX : (o1 >> 8);
+            const bool take_b = db2 < da;   // ties keep the lower database row (half 0 precedes half 1 inside a tile
+                                            // only when the tiles are equal; an exact tie never yields a match anyway)
+            const int best = take_b ? o1 : m1, bu = take_b ? ou : bestunit;
+            const int other = take_b ? m1 : o1;
+            int second = min(min(s2, o2), other);   // second smallest unit minimum over both halves
             const int q = q0 + qrow;
             if (q < NB) {
                 const int nq = normB[q];
                 U8Top2 r;
                 r.d0 = best == INT_MAX ? INT_MAX : (best >> 8) + nq;
                 r.d1 = second == INT_MAX ? INT_MAX : (second >> 8) + nq;
-                r.i0 = best == INT_MAX ? -1 : a_begin + bt * kND + (best & 255);
+                r.i0 = best == INT_MAX ? -1 : a_begin + (bu >> 1) * kND + (best & 255);
                 partial[(size_t)blockIdx.y * NB + q] = r;
             }
         }
@@ -285,21 +280,58 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
     }
 }
 
-__global__ void match_u8_merge_kernel(const U8Top2* __restrict__ partial, int nsplit, int NA, int NB, int* __restrict__ idx,
-                                      int* __restrict__ d01) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= NB) return;
+// Merge of the database splits + the exact second-nearest distance.  The main kernel reports, per (query, split), the
+// nearest row, its distance, and the second smallest UNIT minimum (a unit = 128 consecutive database rows).  The true
+// second-nearest distance is the smaller of that value (merged over splits, with the nearest rows of the losing splits)
+// and the second smallest distance INSIDE the winning unit, which one warp recomputes here from the tables
+// (128 rows x 128 bytes, dp4a).  Ratio rule sqrt(d0) / sqrt(d1) < 0.5  <=>  4 d0 < d1, exact in integers.
+__global__ void __launch_bounds__(128) match_u8_finish_kernel(const U8Top2* __restrict__ partial, int nsplit,
+                                                              const unsigned char* __restrict__ Ablk, const int* __restrict__ normA,
+                                                              int NA, const unsigned char* __restrict__ Bblk,
+                                                              const int* __restrict__ normB, int NB, int* __restrict__ idx,
+                                                              int* __restrict__ d01) {
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= NB) return;
     int d0 = INT_MAX, d1 = INT_MAX, i0 = -1;
     for (int s = 0; s < nsplit; ++s) {
-        const U8Top2 p = partial[(size_t)s * NB + b];
+        const U8Top2 p = partial[(size_t)s * NB + q];
         if (p.i0 < 0) continue;
-        if (p.d0 < d0) { d1 = min(d0, p.d1); d0 = p.d0; i0 = p.i0; }
-        else d1 = min(d1, p.d0);
+        if (p.d0 < d0) { d1 = min(min(d0, d1), p.d1); d0 = p.d0; i0 = p.i0; }
+        else d1 = min(d1, min(p.d0, p.d1));
     }
-    // ratio rule sqrt(d0) / sqrt(d1) < 0.5  <=>  4 d0 < d1 (exact in integers)
-    const bool ok = NA >= 2 && i0 >= 0 && d1 != INT_MAX && 4ll * d0 < (long long)d1;
-    idx[b] = ok ? i0 : -1;
-    if (d01) { d01[3 * b] = d0; d01[3 * b + 1] = d1; d01[3 * b + 2] = i0; }
+    if (i0 >= 0) {
+        // the query (128 bytes) in registers: 8 chunks of 16 bytes
+        uint4 qv[8];
+        const unsigned char* qp = Bblk + (size_t)(q >> 8) * 32768 + (size_t)(q & 255) * 16;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qv[c] = *reinterpret_cast<const uint4*>(qp + c * 4096);
+        const int nq = normB[q];
+        const int u0 = (i0 >> 7) << 7;   // first row of the winning unit (units are 128-row aligned)
+        int local = INT_MAX;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int row = u0 + k * 32 + lane;
+            if (row < NA && row != i0) {
+                const unsigned char* ap = Ablk + (size_t)(row >> 8) * 32768 + (size_t)(row & 255) * 16;
+                unsigned dot = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 av = *reinterpret_cast<const uint4*>(ap + c * 4096);
+                    dot = __dp4a(av.x, qv[c].x, dot); dot = __dp4a(av.y, qv[c].y, dot);
+                    dot = __dp4a(av.z, qv[c].z, dot); dot = __dp4a(av.w, qv[c].w, dot);
+                }
+                local = min(local, nq + normA[row] - 2 * (int)dot);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local = min(local, __shfl_xor_sync(0xffffffffu, local, o));
+        d1 = min(d1, local);
+    }
+    if (lane == 0) {
+        const bool ok = NA >= 2 && i0 >= 0 && d1 != INT_MAX && 4ll * d0 < (long long)d1;
+        idx[q] = ok ? i0 : -1;
+        if (d01) { d01[3 * q] = d0; d01[3 * q + 1] = d1; d01[3 * q + 2] = i0; }
+    }
 }
 
 // VLFeat's uint8 descriptor convention: q = (uint8) min(512 x, 255); also |q|^2
@@ -391,8 +423,8 @@ void launch_match_u8(const unsigned char* dA, const int* normA, int NA, const un
         match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 384, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
         PB_KERNEL_CHECK();
     }
-    KScope ks2("match_u8.merge", st, 0);
-    match_u8_merge_kernel<<<div_up(NB, 128), 128, 0, st>>>(partial, nsplit, NA, NB, idx, d01);
+    KScope ks2("match_u8.finish", st, 0);
+    match_u8_finish_kernel<<<div_up(NB, 4), 128, 0, st>>>(partial, nsplit, dA, normA, NA, dB, normB, NB, idx, d01);
     PB_KERNEL_CHECK();
 }
 
