@@ -9,7 +9,7 @@
 // Everything is integer arithmetic (u8 x u8 -> s32), so distances and indices are exact; the oracle is
 // oracle/match_u8_oracle.py.
 //
-// Kernel shape (one CTA = 128 queries x one slice of the database, 384 threads):
+// Kernel shape (one CTA = 128 queries x one slice of the database, 640 threads):
 //   warp 0      producer: one lane streams 256-row database tiles HBM -> shared memory with ONE 32 KB TMA bulk copy
 //               (cp.async.bulk) per tile, 4 stages, completion by mbarrier transaction bytes.  The quantised tables
 //               are kept in HBM in the UMMA operand layout already ("blocked256": per block of 256 rows, chunk c
@@ -19,9 +19,9 @@
 //               2048 16-byte requests per tile kept the TMA unit, not the tensor core, busy.)
 //   warp 1      lane 0 issues 4 x tcgen05.mma (M128 x N256 x K32) per tile into one of two 256-column TMEM
 //               accumulators; tcgen05.commit releases the shared-memory stage and publishes the accumulator
-//   warps 4-11  epilogue: thread = (query row = TMEM lane, half of the tile's columns); tcgen05.ld 32 columns at a
+//   warps 4-19  epilogue: thread = (query row = TMEM lane, quarter of the tile's columns); tcgen05.ld 32 columns at a
 //               time, two loads in flight; key = (|a|^2 - 2 q.a) * 256 + column with ONE integer multiply-add per
-//               element and a branch-free 3-input min tree per 128-row unit (see the comment in the epilogue);
+//               element and a branch-free 3-input min tree per 64-row unit (see the comment in the epilogue);
 //               the second-nearest row inside the winning unit is recomputed by match_u8_finish_kernel
 // Queries sit on the MMA's M side so that a thread owns a query and scans database columns: the top-2 needs no
 // cross-thread reduction.  Ties between equal distances cannot change an accepted match (a tie of the two best
@@ -39,6 +39,7 @@ namespace {
 constexpr int kMQ = 128;       // queries per CTA  (UMMA M)
 constexpr int kND = 256;       // database rows per MMA (UMMA N)
 constexpr int kStages = 4;     // shared-memory stages of database tiles
+constexpr int kUnit = 64;      // database rows per epilogue unit (a quarter of a tile)
 constexpr int kRowBytes = 128; // one descriptor
 // shared-memory layout of a tile of R rows: chunk c (16 bytes of K) of row r at c * (R * 16) + r * 16, i.e. for every
 // chunk the rows are contiguous: 8 rows x 16 B = one UMMA core matrix, 8-row groups 128 B apart (SBO), chunks R*16 B
@@ -106,15 +107,15 @@ __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
 struct __align__(16) SmemLayout {
     unsigned char q[kMQ * kRowBytes];                 // 16 KB: the CTA's queries (operand A)
     unsigned char db[kStages][kND * kRowBytes];       // 4 x 32 KB: database tiles (operand B)
-    int cstw[8][2][128];                              // per epilogue warp, per accumulator buffer: |a|^2 * 256 + column
+    int cstw[16][2][kUnit];                           // per epilogue warp, per accumulator buffer: |a|^2 * 256 + column
     unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], qfull;
     unsigned tmem_base;
-    int mrg[kMQ][3];                                  // merge of the two column halves of the epilogue
+    int mrg[kMQ][4][3];                               // merge of the four column quarters of the epilogue
 };
 
 }  // namespace
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ normA, int NA,
                 const unsigned char* __restrict__ Bblk, const int* __restrict__ normB, int NB, int rows_per_split,
                 U8Top2* __restrict__ partial) {
@@ -128,7 +129,7 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 16); }
         mbar_init(&S.qfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -177,41 +178,40 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
         }
     } else if (warp >= 4) {
         // ------------------------------------------------ epilogue ------------------------------------------------
-        // 8 warps: warp w reads TMEM lanes 32 * (w % 4) .. +31 (its hardware lane quarter); warps 4-7 scan columns
-        // 0..127 of every tile, warps 8-11 columns 128..255.  A (tile, half) of 128 database rows is a UNIT.  Per unit
-        // and query the thread computes only the unit MINIMUM of the packed keys (128 IMAD + a 3-input min tree, no
-        // branches) and keeps, over its units, the best key, the unit it came from, and the second smallest unit
+        // 16 warps: warp w reads TMEM lanes 32 * (w % 4) .. +31 (its hardware lane quarter); warps 4-7 scan columns
+        // 0..63 of every tile, warps 8-11 columns 64..127, and so on.  A (tile, quarter) of 64 database rows is a UNIT.
+        // Per unit and query the thread computes only the unit MINIMUM of the packed keys (64 IMAD + a 3-input min
+        // tree, no branches) and keeps, over its units, the best key, the unit it came from, and the second smallest unit
         // minimum.  The overall second-nearest row is either another unit's minimum (tracked here) or the second
         // smallest row INSIDE the best unit, which match_u8_finish_kernel recomputes exactly for that one unit.
         const int ew = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int part = (warp - 4) >> 2;              // which 64-column quarter of the tile
         const int qrow = ew * 32 + lane;               // query row within the CTA = TMEM lane
         int* cw = S.cstw[warp - 4][0];                 // this warp's private constants, double-buffered per tile
         int m1 = INT_MAX, s2 = INT_MAX, bestunit = 0;
-        // |a|^2 of the 4 columns this lane prepares for the warp (columns lane*4 .. +3 of the warp's half)
-        int4 nrm_next;
+        // |a|^2 of the 2 columns this lane prepares for the warp (columns lane*2, lane*2+1 of the warp's quarter)
+        int2 nrm_next;
         {
-            const int r0 = a_begin + half * 128 + lane * 4;
-            nrm_next.x = r0 + 0 < a_end ? normA[r0 + 0] : kPadNorm; nrm_next.y = r0 + 1 < a_end ? normA[r0 + 1] : kPadNorm;
-            nrm_next.z = r0 + 2 < a_end ? normA[r0 + 2] : kPadNorm; nrm_next.w = r0 + 3 < a_end ? normA[r0 + 3] : kPadNorm;
+            const int r0 = a_begin + part * kUnit + lane * 2;
+            nrm_next.x = r0 + 0 < a_end ? normA[r0 + 0] : kPadNorm;
+            nrm_next.y = r0 + 1 < a_end ? normA[r0 + 1] : kPadNorm;
         }
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1;
-            int* cst = cw + b * 128;
+            int* cst = cw + b * kUnit;
             {   // constants of this unit: |a|^2 * 256 + column-in-tile (padding rows: a key above every real key);
                 // the norms of the next tile are fetched now so that their latency hides behind this tile's scan
-                const int c0 = half * 128 + lane * 4;
-                *reinterpret_cast<int4*>(&cst[lane * 4]) =
-                    make_int4(nrm_next.x * 256 + c0, nrm_next.y * 256 + c0 + 1, nrm_next.z * 256 + c0 + 2, nrm_next.w * 256 + c0 + 3);
+                const int c0 = part * kUnit + lane * 2;
+                *reinterpret_cast<int2*>(&cst[lane * 2]) = make_int2(nrm_next.x * 256 + c0, nrm_next.y * 256 + c0 + 1);
                 const int r0 = a_begin + (t + 1) * kND + c0;
                 const bool more = t + 1 < ntiles;
-                nrm_next.x = more && r0 + 0 < a_end ? normA[r0 + 0] : kPadNorm; nrm_next.y = more && r0 + 1 < a_end ? normA[r0 + 1] : kPadNorm;
-                nrm_next.z = more && r0 + 2 < a_end ? normA[r0 + 2] : kPadNorm; nrm_next.w = more && r0 + 3 < a_end ? normA[r0 + 3] : kPadNorm;
+                nrm_next.x = more && r0 + 0 < a_end ? normA[r0 + 0] : kPadNorm;
+                nrm_next.y = more && r0 + 1 < a_end ? normA[r0 + 1] : kPadNorm;
             }
             __syncwarp();
             mbar_wait(&S.tmem_full[b], (unsigned)((t >> 1) & 1));
             tc_fence_after();
-            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND + half * 128);
+            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND + part * kUnit);
             int va[32], vb[32];
 #define PB_LDTM(v, col)                                                                                                      \
     asm volatile(                                                                                                            \
@@ -235,39 +235,35 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
             PB_LDTM(va, 0);
             PB_LDTM(vb, 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            PB_SCAN(va, 0);
-            PB_LDTM(va, 64);
-            PB_SCAN(vb, 32);
-            PB_LDTM(vb, 96);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            PB_SCAN(va, 64);
-            PB_SCAN(vb, 96);
-#undef PB_LDTM
-#undef PB_SCAN
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.tmem_empty[b]);
+            if (lane == 0) mbar_arrive(&S.tmem_empty[b]);   // the accumulator quarter is in registers: release it early
+            PB_SCAN(va, 0);
+            PB_SCAN(vb, 32);
+#undef PB_LDTM
+#undef PB_SCAN
             s2 = min(s2, max(umin, m1));
-            if (umin < m1) { m1 = umin; bestunit = t * 2 + half; }
+            if (umin < m1) { m1 = umin; bestunit = t * 4 + part; }
         }
-        // merge the two halves of every query row and write (best distance, its row, second smallest unit minimum)
-        if (half == 1) { S.mrg[qrow][0] = m1; S.mrg[qrow][1] = s2; S.mrg[qrow][2] = bestunit; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0) {
-            const int o1 = S.mrg[qrow][0], o2 = S.mrg[qrow][1], ou = S.mrg[qrow][2];
-            const int da = m1 == INT_MAX ? INT_MAX : (m1 >> 8), db2 = o1 == INT_MAX ? INT_MAX : (o1 >> 8);
-            const bool take_b = db2 < da;   // ties keep the lower database row (half 0 precedes half 1 inside a tile
-                                            // only when the tiles are equal; an exact tie never yields a match anyway)
-            const int best = take_b ? o1 : m1, bu = take_b ? ou : bestunit;
-            const int other = take_b ? m1 : o1;
-            int second = min(min(s2, o2), other);   // second smallest unit minimum over both halves
+        // merge the four quarters of every query row and write (best distance, its row, second smallest unit minimum)
+        if (part != 0) { S.mrg[qrow][part][0] = m1; S.mrg[qrow][part][1] = s2; S.mrg[qrow][part][2] = bestunit; }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (part == 0) {
+            int best = m1, bu = bestunit, second = s2;
+#pragma unroll
+            for (int p = 1; p < 4; ++p) {
+                const int o1 = S.mrg[qrow][p][0], o2 = S.mrg[qrow][p][1], ou = S.mrg[qrow][p][2];
+                second = min(second, o2);
+                if (o1 != INT_MAX && (best == INT_MAX || (o1 >> 8) < (best >> 8))) { second = min(second, best); best = o1; bu = ou; }
+                else second = min(second, o1);
+            }
             const int q = q0 + qrow;
             if (q < NB) {
                 const int nq = normB[q];
                 U8Top2 r;
                 r.d0 = best == INT_MAX ? INT_MAX : (best >> 8) + nq;
                 r.d1 = second == INT_MAX ? INT_MAX : (second >> 8) + nq;
-                r.i0 = best == INT_MAX ? -1 : a_begin + (bu >> 1) * kND + (best & 255);
+                r.i0 = best == INT_MAX ? -1 : a_begin + (bu >> 2) * kND + (best & 255);
                 partial[(size_t)blockIdx.y * NB + q] = r;
             }
         }
@@ -281,10 +277,10 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
 }
 
 // Merge of the database splits + the exact second-nearest distance.  The main kernel reports, per (query, split), the
-// nearest row, its distance, and the second smallest UNIT minimum (a unit = 128 consecutive database rows).  The true
+// nearest row, its distance, and the second smallest UNIT minimum (a unit = 64 consecutive database rows).  The true
 // second-nearest distance is the smaller of that value (merged over splits, with the nearest rows of the losing splits)
 // and the second smallest distance INSIDE the winning unit, which one warp recomputes here from the tables
-// (128 rows x 128 bytes, dp4a).  Ratio rule sqrt(d0) / sqrt(d1) < 0.5  <=>  4 d0 < d1, exact in integers.
+// (64 rows x 128 bytes, dp4a).  Ratio rule sqrt(d0) / sqrt(d1) < 0.5  <=>  4 d0 < d1, exact in integers.
 __global__ void __launch_bounds__(128) match_u8_finish_kernel(const U8Top2* __restrict__ partial, int nsplit,
                                                               const unsigned char* __restrict__ Ablk, const int* __restrict__ normA,
                                                               int NA, const unsigned char* __restrict__ Bblk,
@@ -306,10 +302,10 @@ __global__ void __launch_bounds__(128) match_u8_finish_kernel(const U8Top2* __re
 #pragma unroll
         for (int c = 0; c < 8; ++c) qv[c] = *reinterpret_cast<const uint4*>(qp + c * 4096);
         const int nq = normB[q];
-        const int u0 = (i0 >> 7) << 7;   // first row of the winning unit (units are 128-row aligned)
+        const int u0 = (i0 / kUnit) * kUnit;   // first row of the winning unit (units are kUnit-row aligned)
         int local = INT_MAX;
 #pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kUnit / 32; ++k) {
             const int row = u0 + k * 32 + lane;
             if (row < NA && row != i0) {
                 const unsigned char* ap = Ablk + (size_t)(row >> 8) * 32768 + (size_t)(row & 255) * 16;
@@ -420,7 +416,7 @@ void launch_match_u8(const unsigned char* dA, const int* normA, int NA, const un
     nsplit = div_up(NA, rps);
     {
         KScope ks("match_u8.mma", st, 2.0 * 128.0 * (double)NA * (double)NB);
-        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 384, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
+        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 640, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
         PB_KERNEL_CHECK();
     }
     KScope ks2("match_u8.finish", st, 0);
