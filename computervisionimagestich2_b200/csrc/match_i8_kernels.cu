@@ -36,9 +36,10 @@ namespace pb {
 
 namespace {
 
-constexpr int kMQ = 128;       // queries per CTA  (UMMA M)
-constexpr int kND = 256;       // database rows per MMA (UMMA N)
-constexpr int kStages = 4;     // shared-memory stages of database tiles
+constexpr int kMQ = 128;       // queries per MMA (UMMA M)
+constexpr int kQB = 2;         // query blocks per CTA: every database tile in shared memory feeds kQB MMAs
+constexpr int kND = 128;       // database rows per MMA (UMMA N)
+constexpr int kStages = 6;     // shared-memory stages of database tiles
 constexpr int kUnit = 64;      // database rows per epilogue unit (a quarter of a tile)
 constexpr int kRowBytes = 128; // one descriptor
 // shared-memory layout of a tile of R rows: chunk c (16 bytes of K) of row r at c * (R * 16) + r * 16, i.e. for every
@@ -105,12 +106,12 @@ __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
 }
 
 struct __align__(16) SmemLayout {
-    unsigned char q[kMQ * kRowBytes];                 // 16 KB: the CTA's queries (operand A)
-    unsigned char db[kStages][kND * kRowBytes];       // 4 x 32 KB: database tiles (operand B)
+    unsigned char q[kQB][kMQ * kRowBytes];            // 2 x 16 KB: the CTA's queries (operand A), two blocks of 128
+    unsigned char db[kStages][kND * kRowBytes];       // 6 x 16 KB: database tiles (operand B)
     int cstw[16][2][kUnit];                           // per epilogue warp, per accumulator buffer: |a|^2 * 256 + column
     unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], qfull;
     unsigned tmem_base;
-    int mrg[kMQ][4][3];                               // merge of the four column quarters of the epilogue
+    int mrg[kQB * kMQ][2][3];                         // merge of the two column halves of the epilogue
 };
 
 }  // namespace
@@ -122,7 +123,7 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * kMQ;
+    const int q0 = blockIdx.x * (kQB * kMQ);
     const int a_begin = blockIdx.y * rows_per_split;
     const int a_end = min(NA, a_begin + rows_per_split);
     const int ntiles = (a_end - a_begin + kND - 1) / kND;
@@ -146,21 +147,28 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
         // ------------------------------------------------ producer ------------------------------------------------
         if (lane == 0) {
             // the CTA's queries (operand A of the MMA): 8 boxes of {16 B, 128 rows}
-            mbar_expect_tx(&S.qfull, kMQ * kRowBytes);
-            const unsigned char* qsrc = Bblk + (size_t)(q0 / kND) * (kND * kRowBytes) + (size_t)(q0 % kND) * 16;
+            // the CTA's 256 queries = one block of the blocked256 table: query block qb = rows qb*128 .. +127 of it
+            mbar_expect_tx(&S.qfull, kQB * kMQ * kRowBytes);
+            const unsigned char* qsrc = Bblk + (size_t)(q0 / 256) * 32768;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) tma_bulk_load(S.q + c * (kMQ * 16), qsrc + c * (kND * 16), kMQ * 16, &S.qfull);
+            for (int qb = 0; qb < kQB; ++qb)
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    tma_bulk_load(S.q[qb] + c * (kMQ * 16), qsrc + c * 4096 + qb * (kMQ * 16), kMQ * 16, &S.qfull);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages;
                 if (t >= kStages) mbar_wait(&S.empty[s], (unsigned)(((t / kStages) - 1) & 1));
+                // tile t = rows a_begin + t*128 .. +127 = half (t & 1) of block (a_begin / 256 + t / 2): 8 runs of 2 KB
                 mbar_expect_tx(&S.full[s], kND * kRowBytes);
-                tma_bulk_load(S.db[s], Ablk + (size_t)(a_begin / kND + t) * (kND * kRowBytes), kND * kRowBytes, &S.full[s]);
+                const unsigned char* src = Ablk + (size_t)(a_begin / 256 + (t >> 1)) * 32768 + (size_t)(t & 1) * (kND * 16);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) tma_bulk_load(S.db[s] + c * (kND * 16), src + c * 4096, kND * 16, &S.full[s]);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer ------------------------------------------------
         if (lane == 0) {
-            const unsigned qa = smem_u32(S.q);
+            const unsigned qa = smem_u32(S.q[0]);
             mbar_wait(&S.qfull, 0);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages, b = t & 1;
@@ -169,9 +177,12 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
                 tc_fence_after();
                 const unsigned ba = smem_u32(S.db[s]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)   // K = 128 = 4 steps of 32 bytes = chunks 2j, 2j+1
-                    umma_i8(tmem + (unsigned)(b * kND), umma_desc(qa + j * 2 * (kMQ * 16), kMQ * 16, kSbo),
-                            umma_desc(ba + j * 2 * (kND * 16), kND * 16, kSbo), j > 0 ? 1u : 0u);
+                for (int qb = 0; qb < kQB; ++qb)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)   // K = 128 = 4 steps of 32 bytes = chunks 2j, 2j+1
+                        umma_i8(tmem + (unsigned)((b * kQB + qb) * kND),
+                                umma_desc(qa + qb * (kMQ * kRowBytes) + j * 2 * (kMQ * 16), kMQ * 16, kSbo),
+                                umma_desc(ba + j * 2 * (kND * 16), kND * 16, kSbo), j > 0 ? 1u : 0u);
                 umma_commit(&S.empty[s]);        // the stage may be refilled once these MMAs have read it
                 umma_commit(&S.tmem_full[b]);    // the accumulator is complete
             }
@@ -185,8 +196,9 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
         // minimum.  The overall second-nearest row is either another unit's minimum (tracked here) or the second
         // smallest row INSIDE the best unit, which match_u8_finish_kernel recomputes exactly for that one unit.
         const int ew = warp & 3;
-        const int part = (warp - 4) >> 2;              // which 64-column quarter of the tile
-        const int qrow = ew * 32 + lane;               // query row within the CTA = TMEM lane
+        const int part = ((warp - 4) >> 2) & 1;        // which 64-column half of the tile
+        const int qb = (warp - 4) >> 3;                // which query block (accumulator) of the CTA
+        const int qrow = qb * kMQ + ew * 32 + lane;    // query row within the CTA; TMEM lane = ew * 32 + lane
         int* cw = S.cstw[warp - 4][0];                 // this warp's private constants, double-buffered per tile
         int m1 = INT_MAX, s2 = INT_MAX, bestunit = 0;
         // |a|^2 of the 2 columns this lane prepares for the warp (columns lane*2, lane*2+1 of the warp's quarter)
@@ -211,7 +223,7 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
             __syncwarp();
             mbar_wait(&S.tmem_full[b], (unsigned)((t >> 1) & 1));
             tc_fence_after();
-            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)(b * kND + part * kUnit);
+            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)((b * kQB + qb) * kND + part * kUnit);
             int va[32], vb[32];
 #define PB_LDTM(v, col)                                                                                                      \
     asm volatile(                                                                                                            \
@@ -243,16 +255,15 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
 #undef PB_LDTM
 #undef PB_SCAN
             s2 = min(s2, max(umin, m1));
-            if (umin < m1) { m1 = umin; bestunit = t * 4 + part; }
+            if (umin < m1) { m1 = umin; bestunit = t * 2 + part; }
         }
-        // merge the four quarters of every query row and write (best distance, its row, second smallest unit minimum)
-        if (part != 0) { S.mrg[qrow][part][0] = m1; S.mrg[qrow][part][1] = s2; S.mrg[qrow][part][2] = bestunit; }
+        // merge the two column halves of every query row and write (best distance, its row, 2nd smallest unit minimum)
+        if (part != 0) { S.mrg[qrow][1][0] = m1; S.mrg[qrow][1][1] = s2; S.mrg[qrow][1][2] = bestunit; }
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (part == 0) {
             int best = m1, bu = bestunit, second = s2;
-#pragma unroll
-            for (int p = 1; p < 4; ++p) {
-                const int o1 = S.mrg[qrow][p][0], o2 = S.mrg[qrow][p][1], ou = S.mrg[qrow][p][2];
+            {
+                const int o1 = S.mrg[qrow][1][0], o2 = S.mrg[qrow][1][1], ou = S.mrg[qrow][1][2];
                 second = min(second, o2);
                 if (o1 != INT_MAX && (best == INT_MAX || (o1 >> 8) < (best >> 8))) { second = min(second, best); best = o1; bu = ou; }
                 else second = min(second, o1);
@@ -263,7 +274,7 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, const int* __restrict__ 
                 U8Top2 r;
                 r.d0 = best == INT_MAX ? INT_MAX : (best >> 8) + nq;
                 r.d1 = second == INT_MAX ? INT_MAX : (second >> 8) + nq;
-                r.i0 = best == INT_MAX ? -1 : a_begin + (bu >> 2) * kND + (best & 255);
+                r.i0 = best == INT_MAX ? -1 : a_begin + (bu >> 1) * kND + (best & 255);
                 partial[(size_t)blockIdx.y * NB + q] = r;
             }
         }
@@ -392,9 +403,9 @@ void launch_norm_u8(const unsigned char* src, int n, int* norm, cudaStream_t st)
 }
 
 int match_u8_num_splits(int NA, int NB) {
-    const int qtiles = div_up(NB, kMQ);
+    const int qtiles = div_up(NB, kQB * kMQ);
     int want = div_up(148, qtiles);                    // one CTA per SM (each CTA owns all 512 TMEM columns)
-    const int maxs = std::max(1, div_up(NA, 4 * kND)); // at least four database tiles per split
+    const int maxs = std::max(1, div_up(NA, 1024));    // at least 1024 database rows per split
     want = std::min(want, maxs);
     return std::max(1, want);
 }
@@ -412,11 +423,11 @@ void launch_match_u8(const unsigned char* dA, const int* normA, int NA, const un
         PB_CUDA(cudaFuncSetAttribute(match_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    int rps = align_up(div_up(NA, nsplit), kND);
+    int rps = align_up(div_up(NA, nsplit), 256);   // splits start on block boundaries of the blocked256 layout
     nsplit = div_up(NA, rps);
     {
         KScope ks("match_u8.mma", st, 2.0 * 128.0 * (double)NA * (double)NB);
-        match_u8_kernel<<<dim3(div_up(NB, kMQ), nsplit), 640, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
+        match_u8_kernel<<<dim3(div_up(NB, kQB * kMQ), nsplit), 640, smem, st>>>(dA, normA, NA, dB, normB, NB, rps, partial);
         PB_KERNEL_CHECK();
     }
     KScope ks2("match_u8.finish", st, 0);
