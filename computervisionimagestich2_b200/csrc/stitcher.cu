@@ -220,34 +220,42 @@ void Stitcher::quantize_u8(const float* descr, int n, u8* out) {
     PB_CUDA(cudaSetDevice(dev_));
     if (n <= 0) return;
     u8f_.ensure((size_t)n * 128);
-    u8a_.ensure(u8_blocked_bytes(n));
-    u8b_.ensure((size_t)n * 128);
-    u8na_.ensure(n);
+    u8a_.ensure(u8_table_bytes(n));
+    u8raw_.ensure((size_t)n * 128);
     PB_CUDA(cudaMemcpyAsync(u8f_.p, descr, (size_t)n * 512, cudaMemcpyHostToDevice, st_));
-    launch_quantize_u8(u8f_.p, n, u8a_.p, u8na_.p, st_);
-    launch_relayout_u8(u8a_.p, n, u8b_.p, false, st_);
-    PB_CUDA(cudaMemcpyAsync(out, u8b_.p, (size_t)n * 128, cudaMemcpyDeviceToHost, st_));
+    launch_quantize_u8(u8f_.p, n, u8a_.p, st_);
+    launch_relayout_u8(u8a_.p, n, u8raw_.p, false, st_);
+    PB_CUDA(cudaMemcpyAsync(out, u8raw_.p, (size_t)n * 128, cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+// uploads two row-major tables into the blocked device layout and prepares them (norms, extension columns)
+void Stitcher::u8_upload(const u8* A, int nA, const u8* B, int nB, U8Table& TA, U8Table& TB) {
+    u8raw_.ensure((size_t)std::max(nA, nB) * 128);
+    u8a_.ensure(u8_table_bytes(nA)); u8b_.ensure(u8_table_bytes(nB));
+    u8na_.ensure(nA); u8nb_.ensure(nB); u8scratch_.ensure(2);
+    PB_CUDA(cudaMemsetAsync(u8a_.p, 0, u8_table_bytes(nA), st_));
+    PB_CUDA(cudaMemsetAsync(u8b_.p, 0, u8_table_bytes(nB), st_));
+    PB_CUDA(cudaMemcpyAsync(u8raw_.p, A, (size_t)nA * 128, cudaMemcpyHostToDevice, st_));
+    launch_relayout_u8(u8raw_.p, nA, u8a_.p, true, st_);
+    PB_CUDA(cudaMemcpyAsync(u8raw_.p, B, (size_t)nB * 128, cudaMemcpyHostToDevice, st_));
+    launch_relayout_u8(u8raw_.p, nB, u8b_.p, true, st_);
+    TA.blk = u8a_.p; TA.norm = u8na_.p; TA.n = nA;
+    TB.blk = u8b_.p; TB.norm = u8nb_.p; TB.n = nB;
+    u8_table_prepare(TA, u8scratch_.p, st_);
+    u8_table_prepare(TB, u8scratch_.p, st_);
 }
 
 void Stitcher::match_u8(const u8* A, int nA, const u8* B, int nB, int* idx, int* d01) {
     PB_CUDA(cudaSetDevice(dev_));
     if (nB <= 0) return;
     if (nA <= 0) { for (int i = 0; i < nB; ++i) idx[i] = -1; return; }
-    u8raw_.ensure((size_t)std::max(nA, nB) * 128);
-    u8a_.ensure(u8_blocked_bytes(nA)); u8b_.ensure(u8_blocked_bytes(nB));
-    u8na_.ensure(nA); u8nb_.ensure(nB); u8idx_.ensure(nB); u8d01_.ensure((size_t)nB * 3);
+    U8Table TA, TB;
+    u8_upload(A, nA, B, nB, TA, TB);
+    u8idx_.ensure(nB); u8d01_.ensure((size_t)nB * 3);
     const int ns = match_u8_num_splits(nA, nB);
     u8part_.ensure((size_t)ns * nB);
-    PB_CUDA(cudaMemsetAsync(u8a_.p, 0, u8_blocked_bytes(nA), st_));
-    PB_CUDA(cudaMemsetAsync(u8b_.p, 0, u8_blocked_bytes(nB), st_));
-    PB_CUDA(cudaMemcpyAsync(u8raw_.p, A, (size_t)nA * 128, cudaMemcpyHostToDevice, st_));
-    launch_relayout_u8(u8raw_.p, nA, u8a_.p, true, st_);
-    PB_CUDA(cudaMemcpyAsync(u8raw_.p, B, (size_t)nB * 128, cudaMemcpyHostToDevice, st_));
-    launch_relayout_u8(u8raw_.p, nB, u8b_.p, true, st_);
-    launch_norm_u8(u8a_.p, nA, u8na_.p, st_);
-    launch_norm_u8(u8b_.p, nB, u8nb_.p, st_);
-    launch_match_u8(u8a_.p, u8na_.p, nA, u8b_.p, u8nb_.p, nB, u8part_.p, ns, u8idx_.p, u8d01_.p, st_);
+    launch_match_u8(TA, TB, u8part_.p, ns, u8idx_.p, u8d01_.p, st_);
     PB_CUDA(cudaMemcpyAsync(idx, u8idx_.p, sizeof(int) * nB, cudaMemcpyDeviceToHost, st_));
     if (d01) PB_CUDA(cudaMemcpyAsync(d01, u8d01_.p, sizeof(int) * 3 * nB, cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
@@ -255,34 +263,23 @@ void Stitcher::match_u8(const u8* A, int nA, const u8* B, int nB, int* idx, int*
 
 float Stitcher::bench_match_u8(const u8* A, int nA, const u8* B, int nB, int reps) {
     PB_CUDA(cudaSetDevice(dev_));
-    const size_t ba = u8_blocked_bytes(nA), bb = u8_blocked_bytes(nB);
-    u8a_.ensure(ba); u8b_.ensure(bb);
-    u8na_.ensure(nA); u8nb_.ensure(nB); u8idx_.ensure(nB);
+    std::vector<u8> ha, hb;
+    if (!(A && B)) {   // uniform pseudo-random bytes
+        ha.resize((size_t)nA * 128); hb.resize((size_t)nB * 128);
+        unsigned x = 12345u;
+        for (auto& v : ha) { x = x * 1664525u + 1013904223u; v = (u8)((x >> 24) & 63); }
+        for (auto& v : hb) { x = x * 1664525u + 1013904223u; v = (u8)((x >> 24) & 63); }
+        A = ha.data(); B = hb.data();
+    }
+    U8Table TA, TB;
+    u8_upload(A, nA, B, nB, TA, TB);
+    u8idx_.ensure(nB);
     const int ns = match_u8_num_splits(nA, nB);
     u8part_.ensure((size_t)ns * nB);
-    if (A && B) {   // caller-provided row-major tables
-        u8raw_.ensure((size_t)std::max(nA, nB) * 128);
-        PB_CUDA(cudaMemsetAsync(u8a_.p, 0, ba, st_));
-        PB_CUDA(cudaMemsetAsync(u8b_.p, 0, bb, st_));
-        PB_CUDA(cudaMemcpyAsync(u8raw_.p, A, (size_t)nA * 128, cudaMemcpyHostToDevice, st_));
-        launch_relayout_u8(u8raw_.p, nA, u8a_.p, true, st_);
-        PB_CUDA(cudaMemcpyAsync(u8raw_.p, B, (size_t)nB * 128, cudaMemcpyHostToDevice, st_));
-        launch_relayout_u8(u8raw_.p, nB, u8b_.p, true, st_);
-    } else {        // uniform pseudo-random bytes (the hardest case for the epilogue's pruning)
-        std::vector<u8> h(std::max(ba, bb) + 64);
-        unsigned x = 12345u;
-        for (auto& v : h) { x = x * 1664525u + 1013904223u; v = (u8)((x >> 24) & 63); }
-        PB_CUDA(cudaMemcpyAsync(u8a_.p, h.data(), ba, cudaMemcpyHostToDevice, st_));
-        PB_CUDA(cudaMemcpyAsync(u8b_.p, h.data() + 64, bb, cudaMemcpyHostToDevice, st_));
-        PB_CUDA(cudaStreamSynchronize(st_));
-    }
-    launch_norm_u8(u8a_.p, nA, u8na_.p, st_);
-    launch_norm_u8(u8b_.p, nB, u8nb_.p, st_);
-    launch_match_u8(u8a_.p, u8na_.p, nA, u8b_.p, u8nb_.p, nB, u8part_.p, ns, u8idx_.p, nullptr, st_);   // warm-up
+    launch_match_u8(TA, TB, u8part_.p, ns, u8idx_.p, nullptr, st_);   // warm-up
     PB_CUDA(cudaStreamSynchronize(st_));
     timer_start();
-    for (int r = 0; r < reps; ++r)
-        launch_match_u8(u8a_.p, u8na_.p, nA, u8b_.p, u8nb_.p, nB, u8part_.p, ns, u8idx_.p, nullptr, st_);
+    for (int r = 0; r < reps; ++r) launch_match_u8(TA, TB, u8part_.p, ns, u8idx_.p, nullptr, st_);
     return timer_stop() / reps;
 }
 

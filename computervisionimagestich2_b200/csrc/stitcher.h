@@ -119,8 +119,9 @@ class Stitcher {
     PinBuf<int> h_midx_;
     DevBuf<MatchJob> mjobs_;
     DevBuf<u8> u8a_, u8b_, u8raw_;
-    DevBuf<int> u8na_, u8nb_, u8idx_, u8d01_;
-    DevBuf<U8Top2> u8part_;
+    DevBuf<int> u8na_, u8nb_, u8idx_, u8d01_, u8scratch_;
+    DevBuf<U8Top3> u8part_;
+    void u8_upload(const u8* A, int nA, const u8* B, int nB, U8Table& TA, U8Table& TB);
     DevBuf<float> u8f_;
     PinBuf<char> h_mjobs_;
     DevBuf<KeyPair> r_pairs_;

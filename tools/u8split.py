@@ -1,0 +1,11 @@
+import ctypes as C, json, os, sys
+sys.path.insert(0, '/root/repo')
+import numpy as np
+import computervisionimagestich2_b200 as pano
+L = pano.lib(); ctx = pano.Context(0)
+L.pano_b200_ktimer_reset(); L.pano_b200_ktimer_enable(1)
+ms = ctx.bench_match_u8(72000, 72000, 5)
+buf = C.create_string_buffer(1 << 16); L.pano_b200_ktimer_report(buf, 1 << 16)
+k = json.loads(buf.value.decode())
+print("total ms/rep", ms)
+for n, v in k.items(): print(n, v["ms"] / v["launches"], v["launches"])
