@@ -20,7 +20,8 @@
 //               mbarrier transaction bytes, 4 stages).  Tables live in HBM in the UMMA operand layout already (see
 //               match_i8_kernels.h), so a tile is (8 + 2 E) contiguous 2 KB runs and lands as the canonical K-major
 //               no-swizzle layout (8-row x 16-byte core matrices) without any address arithmetic.
-//   warp 1      one lane issues tcgen05.mma.cta_group::1.kind::i8 M128 x N128 x K32, (4 + E) per query block and tile;
+//   warp 1      one lane issues tcgen05.mma.cta_group::1.kind::i8 M128 x N128 x K32, (4 + E) per query block and tile
+//               (descriptors prebuilt, K loop unrolled: the single issuing thread must not be the bottleneck);
 //               two query blocks share every database tile; four 128-column accumulators (2 blocks x double buffer).
 //   warps 4-19  epilogue: thread = (query row = TMEM lane, 64 of the tile's 128 columns); tcgen05.ld.32x32b.x32, the
 //               accumulator is released as soon as it is in registers; per 32-row UNIT a 3-input max tree (half an
@@ -42,10 +43,13 @@ namespace {
 constexpr int kMQ = 128;       // queries per MMA (UMMA M)
 constexpr int kQB = 2;         // query blocks per CTA: every database tile in shared memory feeds kQB MMA groups
 constexpr int kND = 128;       // database rows per MMA (UMMA N)
+constexpr int kBuf = 512 / (kQB * kND);   // TMEM accumulator buffers per query block (all 512 columns in use)
 constexpr int kStages = 4;     // shared-memory stages of database tiles
 constexpr int kUnit = 32;      // database rows per epilogue unit (one tcgen05.ld)
-constexpr int kRun = kND * 16; // one chunk of one tile: 128 rows x 16 bytes, contiguous in HBM and in shared memory
+constexpr int kRun = kND * 16; // one chunk of one tile: kND rows x 16 bytes, contiguous in HBM and in shared memory
+constexpr int kQRun = kMQ * 16; // one chunk of one query block
 constexpr int kStageBytes = kU8Chunks * kRun;
+constexpr int kQBytes = kU8Chunks * kQRun;
 constexpr int kSbo = 128;      // distance between 8-row core-matrix groups inside a run
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -88,7 +92,7 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsi
     d |= 1ull << 46;   // descriptor version for sm_100
     return d;          // base_offset = 0, lbo_mode = 0, layout_type = 0 (no swizzle)
 }
-// instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = 128, M = 128
+// instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = kND, M = 128
 constexpr unsigned kIdesc = (2u << 4) | (0u << 7) | (0u << 10) | ((unsigned)(kND >> 3) << 17) | ((unsigned)(kMQ >> 4) << 24);
 
 __device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
@@ -120,13 +124,44 @@ __device__ __forceinline__ void top3_push(Top3& t, int v, int u) {
 }
 
 struct __align__(16) SmemLayout {
-    unsigned char q[kQB][kStageBytes];        // the CTA's queries (operand A): two blocks of 128 rows, incl. constants
+    unsigned char q[kQB][kQBytes];            // the CTA's queries (operand A): two blocks of 128 rows, incl. constants
     unsigned char db[kStages][kStageBytes];   // database tiles (operand B)
-    unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], qfull;
+    unsigned long long full[kStages], empty[kStages], tmem_full[kBuf], tmem_empty[kBuf], qfull;
     unsigned tmem_base;
     int mrg[kQB * kMQ][7];                    // hand-over of the second column half of every query row
 };
 
+}  // namespace
+
+namespace {
+// The issue loop of the MMA lane.  One thread issues every tcgen05.mma of the CTA, so its instruction count per tile
+// bounds the tensor-core rate: descriptors are built once (the K-step / stage offsets only touch the 14-bit start
+// address field, i.e. an add on the low word) and the K loop is unrolled at compile time.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_loop(SmemLayout& S, unsigned tmem, int ntiles) {
+    unsigned long long da[kQB][KSTEPS], db0[KSTEPS];
+#pragma unroll
+    for (int j = 0; j < KSTEPS; ++j) {
+#pragma unroll
+        for (int qb = 0; qb < kQB; ++qb) da[qb][j] = umma_desc(smem_u32(S.q[qb]) + j * 2 * kQRun, kQRun, kSbo);
+        db0[j] = umma_desc(smem_u32(S.db[0]) + j * 2 * kRun, kRun, kSbo);
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kStages, b = t % kBuf;
+        mbar_wait(&S.full[s], (unsigned)((t / kStages) & 1));
+        if (t >= kBuf) mbar_wait(&S.tmem_empty[b], (unsigned)(((t / kBuf) - 1) & 1));
+        tc_fence_after();
+        const unsigned long long soff = (unsigned long long)((s * kStageBytes) >> 4);   // stage offset in the address field
+#pragma unroll
+        for (int qb = 0; qb < kQB; ++qb) {
+            const unsigned d = tmem + (unsigned)((b * kQB + qb) * kND);
+#pragma unroll
+            for (int j = 0; j < KSTEPS; ++j) umma_i8(d, da[qb][j], db0[j] + soff, j > 0 ? 1u : 0u);
+        }
+        umma_commit(&S.empty[s]);        // the stage may be refilled once these MMAs have read it
+        umma_commit(&S.tmem_full[b]);    // the accumulators are complete
+    }
+}
 }  // namespace
 
 __global__ void __launch_bounds__(640, 1)
@@ -144,7 +179,7 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, int NA, const unsigned c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 16); }
+        for (int b = 0; b < kBuf; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 16); }
         mbar_init(&S.qfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -153,12 +188,12 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, int NA, const unsigned c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // the queries' extension columns are constants: 255 everywhere, 1 in the very last column
-    for (int i = threadIdx.x; i < kQB * 2 * ext_steps * kND; i += blockDim.x) {
-        const int qb = i / (2 * ext_steps * kND), rem = i - qb * (2 * ext_steps * kND);
-        const int c = rem / kND, r = rem - c * kND;
+    for (int i = threadIdx.x; i < kQB * 2 * ext_steps * kMQ; i += blockDim.x) {
+        const int qb = i / (2 * ext_steps * kMQ), rem = i - qb * (2 * ext_steps * kMQ);
+        const int c = rem / kMQ, r = rem - c * kMQ;
         uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (c == 2 * ext_steps - 1) v.w = 0x01ffffffu;
-        *reinterpret_cast<uint4*>(S.q[qb] + (8 + c) * kRun + r * 16) = v;
+        *reinterpret_cast<uint4*>(S.q[qb] + (8 + c) * kQRun + r * 16) = v;
     }
     fence_proxy_async();   // generic-proxy writes above -> visible to the async proxy the MMA reads through
     tc_fence_before();
@@ -170,54 +205,43 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, int NA, const unsigned c
         // ------------------------------------------------ producer ------------------------------------------------
         if (lane == 0) {
             // the CTA's 256 queries = one block of the table: query block qb = rows qb*128 .. +127 of it
-            mbar_expect_tx(&S.qfull, kQB * 8 * kRun);
+            mbar_expect_tx(&S.qfull, kQB * 8 * kQRun);
             const unsigned char* qsrc = Bblk + (size_t)(q0 / 256) * kU8BlockBytes;
 #pragma unroll
             for (int qb = 0; qb < kQB; ++qb)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) tma_bulk_load(S.q[qb] + c * kRun, qsrc + c * 4096 + qb * kRun, kRun, &S.qfull);
+                for (int c = 0; c < 8; ++c) tma_bulk_load(S.q[qb] + c * kQRun, qsrc + c * 4096 + qb * kQRun, kQRun, &S.qfull);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages;
                 if (t >= kStages) mbar_wait(&S.empty[s], (unsigned)(((t / kStages) - 1) & 1));
-                // tile t = rows a_begin + t*128 .. +127 = half (t & 1) of block (a_begin / 256 + t / 2)
+                // tile t = rows a_begin + t*kND .. : part (t % (256/kND)) of block (a_begin / 256 + t / (256/kND))
                 mbar_expect_tx(&S.full[s], nch * kRun);
-                const unsigned char* src = Ablk + (size_t)(a_begin / 256 + (t >> 1)) * kU8BlockBytes + (size_t)(t & 1) * kRun;
+                const unsigned char* src = Ablk + (size_t)(a_begin / 256 + t / (256 / kND)) * kU8BlockBytes + (size_t)(t % (256 / kND)) * kRun;
                 for (int c = 0; c < nch; ++c) tma_bulk_load(S.db[s] + c * kRun, src + c * 4096, kRun, &S.full[s]);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer ------------------------------------------------
         if (lane == 0) {
-            const unsigned qa = smem_u32(S.q[0]);
             mbar_wait(&S.qfull, 0);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kStages, b = t & 1;
-                mbar_wait(&S.full[s], (unsigned)((t / kStages) & 1));
-                if (t >= 2) mbar_wait(&S.tmem_empty[b], (unsigned)(((t >> 1) - 1) & 1));
-                tc_fence_after();
-                const unsigned ba = smem_u32(S.db[s]);
-#pragma unroll
-                for (int qb = 0; qb < kQB; ++qb)
-                    for (int j = 0; j < ksteps; ++j)   // K step j = chunks 2j, 2j+1 (4 descriptor steps + the extension)
-                        umma_i8(tmem + (unsigned)((b * kQB + qb) * kND),
-                                umma_desc(qa + qb * kStageBytes + j * 2 * kRun, kRun, kSbo),
-                                umma_desc(ba + j * 2 * kRun, kRun, kSbo), j > 0 ? 1u : 0u);
-                umma_commit(&S.empty[s]);        // the stage may be refilled once these MMAs have read it
-                umma_commit(&S.tmem_full[b]);    // the accumulators are complete
+            switch (ext_steps) {
+            case 1: mma_loop<5>(S, tmem, ntiles); break;
+            case 2: mma_loop<6>(S, tmem, ntiles); break;
+            default: mma_loop<7>(S, tmem, ntiles); break;
             }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------ epilogue ------------------------------------------------
         const int ew = warp & 3;                       // TMEM lane quarter this warp may read
-        const int part = ((warp - 4) >> 2) & 1;        // which 64-column half of the tile
+        const int part = ((warp - 4) >> 2) & 1;        // which half of the tile's columns (kND / 2 = 2 units)
         const int qb = (warp - 4) >> 3;                // which query block (accumulator) of the CTA
         const int qrow = qb * kMQ + ew * 32 + lane;    // query row within the CTA; TMEM lane = ew * 32 + lane
         Top3 T = top3_init();
         for (int t = 0; t < ntiles; ++t) {
-            const int b = t & 1;
-            mbar_wait(&S.tmem_full[b], (unsigned)((t >> 1) & 1));
+            const int b = t % kBuf;
+            mbar_wait(&S.tmem_full[b], (unsigned)((t / kBuf) & 1));
             tc_fence_after();
-            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)((b * kQB + qb) * kND + part * 64);
+            const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)((b * kQB + qb) * kND + part * (kND / 2));
             int va[32], vb[32];
 #define PB_LDTM(v, col)                                                                                                      \
     asm volatile(                                                                                                            \
@@ -246,7 +270,7 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, int NA, const unsigned c
             PB_UMAX(vb, ub);
 #undef PB_LDTM
 #undef PB_UMAX
-            const int unit0 = (a_begin + t * kND + part * 64) / kUnit;
+            const int unit0 = (a_begin + t * kND + part * (kND / 2)) / kUnit;
             top3_push(T, ua, unit0);
             top3_push(T, ub, unit0 + 1);
         }
