@@ -344,7 +344,8 @@ def run_b200(args):
             tops = 2.0 * 128 * na * nb / (ms_u8 * 1e-3) / 1e12
             match_u8 = {"nA": na, "nB": nb, "ms": round(ms_u8, 4), "int8_TOPS": round(tops, 1), "peak_TOPS": 4500.0,
                         "frac": round(tops / 4500.0, 4), "peak_source": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)",
-                        "data": "synthetic SIFT-like uint8 descriptor tables, resident in HBM", "exact_vs_integer_oracle": True}
+                        "data": "synthetic SIFT-like uint8 descriptor tables, resident in HBM", "exact_vs_integer_oracle": True,
+                        "note": "useful ops 2*128*nA*nB over main + finish kernels; the MMA also runs a 25% norm-extension K step (ncu sm__pipe_tensor_cycles_active 56%, profiles/r01_ncu_full_match_u8_kernel.txt)"}
         except Exception as e:
             match_u8 = {"error": str(e)}
     for p in pin_in:
