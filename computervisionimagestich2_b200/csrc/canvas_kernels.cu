@@ -396,26 +396,59 @@ void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, co
 // ---------------------------------------------------------------------------------------------------------
 // 2:1 reduce (moving average, x pass rounded to float then y pass) and linear expand
 // ---------------------------------------------------------------------------------------------------------
-__global__ void reduce_kernel(const float* __restrict__ src, int w, int h, float* __restrict__ dst, int nw, int nh,
-                              DevMovAvg tx, DevMovAvg ty) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    int p = blockIdx.z;
+// One thread = one output pixel of ALL planes: the moving-average taps (<= 3 x 3 for a 2:1 reduce; any count in
+// general) and their weights are fetched once and reused by every plane.
+__global__ void reduce_kernel(const float* __restrict__ src, int w, int h, int nplanes, float* __restrict__ dst, int nw,
+                              int nh, DevMovAvg tx, DevMovAvg ty) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= nw || y >= nh) return;
-    const float* s = src + (size_t)p * w * h;
-    float acc = 0.0f;
-    for (int j = ty.start[y]; j < ty.start[y + 1]; ++j) {
-        const float rowavg = movavg_sample(s + (size_t)ty.src[j] * w, 1, tx.start, tx.src, tx.wgt, x, tx.div);
-        acc += rowavg * ty.wgt[j];
+    const int xs0 = tx.start[x], xs1 = tx.start[x + 1], ys0 = ty.start[y], ys1 = ty.start[y + 1];
+    const size_t plane = (size_t)w * h, nplane = (size_t)nw * nh;
+    if (xs1 - xs0 <= 3 && ys1 - ys0 <= 3) {
+        int sx[3], sy[3];
+        float wx[3], wy[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const bool okx = xs0 + i < xs1, oky = ys0 + i < ys1;
+            sx[i] = okx ? tx.src[xs0 + i] : 0; wx[i] = okx ? tx.wgt[xs0 + i] : 0.0f;
+            sy[i] = oky ? ty.src[ys0 + i] : 0; wy[i] = oky ? ty.wgt[ys0 + i] : 0.0f;
+        }
+        const int nx = xs1 - xs0, ny = ys1 - ys0;
+        for (int p = 0; p < nplanes; ++p) {
+            const float* s = src + p * plane;
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (j < ny) {
+                    const float* row = s + (size_t)sy[j] * w;
+                    float r = 0.0f;   // movavg_sample along x: acc += in * wgt in tap order, then / n
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (i < nx) r += row[sx[i]] * wx[i];
+                    r = r / tx.div;
+                    acc += r * wy[j];
+                }
+            dst[p * nplane + (size_t)y * nw + x] = acc / ty.div;
+        }
+    } else {
+        for (int p = 0; p < nplanes; ++p) {
+            const float* s = src + p * plane;
+            float acc = 0.0f;
+            for (int j = ys0; j < ys1; ++j) {
+                const float rowavg = movavg_sample(s + (size_t)ty.src[j] * w, 1, tx.start, tx.src, tx.wgt, x, tx.div);
+                acc += rowavg * ty.wgt[j];
+            }
+            dst[p * nplane + (size_t)y * nw + x] = acc / ty.div;
+        }
     }
-    dst[((size_t)p * nh + y) * nw + x] = acc / ty.div;
 }
 void launch_reduce(const float* src, int w, int h, int nplanes, float* dst, int nw, int nh, DevMovAvg tx, DevMovAvg ty,
                    cudaStream_t st) {
     if (nw <= 0 || nh <= 0) return;
     KScope ks("blend.reduce", st, 4.0 * nplanes * ((double)w * h + (double)nw * nh));
-    dim3 b(64, 4), g(div_up(nw, 64), div_up(nh, 4), nplanes);
-    reduce_kernel<<<g, b, 0, st>>>(src, w, h, dst, nw, nh, tx, ty);
+    dim3 b(64, 4), g(div_up(nw, 64), div_up(nh, 4));
+    reduce_kernel<<<g, b, 0, st>>>(src, w, h, nplanes, dst, nw, nh, tx, ty);
     PB_KERNEL_CHECK();
 }
 
@@ -456,15 +489,35 @@ __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const
     if (x >= w || y >= h) return;
     const size_t n = (size_t)w * h, o = (size_t)y * w + x, un = (size_t)uw * uh;
     const float m = G[6 * n + o];
+    // the resampling position of this pixel is shared by the nine up-sampled planes
+    int px = 0, py = 0, px1 = 0;
+    double ax = 0, ay = 0;
+    bool has_y1 = false;
+    if (Gup) {
+        px = tx.pos[x]; py = ty.pos[y]; ax = tx.alpha[x]; ay = ty.alpha[y];
+        px1 = px < uw - 1 ? px + 1 : px;
+        has_y1 = py < uh - 1;
+    }
+    auto up = [&](const float* __restrict__ plane) {   // == upsample_at(plane, uw, uh, tx, ty, x, y)
+        const float* r0 = plane + (size_t)py * uw;
+        const float a0 = r0[px], a1 = r0[px1];
+        const float v0 = (float)((1 - ax) * (double)a0 + ax * (double)a1);
+        float v1 = v0;
+        if (has_y1) {
+            const float b0 = r0[uw + px], b1 = r0[uw + px1];
+            v1 = (float)((1 - ax) * (double)b0 + ax * (double)b1);
+        }
+        return (float)((1 - ay) * (double)v0 + ay * (double)v1);
+    };
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float la = G[c * n + o], lb = G[(3 + c) * n + o];
         float e;
         if (Gup) {
-            la = la - upsample_at(Gup + c * un, uw, uh, tx, ty, x, y);
-            lb = lb - upsample_at(Gup + (3 + c) * un, uw, uh, tx, ty, x, y);
+            la = la - up(Gup + c * un);
+            lb = lb - up(Gup + (3 + c) * un);
             const float bl = blend_px(la, lb, m);
-            e = collapse_px(bl, upsample_at(Eup + c * un, uw, uh, tx, ty, x, y));
+            e = collapse_px(bl, up(Eup + c * un));
         } else {
             e = blend_px(la, lb, m);
         }
