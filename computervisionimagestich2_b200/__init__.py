@@ -227,6 +227,19 @@ class Context:
         self._check(self.L.pano_b200_cimg_resize3(self.h, _p(p), w, h, c, nw, nh, _p(out)), "cimg_resize3")
         return out
 
+    def stitch_bmp_files(self, paths):
+        """ImageProcess(dir, n) on BMP files: decode / encode on the GPU -> bytes of the panorama BMP"""
+        blobs = [open(p, "rb").read() for p in paths]
+        n = len(blobs)
+        bufs = [C.create_string_buffer(b, len(b)) for b in blobs]
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        sizes = (C.c_size_t * n)(*[len(b) for b in blobs])
+        out, osz = C.c_void_p(), C.c_size_t()
+        self._check(self.L.pano_b200_stitch_bmp(self.h, ptrs, sizes, n, C.byref(out), C.byref(osz)), "stitch_bmp")
+        data = C.string_at(out, osz.value)
+        self.L.pano_b200_free(out)
+        return data
+
     # ---- sharded jobs (dist.py) -------------------------------------------------------------------------------------
     def extract(self, img):
         """readFile body for one image: -> (projected [3][H][W] u8, descr [n][128] f32, keys [n])"""

@@ -111,6 +111,15 @@ int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const
     return 0;
     PB_API_END
 }
+int pano_b200_stitch_bmp(pano_b200_ctx* ctx, const uint8_t* const* files, const size_t* sizes, int n, uint8_t** out_bmp,
+                         size_t* out_size) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    int rc = ctx->st->stitch_bmp(files, sizes, n, out_bmp, out_size);
+    if (rc) ctx->err = ctx->st->error();
+    return rc;
+    PB_API_END
+}
 int pano_b200_stage_images(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n) {
     PB_API_BEGIN
     ctx->st->stage_images(imgs, w, h, n);

@@ -55,6 +55,40 @@ void launch_gray(const u8* rgb, int w, int h, float* gray_f32, int gray_pitch, u
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// BMP pixel area <-> planar RGB (the container step either side of the path: CImg::_load_bmp 24-bpp branch,
+// CImg.h:48533-48546, and _save_bmp, :52614).  BMP rows are BGR, padded to 4 bytes, bottom-up unless height < 0.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bmp_to_planar_kernel(const u8* __restrict__ bmp, int stride, int w, int h, int bottom_up, u8* __restrict__ dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const u8* p = bmp + (size_t)(bottom_up ? h - 1 - y : y) * stride + 3 * x;
+    const size_t n = (size_t)w * h, o = (size_t)y * w + x;
+    dst[o] = p[2]; dst[n + o] = p[1]; dst[2 * n + o] = p[0];
+}
+__global__ void planar_to_bmp_kernel(const u8* __restrict__ src, int w, int h, int stride, u8* __restrict__ bmp) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;   // x == w .. covers the row padding
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= h) return;
+    u8* row = bmp + (size_t)(h - 1 - y) * stride;
+    const size_t n = (size_t)w * h, o = (size_t)y * w + x;
+    if (x < w) { row[3 * x] = src[2 * n + o]; row[3 * x + 1] = src[n + o]; row[3 * x + 2] = src[o]; }
+    else if (x == w) for (int k = 3 * w; k < stride; ++k) row[k] = 0;
+}
+void launch_bmp_to_planar(const u8* bmp, int stride, int w, int h, bool bottom_up, u8* dst, cudaStream_t st) {
+    KScope ks("io.bmp_decode", st, 6.0 * w * h);
+    dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
+    bmp_to_planar_kernel<<<g, b, 0, st>>>(bmp, stride, w, h, bottom_up ? 1 : 0, dst);
+    PB_KERNEL_CHECK();
+}
+void launch_planar_to_bmp(const u8* src, int w, int h, int stride, u8* bmp, cudaStream_t st) {
+    KScope ks("io.bmp_encode", st, 6.0 * w * h);
+    dim3 b(64, 4), g(div_up(w + 1, 64), div_up(h, 4));
+    planar_to_bmp_kernel<<<g, b, 0, st>>>(src, w, h, stride, bmp);
+    PB_KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // warp + shift
 // ---------------------------------------------------------------------------------------------------------
 __global__ void warp_shift_kernel(const u8* __restrict__ src, int sw, int sh, const double* __restrict__ H8g,

@@ -10,6 +10,9 @@ namespace pb {
 // gray_u8 (optional, [h][w]).  ktab: device copy of hostnum::cylinder_table (length min(w, h)).
 void launch_project_gray(const u8* src, int w, int h, const float* ktab, u8* dst_rgb, float* gray_f32, int gray_pitch,
                          u8* gray_u8, cudaStream_t st);
+// 24-bpp BMP pixel area (BGR rows padded to `stride`, bottom-up unless the header says otherwise) <-> planar RGB
+void launch_bmp_to_planar(const u8* bmp, int stride, int w, int h, bool bottom_up, u8* dst, cudaStream_t st);
+void launch_planar_to_bmp(const u8* src, int w, int h, int stride, u8* bmp, cudaStream_t st);
 void launch_gray(const u8* rgb, int w, int h, float* gray_f32, int gray_pitch, u8* gray_u8, cudaStream_t st);
 
 // a = warp(src image, H8, off) and b = shift(previous canvas, ioff) in one pass over the new canvas

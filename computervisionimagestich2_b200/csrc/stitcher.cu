@@ -813,6 +813,54 @@ int Stitcher::run_staged() {
     return run();
 }
 
+int Stitcher::stitch_bmp(const u8* const* files, const size_t* sizes, int n, u8** out, size_t* out_size) {
+    PB_CUDA(cudaSetDevice(dev_));
+    clear();
+    auto rd32 = [](const u8* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+    staged_.clear();
+    for (int i = 0; i < n; ++i) {
+        const u8* f = files[i];
+        if (sizes[i] < 54 || f[0] != 'B' || f[1] != 'M') { err_ = "not a BMP file"; return -7; }
+        const uint32_t off = rd32(f + 10), hdr = rd32(f + 14);
+        int w = (int)rd32(f + 18), h = (int)rd32(f + 22);
+        const int bpp = f[28] | (f[29] << 8);
+        const uint32_t comp = hdr >= 40 ? rd32(f + 30) : 0;
+        const bool bottom_up = h > 0;
+        if (h < 0) h = -h;
+        const size_t stride = ((size_t)3 * w + 3) & ~(size_t)3;
+        if (bpp != 24 || comp != 0 || w <= 0 || h <= 0 || sizes[i] < off + stride * h) {
+            err_ = "only uncompressed 24-bpp BMP files are on the stitching path";
+            return -7;
+        }
+        std::unique_ptr<Staged> s(new Staged());
+        s->w = w; s->h = h;
+        s->rgb.ensure((size_t)3 * w * h);
+        bmp_raw_.ensure(stride * h);
+        PB_CUDA(cudaMemcpyAsync(bmp_raw_.p, f + off, stride * h, cudaMemcpyHostToDevice, st_));
+        launch_bmp_to_planar(bmp_raw_.p, (int)stride, w, h, bottom_up, s->rgb.p, st_);
+        PB_CUDA(cudaStreamSynchronize(st_));   // bmp_raw_ is reused by the next file
+        staged_.push_back(std::move(s));
+    }
+    const int rc = run_staged();
+    if (rc) return rc;
+    const int w = rw_, h = rh_;
+    const size_t stride = ((size_t)3 * w + 3) & ~(size_t)3, total = 54 + stride * h;
+    bmp_out_.ensure(stride * h);
+    launch_planar_to_bmp(res_[cur_].p, w, h, (int)stride, bmp_out_.p, st_);
+    u8* o = (u8*)malloc(total);
+    if (!o) { err_ = "out of host memory"; return -8; }
+    memset(o, 0, 54);
+    auto wr32 = [](u8* p, uint32_t v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); };
+    o[0] = 'B'; o[1] = 'M';
+    wr32(o + 2, (uint32_t)total); wr32(o + 10, 54); wr32(o + 14, 40); wr32(o + 18, (uint32_t)w); wr32(o + 22, (uint32_t)h);
+    o[26] = 1; o[28] = 24; wr32(o + 34, (uint32_t)(stride * h)); wr32(o + 38, 2835); wr32(o + 42, 2835);
+    PB_CUDA(cudaMemcpyAsync(o + 54, bmp_out_.p, stride * h, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    *out = o;
+    *out_size = total;
+    return 0;
+}
+
 void Stitcher::flush_l2() {
     PB_CUDA(cudaSetDevice(dev_));
     const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2

@@ -75,6 +75,9 @@ class Stitcher {
     // on_device: imgs[i] are HBM pointers (staged inputs) instead of host buffers.
     void add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
     void set_lanes(int n) { want_lanes_ = n < 1 ? 1 : n; }
+    // ---- BMP files in / BMP file out: decode and encode run on the GPU ----------------------------
+    // files[i]: the bytes of an uncompressed 24-bpp BMP.  Returns 0 and the encoded panorama (malloc'ed), or < 0.
+    int stitch_bmp(const u8* const* files, const size_t* sizes, int n, u8** out, size_t* out_size);
     // ---- sharded jobs (features / matches computed on other GPUs) --------------------------------
     void extract(const u8* rgb, int w, int h, u8* proj_out, FeatureTable& t);    // one image -> host projection + table
     void add_precomputed(const u8* proj_rgb, int w, int h, const float* descr, const VlKey* keys, int n);
@@ -150,6 +153,7 @@ class Stitcher {
     int want_lanes_ = 4;
     struct Staged { int w, h; DevBuf<u8> rgb; };
     std::vector<std::unique_ptr<Staged>> staged_;
+    DevBuf<u8> bmp_raw_, bmp_out_;
     DevBuf<char> flush_;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::string log_, err_;

@@ -50,6 +50,13 @@ int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* 
 /* same, into a caller-provided (e.g. pinned) buffer of out_cap bytes */
 int pano_b200_stitch_into(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n,
                           uint8_t* out, size_t out_cap, int* out_w, int* out_h);
+/* BMP files in, BMP file out (the container step either side of the path: CImg<uchar>(file) at ImageProcess.cpp:16,
+ * CImg.h:48395-48546, and CImg::save): files[i] / sizes[i] = the bytes of <dir><i+1>.bmp (uncompressed 24-bpp); the
+ * BGR bottom-up padded rows are decoded to planar RGB, and the panorama encoded back, by GPU kernels.  *out_bmp is
+ * library-allocated (pano_b200_free). */
+int pano_b200_stitch_bmp(pano_b200_ctx* ctx, const uint8_t* const* files, const size_t* sizes, int n, uint8_t** out_bmp,
+                         size_t* out_size);
+
 /* ---- sharded jobs (one process per GPU; the exchange between ranks is the caller's, see
  *      computervisionimagestich2_b200/dist.py).  pano_b200_extract = the body of readFile for ONE image
  *      (ImageProcess.cpp:12-23): projected image (proj_out, w*h*3, may be NULL) + feature table, library-allocated.

@@ -166,3 +166,20 @@ def test_sharded_job_single_rank_equals_the_fused_pipeline(ctx, anchors):
     A = anchors["Input"]
     assert info["nfeat"][:0] == [] and info["log"] == A["log"]
     assert list(pano.shape) == A["pano_shape"] and sha(pano) == A["pano_sha256"]
+
+
+def test_bmp_files_in_bmp_file_out(ctx, anchors, tmp_path):
+    """pano_b200_stitch_bmp: GPU BMP decode -> pipeline -> GPU BMP encode; the encoded file decodes to the golden panorama"""
+    from computervisionimagestich2_b200 import bmpio
+    d = os.path.join(ROOT, "oracle", "_ref", "data", "Input")
+    if not os.path.isdir(d):
+        pytest.skip("bundled inputs not staged")
+    data = ctx.stitch_bmp_files([os.path.join(d, f"{i}.bmp") for i in range(1, 5)])
+    p = tmp_path / "pano.bmp"
+    p.write_bytes(data)
+    pano = bmpio.load_bmp(str(p))
+    assert list(pano.shape) == anchors["Input"]["pano_shape"] and sha(pano) == anchors["Input"]["pano_sha256"]
+    # and the encoder agrees byte for byte with the host encoder
+    q = tmp_path / "host.bmp"
+    bmpio.save_bmp(str(q), pano)
+    assert q.read_bytes() == data
