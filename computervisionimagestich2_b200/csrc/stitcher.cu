@@ -119,7 +119,20 @@ void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t) {
         }
         return false;
     };
-    std::stable_sort(idx.begin(), idx.end(), less);
+    // The first two components, packed order-preservingly into one integer, decide almost every comparison; the full
+    // lexicographic comparison only runs on ties of that prefix.  (Same strict weak order as `less`.)
+    std::vector<uint64_t> prefix(n);
+    auto ord = [](float f) {   // float -> uint32 with the same order (and -0 == +0)
+        f += 0.0f;
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    };
+    for (int i = 0; i < n; ++i) prefix[i] = ((uint64_t)ord(D[(size_t)i * 128]) << 32) | ord(D[(size_t)i * 128 + 1]);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        if (prefix[a] != prefix[b]) return prefix[a] < prefix[b];
+        return less(a, b);
+    });
     t.descr.clear();
     t.keys.clear();
     t.descr.reserve((size_t)n * 128);
