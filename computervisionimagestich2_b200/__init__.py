@@ -95,6 +95,14 @@ class Context:
         if rc != 0:
             raise PanoError(f"{what} failed ({rc}): {self.L.pano_b200_last_error(self.h).decode()}")
 
+    PROFILES = {"root": 0, "ex6": 1}
+
+    def set_profile(self, name: str = "root", ransac_seed: int = 666666):
+        """Which caller of the hot path is reproduced: "root" (ImageProcess.cpp) or "ex6" (src/ex6/ImageProcess.cpp);
+        ransac_seed = the srand() argument of ImageProcess::RANSAC (666666 in root, time(0) in ex6)."""
+        self._check(self.L.pano_b200_set_profile(self.h, self.PROFILES[name], C.c_uint(ransac_seed)), "set_profile")
+        self.profile = name
+
     # ---- stages ------------------------------------------------------------------------------------------------
     def project(self, img, want_gray=False):
         img = _u8(img)
@@ -178,7 +186,8 @@ class Context:
         H = np.ascontiguousarray(fwdH, np.float64)
         b = np.empty(4, np.float32)
         s = np.empty(2, np.int32)
-        self.L.pano_b200_plan_canvas(dw, dh, _p(H), rw, rh, _p(b), _p(s))
+        self.L.pano_b200_plan_canvas_ex(self.PROFILES[getattr(self, "profile", "root")], dw, dh, _p(H), rw, rh, _p(b),
+                                        _p(s))
         return b, s
 
     def warp_shift(self, src, H8, offx, offy, prev, ioffx, ioffy, cw, ch):
@@ -213,11 +222,13 @@ class Context:
         self._check(self.L.pano_b200_equalize_mix(self.h, _p(img), w, h, _p(out)), "equalize_mix")
         return out
 
-    def cimg_blur2(self, planes):
+    def cimg_blur2(self, planes, deriche=False):
+        """get_blur(2, true, true) (Van Vliet; root variant) or get_blur(2) (Deriche; src/ex6)."""
         p = np.ascontiguousarray(planes, np.float32)
         c, h, w = p.shape
         out = np.empty_like(p)
-        self._check(self.L.pano_b200_cimg_blur2(self.h, _p(p), w, h, c, _p(out)), "cimg_blur2")
+        fn = self.L.pano_b200_cimg_blur2_deriche if deriche else self.L.pano_b200_cimg_blur2
+        self._check(fn(self.h, _p(p), w, h, c, _p(out)), "cimg_blur2")
         return out
 
     def cimg_resize3(self, planes, nw, nh):

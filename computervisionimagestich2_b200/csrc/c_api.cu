@@ -163,6 +163,19 @@ void* pano_b200_alloc_pinned(size_t bytes) {
     return p;
 }
 void pano_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+int pano_b200_set_profile(pano_b200_ctx* ctx, int variant, unsigned ransac_seed) {
+    PB_API_BEGIN
+    if (variant != PANO_B200_PROFILE_ROOT && variant != PANO_B200_PROFILE_EX6) {
+        ctx->err = "unknown profile";
+        return -1;
+    }
+    pb::stitch::Profile p;
+    p.variant = variant;
+    p.ransac_seed = ransac_seed;
+    ctx->st->set_profile(p);
+    return 0;
+    PB_API_END
+}
 int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes) {
     PB_API_BEGIN
     ctx->st->set_lanes(nlanes);
@@ -367,6 +380,15 @@ int pano_b200_plan_canvas(int dst_w, int dst_h, const double* forward_H8, int re
     return 0;
 }
 
+int pano_b200_plan_canvas_ex(int variant, int dst_w, int dst_h, const double* forward_H8, int result_w, int result_h,
+                             float* bounds, int* size) {
+    stitch::CanvasPlan p =
+        stitch::plan_canvas(dst_w, dst_h, forward_H8, result_w, result_h, variant == PANO_B200_PROFILE_EX6);
+    bounds[0] = p.min_x; bounds[1] = p.min_y; bounds[2] = p.max_x; bounds[3] = p.max_y;
+    size[0] = p.new_w; size[1] = p.new_h;
+    return 0;
+}
+
 int pano_b200_warp_shift(pano_b200_ctx* ctx, const uint8_t* src, int sw, int sh, const double* H8, float offx,
                          float offy, const uint8_t* prev, int pw, int ph, int ioffx, int ioffy, int cw, int ch,
                          uint8_t* a, uint8_t* b) {
@@ -392,6 +414,12 @@ int pano_b200_equalize_mix(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h,
 int pano_b200_cimg_blur2(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst) {
     PB_API_BEGIN
     ctx->st->cimg_blur2(src, w, h, c, dst);
+    return 0;
+    PB_API_END
+}
+int pano_b200_cimg_blur2_deriche(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst) {
+    PB_API_BEGIN
+    ctx->st->cimg_blur2_deriche(src, w, h, c, dst);
     return 0;
     PB_API_END
 }

@@ -143,6 +143,44 @@ PB_HD void iir_line(float* data, int N, long off, const IirCoef& c) {
     }
 }
 
+// --- CImg deriche order 0 with Neumann boundary on one line (CImg.h:34777-34808), src -> dst -----------------------
+// The filter the src/ex6 variant's pyramid uses: get_blur(2) has is_gaussian = false (CImg.h:35139-35142,
+// src/ex6/ImageProcess.cpp:702-705).  All float; every product is rounded before it is added (no contraction):
+//   causal      Y[m]  = ((a0 x[m] + a1 x[m-1]) - b1 Y[m-1]) - b2 Y[m-2]
+//   anticausal  yc[n] = ((a2 x[n+1] + a3 x[n+2]) - b1 yc[n+1]) - b2 yc[n+2];   out[n] = Y[n] + yc[n]
+struct DericheCoef {
+    float a0, a1, a2, a3, b1, b2, coefp, coefn;
+};
+struct DericheFwd {   // causal state
+    float xp, yp, yb;
+    PB_HD void init(float x0, const DericheCoef& c) { xp = x0; yb = yp = c.coefp * xp; }
+    PB_HD float step(float xc, const DericheCoef& c) {
+        const float yc = c.a0 * xc + c.a1 * xp - c.b1 * yp - c.b2 * yb;
+        xp = xc; yb = yp; yp = yc;
+        return yc;
+    }
+};
+struct DericheBwd {   // anticausal state
+    float xn, xa, yn, ya;
+    PB_HD void init(float xlast, const DericheCoef& c) { xn = xa = xlast; yn = ya = c.coefn * xn; }
+    PB_HD float step(float xc, const DericheCoef& c) {
+        const float yc = c.a2 * xn + c.a3 * xa - c.b1 * yn - c.b2 * ya;
+        xa = xn; xn = xc; ya = yn; yn = yc;
+        return yc;
+    }
+};
+PB_HD void deriche_line(const float* src, float* dst, int N, long off, const DericheCoef& c) {
+    DericheFwd f;
+    f.init(src[0], c);
+    for (int m = 0; m < N; ++m) dst[(long)m * off] = f.step(src[(long)m * off], c);
+    DericheBwd b;
+    b.init(src[(long)(N - 1) * off], c);
+    for (int n = N - 1; n >= 0; --n) {
+        const float yc = b.step(src[(long)n * off], c);
+        dst[(long)n * off] = dst[(long)n * off] + yc;
+    }
+}
+
 // --- CImg moving-average resize along one axis (CImg.h:29543-29555): out = (sum_i in[src_i] * wgt_i) / n --------
 PB_HD float movavg_sample(const float* __restrict__ line, long stride, const int* __restrict__ start,
                           const int* __restrict__ src, const float* __restrict__ wgt, int t, float n_as_float) {
@@ -185,7 +223,10 @@ PB_HD void ycbcr_to_rgb_u8(float Y, float Cb, float Cr, u8* r, u8* g, u8* b) {
     *r = (u8)clamp256(R); *g = (u8)clamp256(G); *b = (u8)clamp256(B);
 }
 // One pixel of the whole tail: rgb (blended panorama) -> final rgb, given the equalisation LUT of the Y channel.
-PB_HD void equalize_mix_px(u8 r, u8 g, u8 b, const int* __restrict__ lut, u8* orr, u8* og, u8* ob) {
+// The luminance mix is Y * num / den + Y_eq / den: 19/20 in the root variant (ImageProcess.cpp:261), 5/6 in src/ex6
+// (src/ex6/ImageProcess.cpp:270).
+PB_HD void equalize_mix_px(u8 r, u8 g, u8 b, const int* __restrict__ lut, u8* orr, u8* og, u8* ob, double num = 19.0,
+                           double den = 20.0) {
     float Y, Cb, Cr;
     rgb_to_ycbcr_f(r, g, b, &Y, &Cb, &Cr);
     // equalization.cpp: the YCbCr image is stored as unsigned char (truncation), Y is mapped, then back to RGB
@@ -195,7 +236,7 @@ PB_HD void equalize_mix_px(u8 r, u8 g, u8 b, const int* __restrict__ lut, u8* or
     ycbcr_to_rgb_u8((float)yeq, (float)cb8, (float)cr8, &tr, &tg, &tb);
     float Yt, Cbt, Crt;
     rgb_to_ycbcr_f(tr, tg, tb, &Yt, &Cbt, &Crt);
-    float Ym = (float)((double)Y * 19.0 / 20.0 + (double)Yt / 20.0);
+    float Ym = (float)((double)Y * num / den + (double)Yt / den);
     ycbcr_to_rgb_u8(Ym, Cb, Cr, orr, og, ob);
 }
 PB_HD u8 luma_bin(u8 r, u8 g, u8 b) {

@@ -2,6 +2,7 @@
 // + canvas shift, multiband blend (recursive Gaussian, reduce, expand/blend/collapse) and the equalisation tail.
 // All of them are HBM-bound byte/float streaming; arithmetic is in canvas_device.cuh (bit-exact bodies).
 #include "canvas_kernels.h"
+#include <type_traits>
 #include "common.h"
 #include "ktimer.h"
 
@@ -129,6 +130,9 @@ void launch_warp_shift(const u8* src, int sw, int sh, const double* H8, float of
 // ---------------------------------------------------------------------------------------------------------
 // seam statistics + level 0 planes
 // ---------------------------------------------------------------------------------------------------------
+// kAllChannels: the src/ex6 variant counts a pixel when ALL THREE channels are non-zero
+// (src/ex6/ImageProcess.cpp:651-660); the root variant tests channel 0 only (ImageProcess.cpp:661-671, quirk Q4).
+template <bool kAllChannels>
 __global__ void seam_stats_kernel(const u8* __restrict__ a, const u8* __restrict__ b, int cw, int ch,
                                   int* __restrict__ stats) {
     __shared__ unsigned s[4];
@@ -136,22 +140,33 @@ __global__ void seam_stats_kernel(const u8* __restrict__ a, const u8* __restrict
     __syncthreads();
     const int mid_y = ch / 2;
     unsigned sa = 0, na = 0, so = 0, no = 0;
+    const size_t n = (size_t)cw * ch;
     for (int x = threadIdx.x; x < cw; x += blockDim.x) {
-        if (a[(size_t)mid_y * cw + x] != 0) {
+        const size_t o = (size_t)mid_y * cw + x;
+        bool ina = a[o] != 0, inb = b[o] != 0;
+        if (kAllChannels) {
+            ina = ina && a[n + o] != 0 && a[2 * n + o] != 0;
+            inb = inb && b[n + o] != 0 && b[2 * n + o] != 0;
+        }
+        if (ina) {
             sa += (unsigned)x; ++na;
-            if (b[(size_t)mid_y * cw + x] != 0) { so += (unsigned)x; ++no; }
+            if (inb) { so += (unsigned)x; ++no; }
         }
     }
     atomicAdd(&s[0], sa); atomicAdd(&s[1], na); atomicAdd(&s[2], so); atomicAdd(&s[3], no);
     __syncthreads();
     if (threadIdx.x < 4) stats[threadIdx.x] = (int)s[threadIdx.x];
 }
-void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, cudaStream_t st) {
-    KScope ks("blend.seam_stats", st, 2.0 * cw);
-    seam_stats_kernel<<<1, 1024, 0, st>>>(a, b, cw, ch, stats);
+void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, bool all_channels, cudaStream_t st) {
+    KScope ks("blend.seam_stats", st, (all_channels ? 6.0 : 2.0) * cw);
+    if (all_channels) seam_stats_kernel<true><<<1, 1024, 0, st>>>(a, b, cw, ch, stats);
+    else seam_stats_kernel<false><<<1, 1024, 0, st>>>(a, b, cw, ch, stats);
     PB_KERNEL_CHECK();
 }
 
+// kDoubleSeam: the src/ex6 variant keeps the seam position in double (src/ex6/ImageProcess.cpp:678-697); the root
+// variant narrows both ratios to float first (ImageProcess.cpp:684-698).
+template <bool kDoubleSeam>
 __global__ void level0_kernel(const u8* __restrict__ a, const u8* __restrict__ b, int cw, int ch,
                               const int* __restrict__ stats, float* __restrict__ G0, int* __restrict__ err_flag) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,11 +177,18 @@ __global__ void level0_kernel(const u8* __restrict__ a, const u8* __restrict__ b
         return;
     }
     if (x >= cw || y >= ch) return;
-    const float ratio = (float)(1.0 * (double)sum_a_x / (double)width_mid_a);
-    const float overlap_ratio = (float)(1.0 * (double)sum_overlap_x / (double)width_mid_overlap);
     float m;
-    if (ratio < overlap_ratio) m = ((float)x < overlap_ratio) ? 1.0f : 0.0f;
-    else m = (x >= (int)(overlap_ratio + 1)) ? 1.0f : 0.0f;
+    if (kDoubleSeam) {   // sums are exact in double (the reference accumulates them in double)
+        const double ratio = (double)(unsigned)sum_a_x / (double)width_mid_a;
+        const double overlap_ratio = (double)(unsigned)sum_overlap_x / (double)width_mid_overlap;
+        if (ratio < overlap_ratio) m = ((double)x < overlap_ratio) ? 1.0f : 0.0f;
+        else m = (x >= (int)(overlap_ratio + 1)) ? 1.0f : 0.0f;
+    } else {
+        const float ratio = (float)(1.0 * (double)sum_a_x / (double)width_mid_a);
+        const float overlap_ratio = (float)(1.0 * (double)sum_overlap_x / (double)width_mid_overlap);
+        if (ratio < overlap_ratio) m = ((float)x < overlap_ratio) ? 1.0f : 0.0f;
+        else m = (x >= (int)(overlap_ratio + 1)) ? 1.0f : 0.0f;
+    }
     const size_t n = (size_t)cw * ch, o = (size_t)y * cw + x;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -176,10 +198,11 @@ __global__ void level0_kernel(const u8* __restrict__ a, const u8* __restrict__ b
     G0[6 * n + o] = m;
 }
 void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
-                   cudaStream_t st) {
+                   bool double_seam, cudaStream_t st) {
     KScope ks("blend.level0", st, 34.0 * cw * ch);
     dim3 bl(128, 2), g(div_up(cw, 128), div_up(ch, 2));
-    level0_kernel<<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+    if (double_seam) level0_kernel<true><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+    else level0_kernel<false><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
     PB_KERNEL_CHECK();
 }
 
@@ -265,10 +288,16 @@ __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, dou
 // spread over all four sub-partitions (with fixed roles every consumer lands on sub-partition 0 and they serialise
 // on its FP64 pipe: measured 62 -> 153 cycles per sample going from 1 to 8 CTAs per SM).  The fourth warp exits.
 // Barriers per stage: full (loader -> consumer), done (consumer -> storer), vacant (storer -> loader).
-template <bool kElemContig>
+//
+// Coef selects the recurrence: IirCoef = Van Vliet (fp64 state; the backward run filters the forward output in place,
+// so pass 1 streams `dst` back in); DericheCoef = Deriche (fp32 state; causal and anticausal runs both filter the
+// INPUT, so pass 1 streams `src` again and the storer adds the anticausal tile onto the causal output already in
+// `dst`: out = Y + yc, CImg.h:34797 -- src and dst must be distinct buffers).
+template <bool kElemContig, class Coef>
 __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
                                                       long nlines, int lines_per_plane, long plane_stride,
-                                                      long elem_stride, IirCoef c) {
+                                                      long elem_stride, Coef c) {
+    constexpr bool kDeriche = std::is_same<Coef, DericheCoef>::value;
     __shared__ float tiles[kIirNS][32 * kIirPitch];
     __shared__ unsigned long long full[kIirNS], done[kIirNS], vacant[kIirNS];
     const int lane = threadIdx.x & 31;
@@ -284,6 +313,38 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
     // of a stage (k = q / NS) completes phase k of each of its barriers.
     if (warp == 0) {
         // ------------------------------------------ consumer ------------------------------------------
+        if constexpr (kDeriche) {
+            DericheFwd f{};
+            DericheBwd b{};
+            for (int q = 0; q < 2 * T; ++q) {
+                const int s = q % kIirNS;
+                mbar_wait(&full[s], (unsigned)((q / kIirNS) & 1));
+                float* t = &tiles[s][lane];
+                const bool fwd = q < T;
+                const int tile = fwd ? q : 2 * T - 1 - q;
+                const int ne = (N - tile * 32) < 32 ? (N - tile * 32) : 32;
+                if (fwd) {
+                    if (q == 0) f.init(t[0], c);
+                    if (ne == 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) t[e * kIirPitch] = f.step(t[e * kIirPitch], c);
+                    } else {
+                        for (int e = 0; e < ne; ++e) t[e * kIirPitch] = f.step(t[e * kIirPitch], c);
+                    }
+                } else {
+                    if (q == T) b.init(t[(ne - 1) * kIirPitch], c);
+                    if (ne == 32) {
+#pragma unroll
+                        for (int e = 31; e >= 0; --e) t[e * kIirPitch] = b.step(t[e * kIirPitch], c);
+                    } else {
+                        for (int e = ne - 1; e >= 0; --e) t[e * kIirPitch] = b.step(t[e * kIirPitch], c);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&done[s]);
+            }
+            return;
+        } else {
         double v1 = 0, v2 = 0, v3 = 0, iplus = 0;
         for (int q = 0; q < 2 * T; ++q) {
             const int s = q % kIirNS;
@@ -333,6 +394,7 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
             if (lane == 0) mbar_arrive(&done[s]);
         }
         return;
+        }
     }
     // ------------------------------------------ loader / storer ------------------------------------------
     // x pass: lane = element, loop over the CTA's lines; y pass: lane = line, loop over the tile's elements
@@ -353,8 +415,8 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
     const long g_step = kElemContig ? (long)N : elem_stride;   // HBM stride between those elements
     if (warp == 1) {
         for (int pass = 0; pass < 2; ++pass) {
-            const float* from = pass == 0 ? src : dst;
-            if (pass == 1)   // the backward run reads the forward output: every forward tile must have reached HBM
+            const float* from = (pass == 0 || kDeriche) ? src : dst;
+            if (pass == 1 && !kDeriche)   // the backward run reads the forward output: every forward tile must have reached HBM
                 for (int j = (T - kIirNS > 0 ? T - kIirNS : 0); j < T; ++j)
                     mbar_wait_relaxed(&vacant[j % kIirNS], (unsigned)((j / kIirNS) & 1));
             for (int i = 0; i < T; ++i) {
@@ -391,14 +453,24 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
                 if (kElemContig) {
                     if (e0 + lane < N) {
                         float* g = dst + mybase + e0;
+                        if (kDeriche && pass == 1) {   // out = Y + yc; this thread wrote Y[g] itself in pass 0
 #pragma unroll 8
-                        for (int r = 0; r < nl; ++r) { *g = *sp; sp += s_step; g += g_step; }
+                            for (int r = 0; r < nl; ++r) { *g = *g + *sp; sp += s_step; g += g_step; }
+                        } else {
+#pragma unroll 8
+                            for (int r = 0; r < nl; ++r) { *g = *sp; sp += s_step; g += g_step; }
+                        }
                     }
                 } else if (line_ok) {
                     const int ne = (N - e0) < 32 ? (N - e0) : 32;
                     float* g = dst + mybase + (long)e0 * elem_stride;
+                    if (kDeriche && pass == 1) {
 #pragma unroll 8
-                    for (int e = 0; e < ne; ++e) { *g = *sp; sp += s_step; g += g_step; }
+                        for (int e = 0; e < ne; ++e) { *g = *g + *sp; sp += s_step; g += g_step; }
+                    } else {
+#pragma unroll 8
+                        for (int e = 0; e < ne; ++e) { *g = *sp; sp += s_step; g += g_step; }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&vacant[s]);   // release: the loader (same CTA) re-reads forward tiles after acquiring this
@@ -412,14 +484,37 @@ void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, co
     if (w > 1) {
         const long nlines = (long)nplanes * h;
         KScope ks("blend.iir", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<true><<<div_up(nlines, 32), 128, 0, st>>>(src, dst, w, nlines, h, plane, 1L, coef);
+        iir_pipe_kernel<true, IirCoef><<<div_up(nlines, 32), 128, 0, st>>>(src, dst, w, nlines, h, plane, 1L, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
     if (h > 1) {
         const long nlines = (long)nplanes * w;
         KScope ks("blend.iir", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<false><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
+        iir_pipe_kernel<false, IirCoef><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
+        PB_KERNEL_CHECK();
+        ysrc = dst;
+    }
+    if (ysrc != dst)
+        PB_CUDA(cudaMemcpyAsync(dst, src, (size_t)nplanes * w * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+void launch_deriche_blur(const float* src, float* tmp, float* dst, int w, int h, int nplanes, const DericheCoef& coef,
+                         cudaStream_t st) {
+    const long plane = (long)w * h;
+    const float* ysrc = src;
+    if (w > 1) {
+        const long nlines = (long)nplanes * h;
+        float* xdst = h > 1 ? tmp : dst;
+        KScope ks("blend.deriche", st, 16.0 * nplanes * w * h);
+        iir_pipe_kernel<true, DericheCoef><<<div_up(nlines, 32), 128, 0, st>>>(src, xdst, w, nlines, h, plane, 1L, coef);
+        PB_KERNEL_CHECK();
+        ysrc = xdst;
+    }
+    if (h > 1) {
+        const long nlines = (long)nplanes * w;
+        KScope ks("blend.deriche", st, 16.0 * nplanes * w * h);
+        iir_pipe_kernel<false, DericheCoef><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
@@ -591,22 +686,23 @@ void launch_luma_hist(const u8* rgb, int w, int h, int* hist256, cudaStream_t st
 }
 
 __global__ void equalize_mix_kernel(const u8* __restrict__ rgb, size_t n, const int* __restrict__ lut,
-                                    u8* __restrict__ out) {
+                                    u8* __restrict__ out, double num, double den) {
     __shared__ int sl[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sl[i] = lut[i];
     __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         u8 r, g, b;
-        equalize_mix_px(rgb[i], rgb[n + i], rgb[2 * n + i], sl, &r, &g, &b);
+        equalize_mix_px(rgb[i], rgb[n + i], rgb[2 * n + i], sl, &r, &g, &b, num, den);
         out[i] = r; out[n + i] = g; out[2 * n + i] = b;
     }
 }
-void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, cudaStream_t st) {
+void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, double num, double den,
+                         cudaStream_t st) {
     size_t n = (size_t)w * h;
     KScope ks("tail.equalize_mix", st, 6.0 * n);
     int blocks = div_up((long)n, 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    equalize_mix_kernel<<<blocks, 256, 0, st>>>(rgb, n, lut256, out);
+    equalize_mix_kernel<<<blocks, 256, 0, st>>>(rgb, n, lut256, out, num, den);
     PB_KERNEL_CHECK();
 }
 

@@ -22,15 +22,21 @@ void launch_warp_shift(const u8* src, int sw, int sh, const double* H8, float of
 
 // Seam statistics of the middle row (ImageProcess.cpp:659-671): stats[4] = {sum_a_x, width_mid_a, sum_overlap_x,
 // width_mid_overlap} (int32 wrap-around like the reference's int sums).
-void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, cudaStream_t st);
+// all_channels: count a pixel only when all three channels are non-zero (src/ex6/ImageProcess.cpp:651-660).
+void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, bool all_channels, cudaStream_t st);
 // Level-0 float planes: G0[0..2] = a, G0[3..5] = b, G0[6] = seam mask (ImageProcess.cpp:678-698). err_flag set to 1
 // when the middle row is empty (the reference would loop forever / divide by zero).
+// double_seam: seam position kept in double (src/ex6/ImageProcess.cpp:678-697) instead of float.
 void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
-                   cudaStream_t st);
+                   bool double_seam, cudaStream_t st);
 
 // CImg get_blur(2, true, true) on `nplanes` planes [nplanes][h][w]: dst = blur(src) (x pass src->dst, y pass in place
 // on dst; src may equal dst).
 void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st);
+// CImg get_blur(2) (is_gaussian = false: Deriche order 0, CImg.h:34777-34869, 35111-35147; the src/ex6 pyramid):
+// dst = blur(src), tmp = scratch of the same size; the three buffers must be distinct.
+void launch_deriche_blur(const float* src, float* tmp, float* dst, int w, int h, int nplanes, const DericheCoef& coef,
+                         cudaStream_t st);
 
 // Moving-average 2:1 reduce (CImg resize type 2 via type 3): src [n][h][w] -> dst [n][nh][nw]; tables on device.
 struct DevMovAvg { const int* start; const int* src; const float* wgt; float div; };  // div = source length (1 for identity)
@@ -50,6 +56,8 @@ void launch_collapse(const float* G_i, int w, int h, const float* G_up, const fl
 
 // Equalisation tail (equalization.cpp:74-131 + ImageProcess.cpp:237-268)
 void launch_luma_hist(const u8* rgb, int w, int h, int* hist256, cudaStream_t st);
-void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, cudaStream_t st);
+// luminance mix Y * num / den + Y_eq / den (19/20: ImageProcess.cpp:261; 5/6: src/ex6/ImageProcess.cpp:270)
+void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, double num, double den,
+                         cudaStream_t st);
 
 }  // namespace pb

@@ -288,6 +288,30 @@ inline VanVliet vanvliet_coeffs(float sigma) {
     return v;
 }
 
+// ---- CImg Deriche recursive filter, order 0 (CImg.h:34809-34823, 34843-34844) --------------------------------------
+// All float, written in the reference's expression order; std::exp on a float is expf, evaluated at run time by the
+// same libm as the reference (the volatile keeps the compiler from folding it with a differently rounded constant).
+struct Deriche {
+    float a0, a1, a2, a3, b1, b2, coefp, coefn;
+};
+inline Deriche deriche_coeffs(float sigma) {
+    volatile float vs = sigma;
+    const float nsigma = vs;
+    const float nnsigma = nsigma < 0.1f ? 0.1f : nsigma, alpha = 1.695f / nnsigma, ema = (float)std::exp(-alpha),
+                ema2 = (float)std::exp(-2 * alpha), b1 = -2 * ema, b2 = ema2;
+    const float k = (1 - ema) * (1 - ema) / (1 + 2 * alpha * ema - ema2);
+    Deriche d;
+    d.a0 = k;
+    d.a1 = k * (alpha - 1) * ema;
+    d.a2 = k * (alpha + 1) * ema;
+    d.a3 = -k * ema2;
+    d.b1 = b1;
+    d.b2 = b2;
+    d.coefp = (d.a0 + d.a1) / (1 + b1 + b2);
+    d.coefn = (d.a2 + d.a3) / (1 + b1 + b2);
+    return d;
+}
+
 // ---- CImg resize tables ------------------------------------------------------------------------------------------
 // moving average n -> m (m < n), CImg.h:29543-29555: out[t] = (sum_i in[src_i] * wgt_i) / n, terms in this order.
 struct MovAvgTable {

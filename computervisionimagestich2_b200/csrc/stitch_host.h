@@ -3,6 +3,8 @@
 // keypoint re-mapping.  Mirrors ImageProcess.cpp:353-436, 500-594, 622-640 of the reference.
 #pragma once
 #include <cstdlib>
+#include <cstdint>
+#include <cstring>
 #include <cmath>
 #include <vector>
 #include <set>
@@ -13,16 +15,40 @@
 namespace pb {
 namespace stitch {
 
+// Which caller of the hot path is reproduced.  kRoot = the reference's root ImageProcess.cpp; kEx6 = its second
+// caller src/ex6/ImageProcess.cpp (same kernels, different control flow and constants):
+//                         kRoot                                   kEx6
+//   stitch order          all-pairs adjacency + middle image      fixed chain 0-1-...-n-1 from image n/2 (:147-160)
+//   RANSAC seed           srand(666666)                           srand(time(0)) -> the caller passes the seed
+//   canvas bounds         min / max over the 4 warped corners     min over 2, max_x over 3 corners (:230-243, 545-580)
+//   seam statistics       channel 0 != 0, float ratios            all 3 channels != 0, double ratios (:651-697)
+//   pyramid levels        floor(log2(max(w, h)))                  floor(log2(min(w, h))) (:662-665)
+//   pyramid blur          get_blur(2,true,true) = Van Vliet       get_blur(2) = Deriche (:702-705)
+//   final luminance mix   19/20 : 1/20                            5/6 : 1/6 (:270)
+struct Profile {
+    enum Variant { kRoot = 0, kEx6 = 1 };
+    int variant = kRoot;
+    unsigned ransac_seed = 666666u;
+    bool ex6() const { return variant == kEx6; }
+};
+
 // ImageProcess.cpp:398: k = ceil(log(1 - 0.99) / log(1 - 0.5^4)) = 72
 inline int ransac_iterations() { return (int)std::ceil(std::log(1 - 0.99) / std::log(1 - std::pow(0.5, 4))); }
 
 // ImageProcess.cpp:397, 409-418: srand(666666), then per iteration 4 distinct rand() % n by rejection.
-// glibc rand() is part of the contract (same libc on the reference side).  idx: [iters][4] in draw order.
-inline bool draw_samples(int npairs, std::vector<int>& idx) {
+// glibc rand() is part of the contract (same libc on the reference side): srand / rand are srandom_r / random_r on a
+// 128-byte (TYPE_3) state, reproduced here on a private state so that concurrent contexts do not share libc's
+// global generator.  idx: [iters][4] in draw order.
+inline bool draw_samples(int npairs, std::vector<int>& idx, unsigned seed = 666666u) {
     if (npairs < 4) return false;  // the reference loops forever (quirk Q8)
     const int iters = ransac_iterations();
     idx.resize((size_t)iters * 4);
-    srand(666666);
+    struct random_data rd;
+    char statebuf[128];
+    std::memset(&rd, 0, sizeof rd);
+    std::memset(statebuf, 0, sizeof statebuf);
+    initstate_r(seed, statebuf, sizeof statebuf, &rd);
+    auto rand = [&rd]() { int32_t r; random_r(&rd, &r); return (int)r; };
     for (int k = 0; k < iters; ++k) {
         std::set<int> chosen;
         for (int i = 0; i < 4; ++i) {
@@ -73,9 +99,10 @@ inline bool refit(const KeyPair* pairs, const std::vector<int>& inl, double* H8)
 }
 
 // Whole RANSAC on the host (test emulator only; the product scores hypotheses on the GPU).
-inline bool ransac_host(const KeyPair* pairs, int n, double* H8, std::vector<int>* inliers_out = nullptr) {
+inline bool ransac_host(const KeyPair* pairs, int n, double* H8, std::vector<int>* inliers_out = nullptr,
+                        unsigned seed = 666666u) {
     std::vector<int> idx;
-    if (!draw_samples(n, idx)) return false;
+    if (!draw_samples(n, idx, seed)) return false;
     const int iters = ransac_iterations();
     std::vector<int> best;
     for (int k = 0; k < iters; ++k) {
@@ -126,15 +153,19 @@ struct CanvasPlan {
     float min_x, min_y, max_x, max_y;
     int new_w, new_h;
 };
-inline CanvasPlan plan_canvas(int dw, int dh, const double* fwd, int res_w, int res_h) {
+// ex6: src/ex6/ImageProcess.cpp:230-243, 545-580 look at fewer corners -- min_x over (0,h-1),(0,0); min_y over
+// (w-1,0),(0,0); max_x over (0,0),(w-1,0),(w-1,h-1); max_y over all four.
+inline CanvasPlan plan_canvas(int dw, int dh, const double* fwd, int res_w, int res_h, bool ex6 = false) {
     const float cx[4] = {0.f, (float)(dw - 1), 0.f, (float)(dw - 1)};
     const float cy[4] = {0.f, 0.f, (float)(dh - 1), (float)(dh - 1)};
+    const bool in_minx[4] = {true, !ex6, true, !ex6}, in_miny[4] = {true, true, !ex6, !ex6};
+    const bool in_maxx[4] = {true, true, !ex6, true};
     float minx = warp_x(fwd, cx[0], cy[0]), maxx = minx, miny = warp_y(fwd, cx[0], cy[0]), maxy = miny;
     for (int i = 1; i < 4; ++i) {
         float x = warp_x(fwd, cx[i], cy[i]), y = warp_y(fwd, cx[i], cy[i]);
-        if (x < minx) minx = x;
-        if (x > maxx) maxx = x;
-        if (y < miny) miny = y;
+        if (in_minx[i] && x < minx) minx = x;
+        if (in_maxx[i] && x > maxx) maxx = x;
+        if (in_miny[i] && y < miny) miny = y;
         if (y > maxy) maxy = y;
     }
     CanvasPlan p;
@@ -168,8 +199,9 @@ inline void update_features_by_offset(VlKey* k, int n, int offx, int offy) {
 
 // blendTwoImages level geometry (ImageProcess.cpp:675-676, 706-707): level_num = floor(log2(max(w,h))),
 // dims halve (integer division) per level; a level with a zero dimension and everything above it is empty (quirk Q7).
-inline int blend_levels(int w, int h, std::vector<int>& lw, std::vector<int>& lh) {
-    int max_len = w >= h ? w : h;
+// ex6: level count from the SHORTER side (src/ex6/ImageProcess.cpp:662-665), so no level is ever empty.
+inline int blend_levels(int w, int h, std::vector<int>& lw, std::vector<int>& lh, bool ex6 = false) {
+    int max_len = ex6 ? (w < h ? w : h) : (w >= h ? w : h);
     int level_num = (int)std::floor(std::log2((double)max_len));
     lw.clear(); lh.clear();
     int cw = w, ch = h;

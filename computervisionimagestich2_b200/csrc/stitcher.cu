@@ -24,6 +24,10 @@ IirCoef make_iir(float sigma) {
     for (int i = 0; i < 9; ++i) c.M[i] = v.M[i];
     return c;
 }
+DericheCoef make_deriche(float sigma) {
+    hostnum::Deriche d = hostnum::deriche_coeffs(sigma);
+    return DericheCoef{d.a0, d.a1, d.a2, d.a3, d.b1, d.b2, d.coefp, d.coefn};
+}
 }  // namespace
 
 Stitcher::Stitcher(int device) : dev_(device) {
@@ -308,7 +312,7 @@ bool Stitcher::ransac(const std::vector<const std::vector<KeyPair>*>& problems, 
         off[p + 1] = off[p] + n;
         maxn = std::max(maxn, n);
         std::vector<int> s;
-        if (!stitch::draw_samples(n, s)) { err_ = "RANSAC needs at least 4 pairs"; return false; }
+        if (!stitch::draw_samples(n, s, profile_.ransac_seed)) { err_ = "RANSAC needs at least 4 pairs"; return false; }
         std::copy(s.begin(), s.end(), samples.begin() + (size_t)p * iters * 4);
     }
     std::vector<KeyPair> all(off[P]);
@@ -347,7 +351,7 @@ bool Stitcher::ransac_debug(const std::vector<KeyPair>& pairs, std::vector<int>&
     const int iters = stitch::ransac_iterations();
     const int n = (int)pairs.size();
     std::vector<int> samples;
-    if (!stitch::draw_samples(n, samples)) return false;
+    if (!stitch::draw_samples(n, samples, profile_.ransac_seed)) return false;
     int off[2] = {0, n};
     const int words = div_up(n, 32);
     r_pairs_.ensure(n); r_off_.ensure(2); r_samples_.ensure(samples.size()); r_counts_.ensure(iters);
@@ -400,13 +404,15 @@ void Stitcher::warp_shift(const u8* src, int sw, int sh, const double* H8, float
 // ------------------------------------------------------------------------------------------------------------
 int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out) {
     std::vector<int> lw, lh;
-    const int L = stitch::blend_levels(cw, ch, lw, lh);
+    const bool ex6 = profile_.ex6();
+    const int L = stitch::blend_levels(cw, ch, lw, lh, ex6);
     if (L < 1) { err_ = "blend: canvas too small"; return -2; }
     // level storage: 7 planes per level
     std::vector<size_t> goff(L + 1, 0);
     for (int i = 0; i < L; ++i) goff[i + 1] = goff[i] + (size_t)7 * lw[i] * lh[i];
     pyr_.ensure(goff[L]);
     tmpf_.ensure((size_t)7 * lw[0] * lh[0]);
+    if (ex6) tmpf2_.ensure((size_t)7 * lw[0] * lh[0]);
     if (L > 1) {
         E_[0].ensure((size_t)3 * lw[1] * lh[1]);
         E_[1].ensure((size_t)3 * lw[1] * lh[1]);
@@ -461,13 +467,15 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
     PB_CUDA(cudaStreamSynchronize(st_));  // the packed tables are pageable temporaries
 
     const IirCoef coef = make_iir(2.0f);
-    launch_seam_stats(d_a, d_b, cw, ch, stats_.p, st_);
-    launch_level0(d_a, d_b, cw, ch, stats_.p, pyr_.p, stats_.p + 4, st_);
+    const DericheCoef dcoef = make_deriche(2.0f);
+    launch_seam_stats(d_a, d_b, cw, ch, stats_.p, ex6, st_);
+    launch_level0(d_a, d_b, cw, ch, stats_.p, pyr_.p, stats_.p + 4, ex6, st_);
     // REDUCE chain (ImageProcess.cpp:705-715)
     for (int i = 1; i < L; ++i) {
         const size_t nprev = (size_t)7 * lw[i - 1] * lh[i - 1];
         (void)nprev;
-        launch_iir_blur(pyr_.p + goff[i - 1], tmpf_.p, lw[i - 1], lh[i - 1], 7, coef, st_);
+        if (ex6) launch_deriche_blur(pyr_.p + goff[i - 1], tmpf2_.p, tmpf_.p, lw[i - 1], lh[i - 1], 7, dcoef, st_);
+        else launch_iir_blur(pyr_.p + goff[i - 1], tmpf_.p, lw[i - 1], lh[i - 1], 7, coef, st_);
         const LevelTab& t = lt[i - 1];
         DevMovAvg mx{tab_i_.p + t.mx_start, tab_i_.p + t.mx_src, tab_f_.p + t.mx_wgt,
                      lw[i] == lw[i - 1] ? 1.0f : (float)lw[i - 1]};
@@ -535,7 +543,8 @@ void Stitcher::equalize_mix_device(const u8* d_rgb, int w, int h, u8* d_out) {
         for (int i = 1; i < 256; ++i) { sum[i] = sum[i - 1] + prob[i]; lut[i] = (int)round(255.0 * sum[i]); }
     }
     PB_CUDA(cudaMemcpyAsync(lut_.p, lut, sizeof lut, cudaMemcpyHostToDevice, st_));
-    launch_equalize_mix(d_rgb, w, h, lut_.p, d_out, st_);
+    // luminance mix: 19/20 + 1/20 (ImageProcess.cpp:261) or 5/6 + 1/6 (src/ex6/ImageProcess.cpp:270)
+    launch_equalize_mix(d_rgb, w, h, lut_.p, d_out, profile_.ex6() ? 5.0 : 19.0, profile_.ex6() ? 6.0 : 20.0, st_);
     PB_CUDA(cudaStreamSynchronize(st_));
 }
 
@@ -555,6 +564,18 @@ void Stitcher::cimg_blur2(const float* src, int w, int h, int c, float* dst) {
     tmpf_.ensure(n);
     PB_CUDA(cudaMemcpyAsync(tmpf_.p, src, n * 4, cudaMemcpyHostToDevice, st_));
     launch_iir_blur(tmpf_.p, tmpf_.p, w, h, c, make_iir(2.0f), st_);
+    PB_CUDA(cudaMemcpyAsync(dst, tmpf_.p, n * 4, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Stitcher::cimg_blur2_deriche(const float* src, int w, int h, int c, float* dst) {
+    PB_CUDA(cudaSetDevice(dev_));
+    size_t n = (size_t)w * h * c;
+    tmpf_.ensure(n);
+    tmpf2_.ensure(n);
+    pyr_.ensure(n);
+    PB_CUDA(cudaMemcpyAsync(pyr_.p, src, n * 4, cudaMemcpyHostToDevice, st_));
+    launch_deriche_blur(pyr_.p, tmpf2_.p, tmpf_.p, w, h, c, make_deriche(2.0f), st_);
     PB_CUDA(cudaMemcpyAsync(dst, tmpf_.p, n * 4, cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
 }
@@ -894,12 +915,164 @@ float Stitcher::timer_stop() {
     return ms;
 }
 
+// One edge of the stitch loop (ImageProcess.cpp:177-233; src/ex6/ImageProcess.cpp:195-258): match lists of both
+// directions -> the larger one mirrored -> two RANSAC fits -> canvas plan -> warp + shift -> feature re-mapping ->
+// blend.  s2d_idx / d2s_idx = getImgPair(imgs[src], imgs[dst]) / getImgPair(imgs[dst], imgs[src]) as row indices.
+int Stitcher::stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d_idx, const std::vector<int>& d2s_idx) {
+    auto pairs_of = [&](int a, int b, const std::vector<int>& idx, std::vector<KeyPair>& out) {   // with the current keys
+        out.clear();
+        const FeatureTable &A = imgs_[a]->feat, &B = imgs_[b]->feat;
+        for (int q = 0; q < B.n; ++q)
+            if (idx[q] >= 0) out.push_back(KeyPair{A.keys[idx[q]], B.keys[q]});
+    };
+    std::vector<KeyPair> s2d, d2s;
+    {
+        WallTimer t;
+        pairs_of(src, dst, s2d_idx, s2d);
+        pairs_of(dst, src, d2s_idx, d2s);
+        tm_.match += t.ms();
+    }
+    if (s2d.size() > d2s.size()) {
+        d2s.clear();
+        for (size_t q = 0; q < s2d.size(); ++q) d2s.push_back(KeyPair{s2d[q].dst, s2d[q].src});
+    } else {
+        s2d.clear();
+        for (size_t q = 0; q < d2s.size(); ++q) s2d.push_back(KeyPair{d2s[q].dst, d2s[q].src});
+    }
+    std::vector<double> H;
+    {
+        WallTimer t;
+        std::vector<const std::vector<KeyPair>*> probs{&d2s, &s2d};
+        if (!ransac(probs, H)) return -3;
+        tm_.ransac += t.ms();
+    }
+    const double* fwd = H.data();       // RANSAC(dstToSrcPair)
+    const double* bwd = H.data() + 8;   // RANSAC(srcToDstPair)
+    Image& D = *imgs_[dst];
+    stitch::CanvasPlan cp = stitch::plan_canvas(D.w, D.h, fwd, rw_, rh_, profile_.ex6());
+    if (cp.new_w <= 0 || cp.new_h <= 0 || (long)cp.new_w * cp.new_h > (1L << 31)) {
+        err_ = "degenerate canvas";
+        return -4;
+    }
+    const size_t cn = (size_t)3 * cp.new_w * cp.new_h;
+    {
+        WallTimer t;
+        a_.ensure(cn);
+        b_.ensure(cn);
+        PB_CUDA(cudaMemcpyAsync(H8_.p, bwd, 8 * sizeof(double), cudaMemcpyHostToDevice, st_));
+        launch_warp_shift(D.proj.p, D.w, D.h, H8_.p, cp.min_x, cp.min_y, res_[cur_].p, rw_, rh_, (int)cp.min_x,
+                          (int)cp.min_y, a_.p, b_.p, cp.new_w, cp.new_h, st_);
+        PB_CUDA(cudaStreamSynchronize(st_));
+        tm_.warp += t.ms();
+    }
+    stitch::update_features_by_homography(D.feat.keys.data(), D.feat.n, fwd, cp.min_x, cp.min_y);
+    stitch::update_features_by_offset(imgs_[pre]->feat.keys.data(), imgs_[pre]->feat.n, (int)cp.min_x, (int)cp.min_y);
+    {
+        WallTimer t;
+        res_[cur_ ^ 1].ensure(cn);
+        int rc = blend_device(a_.p, b_.p, cp.new_w, cp.new_h, res_[cur_ ^ 1].p);
+        if (rc) return rc;
+        cur_ ^= 1;
+        rw_ = cp.new_w; rh_ = cp.new_h;
+        tm_.blend += t.ms();
+    }
+    return 0;
+}
+
+// ImageProcess::matching of the src/ex6 variant (src/ex6/ImageProcess.cpp:147-260): images are assumed to be in
+// left-to-right order; image i is adjacent to i-1 and i+1 (image n-1 lists no neighbour of its own, :152-157), the
+// walk starts at image n/2 and visits each node's neighbours from the back of its list.  No adjacency discovery and no
+// THRESHOLD test: only the 2(n-1) directed problems of the chain are matched, in one batched launch.
+int Stitcher::run_chain(std::ostringstream& log) {
+    const int n = (int)imgs_.size();
+    if (n < 2) { err_ = "the ex6 order needs at least 2 images (the reference indexes imgs[1])"; return -7; }
+    for (int i = 0; i < n; ++i)
+        if (imgs_[i]->w > imgs_[i]->h) {   // src/ex6/ImageProcess.cpp:35-38: exit(1)
+            err_ = "ex6: projected width > height (the reference exits on this input)";
+            return -8;
+        }
+    std::vector<std::vector<int>> next(n);
+    next[0].push_back(1);
+    for (int i = 1; i < n - 1; i++) { next[i].push_back(i + 1); next[i].push_back(i - 1); }
+    const int start = n / 2;
+    // plan the walk, then evaluate every directed problem of its edges at once
+    std::vector<std::pair<int, int>> edges;
+    {
+        std::vector<std::vector<int>> nx = next;
+        std::queue<int> q;
+        q.push(start);
+        while (!q.empty()) {
+            int src = q.front();
+            q.pop();
+            for (int i = (int)nx[src].size() - 1; i >= 0; i--) {
+                int dst = nx[src][i];
+                q.push(dst);
+                nx[src].pop_back();
+                for (auto it = nx[dst].begin(); it != nx[dst].end(); ++it)
+                    if (*it == src) { nx[dst].erase(it); break; }
+                edges.push_back({src, dst});
+            }
+        }
+    }
+    std::vector<std::vector<int>> fwd_idx(edges.size()), bwd_idx(edges.size());
+    {
+        WallTimer t;
+        std::vector<std::pair<FeatureTable*, FeatureTable*>> probs;
+        std::vector<std::vector<int>*> sink;
+        auto want = [&](int a, int b, std::vector<int>& out) {
+            for (auto& pm : preset_)
+                if (pm.i == a && pm.j == b && (int)pm.idx.size() == imgs_[b]->feat.n) { out = pm.idx; return; }
+            probs.push_back({&imgs_[a]->feat, &imgs_[b]->feat});
+            sink.push_back(&out);
+        };
+        for (size_t e = 0; e < edges.size(); ++e) {
+            want(edges[e].first, edges[e].second, fwd_idx[e]);
+            want(edges[e].second, edges[e].first, bwd_idx[e]);
+        }
+        if (!probs.empty()) {
+            std::vector<std::vector<int>> out;
+            match_batch(probs, out);
+            for (size_t k = 0; k < out.size(); ++k) sink[k]->swap(out[k]);
+        }
+        tm_.match += t.ms();
+    }
+    {
+        Image& s = *imgs_[start];
+        rw_ = s.w; rh_ = s.h;
+        cur_ = 0;
+        res_[0].ensure((size_t)3 * rw_ * rh_);
+        PB_CUDA(cudaMemcpyAsync(res_[0].p, s.proj.p, (size_t)3 * rw_ * rh_, cudaMemcpyDeviceToDevice, st_));
+    }
+    H8_.ensure(8);
+    int pre = start;
+    for (size_t e = 0; e < edges.size(); ++e) {
+        const int src = edges[e].first, dst = edges[e].second;
+        log << "src index:" << src << " dst index:" << dst << "\n";   // src/ex6/ImageProcess.cpp:182
+        int rc = stitch_edge(src, dst, pre, fwd_idx[e], bwd_idx[e]);
+        if (rc) return rc;
+        pre = dst;
+    }
+    return 0;
+}
+
 int Stitcher::run() {
     PB_CUDA(cudaSetDevice(dev_));
     WallTimer ttot;
     const int n = (int)imgs_.size();
     if (n == 0) { err_ = "no images"; return -1; }
     std::ostringstream log;
+    if (profile_.ex6()) {
+        int rc = run_chain(log);
+        if (rc) return rc;
+        WallTimer t;
+        res_[cur_ ^ 1].ensure((size_t)3 * rw_ * rh_);
+        equalize_mix_device(res_[cur_].p, rw_, rh_, res_[cur_ ^ 1].p);
+        cur_ ^= 1;
+        tm_.tail += t.ms();
+        log_ = log.str();
+        tm_.total += ttot.ms();
+        return 0;
+    }
     std::vector<std::vector<char>> adj(n, std::vector<char>(n, 0));
     std::vector<std::vector<int>> next(n);
     std::vector<KeyPair> pairs;
@@ -988,13 +1161,6 @@ int Stitcher::run() {
         run_wave(wave);
         tm_.match += t.ms();
     }
-    auto pairs_of = [&](int a, int b, std::vector<KeyPair>& out) {   // getImgPair(imgs[a], imgs[b]) with the current keys
-        out.clear();
-        const FeatureTable &A = imgs_[a]->feat, &B = imgs_[b]->feat;
-        const std::vector<int>& idx = midx[a][b];
-        for (int q = 0; q < B.n; ++q)
-            if (idx[q] >= 0) out.push_back(KeyPair{A.keys[idx[q]], B.keys[q]});
-    };
     while (!wait.empty()) {
         int src = wait.front();
         wait.pop();
@@ -1003,59 +1169,9 @@ int Stitcher::run() {
             if (!adj[src][dst]) continue;
             adj[src][dst] = adj[dst][src] = 0;
             wait.push(dst);
-            std::vector<KeyPair> s2d, d2s;
-            {
-                WallTimer t;
-                pairs_of(src, dst, s2d);
-                pairs_of(dst, src, d2s);
-                tm_.match += t.ms();
-            }
             log << src << " " << dst << "\n";
-            if (s2d.size() > d2s.size()) {
-                d2s.clear();
-                for (size_t q = 0; q < s2d.size(); ++q) d2s.push_back(KeyPair{s2d[q].dst, s2d[q].src});
-            } else {
-                s2d.clear();
-                for (size_t q = 0; q < d2s.size(); ++q) s2d.push_back(KeyPair{d2s[q].dst, d2s[q].src});
-            }
-            std::vector<double> H;
-            {
-                WallTimer t;
-                std::vector<const std::vector<KeyPair>*> probs{&d2s, &s2d};
-                if (!ransac(probs, H)) return -3;
-                tm_.ransac += t.ms();
-            }
-            const double* fwd = H.data();       // RANSAC(dstToSrcPair)
-            const double* bwd = H.data() + 8;   // RANSAC(srcToDstPair)
-            Image& D = *imgs_[dst];
-            stitch::CanvasPlan cp = stitch::plan_canvas(D.w, D.h, fwd, rw_, rh_);
-            if (cp.new_w <= 0 || cp.new_h <= 0 || (long)cp.new_w * cp.new_h > (1L << 31)) {
-                err_ = "degenerate canvas";
-                return -4;
-            }
-            const size_t cn = (size_t)3 * cp.new_w * cp.new_h;
-            {
-                WallTimer t;
-                a_.ensure(cn);
-                b_.ensure(cn);
-                PB_CUDA(cudaMemcpyAsync(H8_.p, bwd, 8 * sizeof(double), cudaMemcpyHostToDevice, st_));
-                launch_warp_shift(D.proj.p, D.w, D.h, H8_.p, cp.min_x, cp.min_y, res_[cur_].p, rw_, rh_, (int)cp.min_x,
-                                  (int)cp.min_y, a_.p, b_.p, cp.new_w, cp.new_h, st_);
-                PB_CUDA(cudaStreamSynchronize(st_));
-                tm_.warp += t.ms();
-            }
-            stitch::update_features_by_homography(D.feat.keys.data(), D.feat.n, fwd, cp.min_x, cp.min_y);
-            stitch::update_features_by_offset(imgs_[pre]->feat.keys.data(), imgs_[pre]->feat.n, (int)cp.min_x,
-                                              (int)cp.min_y);
-            {
-                WallTimer t;
-                res_[cur_ ^ 1].ensure(cn);
-                int rc = blend_device(a_.p, b_.p, cp.new_w, cp.new_h, res_[cur_ ^ 1].p);
-                if (rc) return rc;
-                cur_ ^= 1;
-                rw_ = cp.new_w; rh_ = cp.new_h;
-                tm_.blend += t.ms();
-            }
+            int rc = stitch_edge(src, dst, pre, midx[src][dst], midx[dst][src]);
+            if (rc) return rc;
             pre = dst;
         }
     }

@@ -7,6 +7,7 @@
 #pragma once
 #include <memory>
 #include <string>
+#include <sstream>
 #include <vector>
 #include "common.h"
 #include "types.h"
@@ -14,6 +15,7 @@
 #include "match_kernels.h"
 #include "match_i8_kernels.h"
 #include "canvas_kernels.h"
+#include "stitch_host.h"
 
 namespace pb {
 
@@ -37,6 +39,10 @@ class Stitcher {
     explicit Stitcher(int device);
     ~Stitcher();
     cudaStream_t stream() const { return st_; }
+    // which caller of the hot path is reproduced (root ImageProcess.cpp or src/ex6) and the RANSAC seed; applies to
+    // run(), ransac(), blend(), equalize_mix()
+    void set_profile(const stitch::Profile& p) { profile_ = p; }
+    const stitch::Profile& profile() const { return profile_; }
     SiftEngine& sift_engine() { return *sift_; }
 
     // ---- stages (host in / host out) ---------------------------------------------------------------------
@@ -64,6 +70,7 @@ class Stitcher {
     // ms per repetition of the matcher kernels on resident tables (A, B row-major host tables, or NULL = uniform bytes)
     float bench_match_u8(const u8* A, int nA, const u8* B, int nB, int reps);
     void cimg_blur2(const float* src, int w, int h, int c, float* dst);    // get_blur(2,true,true), host buffers
+    void cimg_blur2_deriche(const float* src, int w, int h, int c, float* dst);   // get_blur(2) (src/ex6), host buffers
     void cimg_resize(const float* src, int w, int h, int c, int nw, int nh, float* dst);
 
     // ---- pipeline ---------------------------------------------------------------------------------------
@@ -108,7 +115,10 @@ class Stitcher {
     void equalize_mix_device(const u8* d_rgb, int w, int h, u8* d_out);
     void ensure_ktab(int short_side);
 
+    int run_chain(std::ostringstream& log);   // the src/ex6 stitch order
+    int stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d_idx, const std::vector<int>& d2s_idx);
     int dev_;
+    stitch::Profile profile_;
     cudaStream_t st_ = nullptr;
     std::unique_ptr<SiftEngine> sift_;
     std::vector<std::unique_ptr<Image>> imgs_;
@@ -131,7 +141,7 @@ class Stitcher {
     DevBuf<int> r_off_, r_samples_, r_counts_;
     DevBuf<unsigned> r_masks_;
     DevBuf<double> r_hyp_, H8_;
-    DevBuf<float> pyr_, tmpf_, E_[2];
+    DevBuf<float> pyr_, tmpf_, tmpf2_, E_[2];
     DevBuf<int> tab_i_, stats_, hist_, lut_;
     DevBuf<float> tab_f_;
     DevBuf<double> tab_d_;

@@ -43,6 +43,18 @@ const char* pano_b200_last_error(pano_b200_ctx* ctx);
 int pano_b200_device_count(void);
 void pano_b200_free(void* p); /* frees any buffer this library returned through an out-pointer */
 
+/* ---- which caller of the hot path is reproduced.  The reference ships the same pipeline twice: the root
+ *      ImageProcess.cpp (PANO_B200_PROFILE_ROOT, the default) and src/ex6/ImageProcess.cpp (PANO_B200_PROFILE_EX6:
+ *      images in left-to-right order stitched as a fixed chain from image n/2, src/ex6/ImageProcess.cpp:147-160;
+ *      canvas bounds from fewer corners, :230-243; 3-channel seam test and min(w,h) level count, :638-665; Deriche
+ *      pyramid blur get_blur(2), :702-705; 5/6 : 1/6 luminance mix, :270).  ransac_seed is the value passed to srand
+ *      at the top of ImageProcess::RANSAC: 666666 in the root variant (ImageProcess.cpp:397), time(0) in src/ex6
+ *      (src/ex6/ImageProcess.cpp:403) -- the caller supplies it.  Applies to the pipeline entry points and to
+ *      pano_b200_ransac / pano_b200_blend / pano_b200_equalize_mix / pano_b200_plan_canvas_ex. */
+#define PANO_B200_PROFILE_ROOT 0
+#define PANO_B200_PROFILE_EX6 1
+int pano_b200_set_profile(pano_b200_ctx* ctx, int variant, unsigned ransac_seed);
+
 /* ---- whole pipeline: `ImageProcess ip(dir, n)` + private member `result` (main.cpp:9, ImageProcess.cpp:3-8,
  *      ImageProcess.h:145).  imgs[i]: planar RGB of size w[i] x h[i].  *out is library-allocated (pano_b200_free). */
 int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n, uint8_t** out,
@@ -119,6 +131,9 @@ int pano_b200_ransac(pano_b200_ctx* ctx, const pano_b200_pair* pairs, int npairs
  * current result size), size[2] = new_width, new_height.  Host arithmetic only. */
 int pano_b200_plan_canvas(int dst_w, int dst_h, const double* forward_H8, int result_w, int result_h, float* bounds,
                           int* size);
+/* same with the profile explicit (src/ex6/ImageProcess.cpp:230-243, 545-580 for PANO_B200_PROFILE_EX6) */
+int pano_b200_plan_canvas_ex(int variant, int dst_w, int dst_h, const double* forward_H8, int result_w, int result_h,
+                             float* bounds, int* size);
 
 /* warpingImageByHomography + movingImageByOffset (ImageProcess.cpp:596-620) in one pass over the new canvas.
  * src (sw x sh) is warped with H8 and float offsets into a; prev (pw x ph) is shifted by the int offsets into b.
@@ -134,6 +149,8 @@ int pano_b200_equalize_mix(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h,
 /* CImg<float>::get_blur(2, true, true) (CImg.h:35111-35147, vanvliet) and get_resize(nw, nh, 1, c, 3)
  * (CImg.h:29321-29700) on float planes [c][h][w]; the two CImg primitives blendTwoImages is made of. */
 int pano_b200_cimg_blur2(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst);
+/* CImg<float>::get_blur(2) = Deriche order 0 (CImg.h:34777-34869), the pyramid blur of src/ex6/ImageProcess.cpp:702-705 */
+int pano_b200_cimg_blur2_deriche(pano_b200_ctx* ctx, const float* src, int w, int h, int c, float* dst);
 int pano_b200_cimg_resize3(pano_b200_ctx* ctx, const float* src, int w, int h, int c, int nw, int nh, float* dst);
 
 /* ---- uint8 / tensor-core matcher (north-star stage 3).  NOT part of the reference-parity path: the reference matches

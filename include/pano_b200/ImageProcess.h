@@ -4,11 +4,18 @@
 // keeps `result` private and only display()s it (ImageProcess.cpp:233,270); here it is public and mimics the part of
 // CImg<unsigned char> callers use: width() / height() / spectrum() / data() / operator()(x, y, c), planar layout
 // data[x + y*W + c*W*H] (CImg.h:48533-48546), plus save_bmp().  Header-only, C++11, no CImg dependency.
+//
+// The reference's second copy of the class, src/ex6/ImageProcess.h, is served by pano_b200/ex6/ImageProcess.h, which
+// includes this file with PANO_B200_IMAGEPROCESS_EX6 defined: same constructor, images stitched as a left-to-right
+// chain, RANSAC seeded with time(0) (src/ex6/ImageProcess.cpp:403; define PANO_B200_RANSAC_SEED to pin it), elapsed
+// time printed and the panorama saved as <dir>result.bmp (src/ex6/ImageProcess.cpp:12-16).
 #ifndef PANO_B200_IMAGEPROCESS_H
 #define PANO_B200_IMAGEPROCESS_H
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
+#include <chrono>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -94,6 +101,14 @@ class ImageProcess {
         for (auto& im : imgs) { p.push_back(im.data()); w.push_back(im.w); h.push_back(im.h); }
         pano_b200_ctx* ctx = nullptr;
         if (pano_b200_create(device, &ctx) != 0) throw std::runtime_error("pano_b200_create failed (no CUDA device? there is no CPU fallback)");
+#ifdef PANO_B200_IMAGEPROCESS_EX6
+        const auto t0 = std::chrono::steady_clock::now();
+#ifdef PANO_B200_RANSAC_SEED
+        pano_b200_set_profile(ctx, PANO_B200_PROFILE_EX6, (unsigned)(PANO_B200_RANSAC_SEED));
+#else
+        pano_b200_set_profile(ctx, PANO_B200_PROFILE_EX6, (unsigned)time(0));   // src/ex6/ImageProcess.cpp:403
+#endif
+#endif
         uint8_t* out = nullptr;
         int ow = 0, oh = 0;
         const int rc = pano_b200_stitch(ctx, p.data(), w.data(), h.data(), n, &out, &ow, &oh);
@@ -102,13 +117,18 @@ class ImageProcess {
             pano_b200_destroy(ctx);
             throw std::runtime_error("pano_b200_stitch failed: " + msg);
         }
-        char log[4096];
-        pano_b200_stitch_log(ctx, log, sizeof log);
-        fputs(log, stdout);  // the reference prints the middle index and each "src dst" edge (ImageProcess.cpp:183,391)
+        std::vector<char> log(1 << 16);
+        pano_b200_stitch_log(ctx, log.data(), (int)log.size());
+        fputs(log.data(), stdout);  // the reference prints the middle index and each "src dst" edge (ImageProcess.cpp:183,391)
         result.w = ow; result.h = oh;
         result.px.assign(out, out + (size_t)3 * ow * oh);
         pano_b200_free(out);
         pano_b200_destroy(ctx);
+#ifdef PANO_B200_IMAGEPROCESS_EX6
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("costs:%gs\n", secs);            // src/ex6/ImageProcess.cpp:12-13
+        result.save_bmp(dir + "result.bmp");    // src/ex6/ImageProcess.cpp:15-16
+#endif
     }
     pano_b200::PlanarImage result;
 };

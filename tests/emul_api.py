@@ -128,12 +128,23 @@ def _pairs(src, dst):
     return p
 
 
-def ransac(src, dst):
+def ransac(src, dst, seed=None):
     p = _pairs(src, dst)
     H = np.empty(8, np.float64)
-    if lib().emul_ransac(_p(p), len(p), _p(H)) != 0:
+    if seed is None:
+        rc = lib().emul_ransac(_p(p), len(p), _p(H))
+    else:
+        rc = lib().emul_ransac_seeded(_p(p), len(p), C.c_uint(seed), _p(H))
+    if rc != 0:
         raise RuntimeError("emul_ransac failed")
     return H
+
+
+def draw_samples(npairs, seed, use_libc=False):
+    idx = np.empty((72, 4), np.int32)
+    n = lib().emul_draw_samples(npairs, C.c_uint(seed), _p(idx), int(use_libc))
+    assert n == 72
+    return idx
 
 
 def fit4(src, dst):
@@ -152,11 +163,11 @@ def refit(src, dst, idx):
     return H
 
 
-def plan_canvas(dw, dh, H8, rw, rh):
+def plan_canvas(dw, dh, H8, rw, rh, ex6=False):
     H8 = np.ascontiguousarray(H8, np.float64)
     mm = np.empty(4, np.float32)
     wh = np.empty(2, np.int32)
-    lib().emul_plan_canvas(dw, dh, _p(H8), rw, rh, _p(mm), _p(wh))
+    (lib().emul_plan_canvas_ex6 if ex6 else lib().emul_plan_canvas)(dw, dh, _p(H8), rw, rh, _p(mm), _p(wh))
     return mm, wh
 
 
@@ -169,11 +180,11 @@ def warp(src, H8, offx, offy, cw, ch):
     return out
 
 
-def cimg_blur2(p):
+def cimg_blur2(p, deriche=False):
     p = np.ascontiguousarray(p, np.float32)
     c, h, w = p.shape
     out = np.empty_like(p)
-    lib().emul_cimg_blur2(_p(p), w, h, c, _p(out))
+    (lib().emul_cimg_blur2_deriche if deriche else lib().emul_cimg_blur2)(_p(p), w, h, c, _p(out))
     return out
 
 
@@ -185,20 +196,20 @@ def cimg_resize3(p, nw, nh):
     return out
 
 
-def blend(a, b):
+def blend(a, b, ex6=False):
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)
     _, h, w = a.shape
     out = np.empty_like(a)
-    rc = lib().emul_blend(_p(a), _p(b), w, h, _p(out))
+    rc = (lib().emul_blend_ex6 if ex6 else lib().emul_blend)(_p(a), _p(b), w, h, _p(out))
     if rc != 0:
         raise RuntimeError("emul_blend: empty middle row")
     return out
 
 
-def equalize_mix(img):
+def equalize_mix(img, ex6=False):
     img = np.ascontiguousarray(img, np.uint8)
     _, h, w = img.shape
     out = np.empty_like(img)
-    lib().emul_equalize_mix(_p(img), w, h, _p(out))
+    (lib().emul_equalize_mix_ex6 if ex6 else lib().emul_equalize_mix)(_p(img), w, h, _p(out))
     return out

@@ -25,8 +25,8 @@ int main() {
             float ms = 0;
             for (int rep = 0; rep < 3; ++rep) {
                 cudaEventRecord(e0, st);
-                if (pass == 0) iir_pipe_kernel<true><<<ctas, 128, 0, st>>>(a, b, w, (long)h, h, (long)w * h, 1L, c);
-                else iir_pipe_kernel<false><<<ctas, 128, 0, st>>>(a, b, w, (long)h, h, (long)w * h, (long)h, c);  // plane viewed as [w rows][h cols]
+                if (pass == 0) iir_pipe_kernel<true, IirCoef><<<ctas, 128, 0, st>>>(a, b, w, (long)h, h, (long)w * h, 1L, c);
+                else iir_pipe_kernel<false, IirCoef><<<ctas, 128, 0, st>>>(a, b, w, (long)h, h, (long)w * h, (long)h, c);  // plane viewed as [w rows][h cols]
                 cudaEventRecord(e1, st);
                 cudaEventSynchronize(e1);
                 cudaEventElapsedTime(&ms, e0, e1);

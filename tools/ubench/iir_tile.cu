@@ -39,6 +39,33 @@ __device__ __forceinline__ void tile(float* t, double& v1, double& v2, double& v
         for (int e = 0; e < 32; ++e) o[e] = (float)d[e];
 #pragma unroll
         for (int e = 0; e < 32; ++e) t[e * kIirPitch] = o[e];
+    } else if (MODE == 3) {  // conversion of the next sample pinned one step ahead of its use (volatile cvt)
+        double cur;
+        { float f = t[0]; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(cur) : "f"(f)); }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            double nxt = 0;
+            if (e + 1 < 32) { float f = t[(e + 1) * kIirPitch]; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(nxt) : "f"(f)); }
+            double v0 = cur;
+            v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+            t[e * kIirPitch] = (float)v0;
+            v3 = v2; v2 = v1; v1 = v0;
+            cur = nxt;
+        }
+    } else if (MODE == 4) {  // same, two steps ahead
+        double c0, c1;
+        { float f = t[0]; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(c0) : "f"(f)); }
+        { float f = t[kIirPitch]; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(c1) : "f"(f)); }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            double nxt = 0;
+            if (e + 2 < 32) { float f = t[(e + 2) * kIirPitch]; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(nxt) : "f"(f)); }
+            double v0 = c0;
+            v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+            t[e * kIirPitch] = (float)v0;
+            v3 = v2; v2 = v1; v1 = v0;
+            c0 = c1; c1 = nxt;
+        }
     } else {   // no memory at all: registers only
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -67,14 +94,16 @@ int main() {
     pb::IirCoef co; co.f1 = 0.5; co.f2 = -0.2; co.f3 = 0.05; co.sum = 0.3; co.sumsq = 0.09; co.bnd = 0.65;
     for (int i = 0; i < 9; ++i) co.M[i] = 0.1 * i;
     const int tiles = 2000;
-    const char* names[] = {"naive (cvt in chain order)", "loads+int-cvt first, F2F+STS last", "registers only"};
-    for (int warps = 1; warps <= 3; warps += 2)
-        for (int m = 0; m < 3; ++m) {
+    const char* names[] = {"naive (cvt in chain order)", "loads+int-cvt first, F2F+STS last", "registers only", "cvt pinned 1 step ahead", "cvt pinned 2 steps ahead"};
+    for (int warps = 1; warps <= 1; warps += 2)
+        for (int m = 0; m < 5; ++m) {
             long long h = 0;
             for (int rep = 0; rep < 2; ++rep) {
                 if (m == 0) pb::k<0><<<1, 32 * warps>>>(d, co, tiles, c);
                 if (m == 1) pb::k<1><<<1, 32 * warps>>>(d, co, tiles, c);
-                if (m == 2) pb::k<2><<<1, 32 * warps>>>(d, co, tiles, c);
+                if (m == 2) pb::k<5><<<1, 32 * warps>>>(d, co, tiles, c);
+                if (m == 3) pb::k<3><<<1, 32 * warps>>>(d, co, tiles, c);
+                if (m == 4) pb::k<4><<<1, 32 * warps>>>(d, co, tiles, c);
                 cudaDeviceSynchronize();
             }
             cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
