@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpano_b200.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["sift_kernels.cu", "sift_engine.cu", "match_kernels.cu", "canvas_kernels.cu", "stitcher.cu", "c_api.cu",
-           "vl_sift_shim.cu", "bench_kernels.cu", "match_i8_kernels.cu"]
+           "vl_sift_shim.cu", "vl_kdforest_shim.cu", "bench_kernels.cu", "match_i8_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-diag-suppress", "550"]

@@ -32,7 +32,15 @@ extern "C" {
 #define VL_ERR_EOF 5
 
 typedef float vl_sift_pix;
-typedef unsigned long long vl_size;
+#ifndef VL_B200_BASIC_TYPES
+#define VL_B200_BASIC_TYPES
+typedef unsigned long long vl_size;   /* vl/host.h:392 */
+typedef unsigned long long vl_uindex; /* vl/host.h:394 */
+typedef unsigned int vl_uint32;       /* vl/host.h:382 */
+typedef vl_uint32 vl_type;            /* vl/generic.h:18 */
+#define VL_TYPE_FLOAT 1               /* vl/generic.h:21 */
+#define VL_TYPE_DOUBLE 2              /* vl/generic.h:22 */
+#endif
 
 typedef struct _VlSiftKeypoint {
     int o;

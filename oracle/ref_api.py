@@ -132,6 +132,20 @@ def match(descA, keysA, descB, keysB):
     return oa[:n].copy(), ob[:n].copy()
 
 
+def kdforest_query(data, queries, k=2, metric=0, per_query=True):
+    """VLFeat kd-forest as getImgPair drives it (ImageProcess.cpp:280-327): (idx [nq][k] int64, dist [nq][k] f64).
+    metric: 0 = VlDistanceL1, 1 = VlDistanceL2."""
+    data = np.ascontiguousarray(data, np.float32)
+    queries = np.ascontiguousarray(queries, np.float32)
+    n, dim = data.shape
+    nq = len(queries)
+    idx = np.empty((nq, k), np.int64)
+    dist = np.empty((nq, k), np.float64)
+    if lib().ref_kdforest_query(_p(data), n, dim, metric, _p(queries), nq, k, int(per_query), _p(idx), _p(dist)) != 0:
+        raise RuntimeError("ref_kdforest_query")
+    return idx, dist
+
+
 def ransac(src, dst) -> np.ndarray:
     src = np.ascontiguousarray(src, KEY_DTYPE)
     dst = np.ascontiguousarray(dst, KEY_DTYPE)

@@ -219,6 +219,35 @@ int ref_match(const float *descA, const VlSiftKeypoint *keysA, int nA, const flo
     return (int)p.size();
 }
 
+// The kd-forest exactly as getImgPair drives it (ImageProcess.cpp:280-327): 1 tree, float data, exact search; the K
+// nearest neighbours of each query through vl_kdforestsearcher_query (per_query != 0) or vl_kdforest_query_with_array.
+// idx [nq][K] (int64, -1 = none), dist [nq][K] (double, the VlKDForestNeighbor.distance values).
+int ref_kdforest_query(const float *data, int n, int dim, int metric, const float *queries, int nq, int K,
+                       int per_query, long long *idx, double *dist) {
+    VlKDForest *forest = vl_kdforest_new(VL_TYPE_FLOAT, dim, 1, (VlVectorComparisonType)metric);
+    if (!forest) return -1;
+    vl_kdforest_build(forest, n, data);
+    if (per_query) {
+        VlKDForestSearcher *searcher = vl_kdforest_new_searcher(forest);
+        std::vector<VlKDForestNeighbor> nb(K);
+        for (int q = 0; q < nq; ++q) {
+            vl_kdforestsearcher_query(searcher, nb.data(), K, queries + (size_t)q * dim);
+            for (int k = 0; k < K; ++k) {
+                idx[(size_t)q * K + k] = (long long)nb[k].index;
+                dist[(size_t)q * K + k] = nb[k].distance;
+            }
+        }
+        vl_kdforestsearcher_delete(searcher);
+    } else {
+        std::vector<vl_uint32> ix((size_t)nq * K);
+        std::vector<float> ds((size_t)nq * K);
+        vl_kdforest_query_with_array(forest, ix.data(), K, nq, ds.data(), queries);
+        for (size_t i = 0; i < ix.size(); ++i) { idx[i] = ix[i] == (vl_uint32)-1 ? -1 : (long long)ix[i]; dist[i] = ds[i]; }
+    }
+    vl_kdforest_delete(forest);
+    return 0;
+}
+
 // ImageProcess::RANSAC (ImageProcess.cpp:395-436): pairs (src -> dst); returns the 8 bilinear coefficients
 // in Homography constructor order (x': a b c d ; y': e f g h).
 int ref_ransac(const VlSiftKeypoint *src, const VlSiftKeypoint *dst, int n, double *H8) {

@@ -55,7 +55,10 @@ def test_headers_compile_as_c_and_layouts_match_vlfeat(tmp_path):
 #include <stddef.h>
 #include "pano_b200.h"
 #include "vl_b200/sift.h"
+#include "vl_b200/kdtree.h"
 int main(void) {
+  if (sizeof(VlKDForestNeighbor) != 16 || offsetof(VlKDForestNeighbor, index) != 8 || VlDistanceL2 != 1 ||
+      VL_TYPE_FLOAT != 1 || VL_ERR_EOF != 5) return 1;   /* vl/kdtree.h:60-63, vl/mathop.h:628-630, vl/generic.h:21,113 */
   printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(VlSiftKeypoint), sizeof(pano_b200_keypoint), sizeof(pano_b200_pair),
          offsetof(VlSiftFilt, keys), offsetof(VlSiftFilt, nkeys), offsetof(VlSiftFilt, peak_thresh), offsetof(VlSiftFilt, grad_o));
   return 0;
@@ -66,6 +69,47 @@ int main(void) {
     # VLFeat 0.9.21 x86-64 layout of VlSiftFilt (vl/sift.h:39-78): 4 doubles, 8 ints, 3 pointers, 2 ints, pointer,
     # double, vl_size, pointer keys @120, nkeys @128, keys_res, 5 doubles @136.., grad pointer, grad_o
     assert got == ["32", "32", "64", "120", "128", "136", "184"]
+
+
+def test_vlfeat_compat_include_path(tmp_path):
+    """A source that keeps the reference's own include lines (ImageProcess.h:33-38) compiles against
+    include/vl_b200/compat and links against libpano_b200.so alone."""
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+extern "C" {
+#include "vl/generic.h"
+#include "vl/sift.h"
+#include "vl/kdtree.h"
+}
+int main() {
+  assert(sizeof(vl_sift_pix) == 4);
+  if (0) {   // link check only: there is no GPU here
+    VlSiftFilt* f = vl_sift_new(8, 8, 1, 2, 0);
+    vl_sift_delete(f);
+    VlKDForest* k = vl_kdforest_new(VL_TYPE_FLOAT, 128, 1, VlDistanceL1);
+    VlKDForestNeighbor nb[2];
+    float q[128] = {0};
+    vl_kdforest_build(k, 1, q);
+    VlKDForestSearcher* s = vl_kdforest_new_searcher(k);
+    vl_kdforestsearcher_query(s, nb, 2, q);
+    vl_kdforestsearcher_delete(s);
+    vl_kdforest_delete(k);
+  }
+  return VL_ERR_OK;
+}''')
+    exe = tmp_path / "t"
+    libdir = os.path.join(ROOT, "computervisionimagestich2_b200")
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(INC, "vl_b200", "compat"), str(src), "-o",
+                    str(exe), "-L", libdir, "-lpano_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    subprocess.run([str(exe)], check=True)
+
+
+def test_kdforest_fails_loudly_without_a_gpu(so):
+    lib = C.CDLL(so)
+    lib.vl_kdforest_new.restype = C.c_void_p
+    if lib.pano_b200_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    assert lib.vl_kdforest_new(1, C.c_ulonglong(128), C.c_ulonglong(1), 0) is None
 
 
 def test_context_fails_loudly_without_a_gpu(so):
