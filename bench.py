@@ -88,7 +88,7 @@ class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region by an in-process NVML thread (a spawned
     `nvidia-smi -lms` loop takes driver locks that stall a launch/sync-heavy host pipeline)."""
 
-    def __init__(self, gpu_index, period_s=0.05):
+    def __init__(self, gpu_index, period_s=0.01):
         import threading
         self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
@@ -348,6 +348,13 @@ def run_b200(args):
                         "note": "useful ops 2*128*nA*nB over main + finish kernels; the MMA also runs a 25% norm-extension K step (ncu sm__pipe_tensor_cycles_active 56%, profiles/r01_ncu_full_match_u8_kernel.txt)"}
         except Exception as e:
             match_u8 = {"error": str(e)}
+    # --- the reference's second caller of the same kernels (src/ex6): its 18-image data set, host buffers in and out
+    ex6 = None
+    if rank == 0 and world == 1 and not args.no_ex6:
+        try:
+            ex6 = bench_ex6(ctx)
+        except Exception as e:
+            ex6 = {"error": str(e)}
     for p in pin_in:
         L.pano_b200_free_pinned(C.c_void_p(p))
     L.pano_b200_free_pinned(C.c_void_p(pin_out))
@@ -369,7 +376,7 @@ def run_b200(args):
     top_name, top_k = top
     roofline = None
     notes = {
-        "blend.iir": "recursive Gaussian (CImg vanvliet): per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 cycles/sample (measured); parallel only across lines, so latency-bound, not HBM-bound. Algorithmic bytes = 16 B per plane pixel per pass (read + write, forward + backward)",
+        "blend.iir": "recursive Gaussian (CImg vanvliet): per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 cycles/sample (measured); parallel only across lines. Small / middle pyramid levels are latency-bound (55-60 cycles per sample per line group), the largest are HBM-bound at ~3.5 TB/s with 128-byte granules a line pitch apart (DESIGN.md 4.5). Algorithmic bytes = 16 B per plane pixel per pass (read + write, forward + backward)",
         "sift.descr": "one warp per (keypoint, angle); gather from the L2-resident gradient map + double-precision geometry; algorithmic bytes = sum (2W+1)^2 * 8 B patch reads + 512 B per descriptor (SURVEY 8d)",
     }
     if top_k["ms"] > 0:
@@ -389,6 +396,7 @@ def run_b200(args):
                         "frac": ach / hbm_peak, "traffic": None, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
                         "share_of_kernel_time": top_k["ms"] / ksum, "peak_source": peak_src,
                         "bytes_per_launch": top_k["bytes"] / top_k["launches"], "note": notes.get(top_name)}
+            roofline.update(ncu_traffic(top_name, args.workload))
     # the HBM-bound scale-space kernels, always reported (north_star: blur GB/s)
     hbm_kernels = {}
     for name, k in kernels.items():
@@ -418,11 +426,61 @@ def run_b200(args):
         "stages_ms_last_step": stages,
         "kernels_ms": {k: round(v["ms"], 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
         "hbm_kernels": hbm_kernels,
+        "sift": sift_summary(kernels, stages, mpix),
         "match_u8": match_u8,
+        "ex6": ex6,
     }
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel, workload):
+    """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/
+    r01_ncu_traffic.json, written by tools/summarize_ncu.py): the capture is of ONE launch -- the largest -- so its own
+    algorithmic bytes are given beside it; `traffic` stays None when no capture of this kernel / workload exists."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))[workload][kernel]
+        return {"traffic": t["dram_bytes"], "traffic_launch": t["launch"], "traffic_launch_algorithmic_bytes": t["algorithmic_bytes"],
+                "traffic_source": t["source"]}
+    except Exception:
+        return {}
+
+
+def sift_summary(kernels, stages, mpix):
+    """north_star: 'SIFT Mpix/s (HBM GB/s)'.  Mpixel/s = input pixels / wall time of the feature stage of the last timed
+    step (projection + SIFT + table for all images, concurrent lanes); GB/s = algorithmic bytes / CUDA-event time of the
+    scale-space kernels (blur, DoG-on-the-fly detector, gradient) in the serial instrumented pass."""
+    ss = [k for n, k in kernels.items() if n in ("sift.blur_v", "sift.blur_h", "sift.detect", "sift.gradient")]
+    ms = sum(k["ms"] for k in ss)
+    by = sum(k["bytes"] for k in ss)
+    feat_ms = stages.get("project", 0) + stages.get("sift", 0) + stages.get("table", 0)
+    return {"mpixel_per_s": round(mpix / (feat_ms * 1e-3), 1) if feat_ms > 0 else None, "feature_stage_ms": round(feat_ms, 3),
+            "scale_space_GBps": round(by / (ms * 1e-3) / 1e9, 1) if ms > 0 else None, "scale_space_ms": round(ms, 4),
+            "all_sift_kernels_ms": round(sum(k["ms"] for n, k in kernels.items() if n.startswith("sift.")), 4)}
+
+
+def bench_ex6(ctx, reps=3):
+    """src/ex6/dataset2 (18 x 600x800 -> 6282x883) with the ex6 profile through the public call (host buffers in/out)."""
+    import hashlib
+    from computervisionimagestich2_b200 import bmpio
+    d = os.path.join(ROOT, "oracle", "_ref", "data", "ex6_dataset2")
+    a = json.load(open(os.path.join(ROOT, "tests", "golden", "anchors.json")))["ex6"]
+    imgs = [bmpio.load_bmp(os.path.join(d, f"{i + 1}.bmp")) for i in range(a["dataset2"]["n"])]
+    mp = megapixels(imgs)
+    ctx.set_profile("ex6", a["ransac_seed"])
+    try:
+        best, out = 1e9, None
+        for _ in range(1 + reps):
+            t0 = time.perf_counter()
+            out, _info = ctx.stitch(imgs)
+            best = min(best, time.perf_counter() - t0)
+    finally:
+        ctx.set_profile("root", 666666)
+    return {"workload": "src/ex6/dataset2: 18 x 600x800 chain panorama, ex6 profile, RANSAC seed pinned", "input_mpixel": mp,
+            "output": [int(out.shape[2]), int(out.shape[1])], "ms": round(best * 1e3, 2), "mpixel_per_s": round(mp / best, 1),
+            "bit_exact_vs_reference": hashlib.sha256(out.tobytes()).hexdigest() == a["dataset2"]["sha256"],
+            "reference_cpu_seconds_one_core": a["dataset2"]["cpu_seconds"]}
 
 
 def main():
@@ -435,6 +493,7 @@ def main():
     ap.add_argument("--ref-procs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-match-u8", action="store_true")
+    ap.add_argument("--no-ex6", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

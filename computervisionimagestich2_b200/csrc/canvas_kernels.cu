@@ -454,8 +454,16 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
                     if (e0 + lane < N) {
                         float* g = dst + mybase + e0;
                         if (kDeriche && pass == 1) {   // out = Y + yc; this thread wrote Y[g] itself in pass 0
-#pragma unroll 8
-                            for (int r = 0; r < nl; ++r) { *g = *g + *sp; sp += s_step; g += g_step; }
+                            // all reads of Y go out before the first add: element by element the tile costs 32 HBM latencies
+                            if (nl == 32) {
+                                float y[32];
+#pragma unroll
+                                for (int r = 0; r < 32; ++r) y[r] = g[(long)r * g_step];
+#pragma unroll
+                                for (int r = 0; r < 32; ++r) g[(long)r * g_step] = y[r] + sp[r * s_step];
+                            } else {
+                                for (int r = 0; r < nl; ++r) { *g = *g + *sp; sp += s_step; g += g_step; }
+                            }
                         } else {
 #pragma unroll 8
                             for (int r = 0; r < nl; ++r) { *g = *sp; sp += s_step; g += g_step; }
@@ -465,8 +473,15 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
                     const int ne = (N - e0) < 32 ? (N - e0) : 32;
                     float* g = dst + mybase + (long)e0 * elem_stride;
                     if (kDeriche && pass == 1) {
-#pragma unroll 8
-                        for (int e = 0; e < ne; ++e) { *g = *g + *sp; sp += s_step; g += g_step; }
+                        if (ne == 32) {
+                            float y[32];
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) y[e] = g[(long)e * g_step];
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) g[(long)e * g_step] = y[e] + sp[e * s_step];
+                        } else {
+                            for (int e = 0; e < ne; ++e) { *g = *g + *sp; sp += s_step; g += g_step; }
+                        }
                     } else {
 #pragma unroll 8
                         for (int e = 0; e < ne; ++e) { *g = *sp; sp += s_step; g += g_step; }
