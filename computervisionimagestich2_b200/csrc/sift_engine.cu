@@ -197,7 +197,7 @@ void SiftEngine::orient_custom(int oi, const std::vector<KeyIn>& keys, std::vect
     nangles_.ensure(n);
     angles_.ensure((size_t)n * 4);
     PB_CUDA(cudaMemcpyAsync(keyin_.p, ki.data(), ki.size() * sizeof(KeyIn), cudaMemcpyHostToDevice, st_));
-    launch_orient(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, n, nangles_.p, angles_.p, st_);
+    launch_orient(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, n, nullptr, nangles_.p, angles_.p, st_);
     PB_CUDA(cudaMemcpyAsync(nang.data(), nangles_.p, n * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(ang.data(), angles_.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
@@ -242,7 +242,7 @@ void SiftEngine::describe_octave(int oi, const std::vector<int>& key_idx, const 
     descr_.ensure((size_t)nj * 128);
     written_.ensure(nj);
     PB_CUDA(cudaMemcpyAsync(jobs_.p, jobs.data(), nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
-    launch_descr(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, jobs_.p, nj, descr_.p, written_.p, 0.0, st_);
+    launch_descr(octave_set(oi, 1), consts(), expn_tab_.p, keyin_.p, jobs_.p, nj, nullptr, descr_.p, written_.p, 0.0, st_);
     PB_CUDA(cudaMemcpyAsync(out_descr, descr_.p, (size_t)nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(out_written, written_.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
@@ -314,10 +314,20 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     keyin_.ensure(nk);
     nangles_.ensure(nk);
     angles_.ensure((size_t)nk * 4);
+    // largest windows first (both kernels: one warp per item, the launch ends with its slowest warp)
+    int* h_ok = (int*)h_order_k_.ensure((size_t)nk * sizeof(int));
+    {
+        std::vector<std::pair<float, int>> byscale(nk);
+        for (int i = 0; i < nk; ++i) byscale[i] = {-(float)((double)hk[i].sigma / os.xper[hk[i].oct]), i};
+        std::stable_sort(byscale.begin(), byscale.end());
+        for (int i = 0; i < nk; ++i) h_ok[i] = byscale[i].second;
+    }
+    order_k_.ensure(nk);
+    PB_CUDA(cudaMemcpyAsync(order_k_.p, h_ok, (size_t)nk * sizeof(int), cudaMemcpyHostToDevice, st_));
     int* h_na = (int*)h_nang_.ensure((size_t)nk * sizeof(int));
     double* h_an = (double*)h_ang_.ensure((size_t)nk * 4 * sizeof(double));
     PB_CUDA(cudaMemcpyAsync(keyin_.p, hk, (size_t)nk * sizeof(KeyIn), cudaMemcpyHostToDevice, st_));
-    launch_orient(os, sc, expn_tab_.p, keyin_.p, nk, nangles_.p, angles_.p, st_);
+    launch_orient(os, sc, expn_tab_.p, keyin_.p, nk, order_k_.p, nangles_.p, angles_.p, st_);
     PB_CUDA(cudaMemcpyAsync(h_na, nangles_.p, (size_t)nk * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(h_an, angles_.p, (size_t)nk * 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
@@ -347,13 +357,22 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     int* hw = (int*)h_written_.ensure(nj * sizeof(int));
     PB_CUDA(cudaMemcpyAsync(jobs_.p, hj, nj * sizeof(DescJob), cudaMemcpyHostToDevice, st_));
     double patch_bytes = 0;   // sum_k (2 W_k + 1)^2 * 8 B of (modulus, angle) reads
-    for (size_t q = 0; q < nj; ++q) {
-        const KeyIn& kk = hk[hj[q].key];
-        const double sbp = p_.magnif * ((double)kk.sigma / os.xper[kk.oct]);
-        const double W = floor(1.4142135623730951 * sbp * 2.5 + 0.5);
-        patch_bytes += (2 * W + 1) * (2 * W + 1) * 8.0;
+    int* h_oj = (int*)h_order_j_.ensure(nj * sizeof(int));
+    {
+        std::vector<std::pair<float, int>> bysize(nj);
+        for (size_t q = 0; q < nj; ++q) {
+            const KeyIn& kk = hk[hj[q].key];
+            const double sbp = p_.magnif * ((double)kk.sigma / os.xper[kk.oct]);
+            const double W = floor(1.4142135623730951 * sbp * 2.5 + 0.5);
+            patch_bytes += (2 * W + 1) * (2 * W + 1) * 8.0;
+            bysize[q] = {-(float)W, (int)q};
+        }
+        std::stable_sort(bysize.begin(), bysize.end());
+        for (size_t q = 0; q < nj; ++q) h_oj[q] = bysize[q].second;
     }
-    launch_descr(os, sc, expn_tab_.p, keyin_.p, jobs_.p, (int)nj, descr_.p, written_.p, patch_bytes, st_);
+    order_j_.ensure(nj);
+    PB_CUDA(cudaMemcpyAsync(order_j_.p, h_oj, nj * sizeof(int), cudaMemcpyHostToDevice, st_));
+    launch_descr(os, sc, expn_tab_.p, keyin_.p, jobs_.p, (int)nj, order_j_.p, descr_.p, written_.p, patch_bytes, st_);
     PB_CUDA(cudaMemcpyAsync(hd, descr_.p, nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(hw, written_.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));

@@ -104,7 +104,8 @@ class SiftEngine {
     DevBuf<double> angles_;
     DevBuf<DescJob> jobs_;
     DevBuf<float> descr_;
-    PinBuf<char> h_keyin_, h_nang_, h_ang_, h_jobs_, h_descr_, h_written_;
+    PinBuf<char> h_keyin_, h_nang_, h_ang_, h_jobs_, h_descr_, h_written_, h_order_k_, h_order_j_;
+    DevBuf<int> order_k_, order_j_;   // issue orders of the orientation / descriptor launches (largest window first)
     OctaveSet octave_set(int first, int count) const;
     bool tab_ready_ = false;
 };

@@ -327,8 +327,12 @@ void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cu
 //            land in its bins.  Every histogram bin therefore receives the reference's addends in the reference's
 //            order (bit-exact), yet no lane ever walks the whole patch serially.
 // ---------------------------------------------------------------------------------------------------------
+// order (optional): slot -> keypoint index, largest window first.  The window radius grows with sigma (13^2 .. 49^2
+// samples and more), one warp works on one keypoint, and the kernel ends when its slowest warp does: issued in array
+// order the big ones land anywhere and the tail of the launch runs at a fraction of the machine.
 __global__ void __launch_bounds__(128) orient_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
                                                      const KeyIn* __restrict__ keys, int nkeys,
+                                                     const int* __restrict__ order,
                                                      int* __restrict__ nangles, double* __restrict__ angles) {
     enum { nbins = 36 };
     __shared__ double tab[257];
@@ -338,8 +342,9 @@ __global__ void __launch_bounds__(128) orient_kernel(OctaveSet os, SiftConsts sc
     for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ki = blockIdx.x * 4 + wid;
-    if (ki >= nkeys) return;
+    const int slot = blockIdx.x * 4 + wid;
+    if (slot >= nkeys) return;
+    const int ki = order ? order[slot] : slot;
     const KeyIn k = keys[ki];
     const OctaveView ov = os.ov[k.oct];
     const double xper = os.xper[k.oct];
@@ -441,10 +446,10 @@ __global__ void __launch_bounds__(128) orient_kernel(OctaveSet os, SiftConsts sc
     }
 }
 void launch_orient(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys, int nkeys,
-                   int* nangles, double* angles, cudaStream_t st) {
+                   const int* order, int* nangles, double* angles, cudaStream_t st) {
     if (nkeys <= 0) return;
     KScope ks("sift.orient", st, 36.0 * nkeys);
-    orient_kernel<<<div_up(nkeys, 4), 128, 0, st>>>(os, sc, expn_tab, keys, nkeys, nangles, angles);
+    orient_kernel<<<div_up(nkeys, 4), 128, 0, st>>>(os, sc, expn_tab, keys, nkeys, order, nangles, angles);
     PB_KERNEL_CHECK();
 }
 
@@ -461,16 +466,19 @@ struct DescWarpSmem {
     float wxy[4][32];
     float hist[128];
 };
+// order (optional): slot -> job index, largest patch first (841 .. 13 k samples per descriptor; see orient_kernel)
 __global__ void __launch_bounds__(128) descr_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
                                                     const KeyIn* __restrict__ keys, const DescJob* __restrict__ jobs,
-                                                    int njobs, float* __restrict__ descr, int* __restrict__ written) {
+                                                    int njobs, const int* __restrict__ order, float* __restrict__ descr,
+                                                    int* __restrict__ written) {
     __shared__ double tab[257];
     __shared__ DescWarpSmem wsm[4];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = expn_tab[i];
     __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int job = blockIdx.x * 4 + wid;
-    if (job >= njobs) return;
+    const int slot = blockIdx.x * 4 + wid;
+    if (slot >= njobs) return;
+    const int job = order ? order[slot] : slot;
     DescWarpSmem& S = wsm[wid];
     const DescJob j = jobs[job];
     const KeyIn k = keys[j.key];
@@ -583,10 +591,11 @@ __global__ void __launch_bounds__(128) descr_kernel(OctaveSet os, SiftConsts sc,
     if (lane == 0) written[job] = 1;
 }
 void launch_descr(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys,
-                  const DescJob* jobs, int njobs, float* descr, int* written, double patch_bytes, cudaStream_t st) {
+                  const DescJob* jobs, int njobs, const int* order, float* descr, int* written, double patch_bytes,
+                  cudaStream_t st) {
     if (njobs <= 0) return;
     KScope ks("sift.descr", st, patch_bytes + 512.0 * njobs);
-    descr_kernel<<<div_up(njobs, 4), 128, 0, st>>>(os, sc, expn_tab, keys, jobs, njobs, descr, written);
+    descr_kernel<<<div_up(njobs, 4), 128, 0, st>>>(os, sc, expn_tab, keys, jobs, njobs, order, descr, written);
     PB_KERNEL_CHECK();
 }
 

@@ -49,9 +49,11 @@ void launch_refine(const OctaveView& ov, const SiftConsts& sc, const Cand* cand,
                    RefinedKey* out, double xper, cudaStream_t st);
 void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cudaStream_t st);
 void launch_orient(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys, int nkeys,
-                   int* nangles, double* angles, cudaStream_t st);
+                   const int* order, int* nangles, double* angles, cudaStream_t st);
+// order (both launchers, optional device array): slot -> item, so that the largest windows are issued first
 // patch_bytes: algorithmic gradient-map bytes of the jobs, sum over jobs of (2W+1)^2 * 8 (reporting only)
 void launch_descr(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys,
-                  const DescJob* jobs, int njobs, float* descr, int* written, double patch_bytes, cudaStream_t st);
+                  const DescJob* jobs, int njobs, const int* order, float* descr, int* written, double patch_bytes,
+                  cudaStream_t st);
 
 }  // namespace pb
