@@ -291,14 +291,17 @@ __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, dou
 //
 // Coef selects the recurrence: IirCoef = Van Vliet (fp64 state; the backward run filters the forward output in place,
 // so pass 1 streams `dst` back in); DericheCoef = Deriche (fp32 state; causal and anticausal runs both filter the
-// INPUT, so pass 1 streams `src` again and the storer adds the anticausal tile onto the causal output already in
-// `dst`: out = Y + yc, CImg.h:34797 -- src and dst must be distinct buffers).
+// INPUT, so pass 1 streams `src` again TOGETHER with the causal output Y already in `dst`, and the consumer stores
+// out = Y + yc, CImg.h:34797 -- src and dst must be distinct buffers).
 template <bool kElemContig, class Coef>
 __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
                                                       long nlines, int lines_per_plane, long plane_stride,
                                                       long elem_stride, Coef c) {
     constexpr bool kDeriche = std::is_same<Coef, DericheCoef>::value;
     __shared__ float tiles[kIirNS][32 * kIirPitch];
+    // Deriche, pass 1: the causal output Y of the same tile, streamed back beside the input so that the consumer forms
+    // out = Y + yc itself (a read-modify-write in the storer exposes one HBM latency per tile)
+    __shared__ float ytiles[kDeriche ? kIirNS : 1][kDeriche ? 32 * kIirPitch : 1];
     __shared__ unsigned long long full[kIirNS], done[kIirNS], vacant[kIirNS];
     const int lane = threadIdx.x & 31;
     const int warp = ((threadIdx.x >> 5) + 4 - (blockIdx.x & 3)) & 3;   // role: 0 consumer, 1 loader, 2 storer, 3 idle
@@ -332,12 +335,13 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
                         for (int e = 0; e < ne; ++e) t[e * kIirPitch] = f.step(t[e * kIirPitch], c);
                     }
                 } else {
+                    const float* ty = &ytiles[s][lane];
                     if (q == T) b.init(t[(ne - 1) * kIirPitch], c);
-                    if (ne == 32) {
+                    if (ne == 32) {   // out = Y + yc (CImg.h:34797)
 #pragma unroll
-                        for (int e = 31; e >= 0; --e) t[e * kIirPitch] = b.step(t[e * kIirPitch], c);
+                        for (int e = 31; e >= 0; --e) t[e * kIirPitch] = ty[e * kIirPitch] + b.step(t[e * kIirPitch], c);
                     } else {
-                        for (int e = ne - 1; e >= 0; --e) t[e * kIirPitch] = b.step(t[e * kIirPitch], c);
+                        for (int e = ne - 1; e >= 0; --e) t[e * kIirPitch] = ty[e * kIirPitch] + b.step(t[e * kIirPitch], c);
                     }
                 }
                 __syncwarp();
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
     if (warp == 1) {
         for (int pass = 0; pass < 2; ++pass) {
             const float* from = (pass == 0 || kDeriche) ? src : dst;
-            if (pass == 1 && !kDeriche)   // the backward run reads the forward output: every forward tile must have reached HBM
+            if (pass == 1)   // the backward run reads the forward output: every forward tile must have reached HBM
                 for (int j = (T - kIirNS > 0 ? T - kIirNS : 0); j < T; ++j)
                     mbar_wait_relaxed(&vacant[j % kIirNS], (unsigned)((j / kIirNS) & 1));
             for (int i = 0; i < T; ++i) {
@@ -426,19 +430,31 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
                 const int tile = pass == 0 ? i : T - 1 - i;
                 const int e0 = tile * 32;
                 float* sp = &tiles[s][s_off];
+                const bool with_y = kDeriche && pass == 1;
+                float* yp = &ytiles[kDeriche ? s : 0][kDeriche ? s_off : 0];
                 if (kElemContig) {
                     if (e0 + lane < N) {
                         const float* g = from + mybase + e0;
+                        const float* gy = dst + mybase + e0;
 #pragma unroll 8
                         for (int r = 0; r < nl; ++r) { cp_async4(sp, g); sp += s_step; g += g_step; }
+                        if (with_y) {
+#pragma unroll 8
+                            for (int r = 0; r < nl; ++r) { cp_async4(yp, gy); yp += s_step; gy += g_step; }
+                        }
                     }
                 } else if (line_ok) {
                     const int ne = (N - e0) < 32 ? (N - e0) : 32;
                     const float* g = from + mybase + (long)e0 * elem_stride;
+                    const float* gy = dst + mybase + (long)e0 * elem_stride;
 #pragma unroll 8
                     for (int e = 0; e < ne; ++e) { cp_async4(sp, g); sp += s_step; g += g_step; }
+                    if (with_y) {
+#pragma unroll 8
+                        for (int e = 0; e < ne; ++e) { cp_async4(yp, gy); yp += s_step; gy += g_step; }
+                    }
                 }
-                cp_async_arrive(&full[s]);
+                cp_async_arrive(&full[s]);   // one arrival per lane once ALL its copies above have landed
             }
         }
     } else {
@@ -453,39 +469,16 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
                 if (kElemContig) {
                     if (e0 + lane < N) {
                         float* g = dst + mybase + e0;
-                        if (kDeriche && pass == 1) {   // out = Y + yc; this thread wrote Y[g] itself in pass 0
-                            // all reads of Y go out before the first add: element by element the tile costs 32 HBM latencies
-                            if (nl == 32) {
-                                float y[32];
-#pragma unroll
-                                for (int r = 0; r < 32; ++r) y[r] = g[(long)r * g_step];
-#pragma unroll
-                                for (int r = 0; r < 32; ++r) g[(long)r * g_step] = y[r] + sp[r * s_step];
-                            } else {
-                                for (int r = 0; r < nl; ++r) { *g = *g + *sp; sp += s_step; g += g_step; }
-                            }
-                        } else {
 #pragma unroll 8
-                            for (int r = 0; r < nl; ++r) { *g = *sp; sp += s_step; g += g_step; }
-                        }
+                        for (int r = 0; r < nl; ++r) { *g = *sp; sp += s_step; g += g_step; }
+
                     }
                 } else if (line_ok) {
                     const int ne = (N - e0) < 32 ? (N - e0) : 32;
                     float* g = dst + mybase + (long)e0 * elem_stride;
-                    if (kDeriche && pass == 1) {
-                        if (ne == 32) {
-                            float y[32];
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) y[e] = g[(long)e * g_step];
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) g[(long)e * g_step] = y[e] + sp[e * s_step];
-                        } else {
-                            for (int e = 0; e < ne; ++e) { *g = *g + *sp; sp += s_step; g += g_step; }
-                        }
-                    } else {
 #pragma unroll 8
-                        for (int e = 0; e < ne; ++e) { *g = *sp; sp += s_step; g += g_step; }
-                    }
+                    for (int e = 0; e < ne; ++e) { *g = *sp; sp += s_step; g += g_step; }
+
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&vacant[s]);   // release: the loader (same CTA) re-reads forward tiles after acquiring this

@@ -5,10 +5,20 @@ sys.path.insert(0, ROOT)
 import bench
 import computervisionimagestich2_b200 as pano
 name = sys.argv[1] if len(sys.argv) > 1 else "input2"
-imgs, desc, _ = bench.load_workload(name)
+ex6 = name.startswith("ex6_dataset")   # ex6_dataset2 / ex6_dataset3: the src/ex6 sets with the ex6 profile
+if ex6:
+    from computervisionimagestich2_b200 import bmpio
+    k = int(name[-1])
+    d = os.path.join(ROOT, "oracle", "_ref", "data", name)
+    imgs = [bmpio.load_bmp(os.path.join(d, f"{i + 1}.bmp")) for i in range({2: 18, 3: 11}[k])]
+    desc = f"src/ex6/dataset{k} ({len(imgs)} images), ex6 profile"
+else:
+    imgs, desc, _ = bench.load_workload(name)
 if len(sys.argv) > 2:
     imgs = imgs[: int(sys.argv[2])]
 L = pano.lib(); ctx = pano.Context(0); n = len(imgs)
+if ex6:
+    ctx.set_profile("ex6", 666666)
 ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
 ws = (C.c_int * n)(*[i.shape[2] for i in imgs]); hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
 ctx._check(L.pano_b200_stage_images(ctx.h, ptrs, ws, hs, n), "stage")
