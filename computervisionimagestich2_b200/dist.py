@@ -33,6 +33,12 @@ def wave2(n: int, counts: dict):
     return [(i, j) for i in range(n) for j in range(i) if counts[(j, i)] < THRESHOLD]
 
 
+def chain_wave(n: int):
+    """The src/ex6 profile matches only neighbours of the fixed chain 0-1-...-(n-1), both directions
+    (src/ex6/ImageProcess.cpp:150-157, 195-196): one wave, no adjacency discovery."""
+    return [p for i in range(n - 1) for p in ((i, i + 1), (i + 1, i))]
+
+
 def _all_gather_ragged(dist, arr: np.ndarray, device):
     """all-gather of one byte blob per rank (ragged): sizes first, then blobs padded to the maximum."""
     import torch
@@ -99,10 +105,12 @@ def _unpack_matches(blob):
     return out
 
 
-def stitch_sharded(engine, images, dist=None, device="cpu"):
+def stitch_sharded(engine, images, dist=None, device="cpu", profile="root"):
     """images: the full list of planar uint8 [3][H][W] inputs (every rank holds it, or at least its own share at the
     right positions).  Returns (panorama, info) on rank 0 and (None, info) elsewhere; info carries the exchanged
-    feature counts and match counts so that callers / tests can check them on every rank."""
+    feature counts and match counts so that callers / tests can check them on every rank.  profile: "root" (all-pairs
+    discovery, two waves) or "ex6" (chain neighbours, one wave); the engine must have been switched to the same profile
+    (Context.set_profile) so that rank 0 stitches accordingly."""
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
     n = len(images)
@@ -127,9 +135,12 @@ def stitch_sharded(engine, images, dist=None, device="cpu"):
         for blob in got:
             midx.update(_unpack_matches(blob))
 
-    run_wave(wave1(n))
-    counts = {k: int((v >= 0).sum()) for k, v in midx.items()}
-    run_wave(wave2(n, counts))
+    if profile == "ex6":
+        run_wave(chain_wave(n))
+    else:
+        run_wave(wave1(n))
+        counts = {k: int((v >= 0).sum()) for k, v in midx.items()}
+        run_wave(wave2(n, counts))
     counts = {k: int((v >= 0).sum()) for k, v in midx.items()}
     info = dict(nfeat=[len(table[i][2]) for i in range(n)], match_counts=counts, world=world)
     # 4. the sequential part on rank 0

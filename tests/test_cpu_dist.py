@@ -34,7 +34,7 @@ class OracleEngine:
         return None, dict(npairs=len(midx), shapes=[p.shape for p in projs])
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, profile="root"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     import torch.distributed as dist
@@ -42,7 +42,7 @@ def _worker(rank, world, port, out_dir):
     from oracle import ref_api
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     imgs = [ref_api.load_bmp(os.path.join(ref_api.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
-    _, info = pdist.stitch_sharded(OracleEngine(), imgs, dist=dist, device="cpu")
+    _, info = pdist.stitch_sharded(OracleEngine(), imgs, dist=dist, device="cpu", profile=profile)
     with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
         json.dump({"nfeat": info["nfeat"], "match_counts": {f"{i},{j}": c for (i, j), c in info["match_counts"].items()},
                    "npairs": info.get("npairs")}, f)
@@ -56,6 +56,7 @@ def test_plan_helpers():
     assert pdist.wave1(3) == [(0, 1), (0, 2), (1, 2)]
     counts = {(0, 1): 87, (0, 2): 3, (1, 2): 54}
     assert pdist.wave2(3, counts) == [(2, 0)]
+    assert pdist.chain_wave(4) == [(0, 1), (1, 0), (1, 2), (2, 1), (2, 3), (3, 2)] and pdist.chain_wave(1) == []
     items = [((2, 0), np.array([1, -1, 5], np.int32)), ((1, 0), np.zeros(0, np.int32))]
     back = pdist._unpack_matches(pdist._pack_matches(items))
     assert np.array_equal(back[(2, 0)], items[0][1]) and len(back[(1, 0)]) == 0
@@ -79,3 +80,20 @@ def test_sharded_job_world2_gloo(ref, tmp_path):
               or anchors["match_counts"][",".join(reversed(k.split(",")))] < 20}
     assert r0["match_counts"] == expect
     assert r0["npairs"] == len(expect) and r1["npairs"] is None
+
+
+def test_sharded_job_world2_gloo_ex6_chain(ref, tmp_path):
+    """src/ex6 profile: only the neighbours of the fixed chain are matched, both directions, in one wave."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path), "ex6"), nprocs=2, join=True)
+    anchors = json.load(open(os.path.join(HERE, "golden", "anchors.json")))["Input"]
+    r0 = json.load(open(tmp_path / "rank0.json"))
+    r1 = json.load(open(tmp_path / "rank1.json"))
+    assert r0["nfeat"] == r1["nfeat"] == anchors["nfeat"]
+    expect = {k: anchors["match_counts"][k] for k in ("0,1", "1,0", "1,2", "2,1", "2,3", "3,2")}
+    assert r0["match_counts"] == r1["match_counts"] == expect
+    assert r0["npairs"] == 6 and r1["npairs"] is None
