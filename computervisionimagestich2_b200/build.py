@@ -20,6 +20,7 @@ OBJ = os.path.join(HERE, "build")
 SOURCES = ["sift_kernels.cu", "sift_engine.cu", "match_kernels.cu", "canvas_kernels.cu", "stitcher.cu", "c_api.cu",
            "vl_sift_shim.cu", "vl_kdforest_shim.cu", "bench_kernels.cu", "match_i8_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+EXTRA = os.environ.get("PANO_B200_NVCC_EXTRA", "").split()   # e.g. -DPB_DESCR_DEBUG for an instrumented build
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-diag-suppress", "550"]
 
@@ -41,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def cc(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *EXTRA, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
