@@ -461,9 +461,9 @@ constexpr int kDescRows = 192;   // rows of the patch handled per pass (taller p
 struct DescWarpSmem {
     int rowstart[kDescRows + 1];
     int rowx0[kDescRows];
-    int packed[32];
-    float at[2][32];
-    float wxy[4][32];
+    // [cell][sample of the batch * 2 + orientation parity]: the addend of that sample for that cell.  Pitch 66, not 64: lane
+    // 2c + p reads column 2q + p of row c, and with a pitch that is a multiple of 32 the sixteen cells would share a bank
+    float vals[16][66];
     float hist[128];
 };
 // order (optional): slot -> job index, largest patch first (841 .. 13 k samples per descriptor; see orient_kernel)
@@ -524,21 +524,34 @@ __global__ void __launch_bounds__(128) descr_kernel(OctaveSet os, SiftConsts sc,
             // ---- phase A ----
             const int i = base + lane;
             unsigned cellmask = 0;
+            int kk0 = 0, kk1 = 0;   // which of the lane-owned bins (parity 0 / parity 1) this sample feeds
             if (i < total) {
                 while (i >= S.rowstart[r + 1]) ++r;
                 const int dxi = S.rowx0[r] + (i - S.rowstart[r]), dyi = rg + r;
                 const float2 g = gp[(long)(F.yi + dyi) * F.pitch + (F.xi + dxi)];
                 const DescSample sm = descriptor_sample(F, tab, dxi, dyi, g.x, g.y);
                 if (sm.active) {
-                    S.packed[lane] = (sm.binx + 8) | ((sm.biny + 8) << 8) | (sm.bint << 16);
-                    S.at[0][lane] = sm.at[0]; S.at[1][lane] = sm.at[1];
-                    S.wxy[0][lane] = sm.wxy[0][0]; S.wxy[1][lane] = sm.wxy[0][1];
-                    S.wxy[2][lane] = sm.wxy[1][0]; S.wxy[3][lane] = sm.wxy[1][1];
-                    // cells (binx + {0,1}, biny + {0,1}) inside the grid, as a 4x4 bit mask (bit = (cy+2)*4 + cx+2)
-                    const unsigned mx = ((3u << (sm.binx + 3)) >> 1) & 0xFu;
-                    const unsigned my = ((3u << (sm.biny + 3)) >> 1) & 0xFu;
-                    cellmask = ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 4 : 0u) | ((my & 4u) ? mx << 8 : 0u) |
-                               ((my & 8u) ? mx << 12 : 0u);
+                    // orientation bins bint and bint + 1: the even one goes to the parity-0 lane of a cell, the odd one to
+                    // the parity-1 lane; within a lane the four owned bins are (bin >> 1)
+                    const int sel0 = (sm.bint & 1) ? 1 : 0, sel1 = 1 - sel0;
+                    kk0 = ((sm.bint + sel0) & 7) >> 1;
+                    kk1 = ((sm.bint + sel1) & 7) >> 1;
+                    const float a0 = sm.at[sel0], a1 = sm.at[sel1];
+                    // the (up to) four cells (binx + dx, biny + dy) inside the grid: the sample's addends are written where
+                    // the owning lanes will pick them up with ONE shared-memory read, and flagged in a 4x4 bit mask
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy) {
+                            const int ccx = sm.binx + dx, ccy = sm.biny + dy;
+                            if (ccx >= -2 && ccx <= 1 && ccy >= -2 && ccy <= 1) {
+                                const int c = (ccy + 2) * 4 + (ccx + 2);
+                                const float w = sm.wxy[dx][dy];
+                                S.vals[c][lane * 2] = w * a0;
+                                S.vals[c][lane * 2 + 1] = w * a1;
+                                cellmask |= 1u << c;
+                            }
+                        }
                 }
             }
             __syncwarp();
@@ -548,18 +561,24 @@ __global__ void __launch_bounds__(128) descr_kernel(OctaveSet os, SiftConsts sc,
                 const unsigned m = __ballot_sync(0xffffffffu, (cellmask >> c) & 1u);
                 if (c == cell) mine = m;
             }
+            // every lane is also a sample: publish ITS bin selectors for both parities
+            const unsigned k0a = __ballot_sync(0xffffffffu, kk0 & 1), k1a = __ballot_sync(0xffffffffu, kk0 >> 1);
+            const unsigned k0b = __ballot_sync(0xffffffffu, kk1 & 1), k1b = __ballot_sync(0xffffffffu, kk1 >> 1);
+            const unsigned klo = par ? k0b : k0a, khi = par ? k1b : k1a;
             // ---- phase B ----
+            // lane 2c + p adds, in sample order, the addends of the samples that reach cell c: one read per addend
+            const float* mv = &S.vals[cell][par];
             for (; mine; mine &= mine - 1) {
                 const int q = __ffs(mine) - 1;
-                const int pk = S.packed[q];
-                const int dbx = cx - ((pk & 0xff) - 8), dby = cy - (((pk >> 8) & 0xff) - 8), bt = pk >> 16;
-                const int sel = ((bt & 1) == par) ? 0 : 1;
-                const float v = S.wxy[dbx * 2 + dby][q] * S.at[sel][q];
-                const int kk = ((bt + sel) & 7) >> 1;
-                if (kk == 0) h0 += v;
-                else if (kk == 1) h1 += v;
-                else if (kk == 2) h2 += v;
-                else h3 += v;
+                const float v = mv[q * 2];
+                const int kk = ((klo >> q) & 1u) | (((khi >> q) & 1u) << 1);
+                // add-then-select: no branch on kk (lanes disagree on it; as an if-chain this loop cost 134 cycles per
+                // addend, 40 % of the kernel), and no "+ 0" that could touch a signed zero
+                const float t0 = h0 + v, t1 = h1 + v, t2 = h2 + v, t3 = h3 + v;
+                h0 = kk == 0 ? t0 : h0;
+                h1 = kk == 1 ? t1 : h1;
+                h2 = kk == 2 ? t2 : h2;
+                h3 = kk == 3 ? t3 : h3;
             }
             __syncwarp();
         }
