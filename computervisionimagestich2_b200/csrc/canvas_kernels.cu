@@ -3,6 +3,7 @@
 // All of them are HBM-bound byte/float streaming; arithmetic is in canvas_device.cuh (bit-exact bodies).
 #include "canvas_kernels.h"
 #include <type_traits>
+#include <cmath>
 #include "common.h"
 #include "ktimer.h"
 
@@ -662,11 +663,77 @@ __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const
         else E[c * n + o] = e;
     }
 }
+// Tiled form of the same level step.  CImg's linear resize interpolates along x, rounds to float, then interpolates along
+// y (CImg.h:29641-29652); in collapse_kernel every output pixel redoes the two x-interpolations of its two source rows for
+// all nine up-sampled planes, although at 2:1 each x-interpolated value is shared by four output rows.  Here a CTA
+// (64 x 16 output pixels) first fills shared memory with the x-interpolated source rows it needs (nine planes, at most
+// kCollapseSrcRows rows), then every pixel only does the y-interpolation and the blend.  Same operations on the same
+// operands; ~15 instead of 27 double-precision interpolations per pixel.
+constexpr int kCollapseTileH = 16, kCollapseSrcRows = 12;
+__global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __restrict__ G, int w, int h,
+                                                             const float* __restrict__ Gup, const float* __restrict__ Eup,
+                                                             int uw, int uh, DevLinear tx, DevLinear ty,
+                                                             float* __restrict__ E, u8* __restrict__ out8) {
+    __shared__ float X[9][kCollapseSrcRows][64];
+    const int x = blockIdx.x * 64 + threadIdx.x;
+    const int yt0 = blockIdx.y * kCollapseTileH;
+    const int yt1 = (yt0 + kCollapseTileH < h ? yt0 + kCollapseTileH : h) - 1;   // last output row of the tile
+    const int r0 = ty.pos[yt0];
+    int r1 = ty.pos[yt1] + 1;
+    if (r1 > uh - 1) r1 = uh - 1;
+    const int nrows = r1 - r0 + 1;   // <= kCollapseSrcRows, guaranteed by the launcher
+    if (nrows > kCollapseSrcRows) __trap();
+    const size_t n = (size_t)w * h, un = (size_t)uw * uh;
+    const bool xin = x < w;
+    if (xin) {
+        const int px = tx.pos[x], px1 = px < uw - 1 ? px + 1 : px;
+        const double ax = tx.alpha[x];
+        for (int r = threadIdx.y; r < nrows; r += 4) {
+            const size_t ro = (size_t)(r0 + r) * uw;
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+                const float* plane = p < 6 ? Gup + (size_t)p * un : Eup + (size_t)(p - 6) * un;
+                const float a0 = plane[ro + px], a1 = plane[ro + px1];
+                X[p][r][threadIdx.x] = (float)((1 - ax) * (double)a0 + ax * (double)a1);
+            }
+        }
+    }
+    __syncthreads();
+    if (!xin) return;
+    for (int y = yt0 + threadIdx.y; y <= yt1; y += 4) {
+        const int py = ty.pos[y], pr = py - r0;
+        const bool has_y1 = py < uh - 1;
+        const double ay = ty.alpha[y];
+        const size_t o = (size_t)y * w + x;
+        const float m = G[6 * n + o];
+        auto up = [&](int p) {
+            const float v0 = X[p][pr][threadIdx.x];
+            const float v1 = has_y1 ? X[p][pr + 1][threadIdx.x] : v0;
+            return (float)((1 - ay) * (double)v0 + ay * (double)v1);
+        };
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float la = G[c * n + o] - up(c), lb = G[(3 + c) * n + o] - up(3 + c);
+            const float e = collapse_px(blend_px(la, lb, m), up(6 + c));
+            if (out8) out8[c * n + o] = (u8)e;
+            else E[c * n + o] = e;
+        }
+    }
+}
 void launch_collapse(const float* G_i, int w, int h, const float* G_up, const float* E_up, int uw, int uh, DevLinear tx,
                      DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st) {
     KScope ks("blend.collapse", st, (28.0 + (out_u8 ? 3.0 : 12.0)) * w * h + 40.0 * uw * uh);
-    dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
-    collapse_kernel<<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+    // the tiled form needs the source rows of a 16-row tile to fit its shared-memory window: pos[y] advances by
+    // fx = (uh - 1) / (h - 1) per output row (hostnum::linear_table), so a tile spans at most ceil(15 fx) + 3 source rows --
+    // 11 for the pyramid's 2:1 steps; anything coarser takes the per-pixel kernel
+    const double fx = h > 1 ? (uh - 1.0) / (h - 1.0) : 1e9;
+    if (G_up && std::ceil((kCollapseTileH - 1) * fx) + 3 <= kCollapseSrcRows) {
+        dim3 b(64, 4), g(div_up(w, 64), div_up(h, kCollapseTileH));
+        collapse_tiled_kernel<<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+    } else {
+        dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
+        collapse_kernel<<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+    }
     PB_KERNEL_CHECK();
 }
 
