@@ -258,7 +258,8 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
 __device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-constexpr int kIirNS = 4;          // tiles in flight per CTA
+constexpr int kIirNSVanVliet = 4;  // tiles in flight per CTA (4.2 KB each); 8 measured slower (22.1 vs 20.0 ms on 8 x 4K)
+constexpr int kIirNSDeriche = 4;   // Deriche keeps two rings (input and causal output)
 constexpr int kIirPitch = 33;      // floats between consecutive elements of a tile
 }  // namespace
 
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__
                                                       long nlines, int lines_per_plane, long plane_stride,
                                                       long elem_stride, Coef c) {
     constexpr bool kDeriche = std::is_same<Coef, DericheCoef>::value;
+    constexpr int kIirNS = kDeriche ? kIirNSDeriche : kIirNSVanVliet;
     __shared__ float tiles[kIirNS][32 * kIirPitch];
     // Deriche, pass 1: the causal output Y of the same tile, streamed back beside the input so that the consumer forms
     // out = Y + yc itself (a read-modify-write in the storer exposes one HBM latency per tile)
