@@ -687,6 +687,18 @@ __global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __rest
     if (nrows > kCollapseSrcRows) __trap();
     const size_t n = (size_t)w * h, un = (size_t)uw * uh;
     const bool xin = x < w;
+    // this thread's level-i values (7 planes x 4 rows) are requested first: they do not depend on the x-interpolation
+    // below, which then hides their latency
+    float gv[kCollapseTileH / 4][7];
+    if (xin) {
+#pragma unroll
+        for (int j = 0; j < kCollapseTileH / 4; ++j) {
+            const int y = yt0 + threadIdx.y + 4 * j;
+            const size_t o = (size_t)(y <= yt1 ? y : yt1) * w + x;
+#pragma unroll
+            for (int p = 0; p < 7; ++p) gv[j][p] = G[p * n + o];
+        }
+    }
     if (xin) {
         const int px = tx.pos[x], px1 = px < uw - 1 ? px + 1 : px;
         const double ax = tx.alpha[x];
@@ -702,12 +714,15 @@ __global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __rest
     }
     __syncthreads();
     if (!xin) return;
-    for (int y = yt0 + threadIdx.y; y <= yt1; y += 4) {
+#pragma unroll
+    for (int j = 0; j < kCollapseTileH / 4; ++j) {
+        const int y = yt0 + threadIdx.y + 4 * j;
+        if (y > yt1) break;
         const int py = ty.pos[y], pr = py - r0;
         const bool has_y1 = py < uh - 1;
         const double ay = ty.alpha[y];
         const size_t o = (size_t)y * w + x;
-        const float m = G[6 * n + o];
+        const float m = gv[j][6];
         auto up = [&](int p) {
             const float v0 = X[p][pr][threadIdx.x];
             const float v1 = has_y1 ? X[p][pr + 1][threadIdx.x] : v0;
@@ -715,7 +730,7 @@ __global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __rest
         };
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float la = G[c * n + o] - up(c), lb = G[(3 + c) * n + o] - up(3 + c);
+            const float la = gv[j][c] - up(c), lb = gv[j][3 + c] - up(3 + c);
             const float e = collapse_px(blend_px(la, lb, m), up(6 + c));
             if (out8) out8[c * n + o] = (u8)e;
             else E[c * n + o] = e;

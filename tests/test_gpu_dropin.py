@@ -58,6 +58,21 @@ def test_kdforest_other_dimensions_and_tiny_tables(shim, ref):
         assert np.array_equal(gd.view(np.uint64), wd.view(np.uint64)) and np.array_equal(gi, wi), (n, nq, dim, k)
 
 
+def test_kdforest_fewer_points_than_neighbours(shim):
+    """One data point, two neighbours asked for (getImgPair on a 1-feature image reads an unset second neighbour in
+    VLFeat): the shim reports the missing neighbour as index -1 / distance NaN instead of leaving it undefined."""
+    data, queries = _tables(3, 1, 4)
+    for per_query in (True, False):
+        gi, gd = shim.kdforest_query(data, queries, 2, 0, per_query)
+        assert np.all(gi[:, 0] == 0) and np.all(gi[:, 1] == -1)
+        assert np.all(np.isfinite(gd[:, 0])) and np.all(np.isnan(gd[:, 1]))
+        want = np.abs(queries.astype(np.float32) - data[0]).astype(np.float32)
+        acc = np.zeros(len(queries), np.float32)
+        for d in range(128):
+            acc = (acc + want[:, d]).astype(np.float32)
+        assert np.array_equal(gd[:, 0].astype(np.float32).view(np.uint32), acc.view(np.uint32))
+
+
 def test_reference_sift_and_matching_on_the_shim(shim, ref, input_sets):
     imgs = input_sets["Input"][2:4]
     g = [ref.gray(ref.project(im)) for im in imgs]
