@@ -248,6 +248,14 @@ void SiftEngine::describe_octave(int oi, const std::vector<int>& key_idx, const 
     PB_CUDA(cudaStreamSynchronize(st_));
 }
 
+// stable counting sort of item indices by descending radius (0..255)
+static void order_by_radius_desc(const int* radius, int n, int* order) {
+    int first[257] = {0};
+    for (int i = 0; i < n; ++i) first[255 - radius[i] + 1]++;
+    for (int b = 0; b < 256; ++b) first[b + 1] += first[b];
+    for (int i = 0; i < n; ++i) order[first[255 - radius[i]]++] = i;
+}
+
 void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     out = RawFeatures();
     const int O = (int)oct_.size();
@@ -314,13 +322,16 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     keyin_.ensure(nk);
     nangles_.ensure(nk);
     angles_.ensure((size_t)nk * 4);
-    // largest windows first (both kernels: one warp per item, the launch ends with its slowest warp)
+    // largest windows first (both kernels: one warp per item, the launch ends with its slowest warp): a counting sort on
+    // the integer window radius -- a comparison sort of the keys costs more host time than the ordering saves
     int* h_ok = (int*)h_order_k_.ensure((size_t)nk * sizeof(int));
     {
-        std::vector<std::pair<float, int>> byscale(nk);
-        for (int i = 0; i < nk; ++i) byscale[i] = {-(float)((double)hk[i].sigma / os.xper[hk[i].oct]), i};
-        std::stable_sort(byscale.begin(), byscale.end());
-        for (int i = 0; i < nk; ++i) h_ok[i] = byscale[i].second;
+        std::vector<int> radius(nk);
+        for (int i = 0; i < nk; ++i) {
+            const double Wd = floor(3.0 * 1.5 * ((double)hk[i].sigma / os.xper[hk[i].oct]));   // vl/sift.c:928
+            radius[i] = Wd > 255 ? 255 : (Wd > 1 ? (int)Wd : 1);
+        }
+        order_by_radius_desc(radius.data(), nk, h_ok);
     }
     order_k_.ensure(nk);
     PB_CUDA(cudaMemcpyAsync(order_k_.p, h_ok, (size_t)nk * sizeof(int), cudaMemcpyHostToDevice, st_));
@@ -359,16 +370,15 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     double patch_bytes = 0;   // sum_k (2 W_k + 1)^2 * 8 B of (modulus, angle) reads
     int* h_oj = (int*)h_order_j_.ensure(nj * sizeof(int));
     {
-        std::vector<std::pair<float, int>> bysize(nj);
+        std::vector<int> radius(nj);
         for (size_t q = 0; q < nj; ++q) {
             const KeyIn& kk = hk[hj[q].key];
             const double sbp = p_.magnif * ((double)kk.sigma / os.xper[kk.oct]);
             const double W = floor(1.4142135623730951 * sbp * 2.5 + 0.5);
             patch_bytes += (2 * W + 1) * (2 * W + 1) * 8.0;
-            bysize[q] = {-(float)W, (int)q};
+            radius[q] = W > 255 ? 255 : (W > 0 ? (int)W : 0);
         }
-        std::stable_sort(bysize.begin(), bysize.end());
-        for (size_t q = 0; q < nj; ++q) h_oj[q] = bysize[q].second;
+        order_by_radius_desc(radius.data(), (int)nj, h_oj);
     }
     order_j_.ensure(nj);
     PB_CUDA(cudaMemcpyAsync(order_j_.p, h_oj, nj * sizeof(int), cudaMemcpyHostToDevice, st_));
