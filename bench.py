@@ -449,12 +449,13 @@ def ncu_traffic(kernel, workload):
 
 def sift_summary(kernels, stages, mpix):
     """north_star: 'SIFT Mpix/s (HBM GB/s)'.  Mpixel/s = input pixels / wall time of the feature stage of the last timed
-    step (projection + SIFT + table for all images, concurrent lanes); GB/s = algorithmic bytes / CUDA-event time of the
+    step (projection + SIFT + table for all images, concurrent lanes; `project` and `table` in stages_ms are per-lane sums
+    that lie inside it); GB/s = algorithmic bytes / CUDA-event time of the
     scale-space kernels (blur, DoG-on-the-fly detector, gradient) in the serial instrumented pass."""
     ss = [k for n, k in kernels.items() if n in ("sift.blur_v", "sift.blur_h", "sift.detect", "sift.gradient")]
     ms = sum(k["ms"] for k in ss)
     by = sum(k["bytes"] for k in ss)
-    feat_ms = stages.get("project", 0) + stages.get("sift", 0) + stages.get("table", 0)
+    feat_ms = stages.get("sift", 0)   # wall time of Stitcher::add_images: projection + SIFT + table of all images, lanes in parallel
     return {"mpixel_per_s": round(mpix / (feat_ms * 1e-3), 1) if feat_ms > 0 else None, "feature_stage_ms": round(feat_ms, 3),
             "scale_space_GBps": round(by / (ms * 1e-3) / 1e9, 1) if ms > 0 else None, "scale_space_ms": round(ms, 4),
             "all_sift_kernels_ms": round(sum(k["ms"] for n, k in kernels.items() if n.startswith("sift.")), 4)}
