@@ -79,11 +79,14 @@ def gray(img: np.ndarray) -> np.ndarray:
 def sift_features(gray_u8: np.ndarray, cap: int = 1 << 20):
     g = np.ascontiguousarray(gray_u8, np.uint8)
     h, w = g.shape
-    n = lib().ref_sift_features(_p(g), w, h, None, None, 0)
-    descr = np.empty((n, 128), np.float32)
-    keys = np.empty(n, KEY_DTYPE)
-    lib().ref_sift_features(_p(g), w, h, _p(descr), _p(keys), n)
-    return descr, keys
+    cap = max(4096, min(cap, (w * h) // 64))   # one run of the reference in the common case (~1 feature per 400 pixels)
+    while True:
+        descr = np.empty((cap, 128), np.float32)
+        keys = np.empty(cap, KEY_DTYPE)
+        n = lib().ref_sift_features(_p(g), w, h, _p(descr), _p(keys), cap)
+        if n <= cap:
+            return descr[:n].copy(), keys[:n].copy()
+        cap = n
 
 
 def sift_dump(im_f32: np.ndarray, noctaves=4, nlevels=2, o_min=0):

@@ -80,3 +80,39 @@ def test_4k_three_view_job_properties(ctx, views):
     assert lines[0] == "1" and len([x for x in lines if x.strip()]) == 3   # middle view first, two edges
     assert p1.shape[1] >= 2160 and p1.shape[2] > 3840
     assert min(i1["nfeat"]) > 10000
+
+
+@pytest.fixture(scope="module")
+def view8k():
+    import bench
+    return bench.synth_scene_views(1, 7680, 4320)[0]
+
+
+def test_8k_blend_and_tail_bit_exact(ctx, ref, view8k):
+    """one multiband blend + equalisation on an 8K-class canvas (11520 x 4320 = 50 Mpixel, 12 pyramid levels, 1.4 GB of
+    level-0 planes): 64-bit offsets in every canvas kernel"""
+    h, w = view8k.shape[1:]
+    cw = w + w // 2
+    a = np.zeros((3, h, cw), np.uint8)
+    b = np.zeros((3, h, cw), np.uint8)
+    a[:, :, :w] = view8k | 1
+    b[:, :, w // 2:] = view8k[:, ::-1, :] | 1
+    out = ctx.blend(a, b)
+    rout = ref.blend(a, b)
+    assert np.array_equal(out, rout)
+    assert np.array_equal(ctx.equalize_mix(out), ref.equalize_mix(rout))
+
+
+def test_8k_projection_and_sift_one_image_bit_exact(ctx, ref, view8k):
+    """BASELINE.json configs[3] image size (7680x4320, 33 Mpixel): one view through projection + gray + SIFT against the
+    compiled reference (about half a minute of CPU).  Exercises 32-bit index limits of the scale-space kernels."""
+    v = view8k
+    assert v.shape == (3, 4320, 7680)
+    p, g = ctx.project(v, want_gray=True)
+    rp = ref.project(v)
+    assert np.array_equal(p, rp)
+    assert np.array_equal(g, ref.gray(rp))
+    d, k = ctx.sift_features(g)
+    rd, rk = ref.sift_features(g)
+    assert len(k) == len(rk) and len(k) > 40000
+    assert np.array_equal(_bits(d), _bits(rd)) and k.tobytes() == rk.tobytes()
