@@ -1,5 +1,7 @@
+"""Per-kernel split of the uint8 / tcgen05 matcher (main MMA kernel, exact finish kernel, table preparation) on uniform
+72k x 72k tables:  python tools/u8split.py   (GPU box)."""
 import ctypes as C, json, os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import computervisionimagestich2_b200 as pano
 L = pano.lib(); ctx = pano.Context(0)
