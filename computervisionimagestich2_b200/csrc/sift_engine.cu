@@ -392,6 +392,8 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     out.keys.reserve(nj);
     out.angles.reserve(nj);
     out.key_index.reserve(nj);
+    out.dev_row.reserve(nj);
+    out.d_descr = descr_.p;
     int oi = 0;
     for (size_t q = 0; q < nj; ++q) {
         if (!hw[q]) { out.dropped_unwritten++; continue; }
@@ -401,6 +403,7 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
         out.angles.push_back(hj[q].angle);
         out.key_index.push_back(gk - kfirst[oi]);
         out.descr.insert(out.descr.end(), hd + q * 128, hd + (q + 1) * 128);
+        out.dev_row.push_back((int)q);
     }
     out.n = (int)out.keys.size();
 }

@@ -29,6 +29,10 @@ struct RawFeatures {
     std::vector<int> noct_keys;     // refined keypoints per octave
     int n = 0;
     int dropped_unwritten = 0;      // (keypoint, angle) pairs whose descriptor the reference leaves unwritten (quirk Q3)
+    // extract() only: the descriptors are still in the engine's device buffer (until its next extract on this stream);
+    // descriptor i is row dev_row[i] of d_descr.  Lets the caller assemble a device table without a host round trip.
+    const float* d_descr = nullptr;
+    std::vector<int> dev_row;
 };
 
 struct OctaveBuf {

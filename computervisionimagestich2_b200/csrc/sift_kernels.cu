@@ -30,6 +30,20 @@ void launch_copy_f32(const float* src, int src_pitch, float* dst, int w, int h, 
                               cudaMemcpyDeviceToDevice, st));
 }
 
+// rows[i] of src -> row i of dst (128 floats each): the sorted, de-duplicated feature table assembled on the device
+__global__ void gather_rows128_kernel(const float* __restrict__ src, const int* __restrict__ rows, int n,
+                                      float* __restrict__ dst) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    reinterpret_cast<float4*>(dst + (size_t)i * 128)[lane] = reinterpret_cast<const float4*>(src + (size_t)rows[i] * 128)[lane];
+}
+void launch_gather_rows128(const float* src, const int* rows, int n, float* dst, cudaStream_t st) {
+    if (n <= 0) return;
+    KScope ks("sift.table_gather", st, 1028.0 * n);
+    gather_rows128_kernel<<<div_up(n, 8), 256, 0, st>>>(src, rows, n, dst);
+    PB_KERNEL_CHECK();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // separable Gaussian blur
 // ---------------------------------------------------------------------------------------------------------

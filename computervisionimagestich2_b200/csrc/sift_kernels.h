@@ -33,6 +33,8 @@ struct OctaveSet {   // the octaves of one image, so that one launch serves the 
 
 void launch_u8_to_f32(const unsigned char* src, int src_pitch, float* dst, int w, int h, int pitch, cudaStream_t st);
 void launch_copy_f32(const float* src, int src_pitch, float* dst, int w, int h, int pitch, cudaStream_t st);
+// dst row i = src row rows[i] (rows of 128 floats; rows: device array)
+void launch_gather_rows128(const float* src, const int* rows, int n, float* dst, cudaStream_t st);
 
 // dst = gaussian(src) (vertical pass into tmp, horizontal pass into dst; src may alias dst).
 // If ds != nullptr the horizontal pass also writes dst sub-sampled by 2 into ds (w/2 x h/2, vl/sift.c:179-194).

@@ -110,7 +110,7 @@ void Stitcher::sift_raw_f32(const float* img, int w, int h, const SiftParams& p,
 
 // std::map<std::vector<float>, VlSiftKeypoint>::insert semantics (ImageProcess.cpp:57, 80-86): ordered by
 // lexicographic descriptor comparison, an equal key keeps the FIRST inserted keypoint.
-void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t) {
+void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t, std::vector<int>* sel) {
     const int n = raw.n;
     std::vector<int> idx(n);
     for (int i = 0; i < n; ++i) idx[i] = i;
@@ -141,9 +141,11 @@ void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t) {
     t.keys.clear();
     t.descr.reserve((size_t)n * 128);
     t.keys.reserve(n);
+    if (sel) { sel->clear(); sel->reserve(n); }
     for (int i = 0; i < n; ++i) {
         if (i > 0 && !less(idx[i - 1], idx[i]) && !less(idx[i], idx[i - 1])) continue;  // duplicate key
         const int s = idx[i];
+        if (sel) sel->push_back(s);
         t.descr.insert(t.descr.end(), D + (size_t)s * 128, D + (size_t)(s + 1) * 128);
         VlKey k = raw.keys[s];
         k.ix = (int)k.x;
@@ -777,8 +779,23 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
             L.eng->extract(L.gray32.p, pitch, raw);
             L.t_sift += t1.ms();
             WallTimer t2;
-            build_table(raw, im.feat);
-            upload_table_on(im.feat, L.st);
+            std::vector<int> sel;
+            build_table(raw, im.feat, &sel);
+            if (raw.d_descr && !sel.empty()) {
+                // the descriptors are still in the engine's device buffer: gather the sorted rows there instead of
+                // sending the 1.2 MB table back over PCIe from pageable memory
+                const int nt = (int)sel.size();
+                int* hr = L.h_rows.ensure(nt);
+                for (int q = 0; q < nt; ++q) hr[q] = raw.dev_row[sel[q]];
+                L.rows.ensure(nt);
+                im.feat.d_descr.ensure((size_t)nt * 128);
+                PB_CUDA(cudaMemcpyAsync(L.rows.p, hr, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, L.st));
+                launch_gather_rows128(raw.d_descr, L.rows.p, nt, im.feat.d_descr.p, L.st);
+                PB_CUDA(cudaStreamSynchronize(L.st));   // the engine's buffer is re-used by the lane's next image
+                im.feat.on_device = true;
+            } else {
+                upload_table_on(im.feat, L.st);
+            }
             L.t_table += t2.ms();
         }
     } catch (const std::exception& e) {

@@ -50,7 +50,8 @@ class Stitcher {
     void gray(const u8* rgb, int w, int h, u8* out_gray);
     void sift_raw_u8(const u8* gray8, int w, int h, const SiftParams& p, RawFeatures& out);
     void sift_raw_f32(const float* img, int w, int h, const SiftParams& p, RawFeatures& out);
-    static void build_table(const RawFeatures& raw, FeatureTable& t);
+    // sel (optional): raw feature index of every table row
+    static void build_table(const RawFeatures& raw, FeatureTable& t, std::vector<int>* sel = nullptr);
     void upload_table(FeatureTable& t);
     // idx[b] = row of A matched by query row b of B, or -1 (ImageProcess.cpp:311-346)
     void match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx);
@@ -151,6 +152,8 @@ class Stitcher {
         std::unique_ptr<SiftEngine> eng;
         DevBuf<u8> in_rgb;
         DevBuf<float> gray32, ktab;
+        DevBuf<int> rows;          // device rows of the sorted table (gather on the device instead of re-uploading it)
+        PinBuf<int> h_rows;
         int ktab_n = 0;
         double t_project = 0, t_sift = 0, t_table = 0;
         std::string err;
