@@ -256,7 +256,7 @@ static void order_by_radius_desc(const int* radius, int n, int* order) {
     for (int i = 0; i < n; ++i) order[first[255 - radius[i]]++] = i;
 }
 
-void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
+void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out, bool copy_descr) {
     out = RawFeatures();
     const int O = (int)oct_.size();
     if (O == 0) return;
@@ -388,12 +388,13 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
     PB_CUDA(cudaStreamSynchronize(st_));
     // 5. assemble in the reference's insertion order (octave, keypoint, angle), dropping descriptors the reference
     //    leaves unwritten
-    out.descr.reserve(nj * 128);
+    if (copy_descr) out.descr.reserve(nj * 128);
     out.keys.reserve(nj);
     out.angles.reserve(nj);
     out.key_index.reserve(nj);
     out.dev_row.reserve(nj);
     out.d_descr = descr_.p;
+    out.h_descr = hd;
     int oi = 0;
     for (size_t q = 0; q < nj; ++q) {
         if (!hw[q]) { out.dropped_unwritten++; continue; }
@@ -402,7 +403,7 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out) {
         out.keys.push_back(oct_[oi].keys[gk - kfirst[oi]]);
         out.angles.push_back(hj[q].angle);
         out.key_index.push_back(gk - kfirst[oi]);
-        out.descr.insert(out.descr.end(), hd + q * 128, hd + (q + 1) * 128);
+        if (copy_descr) out.descr.insert(out.descr.end(), hd + q * 128, hd + (q + 1) * 128);
         out.dev_row.push_back((int)q);
     }
     out.n = (int)out.keys.size();

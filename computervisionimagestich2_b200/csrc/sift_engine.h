@@ -33,6 +33,10 @@ struct RawFeatures {
     // descriptor i is row dev_row[i] of d_descr.  Lets the caller assemble a device table without a host round trip.
     const float* d_descr = nullptr;
     std::vector<int> dev_row;
+    // extract(..., copy_descr = false): `descr` stays empty and the descriptors are read in place from the engine's pinned
+    // download buffer (same lifetime as d_descr): descriptor i = h_descr + dev_row[i] * 128
+    const float* h_descr = nullptr;
+    const float* row(int i) const { return descr.empty() ? h_descr + (size_t)dev_row[i] * 128 : descr.data() + (size_t)i * 128; }
 };
 
 struct OctaveBuf {
@@ -63,7 +67,7 @@ class SiftEngine {
 
     // --- batched path ------------------------------------------------------------------------------------
     // d_img: device float image, rows img_pitch floats apart, values 0..255.
-    void extract(const float* d_img, int img_pitch, RawFeatures& out);
+    void extract(const float* d_img, int img_pitch, RawFeatures& out, bool copy_descr = true);
     // d_descr_out (optional): device buffer receiving the raw descriptors [n][128] in RawFeatures order.
 
     // --- octave-at-a-time path (vl_sift_* shim) ----------------------------------------------------------

@@ -110,13 +110,12 @@ void Stitcher::sift_raw_f32(const float* img, int w, int h, const SiftParams& p,
 
 // std::map<std::vector<float>, VlSiftKeypoint>::insert semantics (ImageProcess.cpp:57, 80-86): ordered by
 // lexicographic descriptor comparison, an equal key keeps the FIRST inserted keypoint.
-void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t, std::vector<int>* sel) {
+void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t, std::vector<int>* sel, bool host_descr) {
     const int n = raw.n;
     std::vector<int> idx(n);
     for (int i = 0; i < n; ++i) idx[i] = i;
-    const float* D = raw.descr.data();
-    auto less = [D](int a, int b) {
-        const float *pa = D + (size_t)a * 128, *pb_ = D + (size_t)b * 128;
+    auto less = [&raw](int a, int b) {
+        const float *pa = raw.row(a), *pb_ = raw.row(b);
         for (int k = 0; k < 128; ++k) {
             if (pa[k] < pb_[k]) return true;
             if (pb_[k] < pa[k]) return false;
@@ -132,21 +131,21 @@ void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t, std::vector<
         memcpy(&u, &f, 4);
         return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     };
-    for (int i = 0; i < n; ++i) prefix[i] = ((uint64_t)ord(D[(size_t)i * 128]) << 32) | ord(D[(size_t)i * 128 + 1]);
+    for (int i = 0; i < n; ++i) prefix[i] = ((uint64_t)ord(raw.row(i)[0]) << 32) | ord(raw.row(i)[1]);
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
         if (prefix[a] != prefix[b]) return prefix[a] < prefix[b];
         return less(a, b);
     });
     t.descr.clear();
     t.keys.clear();
-    t.descr.reserve((size_t)n * 128);
+    if (host_descr) t.descr.reserve((size_t)n * 128);
     t.keys.reserve(n);
     if (sel) { sel->clear(); sel->reserve(n); }
     for (int i = 0; i < n; ++i) {
         if (i > 0 && !less(idx[i - 1], idx[i]) && !less(idx[i], idx[i - 1])) continue;  // duplicate key
         const int s = idx[i];
         if (sel) sel->push_back(s);
-        t.descr.insert(t.descr.end(), D + (size_t)s * 128, D + (size_t)(s + 1) * 128);
+        if (host_descr) t.descr.insert(t.descr.end(), raw.row(s), raw.row(s) + 128);
         VlKey k = raw.keys[s];
         k.ix = (int)k.x;
         k.iy = (int)k.y;
@@ -776,11 +775,11 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
             SiftParams sp;
             RawFeatures raw;
             L.eng->configure(iw, ih, sp);
-            L.eng->extract(L.gray32.p, pitch, raw);
+            L.eng->extract(L.gray32.p, pitch, raw, false);   // descriptors stay in the engine's pinned buffer
             L.t_sift += t1.ms();
             WallTimer t2;
             std::vector<int> sel;
-            build_table(raw, im.feat, &sel);
+            build_table(raw, im.feat, &sel, false);            // ... and the table's device copy is gathered below
             if (raw.d_descr && !sel.empty()) {
                 // the descriptors are still in the engine's device buffer: gather the sorted rows there instead of
                 // sending the 1.2 MB table back over PCIe from pageable memory
@@ -793,8 +792,9 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
                 launch_gather_rows128(raw.d_descr, L.rows.p, nt, im.feat.d_descr.p, L.st);
                 PB_CUDA(cudaStreamSynchronize(L.st));   // the engine's buffer is re-used by the lane's next image
                 im.feat.on_device = true;
-            } else {
-                upload_table_on(im.feat, L.st);
+            } else {   // no descriptors at all
+                im.feat.d_descr.ensure(128);
+                im.feat.on_device = true;
             }
             L.t_table += t2.ms();
         }

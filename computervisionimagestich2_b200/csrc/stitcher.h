@@ -50,8 +50,9 @@ class Stitcher {
     void gray(const u8* rgb, int w, int h, u8* out_gray);
     void sift_raw_u8(const u8* gray8, int w, int h, const SiftParams& p, RawFeatures& out);
     void sift_raw_f32(const float* img, int w, int h, const SiftParams& p, RawFeatures& out);
-    // sel (optional): raw feature index of every table row
-    static void build_table(const RawFeatures& raw, FeatureTable& t, std::vector<int>* sel = nullptr);
+    // sel (optional): raw feature index of every table row; host_descr = false leaves t.descr empty (the pipeline only
+    // needs the device copy, which it gathers from the engine's buffer)
+    static void build_table(const RawFeatures& raw, FeatureTable& t, std::vector<int>* sel = nullptr, bool host_descr = true);
     void upload_table(FeatureTable& t);
     // idx[b] = row of A matched by query row b of B, or -1 (ImageProcess.cpp:311-346)
     void match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx);
