@@ -122,16 +122,16 @@ void SiftEngine::seed_next_octave(int oi) {
 
 static void finish_keys(const RefinedKey* r, int n, int o, double sigma0, int S, std::vector<VlKey>& keys) {
     // the reference refines candidates in detection (raster) order and compacts the good ones in place
-    std::vector<int> idx;
-    idx.reserve(n);
+    // (level, row, column) of the detection packed into one integer: candidates are distinct pixels, so the order is total
+    std::vector<std::pair<unsigned long long, int>> byraster;
+    byraster.reserve(n);
     for (int i = 0; i < n; ++i)
-        if (r[i].good) idx.push_back(i);
-    std::sort(idx.begin(), idx.end(), [&](int a, int b) {
-        const RefinedKey &A = r[a], &B = r[b];
-        if (A.is0 != B.is0) return A.is0 < B.is0;
-        if (A.iy0 != B.iy0) return A.iy0 < B.iy0;
-        return A.ix0 < B.ix0;
-    });
+        if (r[i].good)
+            byraster.push_back({((unsigned long long)(unsigned)r[i].is0 << 48) | ((unsigned long long)(unsigned)r[i].iy0 << 24) |
+                                    (unsigned long long)(unsigned)r[i].ix0, i});
+    std::sort(byraster.begin(), byraster.end());
+    std::vector<int> idx(byraster.size());
+    for (size_t q = 0; q < byraster.size(); ++q) idx[q] = byraster[q].second;
     double xper = pow(2.0, o);
     keys.resize(idx.size());
     for (size_t k = 0; k < idx.size(); ++k) {

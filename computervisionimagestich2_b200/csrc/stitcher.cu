@@ -112,8 +112,6 @@ void Stitcher::sift_raw_f32(const float* img, int w, int h, const SiftParams& p,
 // lexicographic descriptor comparison, an equal key keeps the FIRST inserted keypoint.
 void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t, std::vector<int>* sel, bool host_descr) {
     const int n = raw.n;
-    std::vector<int> idx(n);
-    for (int i = 0; i < n; ++i) idx[i] = i;
     auto less = [&raw](int a, int b) {
         const float *pa = raw.row(a), *pb_ = raw.row(b);
         for (int k = 0; k < 128; ++k) {
@@ -123,19 +121,24 @@ void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t, std::vector<
         return false;
     };
     // The first two components, packed order-preservingly into one integer, decide almost every comparison; the full
-    // lexicographic comparison only runs on ties of that prefix.  (Same strict weak order as `less`.)
-    std::vector<uint64_t> prefix(n);
+    // lexicographic comparison only runs on ties of that prefix.  (Same strict weak order as `less`; ties between equal
+    // descriptors keep insertion order, which decides which duplicate survives.)  The prefix travels with the index so
+    // that the sort touches one small array.
+    struct PI { uint64_t prefix; int i; };
+    std::vector<PI> pi(n);
     auto ord = [](float f) {   // float -> uint32 with the same order (and -0 == +0)
         f += 0.0f;
         uint32_t u;
         memcpy(&u, &f, 4);
         return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     };
-    for (int i = 0; i < n; ++i) prefix[i] = ((uint64_t)ord(raw.row(i)[0]) << 32) | ord(raw.row(i)[1]);
-    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
-        if (prefix[a] != prefix[b]) return prefix[a] < prefix[b];
-        return less(a, b);
+    for (int i = 0; i < n; ++i) pi[i] = PI{((uint64_t)ord(raw.row(i)[0]) << 32) | ord(raw.row(i)[1]), i};
+    std::stable_sort(pi.begin(), pi.end(), [&](const PI& a, const PI& b) {
+        if (a.prefix != b.prefix) return a.prefix < b.prefix;
+        return less(a.i, b.i);
     });
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = pi[i].i;
     t.descr.clear();
     t.keys.clear();
     if (host_descr) t.descr.reserve((size_t)n * 128);
