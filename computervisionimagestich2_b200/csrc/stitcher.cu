@@ -406,7 +406,7 @@ void Stitcher::warp_shift(const u8* src, int sw, int sh, const double* H8, float
 // ------------------------------------------------------------------------------------------------------------
 // multiband blend (ImageProcess.cpp:648-773) on device buffers
 // ------------------------------------------------------------------------------------------------------------
-int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out) {
+int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out, bool defer_check) {
     std::vector<int> lw, lh;
     const bool ex6 = profile_.ex6();
     const int L = stitch::blend_levels(cw, ch, lw, lh, ex6);
@@ -464,16 +464,35 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
     tab_f_.ensure(std::max<size_t>(tf.size(), 1));
     tab_d_.ensure(std::max<size_t>(td.size(), 1));
     stats_.ensure(8);
-    if (!ti.empty()) PB_CUDA(cudaMemcpyAsync(tab_i_.p, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
-    if (!tf.empty()) PB_CUDA(cudaMemcpyAsync(tab_f_.p, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice, st_));
-    if (!td.empty()) PB_CUDA(cudaMemcpyAsync(tab_d_.p, td.data(), td.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+    // through pinned staging: an upload from pageable memory synchronises the stream, i.e. would wait for the warp kernel
+    // issued just before.  The staging is free again by the time the next blend writes it: every edge synchronises on
+    // its RANSAC results first, and the stage API on its output.
+    if (!ti.empty()) {
+        int* hp = h_tab_i_.ensure(ti.size());
+        memcpy(hp, ti.data(), ti.size() * sizeof(int));
+        PB_CUDA(cudaMemcpyAsync(tab_i_.p, hp, ti.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    }
+    if (!tf.empty()) {
+        float* hp = h_tab_f_.ensure(tf.size());
+        memcpy(hp, tf.data(), tf.size() * sizeof(float));
+        PB_CUDA(cudaMemcpyAsync(tab_f_.p, hp, tf.size() * sizeof(float), cudaMemcpyHostToDevice, st_));
+    }
+    if (!td.empty()) {
+        double* hp = h_tab_d_.ensure(td.size());
+        memcpy(hp, td.data(), td.size() * sizeof(double));
+        PB_CUDA(cudaMemcpyAsync(tab_d_.p, hp, td.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+    }
     PB_CUDA(cudaMemsetAsync(stats_.p, 0, 8 * sizeof(int), st_));
-    PB_CUDA(cudaStreamSynchronize(st_));  // the packed tables are pageable temporaries
+    int* err_flag = stats_.p + 4;
+    if (defer_check) {
+        blend_flag_.ensure(1);
+        err_flag = blend_flag_.p;
+    }
 
     const IirCoef coef = make_iir(2.0f);
     const DericheCoef dcoef = make_deriche(2.0f);
     launch_seam_stats(d_a, d_b, cw, ch, stats_.p, ex6, st_);
-    launch_level0(d_a, d_b, cw, ch, stats_.p, pyr_.p, stats_.p + 4, ex6, st_);
+    launch_level0(d_a, d_b, cw, ch, stats_.p, pyr_.p, err_flag, ex6, st_);
     // REDUCE chain (ImageProcess.cpp:705-715)
     for (int i = 1; i < L; ++i) {
         const size_t nprev = (size_t)7 * lw[i - 1] * lh[i - 1];
@@ -511,11 +530,21 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
             eb ^= 1;
         }
     }
+    tm_.n_blends++;
+    if (defer_check) return 0;
     int flag = 0;
     PB_CUDA(cudaMemcpyAsync(&flag, stats_.p + 4, sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
     if (flag) { err_ = "blend: empty middle row (the reference does not terminate on this input)"; return -1; }
-    tm_.n_blends++;
+    return 0;
+}
+
+int Stitcher::check_blend_flag() {
+    if (!blend_flag_.p) return 0;
+    int flag = 0;
+    PB_CUDA(cudaMemcpyAsync(&flag, blend_flag_.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    if (flag) { err_ = "blend: empty middle row (the reference does not terminate on this input)"; return -1; }
     return 0;
 }
 
@@ -991,7 +1020,7 @@ int Stitcher::stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d
     {
         WallTimer t;
         res_[cur_ ^ 1].ensure(cn);
-        int rc = blend_device(a_.p, b_.p, cp.new_w, cp.new_h, res_[cur_ ^ 1].p);
+        int rc = blend_device(a_.p, b_.p, cp.new_w, cp.new_h, res_[cur_ ^ 1].p, true);
         if (rc) return rc;
         cur_ ^= 1;
         rw_ = cp.new_w; rh_ = cp.new_h;
@@ -1082,8 +1111,12 @@ int Stitcher::run() {
     const int n = (int)imgs_.size();
     if (n == 0) { err_ = "no images"; return -1; }
     std::ostringstream log;
+    blend_flag_.ensure(1);
+    PB_CUDA(cudaMemsetAsync(blend_flag_.p, 0, sizeof(int), st_));
     if (profile_.ex6()) {
         int rc = run_chain(log);
+        if (rc) return rc;
+        rc = check_blend_flag();
         if (rc) return rc;
         WallTimer t;
         res_[cur_ ^ 1].ensure((size_t)3 * rw_ * rh_);
@@ -1195,6 +1228,10 @@ int Stitcher::run() {
             if (rc) return rc;
             pre = dst;
         }
+    }
+    {
+        const int rc = check_blend_flag();
+        if (rc) return rc;
     }
     {
         WallTimer t;

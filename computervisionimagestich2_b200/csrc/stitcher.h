@@ -113,7 +113,10 @@ class Stitcher {
         DevBuf<u8> proj;   // projected planar RGB
         FeatureTable feat;
     };
-    int blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out);
+    // defer_check: inside run() the empty-middle-row flag accumulates in blend_flag_ and is read once after the last edge
+    // (no host round trip per blend); the stage API checks at once
+    int blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out, bool defer_check = false);
+    int check_blend_flag();
     void equalize_mix_device(const u8* d_rgb, int w, int h, u8* d_out);
     void ensure_ktab(int short_side);
 
@@ -144,7 +147,10 @@ class Stitcher {
     DevBuf<unsigned> r_masks_;
     DevBuf<double> r_hyp_, H8_;
     DevBuf<float> pyr_, tmpf_, tmpf2_, E_[2];
-    DevBuf<int> tab_i_, stats_, hist_, lut_;
+    DevBuf<int> tab_i_, stats_, hist_, lut_, blend_flag_;
+    PinBuf<int> h_tab_i_;      // pinned staging of the resampling tables: their upload must not synchronise the stream
+    PinBuf<float> h_tab_f_;
+    PinBuf<double> h_tab_d_;
     DevBuf<float> tab_f_;
     DevBuf<double> tab_d_;
     int cur_ = 0, rw_ = 0, rh_ = 0;
