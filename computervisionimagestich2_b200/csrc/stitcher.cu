@@ -33,6 +33,9 @@ DericheCoef make_deriche(float sigma) {
 Stitcher::Stitcher(int device) : dev_(device) {
     PB_CUDA(cudaSetDevice(device));
     PB_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    PB_CUDA(cudaStreamCreateWithFlags(&rst_, cudaStreamNonBlocking));
+    PB_CUDA(cudaEventCreateWithFlags(&ev_tables_, cudaEventDisableTiming));
+    PB_CUDA(cudaEventCreateWithFlags(&ev_h8_, cudaEventDisableTiming));
     sift_.reset(new SiftEngine(st_));
 }
 Stitcher::~Stitcher() {
@@ -46,6 +49,9 @@ Stitcher::~Stitcher() {
         L->st = nullptr;
     }
     lanes_.clear();
+    if (ev_tables_) cudaEventDestroy(ev_tables_);
+    if (ev_h8_) cudaEventDestroy(ev_h8_);
+    if (rst_) cudaStreamDestroy(rst_);
     if (st_) cudaStreamDestroy(st_);
 }
 
@@ -327,15 +333,15 @@ bool Stitcher::ransac(const std::vector<const std::vector<KeyPair>*>& problems, 
     r_samples_.ensure(samples.size());
     r_counts_.ensure((size_t)P * iters);
     r_masks_.ensure((size_t)P * iters * words);
-    PB_CUDA(cudaMemcpyAsync(r_pairs_.p, all.data(), all.size() * sizeof(KeyPair), cudaMemcpyHostToDevice, st_));
-    PB_CUDA(cudaMemcpyAsync(r_off_.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
-    PB_CUDA(cudaMemcpyAsync(r_samples_.p, samples.data(), samples.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
-    launch_ransac_score(r_pairs_.p, r_off_.p, P, r_samples_.p, iters, r_counts_.p, r_masks_.p, words, nullptr, st_);
+    PB_CUDA(cudaMemcpyAsync(r_pairs_.p, all.data(), all.size() * sizeof(KeyPair), cudaMemcpyHostToDevice, rst_));
+    PB_CUDA(cudaMemcpyAsync(r_off_.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, rst_));
+    PB_CUDA(cudaMemcpyAsync(r_samples_.p, samples.data(), samples.size() * sizeof(int), cudaMemcpyHostToDevice, rst_));
+    launch_ransac_score(r_pairs_.p, r_off_.p, P, r_samples_.p, iters, r_counts_.p, r_masks_.p, words, nullptr, rst_);
     std::vector<int> counts((size_t)P * iters);
     std::vector<unsigned> masks((size_t)P * iters * words);
-    PB_CUDA(cudaMemcpyAsync(counts.data(), r_counts_.p, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
-    PB_CUDA(cudaMemcpyAsync(masks.data(), r_masks_.p, masks.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
-    PB_CUDA(cudaStreamSynchronize(st_));
+    PB_CUDA(cudaMemcpyAsync(counts.data(), r_counts_.p, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, rst_));
+    PB_CUDA(cudaMemcpyAsync(masks.data(), r_masks_.p, masks.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, rst_));
+    PB_CUDA(cudaStreamSynchronize(rst_));
     for (int p = 0; p < P; ++p) {
         const int n = (int)problems[p]->size();
         int best = stitch::select_hypothesis(counts.data() + (size_t)p * iters, iters);
@@ -465,8 +471,9 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
     tab_d_.ensure(std::max<size_t>(td.size(), 1));
     stats_.ensure(8);
     // through pinned staging: an upload from pageable memory synchronises the stream, i.e. would wait for the warp kernel
-    // issued just before.  The staging is free again by the time the next blend writes it: every edge synchronises on
-    // its RANSAC results first, and the stage API on its output.
+    // issued just before.  The host may be a whole blend ahead of the GPU, so it first waits until the previous blend's
+    // copies out of the staging buffers have executed (they are the first operations of that blend).
+    PB_CUDA(cudaEventSynchronize(ev_tables_));
     if (!ti.empty()) {
         int* hp = h_tab_i_.ensure(ti.size());
         memcpy(hp, ti.data(), ti.size() * sizeof(int));
@@ -482,6 +489,7 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
         memcpy(hp, td.data(), td.size() * sizeof(double));
         PB_CUDA(cudaMemcpyAsync(tab_d_.p, hp, td.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
     }
+    PB_CUDA(cudaEventRecord(ev_tables_, st_));
     PB_CUDA(cudaMemsetAsync(stats_.p, 0, 8 * sizeof(int), st_));
     int* err_flag = stats_.p + 4;
     if (defer_check) {
@@ -1008,7 +1016,11 @@ int Stitcher::stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d
         WallTimer t;
         a_.ensure(cn);
         b_.ensure(cn);
-        PB_CUDA(cudaMemcpyAsync(H8_.p, bwd, 8 * sizeof(double), cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaEventSynchronize(ev_h8_));   // the previous edge's copy out of the staging buffer has executed
+        double* hh = h_H8_.ensure(8);
+        memcpy(hh, bwd, 8 * sizeof(double));
+        PB_CUDA(cudaMemcpyAsync(H8_.p, hh, 8 * sizeof(double), cudaMemcpyHostToDevice, st_));
+        PB_CUDA(cudaEventRecord(ev_h8_, st_));
         launch_warp_shift(D.proj.p, D.w, D.h, H8_.p, cp.min_x, cp.min_y, res_[cur_].p, rw_, rh_, (int)cp.min_x,
                           (int)cp.min_y, a_.p, b_.p, cp.new_w, cp.new_h, st_);
         // no synchronisation here: the blend's host-side table construction overlaps this kernel (tm_.warp is then the

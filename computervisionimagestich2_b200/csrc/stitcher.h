@@ -125,6 +125,12 @@ class Stitcher {
     int dev_;
     stitch::Profile profile_;
     cudaStream_t st_ = nullptr;
+    // RANSAC of an edge depends on features only, not on the canvas: it runs on its own stream so that the host never
+    // waits for the previous blend; the two events guard the pinned staging buffers the host then re-writes ahead of
+    // the GPU (resampling tables, warp coefficients)
+    cudaStream_t rst_ = nullptr;
+    cudaEvent_t ev_tables_ = nullptr, ev_h8_ = nullptr;
+    PinBuf<double> h_H8_;
     std::unique_ptr<SiftEngine> sift_;
     std::vector<std::unique_ptr<Image>> imgs_;
     std::vector<std::unique_ptr<Image>> pool_;   // recycled Image objects (their HBM buffers stay allocated)
