@@ -149,3 +149,57 @@ def stitch_sharded(engine, images, dist=None, device="cpu", profile="root"):
     pano, sinfo = engine.stitch_features([table[i][0] for i in range(n)], [(table[i][1], table[i][2]) for i in range(n)], midx)
     info.update(sinfo)
     return pano, info
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Batched image pairs (BASELINE.json configs[4], SURVEY.md 8e last row): "replicas only"
+# ----------------------------------------------------------------------------------------------------------------------
+PAIR_RECORD = np.dtype([("pair", "<i8"), ("nfeat", "<i4", 2), ("nmatch", "<i4", 2), ("has_h", "<i4", 2), ("H", "<f8", (2, 8))])
+
+
+def pairs_of_rank(npairs: int, world: int, rank: int):
+    return list(range(rank, npairs, world))
+
+
+def pair_job(engine, img_a, img_b):
+    """One independent pair: readFile body of both images (ImageProcess.cpp:12-23), getImgPair in both directions
+    (:117-137, 273-351) and RANSAC on every direction that reaches the adjacency threshold (:128, 395-436).  Direction
+    0 is getImgPair(a, b): for each feature of b its match in a, RANSAC fits a -> b; direction 1 the reverse.
+    Returns one PAIR_RECORD (pair index left at -1)."""
+    _, da, ka = engine.extract(img_a)
+    _, db, kb = engine.extract(img_b)
+    ka = np.ascontiguousarray(ka, KEY_DTYPE)
+    kb = np.ascontiguousarray(kb, KEY_DTYPE)
+    rec = np.zeros((), PAIR_RECORD)
+    rec["pair"] = -1
+    rec["nfeat"] = (len(ka), len(kb))
+    for d, (dsrc, ksrc, ddst, kdst) in enumerate(((da, ka, db, kb), (db, kb, da, ka))):
+        if len(ksrc) < 2 or len(kdst) == 0:  # the 2-NN query needs two database rows (ImageProcess.cpp:327)
+            continue
+        idx = np.asarray(engine.match_idx(dsrc, ddst))
+        sel = idx >= 0
+        rec["nmatch"][d] = int(sel.sum())
+        if rec["nmatch"][d] >= THRESHOLD:
+            rec["H"][d] = engine.ransac(ksrc[idx[sel]].copy(), kdst[sel].copy())
+            rec["has_h"][d] = 1
+    return rec
+
+
+def pairs_batch(engine, pairs, dist=None, device="cpu", gather=True):
+    """pairs: list of (img_a, img_b) planar uint8 [3][H][W]; every rank holds the list (or at least its own share at
+    the right positions).  Pair p runs on rank p % world; there is no data-path collective.  With gather=True the
+    small result records (PAIR_RECORD, 160 B per pair) are all-gathered afterwards so that every rank returns the
+    full table in pair order; with gather=False each rank returns only its own records."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    mine = np.zeros(len(pairs_of_rank(len(pairs), world, rank)), PAIR_RECORD)
+    for k, p in enumerate(pairs_of_rank(len(pairs), world, rank)):
+        mine[k] = pair_job(engine, pairs[p][0], pairs[p][1])
+        mine[k]["pair"] = p
+    if dist is None or not gather:
+        return mine
+    blobs = _all_gather_ragged(dist, mine.view(np.uint8), device)
+    table = np.concatenate([np.frombuffer(b.tobytes(), PAIR_RECORD) for b in blobs])
+    table = table[np.argsort(table["pair"], kind="stable")]
+    assert np.array_equal(table["pair"], np.arange(len(pairs)))
+    return table
