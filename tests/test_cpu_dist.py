@@ -97,3 +97,68 @@ def test_sharded_job_world2_gloo_ex6_chain(ref, tmp_path):
     expect = {k: anchors["match_counts"][k] for k in ("0,1", "1,0", "1,2", "2,1", "2,3", "3,2")}
     assert r0["match_counts"] == r1["match_counts"] == expect
     assert r0["npairs"] == 6 and r1["npairs"] is None
+
+
+# ---- batched pairs (BASELINE.json configs[4]): replicas only ----------------------------------------------------------
+PAIR_LIST = [(0, 1), (1, 2), (2, 3), (0, 3), (3, 2)]
+
+
+class OraclePairEngine(OracleEngine):
+    def ransac(self, src, dst):
+        return self.ref.ransac(src, dst)
+
+
+def _pairs_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    from computervisionimagestich2_b200 import dist as pdist
+    from oracle import ref_api
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    imgs = [ref_api.load_bmp(os.path.join(ref_api.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
+    table = pdist.pairs_batch(OraclePairEngine(), [(imgs[a], imgs[b]) for a, b in PAIR_LIST], dist=dist, device="cpu")
+    own = pdist.pairs_batch(OraclePairEngine(), [(imgs[a], imgs[b]) for a, b in PAIR_LIST[:3]], dist=dist, device="cpu",
+                            gather=False)
+    np.save(os.path.join(out_dir, f"pairs_rank{rank}.npy"), table)
+    np.save(os.path.join(out_dir, f"own_rank{rank}.npy"), own)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pairs_plan():
+    from computervisionimagestich2_b200 import dist as pdist
+    assert pdist.pairs_of_rank(5, 2, 0) == [0, 2, 4] and pdist.pairs_of_rank(5, 2, 1) == [1, 3]
+    assert pdist.pairs_of_rank(1, 8, 3) == [] and pdist.PAIR_RECORD.itemsize == 160
+
+
+def test_pairs_batch_world2_gloo(ref, tmp_path):
+    """Pair p runs on rank p % 2; both ranks end with the same table, equal to a single-process run and to the anchors;
+    the fitted coefficients are the reference's RANSAC on the reference's match list, bit for bit."""
+    import socket
+    import torch.multiprocessing as mp
+    from computervisionimagestich2_b200 import dist as pdist
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_pairs_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    t0 = np.load(tmp_path / "pairs_rank0.npy")
+    t1 = np.load(tmp_path / "pairs_rank1.npy")
+    assert t0.tobytes() == t1.tobytes() and len(t0) == len(PAIR_LIST)
+    assert [int(p) for p in np.load(tmp_path / "own_rank0.npy")["pair"]] == [0, 2]
+    assert [int(p) for p in np.load(tmp_path / "own_rank1.npy")["pair"]] == [1]
+    imgs = [ref.load_bmp(os.path.join(ref.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
+    single = pdist.pairs_batch(OraclePairEngine(), [(imgs[a], imgs[b]) for a, b in PAIR_LIST])
+    assert single.tobytes() == t0.tobytes()
+    anchors = json.load(open(os.path.join(HERE, "golden", "anchors.json")))["Input"]
+    feats = [ref.sift_features(ref.gray(ref.project(im))) for im in imgs]
+    for rec, (a, b) in zip(t0, PAIR_LIST):
+        assert list(rec["nfeat"]) == [anchors["nfeat"][a], anchors["nfeat"][b]]
+        assert list(rec["nmatch"]) == [anchors["match_counts"][f"{a},{b}"], anchors["match_counts"][f"{b},{a}"]]
+        for d, (i, j) in enumerate(((a, b), (b, a))):
+            assert bool(rec["has_h"][d]) == (rec["nmatch"][d] >= 20)
+            if rec["has_h"][d]:
+                src, dst = ref.match(feats[i][0], feats[i][1], feats[j][0], feats[j][1])
+                assert ref.ransac(src, dst).tobytes() == rec["H"][d].tobytes()
+            else:
+                assert not rec["H"][d].any()
+    assert t0["has_h"].sum() >= 6   # the chain neighbours of Input are adjacent in both directions
