@@ -266,6 +266,20 @@ class Context:
         self.L.pano_b200_free(pk)
         return proj, descr, keys
 
+    def pairs(self, pairs):
+        """Batched independent pairs (pano_b200_pairs): [(img_a, img_b), ...] -> PAIR_RECORD array (pair = position)."""
+        from .dist import PAIR_RECORD
+        flat = [_u8(im) for ab in pairs for im in ab]
+        n = len(flat)
+        rec = np.zeros(len(pairs), PAIR_RECORD)
+        rec["pair"] = np.arange(len(pairs))
+        if n:
+            pp = (C.c_void_p * n)(*[im.ctypes.data for im in flat])
+            ws = (C.c_int * n)(*[im.shape[2] for im in flat])
+            hs = (C.c_int * n)(*[im.shape[1] for im in flat])
+            self._check(self.L.pano_b200_pairs(self.h, pp, ws, hs, len(pairs), _p(rec)), "pairs")
+        return rec
+
     def stitch_features(self, projs, feats, match_idx=None):
         """matching() on precomputed projections / feature tables; match_idx: {(i, j): idx array} of preset pairs."""
         n = len(projs)

@@ -89,6 +89,17 @@ int pano_b200_extract(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint
     return 0;
     PB_API_END
 }
+int pano_b200_pairs(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int npairs,
+                    pano_b200_pair_record* out) {
+    PB_API_BEGIN
+    static_assert(sizeof(pano_b200_pair_record) == sizeof(Stitcher::PairRecord) && sizeof(pano_b200_pair_record) == 160,
+                  "pair record layout");
+    ctx->err.clear();
+    int rc = ctx->st->pairs(imgs, w, h, npairs, reinterpret_cast<Stitcher::PairRecord*>(out));
+    if (rc) ctx->err = ctx->st->error();
+    return rc;
+    PB_API_END
+}
 int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const* proj, const int* w, const int* h,
                               const float* const* descr, const pano_b200_keypoint* const* keys, const int* nfeat,
                               const int* const* match_idx, uint8_t** out, int* out_w, int* out_h) {

@@ -880,6 +880,60 @@ void Stitcher::add_images(const u8* const* imgs, const int* w, const int* h, int
     tm_.sift += tw.ms();
 }
 
+// Independent pairs: readFile of all 2K images on the lanes, the 2K directed matching problems in one launch, the RANSAC
+// problems of the adjacent directions in one launch.  Nothing is stitched.
+int Stitcher::pairs(const u8* const* imgs, const int* w, const int* h, int npairs, PairRecord* out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    clear();
+    if (npairs <= 0) return 0;
+    add_images(imgs, w, h, 2 * npairs, false);
+    std::vector<std::pair<FeatureTable*, FeatureTable*>> probs;
+    for (int p = 0; p < npairs; ++p) {
+        FeatureTable &A = imgs_[2 * p]->feat, &B = imgs_[2 * p + 1]->feat;
+        probs.push_back({&A, &B});
+        probs.push_back({&B, &A});
+    }
+    std::vector<std::vector<int>> idx;
+    {
+        WallTimer t;
+        match_batch(probs, idx);
+        tm_.match += t.ms();
+    }
+    std::vector<std::vector<KeyPair>> lists(probs.size());
+    std::vector<const std::vector<KeyPair>*> problems;
+    std::vector<int> prob_of;
+    for (size_t q = 0; q < probs.size(); ++q) {
+        const FeatureTable &S = *probs[q].first, &D = *probs[q].second;
+        PairRecord& r = out[q / 2];
+        const int d = (int)(q & 1);
+        r.nfeat[d] = S.n;
+        int c = 0;
+        for (int v : idx[q]) c += v >= 0;
+        r.nmatch[d] = c;
+        r.has_h[d] = 0;
+        for (int k = 0; k < 8; ++k) r.H[d][k] = 0.0;
+        if (c < 20) continue;   // not adjacent (ImageProcess.cpp:128)
+        lists[q].reserve(c);
+        for (int b = 0; b < D.n; ++b)
+            if (idx[q][b] >= 0) lists[q].push_back(KeyPair{S.keys[idx[q][b]], D.keys[b]});
+        problems.push_back(&lists[q]);
+        prob_of.push_back((int)q);
+    }
+    if (!problems.empty()) {
+        WallTimer t;
+        std::vector<double> H8s;
+        if (!ransac(problems, H8s)) return -3;
+        for (size_t k = 0; k < problems.size(); ++k) {
+            PairRecord& r = out[prob_of[k] / 2];
+            const int d = prob_of[k] & 1;
+            r.has_h[d] = 1;
+            std::copy(H8s.begin() + 8 * k, H8s.begin() + 8 * k + 8, r.H[d]);
+        }
+        tm_.ransac += t.ms();
+    }
+    return 0;
+}
+
 void Stitcher::stage_images(const u8* const* imgs, const int* w, const int* h, int n) {
     PB_CUDA(cudaSetDevice(dev_));
     staged_.clear();

@@ -91,6 +91,9 @@ class Stitcher {
     void extract(const u8* rgb, int w, int h, u8* proj_out, FeatureTable& t);    // one image -> host projection + table
     void add_precomputed(const u8* proj_rgb, int w, int h, const float* descr, const VlKey* keys, int n);
     void preset_match(int i, int j, const int* idx, int nB);   // getImgPair(imgs[i], imgs[j]) indices, evaluated elsewhere
+    // ---- batched independent pairs (BASELINE configs[4]): imgs[2p], imgs[2p+1]; see pano_b200_pairs ----------------
+    struct PairRecord { long long pair; int nfeat[2], nmatch[2], has_h[2]; double H[2][8]; };
+    int pairs(const u8* const* imgs, const int* w, const int* h, int npairs, PairRecord* out);
     // inputs staged in HBM once (outside any timed region), then stitched any number of times
     void stage_images(const u8* const* imgs, const int* w, const int* h, int n);
     int run_staged();

@@ -185,17 +185,32 @@ def pair_job(engine, img_a, img_b):
     return rec
 
 
-def pairs_batch(engine, pairs, dist=None, device="cpu", gather=True):
+def pairs_by_calls(engine, pairs):
+    """The same table as engine.pairs, composed from the single-stage calls (pair_job per pair).  The product engine
+    (Context.pairs -> pano_b200_pairs) batches the images, the matching problems and the RANSAC problems of a chunk into
+    one call instead; this composition is what the tests cross-check it with."""
+    rec = np.zeros(len(pairs), PAIR_RECORD)
+    for k, (a, b) in enumerate(pairs):
+        rec[k] = pair_job(engine, a, b)
+        rec[k]["pair"] = k
+    return rec
+
+
+def pairs_batch(engine, pairs, dist=None, device="cpu", gather=True, chunk=8):
     """pairs: list of (img_a, img_b) planar uint8 [3][H][W]; every rank holds the list (or at least its own share at
-    the right positions).  Pair p runs on rank p % world; there is no data-path collective.  With gather=True the
-    small result records (PAIR_RECORD, 160 B per pair) are all-gathered afterwards so that every rank returns the
-    full table in pair order; with gather=False each rank returns only its own records."""
+    the right positions).  Pair p runs on rank p % world, `chunk` pairs per engine.pairs call (2 * chunk images on the
+    engine's lanes, 2 * chunk directed matching problems in one launch); there is no data-path collective.  With
+    gather=True the small result records (PAIR_RECORD, 160 B per pair) are all-gathered afterwards so that every rank
+    returns the full table in pair order; with gather=False each rank returns only its own records."""
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
-    mine = np.zeros(len(pairs_of_rank(len(pairs), world, rank)), PAIR_RECORD)
-    for k, p in enumerate(pairs_of_rank(len(pairs), world, rank)):
-        mine[k] = pair_job(engine, pairs[p][0], pairs[p][1])
-        mine[k]["pair"] = p
+    ids = pairs_of_rank(len(pairs), world, rank)
+    mine = np.zeros(len(ids), PAIR_RECORD)
+    for k in range(0, len(ids), chunk):
+        sub = ids[k:k + chunk]
+        rec = engine.pairs([pairs[p] for p in sub])
+        rec["pair"] = sub
+        mine[k:k + len(sub)] = rec
     if dist is None or not gather:
         return mine
     blobs = _all_gather_ragged(dist, mine.view(np.uint8), device)

@@ -81,6 +81,19 @@ int pano_b200_extract(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint
 int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const* proj, const int* w, const int* h,
                               const float* const* descr, const pano_b200_keypoint* const* keys, const int* nfeat,
                               const int* const* match_idx, uint8_t** out, int* out_w, int* out_h);
+/* Batched independent image pairs (BASELINE.json configs[4]).  imgs[2p], imgs[2p+1] = planar RGB host buffers of pair p.
+ * Per pair: the body of readFile for both images (ImageProcess.cpp:12-23; all 2*npairs images of the call run
+ * concurrently on the context's lanes), getImgPair in both directions (ImageProcess.cpp:273-351; all 2*npairs directed
+ * problems in ONE launch) and RANSAC (ImageProcess.cpp:395-436) on every direction that reaches the adjacency threshold
+ * of 20 matches (ImageProcess.cpp:128; all of them in ONE launch).  Direction 0 = getImgPair(a, b): for each feature of b
+ * its match in a, coefficients map a -> b; direction 1 the reverse.  out[p].pair is left untouched. */
+typedef struct pano_b200_pair_record {
+    int64_t pair;
+    int32_t nfeat[2], nmatch[2], has_h[2];
+    double H[2][8];
+} pano_b200_pair_record;
+int pano_b200_pairs(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int npairs,
+                    pano_b200_pair_record* out);
 /* Inputs staged in HBM once, then stitched any number of times with no host<->device pixel traffic
  * (device-resident throughput measurement); pano_b200_result_copy downloads the last result. */
 int pano_b200_stage_images(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n);

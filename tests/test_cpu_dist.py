@@ -107,6 +107,10 @@ class OraclePairEngine(OracleEngine):
     def ransac(self, src, dst):
         return self.ref.ransac(src, dst)
 
+    def pairs(self, pairs):
+        from computervisionimagestich2_b200 import dist as pdist
+        return pdist.pairs_by_calls(self, pairs)
+
 
 def _pairs_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
@@ -116,7 +120,7 @@ def _pairs_worker(rank, world, port, out_dir):
     from oracle import ref_api
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     imgs = [ref_api.load_bmp(os.path.join(ref_api.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
-    table = pdist.pairs_batch(OraclePairEngine(), [(imgs[a], imgs[b]) for a, b in PAIR_LIST], dist=dist, device="cpu")
+    table = pdist.pairs_batch(OraclePairEngine(), [(imgs[a], imgs[b]) for a, b in PAIR_LIST], dist=dist, device="cpu", chunk=2)
     own = pdist.pairs_batch(OraclePairEngine(), [(imgs[a], imgs[b]) for a, b in PAIR_LIST[:3]], dist=dist, device="cpu",
                             gather=False)
     np.save(os.path.join(out_dir, f"pairs_rank{rank}.npy"), table)

@@ -17,7 +17,9 @@ def test_pairs_batch_matches_reference(ctx, ref):
     from computervisionimagestich2_b200 import dist as pdist
     ctx.set_profile("root", 666666)
     imgs = [ref.load_bmp(os.path.join(ref.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
-    table = pdist.pairs_batch(ctx, [(imgs[a], imgs[b]) for a, b in PAIR_LIST])
+    table = pdist.pairs_batch(ctx, [(imgs[a], imgs[b]) for a, b in PAIR_LIST], chunk=3)
+    # the batched entry (pano_b200_pairs) and the composition of single-stage calls give the same table
+    assert pdist.pairs_by_calls(ctx, [(imgs[a], imgs[b]) for a, b in PAIR_LIST]).tobytes() == table.tobytes()
     anchors = json.load(open(os.path.join(HERE, "golden", "anchors.json")))["Input"]
     feats = [ref.sift_features(ref.gray(ref.project(im))) for im in imgs]
     assert [int(p) for p in table["pair"]] == list(range(len(PAIR_LIST)))
@@ -41,5 +43,6 @@ def test_pair_job_degenerate_images(ctx, ref):
         img = np.full((3, 96, 128), value, np.uint8)
         want = len(ref.sift_features(ref.gray(ref.project(img)))[1])
         assert want == (1 if value else 0)
-        rec = pdist.pair_job(ctx, img, img)
-        assert list(rec["nfeat"]) == [want, want] and list(rec["nmatch"]) == [0, 0] and not rec["has_h"].any()
+        for rec in (pdist.pair_job(ctx, img, img), ctx.pairs([(img, img)])[0]):
+            assert list(rec["nfeat"]) == [want, want] and list(rec["nmatch"]) == [0, 0] and not rec["has_h"].any()
+    assert len(ctx.pairs([])) == 0
