@@ -355,6 +355,13 @@ def run_b200(args):
             ex6 = bench_ex6(ctx)
         except Exception as e:
             ex6 = {"error": str(e)}
+    # --- BASELINE.json configs[4] (batched independent pairs), a bounded sample through the public call
+    pairs = None
+    if rank == 0 and world == 1 and not args.no_pairs:
+        try:
+            pairs = bench_pairs(ctx)
+        except Exception as e:
+            pairs = {"error": str(e)}
     for p in pin_in:
         L.pano_b200_free_pinned(C.c_void_p(p))
     L.pano_b200_free_pinned(C.c_void_p(pin_out))
@@ -429,6 +436,7 @@ def run_b200(args):
         "sift": sift_summary(kernels, stages, mpix),
         "match_u8": match_u8,
         "ex6": ex6,
+        "pairs": pairs,
     }
     print(json.dumps(line))
     if dist is not None:
@@ -484,6 +492,24 @@ def bench_ex6(ctx, reps=3):
             "reference_cpu_seconds_one_core": a["dataset2"]["cpu_seconds"]}
 
 
+def bench_pairs(ctx, npairs=8, w=1920, h=1080, reps=3):
+    """npairs synthetic 1080p pairs (two 50 %-overlap views of a seeded scene each) through Context.pairs
+    (pano_b200_pairs): SIFT of both images, both directed matches, RANSAC of the adjacent directions; host buffers in,
+    160-byte records out.  Best of `reps` after one warm-up call."""
+    pairs = [tuple(synth_scene_views(2, w, h, seed=20181126 + p)) for p in range(npairs)]
+    best, rec = 1e9, None
+    for _ in range(1 + reps):
+        t0 = time.perf_counter()
+        rec = ctx.pairs(pairs)
+        best = min(best, time.perf_counter() - t0)
+    return {"workload": f"{npairs} synthetic {w}x{h} image pairs: SIFT + both directed matches + RANSAC, one call",
+            "ms": round(best * 1e3, 2), "pairs_per_s": round(npairs / best, 1),
+            "mpixel_per_s": round(2 * npairs * w * h / 1e6 / best, 1),
+            "features_per_image_mean": round(float(rec["nfeat"].mean()), 1),
+            "matches_per_direction_mean": round(float(rec["nmatch"].mean()), 1),
+            "directions_fitted": int(rec["has_h"].sum())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -495,6 +521,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-match-u8", action="store_true")
     ap.add_argument("--no-ex6", action="store_true")
+    ap.add_argument("--no-pairs", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
