@@ -74,6 +74,8 @@ def load_workload(name):
         return imgs, desc, "bundled reference fixtures (Input2 BMPs)" if name == "input2" else "bundled reference fixtures (Input BMPs)"
     if name == "synth4k":
         return synth_scene_views(8, 3840, 2160), "synthetic 8-image 3840x2160 horizontal panorama, BASELINE.json configs[2]", "synthetic"
+    if name == "synth8k":   # not a bench line (does not fit the default time budget): tools/run_sharded.py synth8k
+        return synth_scene_views(24, 7680, 4320), "synthetic 24-image 7680x4320 panorama, BASELINE.json configs[3]", "synthetic"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -516,7 +518,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="input2", choices=["input", "input2", "synth4k"])
+    ap.add_argument("--workload", default="input2", choices=["input", "input2", "synth4k", "synth8k"])
     ap.add_argument("--ref-procs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-match-u8", action="store_true")

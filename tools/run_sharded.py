@@ -2,7 +2,7 @@
 matching, rank 0 stitches.  Prints one JSON line on rank 0.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/run_sharded.py [input|input2|synth4k|ex6_dataset2|ex6_dataset3] [reps]
+        tools/run_sharded.py [input|input2|synth4k|synth8k|ex6_dataset2|ex6_dataset3] [reps]
 
 ex6_dataset2 / ex6_dataset3 run the reference's src/ex6 sets (18 / 11 images) with the ex6 profile; the SHA-256 is
 checked against tests/golden/anchors.json.
