@@ -14,6 +14,8 @@ struct pano_b200_ctx {
     std::unique_ptr<Stitcher> st;
     std::string err;
     RawFeatures last_raw;
+    FeatureTable match_a, match_b;   // pano_b200_match: the device tables persist between calls (cudaMalloc / cudaFree
+                                     // cost more than the matching kernel at a few thousand features)
 };
 
 static_assert(sizeof(pano_b200_keypoint) == sizeof(VlKey), "keypoint ABI");
@@ -356,9 +358,9 @@ int pano_b200_sift_octave_dump(pano_b200_ctx* ctx, int octave, float* gss, float
 int pano_b200_match(pano_b200_ctx* ctx, const float* descrA, int nA, const float* descrB, int nB, int* match_idx,
                     int* nmatches) {
     PB_API_BEGIN
-    FeatureTable A, B;
-    A.n = nA; A.descr.assign(descrA, descrA + (size_t)nA * 128);
-    B.n = nB; B.descr.assign(descrB, descrB + (size_t)nB * 128);
+    FeatureTable &A = ctx->match_a, &B = ctx->match_b;
+    A.n = nA; A.descr.assign(descrA, descrA + (size_t)nA * 128); A.on_device = false;
+    B.n = nB; B.descr.assign(descrB, descrB + (size_t)nB * 128); B.on_device = false;
     std::vector<int> idx;
     ctx->st->match_idx(A, B, idx);
     int c = 0;
