@@ -46,3 +46,35 @@ def test_pair_job_degenerate_images(ctx, ref):
         for rec in (pdist.pair_job(ctx, img, img), ctx.pairs([(img, img)])[0]):
             assert list(rec["nfeat"]) == [want, want] and list(rec["nmatch"]) == [0, 0] and not rec["has_h"].any()
     assert len(ctx.pairs([])) == 0
+
+
+def parse_pairs_main(text):
+    """lines of examples/pairs_main: 'a b nfeat N matches M [8 coefficients]' -> {(a, b): (N, M, H or None)}"""
+    out = {}
+    for line in text.splitlines():
+        t = line.split()
+        assert t[2] == "nfeat" and t[4] == "matches" and len(t) in (6, 14), line
+        out[(int(t[0]), int(t[1]))] = (int(t[3]), int(t[5]), np.array([float(v) for v in t[6:]]) if len(t) == 14 else None)
+    return out
+
+
+def test_cpp_host_pairs_main(ctx, ref):
+    """examples/pairs_main.cpp (C++ host, one pano_b200_pairs call for the chain neighbours of Input) prints what the
+    Python binding returns for the same pairs, coefficients bit for bit (%.17g round-trips a double)."""
+    import subprocess
+    from computervisionimagestich2_b200 import dist as pdist
+    d = os.path.join(ref.REF_DATA, "Input")
+    exe = os.path.join(os.path.dirname(HERE), "examples", "pairs_main")
+    subprocess.run(["make", "-C", os.path.dirname(exe)], check=True, stdout=subprocess.DEVNULL)
+    got = parse_pairs_main(subprocess.run([exe, d + "/", "4"], capture_output=True, text=True, check=True).stdout)
+    imgs = [ref.load_bmp(os.path.join(d, f"{i}.bmp")) for i in range(1, 5)]
+    ctx.set_profile("root", 666666)
+    table = ctx.pairs([(imgs[p], imgs[p + 1]) for p in range(3)])
+    assert sorted(got) == sorted([(p, p + 1) for p in range(3)] + [(p + 1, p) for p in range(3)])
+    for p in range(3):
+        for dname, (a, b) in enumerate(((p, p + 1), (p + 1, p))):
+            n, m, H = got[(a, b)]
+            assert n == table[p]["nfeat"][dname] and m == table[p]["nmatch"][dname]
+            assert (H is not None) == bool(table[p]["has_h"][dname])
+            if H is not None:
+                assert H.tobytes() == table[p]["H"][dname].tobytes()
