@@ -154,6 +154,15 @@ class Context:
         self._check(self.L.pano_b200_sift_octave_dump(self.h, octave, _p(gss), _p(grad)), "octave_dump")
         return gss, grad
 
+    def set_match_mode(self, mode: str = "prefilter"):
+        """'prefilter' (default: uint8 SAD pre-filter + exact re-rank) or 'full' (exact float scan of every pair)."""
+        self._check(self.L.pano_b200_set_match_mode(self.h, {"prefilter": 0, "full": 1}[mode]), "set_match_mode")
+
+    def match_stats(self, reset=False):
+        out = (C.c_longlong * 4)()
+        self._check(self.L.pano_b200_match_stats(self.h, out, int(reset)), "match_stats")
+        return {"queries": out[0], "survivors": out[1], "overflow": out[2], "problems": out[3]}
+
     def match_idx(self, descA, descB):
         dA = np.ascontiguousarray(descA, np.float32)
         dB = np.ascontiguousarray(descB, np.float32)

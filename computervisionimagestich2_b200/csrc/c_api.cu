@@ -195,6 +195,21 @@ int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes) {
     return 0;
     PB_API_END
 }
+int pano_b200_set_match_mode(pano_b200_ctx* ctx, int mode) {
+    PB_API_BEGIN
+    if (mode != PANO_B200_MATCH_PREFILTER && mode != PANO_B200_MATCH_FULL) return -1;
+    ctx->st->set_match_mode(mode);
+    return 0;
+    PB_API_END
+}
+int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[4], int reset) {
+    PB_API_BEGIN
+    const MatchStats& m = ctx->st->match_stats();
+    if (out) { out[0] = m.queries; out[1] = m.survivors; out[2] = m.overflow; out[3] = m.problems; }
+    if (reset) ctx->st->reset_match_stats();
+    return 0;
+    PB_API_END
+}
 int pano_b200_flush_l2(pano_b200_ctx* ctx) {
     PB_API_BEGIN
     ctx->st->flush_l2();
@@ -359,8 +374,8 @@ int pano_b200_match(pano_b200_ctx* ctx, const float* descrA, int nA, const float
                     int* nmatches) {
     PB_API_BEGIN
     FeatureTable &A = ctx->match_a, &B = ctx->match_b;
-    A.n = nA; A.descr.assign(descrA, descrA + (size_t)nA * 128); A.on_device = false;
-    B.n = nB; B.descr.assign(descrB, descrB + (size_t)nB * 128); B.on_device = false;
+    A.n = nA; A.descr.assign(descrA, descrA + (size_t)nA * 128); A.on_device = false; A.quantised = false;
+    B.n = nB; B.descr.assign(descrB, descrB + (size_t)nB * 128); B.on_device = false; B.quantised = false;
     std::vector<int> idx;
     ctx->st->match_idx(A, B, idx);
     int c = 0;

@@ -19,20 +19,26 @@ namespace pb {
 constexpr int kQ = 128;   // queries per CTA (one per thread)
 constexpr int kTA = 32;   // database rows per shared-memory tile
 
+// LIST: scan only the queries of J.overflow[0 .. J.counters[1]) (the pre-filter's fallback); partial is then indexed
+// by list position.
+template <bool LIST>
 __global__ void __launch_bounds__(kQ) match_l1_kernel(const MatchJob* __restrict__ jobs) {
     __shared__ __align__(16) float tile[kTA][128];
-    const MatchJob J = jobs[blockIdx.z];
+    const MatchJob& J = jobs[blockIdx.z];
     const float* __restrict__ A = J.A;
     const float* __restrict__ B = J.B;
-    const int NA = J.NA, NB = J.NB, rows_per_split = J.rows_per_split;
+    const int NA = J.NA, rows_per_split = J.rows_per_split;
+    const int NB = LIST ? J.counters[1] : J.NB;    // number of queries scanned
+    const int pstride = J.NB;
     Top2* __restrict__ partial = J.partial;
     if (blockIdx.x * kQ >= NB || blockIdx.y >= J.nsplit) return;   // grid is sized for the largest job of the batch
-    const int b = blockIdx.x * kQ + threadIdx.x;
+    const int pos = blockIdx.x * kQ + threadIdx.x;
+    const int b = LIST ? J.overflow[min(pos, NB - 1)] : pos;
     const int a_begin = blockIdx.y * rows_per_split;
     const int a_end = min(NA, a_begin + rows_per_split);
     float q[128];
     {
-        const float4* src = reinterpret_cast<const float4*>(B + (size_t)min(b, NB - 1) * 128);
+        const float4* src = reinterpret_cast<const float4*>(B + (size_t)min(b, J.NB - 1) * 128);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
             float4 t = src[k];
@@ -76,22 +82,218 @@ __global__ void __launch_bounds__(kQ) match_l1_kernel(const MatchJob* __restrict
             if (a + 3 < a_end) top2_push(best, acc3, a + 3);
         }
     }
-    if (b < NB) partial[(size_t)blockIdx.y * NB + b] = best;
+    if (pos < NB) partial[(size_t)blockIdx.y * pstride + pos] = best;
 }
 
+template <bool LIST>
 __global__ void match_merge_kernel(const MatchJob* __restrict__ jobs) {
-    const MatchJob J = jobs[blockIdx.y];
+    const MatchJob& J = jobs[blockIdx.y];
     const Top2* __restrict__ partial = J.partial;
-    const int nsplit = J.nsplit, NA = J.NA, NB = J.NB;
+    const int nsplit = J.nsplit, NA = J.NA, pstride = J.NB;
+    const int NB = LIST ? J.counters[1] : J.NB;
     int* __restrict__ idx = J.idx;
     float* __restrict__ d01 = J.d01;
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= NB) return;
-    Top2 t = partial[b];
-    for (int s = 1; s < nsplit; ++s) top2_merge(t, partial[(size_t)s * NB + b]);
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= NB) return;
+    const int b = LIST ? J.overflow[pos] : pos;
+    Top2 t = partial[pos];
+    for (int s = 1; s < nsplit; ++s) top2_merge(t, partial[(size_t)s * pstride + pos]);
     bool ok = NA >= 2 && t.i0 >= 0 && ratio_test(t.d0, t.d1);
     idx[b] = ok ? t.i0 : -1;
-    if (d01) { d01[2 * b] = t.d0; d01[2 * b + 1] = t.d1; }
+    if (!LIST && d01) { d01[2 * b] = t.d0; d01[2 * b + 1] = t.d1; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pre-filter (arithmetic and proof: match_device.cuh).  Tables are quantised once per image.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sad_quantize_kernel(const float* __restrict__ descr, int n,
+                                                           unsigned* __restrict__ q8, int* __restrict__ qe) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float4 v = reinterpret_cast<const float4*>(descr + (size_t)row * 128)[lane];
+    double e = 0.0;
+    const unsigned w = sad_quantize(v.x, &e) | (sad_quantize(v.y, &e) << 8) | (sad_quantize(v.z, &e) << 16) |
+                       (sad_quantize(v.w, &e) << 24);
+    q8[(size_t)row * 32 + lane] = w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);   // any order: the bound is rounded up
+    if (lane == 0) qe[row] = sad_row_error(e);
+}
+
+void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, cudaStream_t st) {
+    if (n <= 0) return;
+    KScope ks("match.quantize", st, (double)n * (512 + 128 + 4));
+    sad_quantize_kernel<<<div_up((long)n * 32, 128), 128, 0, st>>>(descr, n, q8, qe);
+    PB_KERNEL_CHECK();
+}
+
+constexpr int kST = 128;      // threads per CTA of the SAD kernels
+constexpr int kSQ = 2;        // queries per thread (each database word read from shared memory serves both)
+constexpr int kSRows = 64;    // database rows per shared-memory tile (8 KB of bytes + 256 B of error bounds)
+
+__device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // SASS: VABSDIFF4.U8.ACC
+    return d;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+// MODE 0: statistics pass over all queries (thread = kSQ queries; SadStat per query and database split).
+// MODE 1: candidate pass over the surviving queries: rows with SAD - e(a) <= thr are appended to the query's list.
+// One VABSDIFF4.U8.ACC per four dimensions: 32 instructions per (query, row) against 256 for the float scan; the
+// accumulator starts at e(a), so SAD + e(a) costs nothing.
+template <int MODE>
+__global__ void __launch_bounds__(kST) match_sad_kernel(const MatchJob* __restrict__ jobs) {
+    __shared__ __align__(16) unsigned tile[2][kSRows][32];
+    __shared__ int terr[2][kSRows];
+    const MatchJob& J = jobs[blockIdx.z];
+    const int NA = J.NA;
+    const int nq = MODE == 0 ? J.NB : J.counters[0];
+    if (blockIdx.x * (kST * kSQ) >= nq || blockIdx.y >= J.sad_nsplit) return;
+    const unsigned* __restrict__ A8 = J.A8;
+    const int* __restrict__ Ae = J.Ae;
+    const int a_begin = blockIdx.y * J.sad_rows_per_split;
+    const int a_end = min(NA, a_begin + J.sad_rows_per_split);
+    const int tid = threadIdx.x;
+
+    unsigned q[kSQ][32];
+    int slot[kSQ], thr[kSQ];
+    bool live[kSQ];
+#pragma unroll
+    for (int j = 0; j < kSQ; ++j) {
+        const int s = blockIdx.x * (kST * kSQ) + j * kST + tid;
+        live[j] = s < nq;
+        slot[j] = min(s, nq - 1);
+        const int b = MODE == 0 ? slot[j] : J.surv[slot[j]];
+        thr[j] = MODE == 0 ? 0 : J.thr[slot[j]];
+        const uint4* src = reinterpret_cast<const uint4*>(J.B8 + (size_t)b * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 t = src[k];
+            q[j][4 * k] = t.x; q[j][4 * k + 1] = t.y; q[j][4 * k + 2] = t.z; q[j][4 * k + 3] = t.w;
+        }
+    }
+    SadStat st[kSQ];
+#pragma unroll
+    for (int j = 0; j < kSQ; ++j) st[j] = sadstat_init();
+
+    const int ntiles = (a_end - a_begin + kSRows - 1) / kSRows;
+    auto issue = [&](int t) {
+        const int buf = t & 1, a0 = a_begin + t * kSRows, rows = min(kSRows, a_end - a0);
+        for (int i = tid; i < rows * 8; i += kST)
+            cp_async16(&tile[buf][i >> 3][(i & 7) * 4], A8 + (size_t)(a0 + (i >> 3)) * 32 + (i & 7) * 4);
+        if (tid < rows) cp_async4(&terr[buf][tid], Ae + a0 + tid);
+        asm volatile("cp.async.commit_group;");
+    };
+    if (ntiles > 0) issue(0);
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) {
+            issue(t + 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        const int buf = t & 1, a0 = a_begin + t * kSRows, rows = min(kSRows, a_end - a0);
+#pragma unroll 1
+        for (int r = 0; r < rows; r += 2) {
+            const bool two = r + 1 < rows;     // uniform; row r + 1 of the tile holds stale bytes otherwise (ignored)
+            const int e0 = terr[buf][r], e1 = two ? terr[buf][r + 1] : 0;
+            unsigned acc[kSQ][2];
+#pragma unroll
+            for (int j = 0; j < kSQ; ++j) { acc[j][0] = (unsigned)e0; acc[j][1] = (unsigned)e1; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 w0 = reinterpret_cast<const uint4*>(&tile[buf][r][0])[k];
+                const uint4 w1 = reinterpret_cast<const uint4*>(&tile[buf][r + 1][0])[k];
+#pragma unroll
+                for (int j = 0; j < kSQ; ++j) {
+                    acc[j][0] = sad4_acc(q[j][4 * k], w0.x, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k], w1.x, acc[j][1]);
+                    acc[j][0] = sad4_acc(q[j][4 * k + 1], w0.y, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k + 1], w1.y, acc[j][1]);
+                    acc[j][0] = sad4_acc(q[j][4 * k + 2], w0.z, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k + 2], w1.z, acc[j][1]);
+                    acc[j][0] = sad4_acc(q[j][4 * k + 3], w0.w, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k + 3], w1.w, acc[j][1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kSQ; ++j) {
+                if (MODE == 0) {
+                    sadstat_push(st[j], (int)acc[j][0], e0);
+                    if (two) sadstat_push(st[j], (int)acc[j][1], e1);
+                } else {
+                    if (live[j] && (int)acc[j][0] - 2 * e0 <= thr[j]) {
+                        const int p = atomicAdd(&J.cand_cnt[slot[j]], 1);
+                        if (p < kMatchCand) J.cand[(size_t)slot[j] * kMatchCand + p] = a0 + r;
+                    }
+                    if (two && live[j] && (int)acc[j][1] - 2 * e1 <= thr[j]) {
+                        const int p = atomicAdd(&J.cand_cnt[slot[j]], 1);
+                        if (p < kMatchCand) J.cand[(size_t)slot[j] * kMatchCand + p] = a0 + r + 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // the buffer is refilled by the copy issued in the next iteration
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < kSQ; ++j)
+            if (live[j]) J.spartial[(size_t)blockIdx.y * J.NB + slot[j]] = st[j];
+    }
+}
+
+// merges the splits' statistics, rejects what can be rejected with certainty, compacts the rest
+__global__ void match_sad_decide_kernel(const MatchJob* __restrict__ jobs) {
+    const MatchJob& J = jobs[blockIdx.y];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= J.NB) return;
+    SadStat s = J.spartial[b];
+    for (int k = 1; k < J.sad_nsplit; ++k) sadstat_merge(s, J.spartial[(size_t)k * J.NB + b]);
+    int thr = 0;
+    J.idx[b] = -1;
+    if (sad_certain_reject(s, J.Be[b], &thr)) return;
+    const int slot = atomicAdd(&J.counters[0], 1);
+    J.surv[slot] = b;
+    J.thr[slot] = thr;
+    J.cand_cnt[slot] = 0;
+}
+
+// one warp per surviving query: lane = candidate row, exact sequential float L1 (the reference's arithmetic), top-2
+// over the lanes, ratio rule.  Lists that overflowed go to the full scan.
+__global__ void __launch_bounds__(128) match_exact_kernel(const MatchJob* __restrict__ jobs) {
+    const MatchJob& J = jobs[blockIdx.y];
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= J.counters[0]) return;
+    const int n = J.cand_cnt[slot], b = J.surv[slot];
+    if (n > kMatchCand) {
+        if (lane == 0) J.overflow[atomicAdd(&J.counters[1], 1)] = b;
+        return;
+    }
+    Top2 t = top2_init();
+    if (lane < n) {
+        const int a = J.cand[(size_t)slot * kMatchCand + lane];
+        const float4* __restrict__ qa = reinterpret_cast<const float4*>(J.B + (size_t)b * 128);
+        const float4* __restrict__ ra = reinterpret_cast<const float4*>(J.A + (size_t)a * 128);
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float4 x = qa[k], y = ra[k];
+            acc += fabsf(x.x - y.x); acc += fabsf(x.y - y.y); acc += fabsf(x.z - y.z); acc += fabsf(x.w - y.w);
+        }
+        t.d0 = acc; t.i0 = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Top2 u;
+        u.d0 = __shfl_xor_sync(0xffffffffu, t.d0, o);
+        u.d1 = __shfl_xor_sync(0xffffffffu, t.d1, o);
+        u.i0 = __shfl_xor_sync(0xffffffffu, t.i0, o);
+        top2_merge(t, u);
+    }
+    if (lane == 0) J.idx[b] = (J.NA >= 2 && t.i0 >= 0 && ratio_test(t.d0, t.d1)) ? t.i0 : -1;
 }
 
 int match_num_splits(int NA, int NB) {
@@ -104,7 +306,7 @@ int match_num_splits(int NA, int NB) {
 
 MatchJob make_match_job(const float* dA, int NA, const float* dB, int NB, Top2* partial, int nsplit, int* idx,
                         float* d01) {
-    MatchJob J;
+    MatchJob J{};
     J.A = dA; J.B = dB; J.NA = NA; J.NB = NB;
     J.rows_per_split = align_up(div_up(NA > 0 ? NA : 1, nsplit > 0 ? nsplit : 1), 4);
     J.nsplit = div_up(NA > 0 ? NA : 1, J.rows_per_split);
@@ -123,11 +325,77 @@ void launch_match_batch(const MatchJob* d_jobs, const MatchJob* h_jobs, int njob
     }
     {
         KScope ks("match.l1", st, work);
-        match_l1_kernel<<<dim3(gx, gy, njobs), kQ, 0, st>>>(d_jobs);
+        match_l1_kernel<false><<<dim3(gx, gy, njobs), kQ, 0, st>>>(d_jobs);
         PB_KERNEL_CHECK();
     }
     KScope ks2("match.merge", st, 0);
-    match_merge_kernel<<<dim3(div_up(gx * kQ, 128), njobs), 128, 0, st>>>(d_jobs);
+    match_merge_kernel<false><<<dim3(div_up(gx * kQ, 128), njobs), 128, 0, st>>>(d_jobs);
+    PB_KERNEL_CHECK();
+}
+
+int match_sad_num_splits(int NA, int NB, int njobs) {
+    const int qblocks = div_up(NB, kST * kSQ) * (njobs > 0 ? njobs : 1);
+    const int want = div_up(148 * 6, qblocks);            // ~6 CTAs per SM over the whole batch
+    const int maxs = div_up(NA, 2 * kSRows);              // at least two tiles per split
+    const int s = want < maxs ? want : maxs;
+    return s < 1 ? 1 : s;
+}
+
+size_t match_prefilter_ints(int NB) { return (size_t)align_up(NB, 4) * (4 + kMatchCand) + 4; }
+
+void match_prefilter_attach(MatchJob& J, const unsigned* A8, const int* Ae, const unsigned* B8, const int* Be,
+                            int sad_nsplit, SadStat* spartial, int* scratch) {
+    J.A8 = A8; J.Ae = Ae; J.B8 = B8; J.Be = Be;
+    J.sad_rows_per_split = align_up(div_up(J.NA > 0 ? J.NA : 1, sad_nsplit > 0 ? sad_nsplit : 1), 2);
+    J.sad_nsplit = div_up(J.NA > 0 ? J.NA : 1, J.sad_rows_per_split);
+    J.spartial = spartial;
+    const size_t n = (size_t)align_up(J.NB, 4);
+    J.counters = scratch;
+    J.surv = scratch + 4;
+    J.thr = J.surv + n;
+    J.cand_cnt = J.thr + n;
+    J.overflow = J.cand_cnt + n;
+    J.cand = J.overflow + n;
+}
+
+void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, cudaStream_t st) {
+    if (njobs <= 0) return;
+    int nbmax = 1, sy = 1, fy = 1;
+    double pairs = 0;
+    for (int i = 0; i < njobs; ++i) {
+        nbmax = std::max(nbmax, h_jobs[i].NB);
+        sy = std::max(sy, h_jobs[i].sad_nsplit);
+        fy = std::max(fy, h_jobs[i].nsplit);
+        pairs += (double)h_jobs[i].NA * h_jobs[i].NB;
+    }
+    const int sx = div_up(nbmax, kST * kSQ);
+    {
+        KScope ks("match.sad", st, 32.0 * pairs);   // VABSDIFF4 thread-instructions
+        match_sad_kernel<0><<<dim3(sx, sy, njobs), kST, 0, st>>>(d_jobs);
+        PB_KERNEL_CHECK();
+    }
+    {
+        KScope ks("match.decide", st, 0);
+        match_sad_decide_kernel<<<dim3(div_up(nbmax, 128), njobs), 128, 0, st>>>(d_jobs);
+        PB_KERNEL_CHECK();
+    }
+    {   // grids are sized for "every query survives"; CTAs beyond the survivor count leave at once
+        KScope ks("match.cand", st, 0);
+        match_sad_kernel<1><<<dim3(sx, sy, njobs), kST, 0, st>>>(d_jobs);
+        PB_KERNEL_CHECK();
+    }
+    {
+        KScope ks("match.exact", st, 0);
+        match_exact_kernel<<<dim3(div_up((long)nbmax * 32, 128), njobs), 128, 0, st>>>(d_jobs);
+        PB_KERNEL_CHECK();
+    }
+    {
+        KScope ks("match.l1", st, 0);
+        match_l1_kernel<true><<<dim3(div_up(nbmax, kQ), fy, njobs), kQ, 0, st>>>(d_jobs);
+        PB_KERNEL_CHECK();
+    }
+    KScope ks2("match.merge", st, 0);
+    match_merge_kernel<true><<<dim3(div_up(nbmax, 128), njobs), 128, 0, st>>>(d_jobs);
     PB_KERNEL_CHECK();
 }
 

@@ -19,10 +19,36 @@ struct MatchJob {
     Top2* partial;
     int* idx;
     float* d01;
+    // ---- rigorous uint8 pre-filter (match_device.cuh); unused (null) in the full-scan mode ----
+    const unsigned* A8;     // [NA][32] words = 128 quantised bytes per row
+    const int* Ae;          // [NA] quantisation error bound of each row, SAD units
+    const unsigned* B8;
+    const int* Be;
+    int sad_rows_per_split, sad_nsplit;
+    SadStat* spartial;      // [sad_nsplit][NB]
+    int* surv;              // [NB] query rows the SAD pass could not reject (compacted, any order)
+    int* thr;               // [NB] per survivor slot: candidate threshold on SAD - e(a)
+    int* cand_cnt;          // [NB] per survivor slot
+    int* cand;              // [NB][kMatchCand] candidate rows of A
+    int* overflow;          // [NB] query rows with more than kMatchCand candidates: full exact scan
+    int* counters;          // [0] survivors, [1] overflow queries
 };
+constexpr int kMatchCand = 32;
 MatchJob make_match_job(const float* dA, int NA, const float* dB, int NB, Top2* partial, int nsplit, int* idx, float* d01);
-// Exact L1 2-NN + ratio rule for a batch of problems in one launch (grid.z = job); d_jobs = device copy of h_jobs.
+// Exact L1 2-NN + ratio rule for a batch of problems by a full float scan, one launch (grid.z = job); d_jobs = device
+// copy of h_jobs.
 void launch_match_batch(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, cudaStream_t st);
+// The same result through the pre-filter: SAD pass over the quantised tables, decision, candidate pass for the
+// surviving queries, exact float distances of the candidates, full scan of the queries whose candidate list overflowed.
+// The jobs' pre-filter fields must be set (match_prefilter_attach); counters must be zero.
+void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, cudaStream_t st);
+int match_sad_num_splits(int NA, int NB, int njobs);
+// ints of scratch the pre-filter of one job needs (after the SadStat partials), and the attachment of that scratch
+size_t match_prefilter_ints(int NB);
+void match_prefilter_attach(MatchJob& J, const unsigned* A8, const int* Ae, const unsigned* B8, const int* Be,
+                            int sad_nsplit, SadStat* spartial, int* scratch);
+// float table [n][128] -> quantised words [n][32] + per-row error bound
+void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, cudaStream_t st);
 
 // Scores `iters` hypotheses for each of nproblems pair lists.  pairs: concatenated lists, pair_off [nproblems+1];
 // samples [nproblems][iters][4] indices into each list; counts [nproblems][iters]; masks [nproblems][iters][words_stride]

@@ -161,7 +161,7 @@ void Stitcher::build_table(const RawFeatures& raw, FeatureTable& t, std::vector<
         t.keys.push_back(k);
     }
     t.n = (int)t.keys.size();
-    t.on_device = false;
+    t.on_device = false; t.quantised = false;
 }
 
 void Stitcher::upload_table_on(FeatureTable& t, cudaStream_t st) {
@@ -171,28 +171,43 @@ void Stitcher::upload_table_on(FeatureTable& t, cudaStream_t st) {
         PB_CUDA(cudaMemcpyAsync(t.d_descr.p, t.descr.data(), (size_t)t.n * 128 * sizeof(float), cudaMemcpyHostToDevice,
                                 st));
     PB_CUDA(cudaStreamSynchronize(st));
-    t.on_device = true;
+    t.on_device = true; t.quantised = false;
 }
 void Stitcher::upload_table(FeatureTable& t) { upload_table_on(t, st_); }
 
-// Several directed matching problems (A = database, B = queries) in ONE launch.  out[k][b] = row of A matched by
-// query row b, or -1 (ImageProcess.cpp:311-346).
+void Stitcher::quantise_table(FeatureTable& t) {
+    if (t.quantised) return;
+    t.d_q8.ensure(std::max<size_t>((size_t)t.n * 32, 32));
+    t.d_qe.ensure(std::max<size_t>(t.n, 1));
+    launch_sad_quantize(t.d_descr.p, t.n, t.d_q8.p, t.d_qe.p, st_);
+    t.quantised = true;
+}
+
+// Several directed matching problems (A = database, B = queries) in ONE batch of launches.  out[k][b] = row of A
+// matched by query row b, or -1 (ImageProcess.cpp:311-346).
 void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTable*>>& probs,
                            std::vector<std::vector<int>>& out) {
     PB_CUDA(cudaSetDevice(dev_));
     const int P = (int)probs.size();
+    const bool pre = match_mode_ == 0;
     out.assign(P, std::vector<int>());
     std::vector<MatchJob> jobs;
     std::vector<int> job_of(P, -1);
-    size_t npart = 0, nidx = 0;
-    std::vector<size_t> poff, ioff;
-    std::vector<int> nsplits;
+    size_t npart = 0, nidx = 0, nspart = 0, nscratch = 0;
+    std::vector<size_t> poff, ioff, soff, coff;
+    std::vector<int> nsplits, snsplits;
+    int njobs = 0;
+    for (int k = 0; k < P; ++k) {
+        FeatureTable &A = *probs[k].first, &B = *probs[k].second;
+        if (B.n > 0 && A.n >= 2) ++njobs;
+    }
     for (int k = 0; k < P; ++k) {
         FeatureTable &A = *probs[k].first, &B = *probs[k].second;
         upload_table(A);
         upload_table(B);
         out[k].assign(B.n, -1);
         if (B.n == 0 || A.n < 2) continue;  // the reference reads an unset second neighbour when NA < 2
+        if (pre) { quantise_table(A); quantise_table(B); }
         const int ns = match_num_splits(A.n, B.n);
         job_of[k] = (int)nsplits.size();
         nsplits.push_back(ns);
@@ -200,31 +215,59 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         ioff.push_back(nidx);
         npart += (size_t)ns * B.n;
         nidx += B.n;
+        if (pre) {
+            const int sns = match_sad_num_splits(A.n, B.n, njobs);
+            snsplits.push_back(sns);
+            soff.push_back(nspart);
+            coff.push_back(nscratch);
+            nspart += (size_t)(sns + 1) * B.n;     // attach may round the split count up by one
+            nscratch += match_prefilter_ints(B.n);
+        }
         tm_.match_pairs_evaluated += (long)A.n * B.n;
         tm_.n_match_calls++;
     }
     if (nsplits.empty()) return;
     partial_.ensure(npart);
     midx_.ensure(nidx);
-    int* h = h_midx_.ensure(nidx);
+    if (pre) {
+        spartial_.ensure(nspart);
+        mscratch_.ensure(nscratch);
+    }
+    int* h = h_midx_.ensure(nidx + 4 * nsplits.size());
     for (int k = 0; k < P; ++k) {
         if (job_of[k] < 0) continue;
         const int q = job_of[k];
         FeatureTable &A = *probs[k].first, &B = *probs[k].second;
-        jobs.push_back(make_match_job(A.d_descr.p, A.n, B.d_descr.p, B.n, partial_.p + poff[q], nsplits[q],
-                                      midx_.p + ioff[q], nullptr));
+        MatchJob J = make_match_job(A.d_descr.p, A.n, B.d_descr.p, B.n, partial_.p + poff[q], nsplits[q],
+                                    midx_.p + ioff[q], nullptr);
+        if (pre) {
+            match_prefilter_attach(J, A.d_q8.p, A.d_qe.p, B.d_q8.p, B.d_qe.p, snsplits[q], spartial_.p + soff[q],
+                                   mscratch_.p + coff[q]);
+            PB_CUDA(cudaMemsetAsync(J.counters, 0, 4 * sizeof(int), st_));
+        }
+        jobs.push_back(J);
     }
     MatchJob* hj = (MatchJob*)h_mjobs_.ensure(jobs.size() * sizeof(MatchJob));
     memcpy(hj, jobs.data(), jobs.size() * sizeof(MatchJob));
     mjobs_.ensure(jobs.size());
     PB_CUDA(cudaMemcpyAsync(mjobs_.p, hj, jobs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st_));
-    launch_match_batch(mjobs_.p, hj, (int)jobs.size(), st_);
+    if (pre) launch_match_batch_prefilter(mjobs_.p, hj, (int)jobs.size(), st_);
+    else launch_match_batch(mjobs_.p, hj, (int)jobs.size(), st_);
     PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * nidx, cudaMemcpyDeviceToHost, st_));
+    if (pre)
+        for (size_t q = 0; q < jobs.size(); ++q)
+            PB_CUDA(cudaMemcpyAsync(h + nidx + 4 * q, jobs[q].counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
     for (int k = 0; k < P; ++k) {
         if (job_of[k] < 0) continue;
         const int q = job_of[k];
         std::copy(h + ioff[q], h + ioff[q] + out[k].size(), out[k].begin());
+        mstats_.problems++;
+        mstats_.queries += (long long)out[k].size();
+        if (pre) {
+            mstats_.survivors += h[nidx + 4 * q];
+            mstats_.overflow += h[nidx + 4 * q + 1];
+        }
     }
 }
 
@@ -700,7 +743,7 @@ void Stitcher::add_precomputed(const u8* proj_rgb, int w, int h, const float* de
     im->feat.n = n;
     im->feat.descr.assign(descr, descr + (size_t)n * 128);
     im->feat.keys.assign(keys, keys + n);
-    im->feat.on_device = false;
+    im->feat.on_device = false; im->feat.quantised = false;
     upload_table(im->feat);   // synchronises the stream: proj_rgb may be released by the caller
     imgs_.push_back(std::move(im));
 }
@@ -831,10 +874,10 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
                 PB_CUDA(cudaMemcpyAsync(L.rows.p, hr, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, L.st));
                 launch_gather_rows128(raw.d_descr, L.rows.p, nt, im.feat.d_descr.p, L.st);
                 PB_CUDA(cudaStreamSynchronize(L.st));   // the engine's buffer is re-used by the lane's next image
-                im.feat.on_device = true;
+                im.feat.on_device = true; im.feat.quantised = false;
             } else {   // no descriptors at all
                 im.feat.d_descr.ensure(128);
-                im.feat.on_device = true;
+                im.feat.on_device = true; im.feat.quantised = false;
             }
             L.t_table += t2.ms();
         }

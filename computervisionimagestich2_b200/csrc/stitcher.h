@@ -25,6 +25,10 @@ struct FeatureTable {   // == std::map<std::vector<float>, VlSiftKeypoint> flatt
     std::vector<VlKey> keys;    // ix, iy = (int)x, (int)y (ImageProcess.cpp:84-85); coordinates move during stitching
     DevBuf<float> d_descr;      // device copy of descr
     bool on_device = false;
+    // quantised copy for the matcher's pre-filter (match_device.cuh): 128 bytes per row + the row's error bound
+    DevBuf<unsigned> d_q8;
+    DevBuf<int> d_qe;
+    bool quantised = false;
 };
 
 struct StageTimes {  // milliseconds, CUDA events on the stitcher's stream (host work between kernels included)
@@ -32,6 +36,10 @@ struct StageTimes {  // milliseconds, CUDA events on the stitcher's stream (host
     long match_pairs_evaluated = 0;   // sum of NA*NB over all getImgPair calls
     long sift_pixels = 0;
     int n_match_calls = 0, n_blends = 0;
+};
+
+struct MatchStats {   // pre-filter bookkeeping since the last clear(): queries, survivors of the SAD pass, full-scan fallbacks
+    long long queries = 0, survivors = 0, overflow = 0, problems = 0;
 };
 
 class Stitcher {
@@ -84,6 +92,12 @@ class Stitcher {
     // on_device: imgs[i] are HBM pointers (staged inputs) instead of host buffers.
     void add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
     void set_lanes(int n) { want_lanes_ = n < 1 ? 1 : n; }
+    // matcher: 0 = rigorous uint8 pre-filter + exact float re-rank (default), 1 = full exact float scan.  Both give
+    // the reference's match lists bit for bit; the second is the round-1 kernel, kept as the cross-check.
+    void set_match_mode(int m) { match_mode_ = m; }
+    int match_mode() const { return match_mode_; }
+    const MatchStats& match_stats() const { return mstats_; }
+    void reset_match_stats() { mstats_ = MatchStats(); }
     // ---- BMP files in / BMP file out: decode and encode run on the GPU ----------------------------
     // files[i]: the bytes of an uncompressed 24-bpp BMP.  Returns 0 and the encoded panorama (malloc'ed), or < 0.
     int stitch_bmp(const u8* const* files, const size_t* sizes, int n, u8** out, size_t* out_size);
@@ -142,6 +156,11 @@ class Stitcher {
     DevBuf<float> gray32_, ktab_;
     int ktab_n_ = 0;
     DevBuf<Top2> partial_;
+    DevBuf<SadStat> spartial_;
+    DevBuf<int> mscratch_;
+    int match_mode_ = 0;
+    MatchStats mstats_;
+    void quantise_table(FeatureTable& t);
     DevBuf<int> midx_;
     PinBuf<int> h_midx_;
     DevBuf<MatchJob> mjobs_;

@@ -183,6 +183,16 @@ void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory
 void pano_b200_free_pinned(void* p);
 /* number of concurrent per-image lanes (stream + SIFT engine + host thread) used by the pipeline; default 4 */
 int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes);
+/* matcher of getImgPair (ImageProcess.cpp:273-351): PANO_B200_MATCH_PREFILTER (default) = rigorous uint8 SAD pre-filter
+ * + exact float-L1 re-rank of the candidates; PANO_B200_MATCH_FULL = exact float-L1 scan of every (query, row) pair.
+ * Both return the reference's match lists bit for bit (the pre-filter never drops a row the exact rule needs). */
+#define PANO_B200_MATCH_PREFILTER 0
+#define PANO_B200_MATCH_FULL 1
+int pano_b200_set_match_mode(pano_b200_ctx* ctx, int mode);
+/* pre-filter bookkeeping since the last reset: out[0] = queries, out[1] = queries the SAD pass could not reject,
+ * out[2] = queries that fell back to the full scan (candidate list overflow), out[3] = directed problems; reset != 0
+ * clears the counters after reading */
+int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[4], int reset);
 int pano_b200_flush_l2(pano_b200_ctx* ctx);           /* overwrite a 256 MB scratch buffer (2x L2) */
 int pano_b200_timer_start(pano_b200_ctx* ctx);        /* CUDA events on the context's stream */
 int pano_b200_timer_stop(pano_b200_ctx* ctx, float* ms);

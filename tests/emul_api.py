@@ -121,6 +121,17 @@ def match_idx(dA, dB):
     return idx
 
 
+def match_idx_prefilter(dA, dB, cand_cap=0):
+    """The pre-filter pipeline (quantise, SAD statistics, decision, candidates, exact re-rank) on the CPU.
+    Returns (idx, stats) with stats = survivors, overflow queries, largest candidate list, unbounded rows."""
+    dA = np.ascontiguousarray(dA, np.float32)
+    dB = np.ascontiguousarray(dB, np.float32)
+    idx = np.empty(len(dB), np.int32)
+    st = np.zeros(4, np.int64)
+    lib().emul_match_prefilter(_p(dA), len(dA), _p(dB), len(dB), _p(idx), _p(st), int(cand_cap))
+    return idx, {"survivors": int(st[0]), "overflow": int(st[1]), "max_candidates": int(st[2]), "unbounded_rows": int(st[3])}
+
+
 def _pairs(src, dst):
     p = np.empty(len(src), PAIR_DTYPE)
     p["src"] = src
