@@ -39,8 +39,9 @@ UNIT = "Mpixel/s"
 # ----------------------------------------------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------------------------------------------
-def synth_scene_views(n, w, h, seed=20181126):
-    """n overlapping views (50 % overlap) of one deterministic textured scene, planar uint8."""
+def synth_scene_views_r1(n, w, h, seed=20181126):
+    """Round-1 generator (pure translations of a blocky scene), kept so that round-1 numbers can be re-measured:
+    --workload synth4k_r1."""
     rng = np.random.default_rng(seed)
     W = w // 2 * (n + 1)
     scene = np.zeros((3, h + 32, W), np.float32)
@@ -63,18 +64,47 @@ def synth_scene_views(n, w, h, seed=20181126):
     return views
 
 
+def synth_scene_views(n, w, h, seed=20181126, cache=True):
+    """SURVEY.md 8(d) generator (tools/synth_scene.py): fractal noise + soft-edged shapes + salt; 50 % overlap views with
+    +-8 px / +-0.5 degree / +-3 % gain jitter.  Generation takes tens of seconds at 4K, so the views are cached in the
+    temp directory (both arms of a bench run, and repeated runs, read the same bytes)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import synth_scene
+    path = os.path.join(tempfile.gettempdir(), f"pano_b200_synth_v2_{n}x{w}x{h}_{seed}.npy")
+    if cache and os.path.exists(path):
+        try:
+            a = np.load(path)
+            if a.shape == (n, 3, h, w):
+                return [np.ascontiguousarray(a[i]) for i in range(n)]
+        except Exception:
+            pass
+    v = synth_scene.views(n, w, h, seed)
+    if cache:
+        try:
+            tmp = path + f".{os.getpid()}.tmp.npy"
+            np.save(tmp, np.stack(v))
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return v
+
+
 def load_workload(name):
     from computervisionimagestich2_b200 import bmpio
     data = os.path.join(ROOT, "oracle", "_ref", "data")
     if name in ("input", "input2"):
         d = os.path.join(data, "Input" if name == "input" else "Input2")
         imgs = [bmpio.load_bmp(os.path.join(d, f"{i}.bmp")) for i in range(1, 5)]
-        desc = ("Input/1-4.bmp 4-image panorama (384x512)" if name == "input"
+        desc = ("Input/1-4.bmp 4-image panorama (384x512), BASELINE.json configs[0]" if name == "input"
                 else "Input2/1-4.bmp 4-image panorama (1210x907), BASELINE.json configs[1]")
         return imgs, desc, "bundled reference fixtures (Input2 BMPs)" if name == "input2" else "bundled reference fixtures (Input BMPs)"
     if name == "synth4k":
-        return synth_scene_views(8, 3840, 2160), "synthetic 8-image 3840x2160 horizontal panorama, BASELINE.json configs[2]", "synthetic"
-    if name == "synth8k":   # not a bench line (does not fit the default time budget): tools/run_sharded.py synth8k
+        return synth_scene_views(8, 3840, 2160), "synthetic 8-image 3840x2160 horizontal panorama, BASELINE.json configs[2] (the largest single-GPU configuration)", "synthetic"
+    if name == "synth4k_r1":
+        return synth_scene_views_r1(8, 3840, 2160), "synthetic 8-image 3840x2160 panorama, round-1 generator (pure translations)", "synthetic"
+    if name == "synth1080":   # quick variant of the same generator (tests, smoke runs)
+        return synth_scene_views(8, 1920, 1080), "synthetic 8-image 1920x1080 horizontal panorama (small variant of configs[2])", "synthetic"
+    if name == "synth8k":   # BASELINE.json configs[3]; sharded over the GPUs of the box (--gpus 8)
         return synth_scene_views(24, 7680, 4320), "synthetic 24-image 7680x4320 panorama, BASELINE.json configs[3]", "synthetic"
     raise SystemExit(f"unknown workload {name}")
 
@@ -239,6 +269,7 @@ def run_b200(args):
     n = len(imgs)
     mpix = megapixels(imgs)
     ctx = pano.Context(local_rank)
+    ctx.set_match_mode(args.match_mode)
     ws = (C.c_int * n)(*[i.shape[2] for i in imgs])
     hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
 
@@ -518,8 +549,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="input2", choices=["input", "input2", "synth4k", "synth8k"])
+    ap.add_argument("--workload", default="synth4k", choices=["input", "input2", "synth4k", "synth4k_r1", "synth1080", "synth8k"])
     ap.add_argument("--ref-procs", type=int, default=64)
+    ap.add_argument("--match-mode", default="prefilter", choices=["prefilter", "full"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-match-u8", action="store_true")
     ap.add_argument("--no-ex6", action="store_true")

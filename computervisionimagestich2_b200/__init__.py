@@ -275,6 +275,75 @@ class Context:
         self.L.pano_b200_free(pk)
         return proj, descr, keys
 
+    # ---- sharded job, device-resident exchange (dist.stitch_sharded_device).  Tensors are torch tensors on this
+    #      context's device; the library copies device-to-device from / into them. -----------------------------------
+    def shard_begin(self, n_global):
+        self._check(self.L.pano_b200_shard_begin(self.h, int(n_global)), "shard_begin")
+
+    def shard_extract(self, imgs, slots, staged_ptrs=None, sizes=None):
+        """readFile of the images this rank owns.  imgs: planar uint8 host arrays, or staged_ptrs: device pointers of
+        inputs already resident in HBM with sizes = [(w, h), ...]."""
+        n = len(slots)
+        if n == 0:
+            return
+        if staged_ptrs is None:
+            imgs = [_u8(i) for i in imgs]
+            ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+            ws = (C.c_int * n)(*[i.shape[2] for i in imgs])
+            hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
+            self._keep = imgs
+        else:
+            ptrs = (C.c_void_p * n)(*staged_ptrs)
+            ws = (C.c_int * n)(*[s[0] for s in sizes])
+            hs = (C.c_int * n)(*[s[1] for s in sizes])
+        sl = (C.c_int * n)(*[int(x) for x in slots])
+        self._check(self.L.pano_b200_shard_extract(self.h, ptrs, ws, hs, sl, n, int(staged_ptrs is not None)), "shard_extract")
+
+    def nfeatures(self, i):
+        return int(self.L.pano_b200_stitch_nfeatures(self.h, int(i)))
+
+    def shard_export(self, i, descr_t, keys, proj_t):
+        self._check(self.L.pano_b200_shard_export(self.h, int(i), C.c_void_p(descr_t.data_ptr() if descr_t is not None else None),
+                                                  _p(keys) if keys is not None else None,
+                                                  C.c_void_p(proj_t.data_ptr() if proj_t is not None else None)), "shard_export")
+
+    def shard_import(self, i, w, h, n, descr_t, keys, proj_t):
+        keys = np.ascontiguousarray(keys, KEY_DTYPE)
+        self._check(self.L.pano_b200_shard_import(self.h, int(i), int(w), int(h), int(n),
+                                                  C.c_void_p(descr_t.data_ptr() if n > 0 else None), _p(keys) if n > 0 else None,
+                                                  C.c_void_p(proj_t.data_ptr() if proj_t is not None else None)), "shard_import")
+
+    def shard_match(self, I, J, out_t):
+        n = len(I)
+        if n == 0:
+            return
+        ia = (C.c_int * n)(*[int(x) for x in I])
+        ja = (C.c_int * n)(*[int(x) for x in J])
+        self._check(self.L.pano_b200_shard_match(self.h, ia, ja, n, C.c_void_p(out_t.data_ptr())), "shard_match")
+
+    def shard_preset(self, i, j, idx):
+        a = np.ascontiguousarray(idx, np.int32)
+        self._check(self.L.pano_b200_shard_preset(self.h, int(i), int(j), _p(a), len(a)), "shard_preset")
+
+    def shard_stitch(self, want_output=True, pinned_out=None, pinned_cap=0):
+        """rank 0: the sequential part.  -> (panorama or None, info)"""
+        ow, oh = C.c_int(), C.c_int()
+        if pinned_out is not None:
+            self._check(self.L.pano_b200_shard_stitch(self.h, C.c_void_p(pinned_out), C.c_size_t(pinned_cap), C.byref(ow), C.byref(oh)),
+                        "shard_stitch")
+            pano = None
+        else:
+            self._check(self.L.pano_b200_shard_stitch(self.h, None, C.c_size_t(0), C.byref(ow), C.byref(oh)), "shard_stitch")
+            pano = None
+            if want_output:
+                pano = np.empty((3, oh.value, ow.value), np.uint8)
+                self._check(self.L.pano_b200_result_copy(self.h, _p(pano)), "result_copy")
+        buf = C.create_string_buffer(1 << 16)
+        self.L.pano_b200_stitch_log(self.h, buf, 1 << 16)
+        t = Times()
+        self.L.pano_b200_stitch_times(self.h, C.byref(t))
+        return pano, dict(log=buf.value.decode(), size=(ow.value, oh.value), times={f[0]: getattr(t, f[0]) for f in Times._fields_})
+
     def pairs(self, pairs):
         """Batched independent pairs (pano_b200_pairs): [(img_a, img_b), ...] -> PAIR_RECORD array (pair = position)."""
         from .dist import PAIR_RECORD

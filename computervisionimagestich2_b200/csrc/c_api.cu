@@ -124,6 +124,65 @@ int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const
     return 0;
     PB_API_END
 }
+int pano_b200_shard_begin(pano_b200_ctx* ctx, int n_global) {
+    PB_API_BEGIN
+    if (n_global <= 0) return -1;
+    ctx->err.clear();
+    ctx->st->shard_begin(n_global);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_extract(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, const int* slot,
+                            int n_local, int on_device) {
+    PB_API_BEGIN
+    if (n_local < 0 || (n_local > 0 && (!imgs || !w || !h || !slot))) return -1;
+    ctx->st->add_images(imgs, w, h, n_local, on_device != 0, slot);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_export(pano_b200_ctx* ctx, int i, float* d_descr_out, pano_b200_keypoint* keys_out, uint8_t* d_proj_out) {
+    PB_API_BEGIN
+    ctx->st->shard_export(i, d_descr_out, reinterpret_cast<VlKey*>(keys_out), d_proj_out);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_import(pano_b200_ctx* ctx, int i, int w, int h, int nfeat, const float* d_descr,
+                           const pano_b200_keypoint* keys, const uint8_t* d_proj) {
+    PB_API_BEGIN
+    if (nfeat < 0 || w <= 0 || h <= 0 || (nfeat > 0 && (!d_descr || !keys))) return -1;
+    ctx->st->shard_import(i, w, h, nfeat, d_descr, reinterpret_cast<const VlKey*>(keys), d_proj);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_match(pano_b200_ctx* ctx, const int* I, const int* J, int nprob, int* d_idx_out) {
+    PB_API_BEGIN
+    if (nprob < 0 || (nprob > 0 && (!I || !J))) return -1;
+    ctx->st->shard_match(I, J, nprob, d_idx_out);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_preset(pano_b200_ctx* ctx, int i, int j, const int* idx, int n) {
+    PB_API_BEGIN
+    if (n < 0 || (n > 0 && !idx)) return -1;
+    ctx->st->preset_match(i, j, idx, n);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_stitch(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* out_w, int* out_h) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    Stitcher& S = *ctx->st;
+    int rc = S.run();
+    if (rc) { ctx->err = S.error(); return rc; }
+    if (out_w) *out_w = S.result_width();
+    if (out_h) *out_h = S.result_height();
+    if (out) {
+        if (out_cap < (size_t)3 * S.result_width() * S.result_height()) return -4;
+        S.copy_result(out);
+    }
+    return 0;
+    PB_API_END
+}
 int pano_b200_stitch_bmp(pano_b200_ctx* ctx, const uint8_t* const* files, const size_t* sizes, int n, uint8_t** out_bmp,
                          size_t* out_size) {
     PB_API_BEGIN

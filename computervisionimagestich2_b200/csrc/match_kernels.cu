@@ -154,11 +154,12 @@ __global__ void __launch_bounds__(kST) match_sad_kernel(const MatchJob* __restri
     const MatchJob& J = jobs[blockIdx.z];
     const int NA = J.NA;
     const int nq = MODE == 0 ? J.NB : J.counters[0];
-    if (blockIdx.x * (kST * kSQ) >= nq || blockIdx.y >= J.sad_nsplit) return;
+    const int rps = MODE == 0 ? J.sad_rows_per_split : J.cand_rows_per_split;
+    if (blockIdx.x * (kST * kSQ) >= nq || blockIdx.y >= (MODE == 0 ? J.sad_nsplit : J.cand_nsplit)) return;
     const unsigned* __restrict__ A8 = J.A8;
     const int* __restrict__ Ae = J.Ae;
-    const int a_begin = blockIdx.y * J.sad_rows_per_split;
-    const int a_end = min(NA, a_begin + J.sad_rows_per_split);
+    const int a_begin = blockIdx.y * rps;
+    const int a_end = min(NA, a_begin + rps);
     const int tid = threadIdx.x;
 
     unsigned q[kSQ][32];
@@ -348,6 +349,9 @@ void match_prefilter_attach(MatchJob& J, const unsigned* A8, const int* Ae, cons
     J.A8 = A8; J.Ae = Ae; J.B8 = B8; J.Be = Be;
     J.sad_rows_per_split = align_up(div_up(J.NA > 0 ? J.NA : 1, sad_nsplit > 0 ? sad_nsplit : 1), 2);
     J.sad_nsplit = div_up(J.NA > 0 ? J.NA : 1, J.sad_rows_per_split);
+    const int cns = std::max(J.sad_nsplit, std::min(8, div_up(J.NA > 0 ? J.NA : 1, 4 * kSRows)));
+    J.cand_rows_per_split = align_up(div_up(J.NA > 0 ? J.NA : 1, cns), 2);
+    J.cand_nsplit = div_up(J.NA > 0 ? J.NA : 1, J.cand_rows_per_split);
     J.spartial = spartial;
     const size_t n = (size_t)align_up(J.NB, 4);
     J.counters = scratch;
@@ -360,12 +364,13 @@ void match_prefilter_attach(MatchJob& J, const unsigned* A8, const int* Ae, cons
 
 void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, cudaStream_t st) {
     if (njobs <= 0) return;
-    int nbmax = 1, sy = 1, fy = 1;
+    int nbmax = 1, sy = 1, fy = 1, cy = 1;
     double pairs = 0;
     for (int i = 0; i < njobs; ++i) {
         nbmax = std::max(nbmax, h_jobs[i].NB);
         sy = std::max(sy, h_jobs[i].sad_nsplit);
         fy = std::max(fy, h_jobs[i].nsplit);
+        cy = std::max(cy, h_jobs[i].cand_nsplit);
         pairs += (double)h_jobs[i].NA * h_jobs[i].NB;
     }
     const int sx = div_up(nbmax, kST * kSQ);
@@ -381,7 +386,7 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
     }
     {   // grids are sized for "every query survives"; CTAs beyond the survivor count leave at once
         KScope ks("match.cand", st, 0);
-        match_sad_kernel<1><<<dim3(sx, sy, njobs), kST, 0, st>>>(d_jobs);
+        match_sad_kernel<1><<<dim3(sx, cy, njobs), kST, 0, st>>>(d_jobs);
         PB_KERNEL_CHECK();
     }
     {

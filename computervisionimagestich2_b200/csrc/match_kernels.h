@@ -25,6 +25,7 @@ struct MatchJob {
     const unsigned* B8;
     const int* Be;
     int sad_rows_per_split, sad_nsplit;
+    int cand_rows_per_split, cand_nsplit;   // the candidate pass runs over few queries: it splits the database finer
     SadStat* spartial;      // [sad_nsplit][NB]
     int* surv;              // [NB] query rows the SAD pass could not reject (compacted, any order)
     int* thr;               // [NB] per survivor slot: candidate threshold on SAD - e(a)

@@ -186,7 +186,7 @@ void Stitcher::quantise_table(FeatureTable& t) {
 // Several directed matching problems (A = database, B = queries) in ONE batch of launches.  out[k][b] = row of A
 // matched by query row b, or -1 (ImageProcess.cpp:311-346).
 void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTable*>>& probs,
-                           std::vector<std::vector<int>>& out) {
+                           std::vector<std::vector<int>>& out, int* d_out) {
     PB_CUDA(cudaSetDevice(dev_));
     const int P = (int)probs.size();
     const bool pre = match_mode_ == 0;
@@ -226,6 +226,15 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         tm_.match_pairs_evaluated += (long)A.n * B.n;
         tm_.n_match_calls++;
     }
+    if (d_out) {   // degenerate problems never reach a kernel: their lists are all -1
+        size_t off = 0;
+        for (int k = 0; k < P; ++k) {
+            const size_t nb = out[k].size();
+            if (job_of[k] < 0 && nb) PB_CUDA(cudaMemsetAsync(d_out + off, 0xff, nb * sizeof(int), st_));
+            off += nb;
+        }
+        if (nsplits.empty()) PB_CUDA(cudaStreamSynchronize(st_));
+    }
     if (nsplits.empty()) return;
     partial_.ensure(npart);
     midx_.ensure(nidx);
@@ -254,6 +263,15 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
     if (pre) launch_match_batch_prefilter(mjobs_.p, hj, (int)jobs.size(), st_);
     else launch_match_batch(mjobs_.p, hj, (int)jobs.size(), st_);
     PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * nidx, cudaMemcpyDeviceToHost, st_));
+    if (d_out) {
+        size_t off = 0;
+        for (int k = 0; k < P; ++k) {
+            const size_t nb = out[k].size();
+            if (job_of[k] >= 0)
+                PB_CUDA(cudaMemcpyAsync(d_out + off, midx_.p + ioff[job_of[k]], nb * sizeof(int), cudaMemcpyDeviceToDevice, st_));
+            off += nb;
+        }
+    }
     if (pre)
         for (size_t q = 0; q < jobs.size(); ++q)
             PB_CUDA(cudaMemcpyAsync(h + nidx + 4 * q, jobs[q].counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
@@ -747,12 +765,85 @@ void Stitcher::add_precomputed(const u8* proj_rgb, int w, int h, const float* de
     upload_table(im->feat);   // synchronises the stream: proj_rgb may be released by the caller
     imgs_.push_back(std::move(im));
 }
+// a preset list must have one entry per feature of image j, each -1 or a row of image i's table (it indexes A.keys)
+bool Stitcher::preset_fits(const PresetMatch& pm) const {
+    const int n = (int)imgs_.size();
+    if (pm.i < 0 || pm.i >= n || pm.j < 0 || pm.j >= n || (int)pm.idx.size() != imgs_[pm.j]->feat.n) return false;
+    const int na = imgs_[pm.i]->feat.n;
+    for (int v : pm.idx)
+        if (v < -1 || v >= na) return false;
+    return true;
+}
 void Stitcher::preset_match(int i, int j, const int* idx, int nB) {
     PresetMatch pm;
     pm.i = i; pm.j = j;
     pm.idx.assign(idx, idx + nB);
     preset_.push_back(std::move(pm));
 }
+std::unique_ptr<Stitcher::Image> Stitcher::new_image() {
+    std::unique_ptr<Image> im;
+    if (!pool_.empty()) { im = std::move(pool_.back()); pool_.pop_back(); }
+    else im.reset(new Image());
+    im->w = im->h = 0;
+    im->feat.n = 0;
+    im->feat.keys.clear();
+    im->feat.descr.clear();
+    im->feat.on_device = false;
+    im->feat.quantised = false;
+    return im;
+}
+
+// ---- sharded job with a device-resident exchange (computervisionimagestich2_b200/dist.py) ------------------
+// Every rank holds the job's image list 0..n-1; a rank fills the slots of the images it owns (shard_extract), exports
+// their blocks into the exchange buffers (device memory owned by the caller: the NCCL send buffers), and imports the
+// other ranks' blocks from the receive buffers.  Copies are device-to-device on the stitcher's stream.
+void Stitcher::shard_begin(int n_global) {
+    PB_CUDA(cudaSetDevice(dev_));
+    clear();
+    for (int i = 0; i < n_global; ++i) imgs_.push_back(new_image());
+}
+void Stitcher::shard_export(int i, float* d_descr_out, VlKey* keys_out, u8* d_proj_out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (i < 0 || i >= (int)imgs_.size()) throw std::runtime_error("shard_export: image index out of range");
+    Image& im = *imgs_[i];
+    upload_table(im.feat);
+    if (d_descr_out && im.feat.n > 0)
+        PB_CUDA(cudaMemcpyAsync(d_descr_out, im.feat.d_descr.p, (size_t)im.feat.n * 512, cudaMemcpyDeviceToDevice, st_));
+    if (keys_out && im.feat.n > 0) memcpy(keys_out, im.feat.keys.data(), (size_t)im.feat.n * sizeof(VlKey));
+    if (d_proj_out) PB_CUDA(cudaMemcpyAsync(d_proj_out, im.proj.p, (size_t)3 * im.w * im.h, cudaMemcpyDeviceToDevice, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+void Stitcher::shard_import(int i, int w, int h, int n, const float* d_descr, const VlKey* keys, const u8* d_proj) {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (i < 0 || i >= (int)imgs_.size()) throw std::runtime_error("shard_import: image index out of range");
+    Image& im = *imgs_[i];
+    im.w = w; im.h = h;
+    im.feat.n = n;
+    im.feat.descr.clear();
+    im.feat.keys.assign(keys, keys + n);
+    im.feat.d_descr.ensure(std::max<size_t>((size_t)n * 128, 128));
+    if (n > 0) PB_CUDA(cudaMemcpyAsync(im.feat.d_descr.p, d_descr, (size_t)n * 512, cudaMemcpyDeviceToDevice, st_));
+    im.feat.on_device = true; im.feat.quantised = false;
+    if (d_proj) {
+        im.proj.ensure((size_t)3 * w * h);
+        PB_CUDA(cudaMemcpyAsync(im.proj.p, d_proj, (size_t)3 * w * h, cudaMemcpyDeviceToDevice, st_));
+    }
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+// directed problems (I[k], J[k]) = getImgPair(imgs[I[k]], imgs[J[k]]): database I, queries J; the match lists are left
+// in device memory, concatenated in problem order (nfeat[J[k]] ints each)
+void Stitcher::shard_match(const int* I, const int* J, int nprob, int* d_idx_out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    std::vector<std::pair<FeatureTable*, FeatureTable*>> probs;
+    for (int k = 0; k < nprob; ++k) {
+        if (I[k] < 0 || I[k] >= (int)imgs_.size() || J[k] < 0 || J[k] >= (int)imgs_.size())
+            throw std::runtime_error("shard_match: image index out of range");
+        probs.push_back({&imgs_[I[k]]->feat, &imgs_[J[k]]->feat});
+    }
+    std::vector<std::vector<int>> out;
+    match_batch(probs, out, d_idx_out);
+}
+
 // readFile() body for one image with everything returned to the host (sharded jobs exchange these between ranks)
 void Stitcher::extract(const u8* rgb, int w, int h, u8* proj_out, FeatureTable& t) {
     PB_CUDA(cudaSetDevice(dev_));
@@ -825,11 +916,11 @@ void Stitcher::add_image_device(const u8* d_rgb, int w, int h) {
 
 // One lane's share of readFile(): images first, first + step, ...  Runs on its own host thread.
 void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, const int* w, const int* h, int n,
-                         bool on_device) {
+                         bool on_device, const int* slots) {
     try {
         PB_CUDA(cudaSetDevice(dev_));
         for (int i = first; i < n; i += step) {
-            Image& im = *imgs_[i];
+            Image& im = *imgs_[slots[i]];
             const int iw = w[i], ih = h[i];
             im.w = iw; im.h = ih;
             const size_t np = (size_t)iw * ih;
@@ -886,9 +977,10 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
     }
 }
 
-void Stitcher::add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device) {
+void Stitcher::add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device, const int* slots) {
     PB_CUDA(cudaSetDevice(dev_));
     WallTimer tw;
+    if (n <= 0) return;
     const int nl = std::max(1, std::min(want_lanes_, n));
     while ((int)lanes_.size() < nl) {
         std::unique_ptr<Lane> L(new Lane());
@@ -896,22 +988,27 @@ void Stitcher::add_images(const u8* const* imgs, const int* w, const int* h, int
         L->eng.reset(new SiftEngine(L->st));
         lanes_.push_back(std::move(L));
     }
-    const int base = (int)imgs_.size();
-    (void)base;
-    for (int i = 0; i < n; ++i) {
-        std::unique_ptr<Image> im;
-        if (!pool_.empty()) { im = std::move(pool_.back()); pool_.pop_back(); }
-        else im.reset(new Image());
-        imgs_.push_back(std::move(im));
+    // image i of this call goes to imgs_[slot[i]]: the slots given by the caller (sharded jobs: global image index,
+    // shard_begin made the list) or n new slots appended to the list
+    std::vector<int> own_slots;
+    if (!slots) {
+        const int base = (int)imgs_.size();
+        for (int i = 0; i < n; ++i) {
+            imgs_.push_back(new_image());
+            own_slots.push_back(base + i);
+        }
+        slots = own_slots.data();
+    } else {
+        for (int i = 0; i < n; ++i)
+            if (slots[i] < 0 || slots[i] >= (int)imgs_.size()) throw std::runtime_error("add_images: image slot out of range");
     }
-    // the lanes index imgs_ from 0: add_images is the only producer of a job's image list
     for (int k = 0; k < nl; ++k) { lanes_[k]->err.clear(); lanes_[k]->t_project = lanes_[k]->t_sift = lanes_[k]->t_table = 0; }
     if (nl == 1) {
-        lane_work(*lanes_[0], 0, 1, imgs, w, h, n, on_device);
+        lane_work(*lanes_[0], 0, 1, imgs, w, h, n, on_device, slots);
     } else {
         std::vector<std::thread> th;
         for (int k = 0; k < nl; ++k)
-            th.emplace_back([this, k, nl, imgs, w, h, n, on_device] { lane_work(*lanes_[k], k, nl, imgs, w, h, n, on_device); });
+            th.emplace_back([this, k, nl, imgs, w, h, n, on_device, slots] { lane_work(*lanes_[k], k, nl, imgs, w, h, n, on_device, slots); });
         for (auto& t : th) t.join();
     }
     for (int k = 0; k < nl; ++k) {
@@ -1174,13 +1271,18 @@ int Stitcher::run_chain(std::ostringstream& log) {
         }
     }
     std::vector<std::vector<int>> fwd_idx(edges.size()), bwd_idx(edges.size());
+    for (auto& pm : preset_)
+        if (!preset_fits(pm)) {   // same contract as run(): a preset that does not fit is an error, never dropped
+            err_ = "preset match list does not fit the images";
+            return -6;
+        }
     {
         WallTimer t;
         std::vector<std::pair<FeatureTable*, FeatureTable*>> probs;
         std::vector<std::vector<int>*> sink;
         auto want = [&](int a, int b, std::vector<int>& out) {
             for (auto& pm : preset_)
-                if (pm.i == a && pm.j == b && (int)pm.idx.size() == imgs_[b]->feat.n) { out = pm.idx; return; }
+                if (pm.i == a && pm.j == b) { out = pm.idx; return; }
             probs.push_back({&imgs_[a]->feat, &imgs_[b]->feat});
             sink.push_back(&out);
         };
@@ -1246,7 +1348,7 @@ int Stitcher::run() {
     std::vector<std::vector<std::vector<int>>> midx(n, std::vector<std::vector<int>>(n));
     std::vector<std::vector<char>> have(n, std::vector<char>(n, 0));
     for (auto& pm : preset_) {   // directed problems evaluated elsewhere (another GPU of a sharded job)
-        if (pm.i < 0 || pm.i >= n || pm.j < 0 || pm.j >= n || (int)pm.idx.size() != imgs_[pm.j]->feat.n) {
+        if (!preset_fits(pm)) {
             err_ = "preset match list does not fit the images";
             return -6;
         }

@@ -64,7 +64,10 @@ class Stitcher {
     void upload_table(FeatureTable& t);
     // idx[b] = row of A matched by query row b of B, or -1 (ImageProcess.cpp:311-346)
     void match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx);
-    void match_batch(const std::vector<std::pair<FeatureTable*, FeatureTable*>>& probs, std::vector<std::vector<int>>& out);
+    // d_out (optional, device): the match lists concatenated in problem order (B.n ints each, -1 rows for the
+    // degenerate problems); the host copies in `out` are always filled
+    void match_batch(const std::vector<std::pair<FeatureTable*, FeatureTable*>>& probs, std::vector<std::vector<int>>& out,
+                     int* d_out = nullptr);
     void match(FeatureTable& A, FeatureTable& B, std::vector<KeyPair>& pairs);
     // several RANSAC problems in one launch; returns false for a problem the reference cannot solve (<4 pairs ...)
     bool ransac(const std::vector<const std::vector<KeyPair>*>& problems, std::vector<double>& H8s);
@@ -90,7 +93,8 @@ class Stitcher {
     // readFile() for all images at once (ImageProcess.cpp:12-23): images are independent until matching, so they
     // are processed concurrently, image i on lane i % nlanes (one CUDA stream + SIFT engine + host thread per lane).
     // on_device: imgs[i] are HBM pointers (staged inputs) instead of host buffers.
-    void add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
+    // slots (optional): imgs_[slots[i]] receives image i (the slots must exist: shard_begin); default = n appended slots
+    void add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device, const int* slots = nullptr);
     void set_lanes(int n) { want_lanes_ = n < 1 ? 1 : n; }
     // matcher: 0 = rigorous uint8 pre-filter + exact float re-rank (default), 1 = full exact float scan.  Both give
     // the reference's match lists bit for bit; the second is the round-1 kernel, kept as the cross-check.
@@ -105,6 +109,13 @@ class Stitcher {
     void extract(const u8* rgb, int w, int h, u8* proj_out, FeatureTable& t);    // one image -> host projection + table
     void add_precomputed(const u8* proj_rgb, int w, int h, const float* descr, const VlKey* keys, int n);
     void preset_match(int i, int j, const int* idx, int nB);   // getImgPair(imgs[i], imgs[j]) indices, evaluated elsewhere
+    // device-resident exchange of a sharded job (see stitcher.cu): all pointers named d_* are device memory
+    void shard_begin(int n_global);
+    void shard_export(int i, float* d_descr_out, VlKey* keys_out, u8* d_proj_out);
+    void shard_import(int i, int w, int h, int n, const float* d_descr, const VlKey* keys, const u8* d_proj);
+    void shard_match(const int* I, const int* J, int nprob, int* d_idx_out);
+    int image_width(int i) const { return imgs_[i]->w; }
+    int image_height(int i) const { return imgs_[i]->h; }
     // ---- batched independent pairs (BASELINE configs[4]): imgs[2p], imgs[2p+1]; see pano_b200_pairs ----------------
     struct PairRecord { long long pair; int nfeat[2], nmatch[2], has_h[2]; double H[2][8]; };
     int pairs(const u8* const* imgs, const int* w, const int* h, int npairs, PairRecord* out);
@@ -193,9 +204,12 @@ class Stitcher {
         double t_project = 0, t_sift = 0, t_table = 0;
         std::string err;
     };
-    void lane_work(Lane& L, int first, int step, const u8* const* imgs, const int* w, const int* h, int n, bool on_device);
+    void lane_work(Lane& L, int first, int step, const u8* const* imgs, const int* w, const int* h, int n, bool on_device,
+                   const int* slots);
+    std::unique_ptr<Image> new_image();
     void upload_table_on(FeatureTable& t, cudaStream_t st);
     struct PresetMatch { int i, j; std::vector<int> idx; };
+    bool preset_fits(const PresetMatch& pm) const;
     std::vector<PresetMatch> preset_;
     std::vector<std::unique_ptr<Lane>> lanes_;
     int want_lanes_ = 4;

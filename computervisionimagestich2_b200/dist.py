@@ -152,6 +152,146 @@ def stitch_sharded(engine, images, dist=None, device="cpu", profile="root"):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# The same job with a DEVICE-RESIDENT exchange: descriptor blocks go from the SIFT engine's HBM buffers through NCCL
+# into the matcher's tables without touching the host; projected images travel to rank 0 only; match lists come back
+# to rank 0 only.  (The host-staged stitch_sharded above stays as the engine-agnostic form the CPU tests drive.)
+# ----------------------------------------------------------------------------------------------------------------------
+def all_directed(n: int):
+    """Every directed problem of an n-image job: a superset of what the reference evaluates (wave1 + wave2 + tree-edge
+    directions, ImageProcess.cpp:117-137, 177-178); the stitcher only consults the lists the reference would compute."""
+    return [(i, j) for i in range(n) for j in range(n) if i != j]
+
+
+def deal_problems(problems, nfeat, world):
+    """Longest-processing-time-first assignment of directed problems to ranks; cost = NA * NB.  Both directions of an
+    image pair go to the same rank (they share the two tables).  Deterministic: every rank computes the same plan."""
+    groups = {}
+    for (i, j) in problems:
+        groups.setdefault((min(i, j), max(i, j)), []).append((i, j))
+    items = sorted(groups.items(), key=lambda kv: (-len(kv[1]) * nfeat[kv[0][0]] * nfeat[kv[0][1]], kv[0]))
+    load = [0] * world
+    plan = [[] for _ in range(world)]
+    for key, probs in items:
+        r = min(range(world), key=lambda q: (load[q], q))
+        plan[r] += sorted(probs)
+        load[r] += len(probs) * nfeat[key[0]] * nfeat[key[1]] + 1
+    return plan
+
+
+def _pad_gather(dist, t, cap, dst=None):
+    """all-gather (dst None) or gather-to-dst of one 1-D tensor per rank, padded to `cap` elements"""
+    import torch
+    world = dist.get_world_size()
+    buf = torch.zeros(cap, dtype=t.dtype, device=t.device)
+    buf[: t.numel()] = t
+    if dst is None:
+        out = torch.empty(world * cap, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, buf)
+        return out.view(world, cap)
+    outs = [torch.empty(cap, dtype=t.dtype, device=t.device) for _ in range(world)] if dist.get_rank() == dst else None
+    dist.gather(buf, outs, dst=dst)
+    return outs
+
+
+def stitch_sharded_device(engine, images, dist, device, profile="root", staged=None, want_output=True, sync=None, timers=None):
+    """images: list of n planar uint8 arrays (only the entries this rank owns are read), or staged = {i: (device_ptr, w, h)}
+    for inputs already resident in HBM.  Returns (panorama | None, info).  `sync()` must wait for the device (torch
+    collectives run on torch's stream, the engine on its own; each hand-over is a host synchronisation).  `timers`
+    (dict) receives the phase wall times of this rank in ms."""
+    import time
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = len(images) if images is not None else max(staged) + 1
+    sync = sync or (lambda: None)
+    tm = timers if timers is not None else {}
+    t0 = time.perf_counter()
+
+    def lap(name):
+        nonlocal t0
+        sync()
+        t1 = time.perf_counter()
+        tm[name] = tm.get(name, 0.0) + (t1 - t0) * 1e3
+        t0 = t1
+
+    mine = images_of_rank(n, world, rank)
+    engine.shard_begin(n)
+    if staged is not None:
+        engine.shard_extract(None, mine, staged_ptrs=[staged[i][0] for i in mine], sizes=[staged[i][1:] for i in mine])
+    else:
+        engine.shard_extract([images[i] for i in mine], mine)
+    lap("extract")
+    # ---- meta: (w, h, nfeat) of every image, one tiny all-reduce -------------------------------------------------
+    meta = torch.zeros((n, 3), dtype=torch.int64, device=device)
+    for i in mine:
+        w, h = (staged[i][1], staged[i][2]) if staged is not None else (images[i].shape[2], images[i].shape[1])
+        meta[i] = torch.tensor([w, h, engine.nfeatures(i)], dtype=torch.int64)
+    dist.all_reduce(meta)
+    meta = meta.cpu().numpy()
+    W, H, NF = [int(x) for x in meta[:, 0]], [int(x) for x in meta[:, 1]], [int(x) for x in meta[:, 2]]
+    owner = [i % world for i in range(n)]
+    # ---- descriptors + keypoints: all-gather; projections: gather to rank 0 ----------------------------------------
+    rows_of = [sum(NF[i] for i in images_of_rank(n, world, r)) for r in range(world)]
+    cap_rows = max(max(rows_of), 1)
+    send_d = torch.empty((cap_rows, 128), dtype=torch.float32, device=device)
+    keys_mine = np.zeros(rows_of[rank], KEY_DTYPE)
+    px_of = [sum(3 * W[i] * H[i] for i in images_of_rank(n, world, r)) for r in range(world)]
+    cap_px = max(max(px_of), 1)
+    send_p = torch.empty(cap_px, dtype=torch.uint8, device=device) if world > 1 else None
+    ro = po = 0
+    for i in mine:
+        engine.shard_export(i, send_d[ro:ro + NF[i]] if NF[i] else None, keys_mine[ro:ro + NF[i]] if NF[i] else None,
+                            send_p[po:po + 3 * W[i] * H[i]] if (send_p is not None and rank != 0) else None)
+        ro += NF[i]
+        po += 3 * W[i] * H[i]
+    all_d = _pad_gather(dist, send_d.view(-1), cap_rows * 128).view(world, cap_rows, 128)
+    kbytes = torch.from_numpy(keys_mine.view(np.uint8).copy()).to(device)
+    all_k = _pad_gather(dist, kbytes, cap_rows * KEY_DTYPE.itemsize).cpu().numpy()
+    all_p = _pad_gather(dist, send_p, cap_px, dst=0) if world > 1 else None
+    sync()
+    ro = [0] * world
+    po = [0] * world
+    for i in range(n):
+        r = owner[i]
+        if r != rank:
+            k = np.frombuffer(all_k[r].tobytes(), KEY_DTYPE, NF[i], ro[r] * KEY_DTYPE.itemsize)
+            proj = all_p[r][po[r]:po[r] + 3 * W[i] * H[i]] if rank == 0 else None
+            engine.shard_import(i, W[i], H[i], NF[i], all_d[r, ro[r]:ro[r] + NF[i]], k, proj)
+        ro[r] += NF[i]
+        po[r] += 3 * W[i] * H[i]
+    lap("exchange")
+    # ---- matching: directed problems dealt to the ranks, lists gathered on rank 0 ------------------------------------
+    problems = chain_wave(n) if profile == "ex6" else all_directed(n)
+    plan = deal_problems(problems, NF, world)
+    len_of = [sum(NF[j] for (_, j) in plan[r]) for r in range(world)]
+    cap_idx = max(max(len_of), 1)
+    out_idx = torch.empty(cap_idx, dtype=torch.int32, device=device)
+    engine.shard_match([p[0] for p in plan[rank]], [p[1] for p in plan[rank]], out_idx)
+    lap("match")
+    got = _pad_gather(dist, out_idx, cap_idx, dst=0) if world > 1 else [out_idx]
+    info = dict(nfeat=NF, world=world, plan=[len(p) for p in plan])
+    if rank != 0:
+        lap("gather")
+        dist.barrier()
+        return None, info
+    counts = {}
+    for r in range(world):
+        lists = got[r].cpu().numpy()
+        off = 0
+        for (i, j) in plan[r]:
+            idx = lists[off:off + NF[j]]
+            off += NF[j]
+            engine.shard_preset(i, j, idx)
+            counts[(i, j)] = int((idx >= 0).sum())
+    lap("gather")
+    pano, sinfo = engine.shard_stitch(want_output=want_output)
+    lap("stitch")
+    info.update(sinfo)
+    info["match_counts"] = counts
+    dist.barrier()
+    return pano, info
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # Batched image pairs (BASELINE.json configs[4], SURVEY.md 8e last row): "replicas only"
 # ----------------------------------------------------------------------------------------------------------------------
 PAIR_RECORD = np.dtype([("pair", "<i8"), ("nfeat", "<i4", 2), ("nmatch", "<i4", 2), ("has_h", "<i4", 2), ("H", "<f8", (2, 8))])

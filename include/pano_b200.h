@@ -178,6 +178,31 @@ int pano_b200_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const 
 int pano_b200_bench_match_u8(pano_b200_ctx* ctx, const uint8_t* descrA, int nA, const uint8_t* descrB, int nB, int reps,
                              float* ms_per_rep);
 
+/* ---- sharded panorama job with a device-resident exchange (images shard over the GPUs of a box, one
+ *      all-gather of descriptor blocks, directed matching problems dealt to the ranks, rank 0 stitches).  The reference has
+ *      no counterpart: its readFile / getImgPair loops (ImageProcess.cpp:12-23, 117-137) are what is being partitioned.
+ *      Pointers named d_* are DEVICE memory owned by the caller (the NCCL send / receive buffers); the library copies
+ *      device-to-device on its own stream and returns when the copy is complete. -------------------------------------- */
+int pano_b200_shard_begin(pano_b200_ctx* ctx, int n_global);            /* new job with image slots 0 .. n_global-1 */
+/* readFile (projection + SIFT + table) of the n_local images this rank owns; slot[k] = global index of image k;
+ * on_device != 0: imgs[k] are device pointers (inputs already staged in HBM) */
+int pano_b200_shard_extract(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, const int* slot,
+                            int n_local, int on_device);
+/* copies image i's descriptor table [nfeat][128] f32 and projected planar RGB into device buffers, its keypoints into a
+ * host buffer; any of the three may be NULL */
+int pano_b200_shard_export(pano_b200_ctx* ctx, int i, float* d_descr_out, pano_b200_keypoint* keys_out, uint8_t* d_proj_out);
+/* fills slot i from exchange buffers; d_proj may be NULL on ranks that do not stitch */
+int pano_b200_shard_import(pano_b200_ctx* ctx, int i, int w, int h, int nfeat, const float* d_descr,
+                           const pano_b200_keypoint* keys, const uint8_t* d_proj);
+/* getImgPair(image I[k], image J[k]) for k < nprob in one batch; d_idx_out receives the lists back to back
+ * (nfeat[J[k]] ints each) */
+int pano_b200_shard_match(pano_b200_ctx* ctx, const int* I, const int* J, int nprob, int* d_idx_out);
+/* match list of the directed problem (i, j), evaluated on another rank (host memory, nfeat[j] entries) */
+int pano_b200_shard_preset(pano_b200_ctx* ctx, int i, int j, const int* idx, int n);
+/* the sequential part (adjacency, order, RANSAC, warp, blend, equalisation) on the job's images with the preset lists;
+ * out (optional, host) receives the panorama when out_cap is large enough (else -4) */
+int pano_b200_shard_stitch(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* out_w, int* out_h);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
 void pano_b200_free_pinned(void* p);

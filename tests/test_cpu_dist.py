@@ -166,3 +166,122 @@ def test_pairs_batch_world2_gloo(ref, tmp_path):
             else:
                 assert not rec["H"][d].any()
     assert t0["has_h"].sum() >= 6   # the chain neighbours of Input are adjacent in both directions
+
+
+# ---- the device-resident exchange (dist.stitch_sharded_device): same host logic, tensors on the CPU over gloo ----------
+class OracleShardEngine:
+    """shard_* interface of Context backed by the compiled reference; "device" tensors are CPU torch tensors."""
+
+    def __init__(self):
+        from oracle import ref_api
+        self.ref = ref_api
+
+    def shard_begin(self, n):
+        self.im, self.presets, self.n = {}, {}, n
+
+    def shard_extract(self, imgs, slots, staged_ptrs=None, sizes=None):
+        for img, s in zip(imgs, slots):
+            p = self.ref.project(img)
+            d, k = self.ref.sift_features(self.ref.gray(p))
+            self.im[s] = dict(w=img.shape[2], h=img.shape[1], proj=p, d=d, k=k)
+
+    def nfeatures(self, i):
+        return len(self.im[i]["k"])
+
+    def shard_export(self, i, descr_t, keys, proj_t):
+        if descr_t is not None:
+            descr_t.numpy()[:] = self.im[i]["d"]
+            keys[:] = self.im[i]["k"]
+        if proj_t is not None:
+            proj_t.numpy()[:] = self.im[i]["proj"].ravel()
+
+    def shard_import(self, i, w, h, n, descr_t, keys, proj_t):
+        self.im[i] = dict(w=w, h=h, d=descr_t.numpy()[:n].copy().reshape(n, 128), k=np.array(keys).copy(),
+                          proj=None if proj_t is None else proj_t.numpy().copy().reshape(3, h, w))
+
+    def shard_match(self, I, J, out_t):
+        sys.path.insert(0, HERE)
+        import emul_api
+        off = 0
+        for i, j in zip(I, J):
+            idx = emul_api.match_idx(self.im[i]["d"], self.im[j]["d"])
+            out_t.numpy()[off:off + len(idx)] = idx
+            off += len(idx)
+
+    def shard_preset(self, i, j, idx):
+        self.presets[(i, j)] = np.array(idx).copy()
+
+    def shard_stitch(self, want_output=True):
+        return None, dict(log="")
+
+
+def _shard_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import hashlib
+    import torch.distributed as dist
+    from computervisionimagestich2_b200 import dist as pdist
+    from oracle import ref_api
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    imgs = [ref_api.load_bmp(os.path.join(ref_api.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
+    eng = OracleShardEngine()
+    tm = {}
+    _, info = pdist.stitch_sharded_device(eng, imgs, dist, "cpu", timers=tm)
+    rec = {"nfeat": info["nfeat"], "plan": info["plan"], "timers": sorted(tm),
+           "have_proj": [eng.im[i]["proj"] is not None for i in range(4)],
+           "proj_sha": [hashlib.sha256(eng.im[i]["proj"].tobytes()).hexdigest() if eng.im[i]["proj"] is not None else None for i in range(4)],
+           "descr_sha": [hashlib.sha256(eng.im[i]["d"].tobytes()).hexdigest() for i in range(4)],
+           "keys_sha": [hashlib.sha256(eng.im[i]["k"].tobytes()).hexdigest() for i in range(4)],
+           "presets": {f"{i},{j}": hashlib.sha256(v.tobytes()).hexdigest() for (i, j), v in eng.presets.items()},
+           "match_counts": {f"{i},{j}": c for (i, j), c in info.get("match_counts", {}).items()}}
+    with open(os.path.join(out_dir, f"shard{rank}.json"), "w") as f:
+        json.dump(rec, f)
+    dist.destroy_process_group()
+
+
+def test_deal_problems_plan():
+    from computervisionimagestich2_b200 import dist as pdist
+    probs = pdist.all_directed(4)
+    assert len(probs) == 12 and (0, 0) not in probs
+    plan = pdist.deal_problems(probs, [100, 200, 300, 400], 3)
+    flat = sorted(p for r in plan for p in r)
+    assert flat == sorted(probs)                                  # every problem exactly once
+    for r in plan:                                                # both directions of a pair on the same rank
+        assert all((j, i) in r for (i, j) in r)
+    cost = [sum(100 * (i + 1) * 100 * (j + 1) for (i, j) in r) for r in plan]
+    assert max(cost) <= 1.5 * (sum(cost) / 3)                     # and roughly balanced
+    assert pdist.deal_problems(probs, [0, 0, 0, 0], 2) == pdist.deal_problems(probs, [0, 0, 0, 0], 2)   # deterministic
+    assert [len(r) for r in pdist.deal_problems(pdist.chain_wave(3), [5, 5, 5], 8)].count(2) == 2
+
+
+def test_sharded_device_exchange_world2_gloo(ref, tmp_path):
+    """Descriptors and keypoints reach every rank, projections only rank 0, every directed match list reaches rank 0 --
+    all byte-identical to a single process computing them from the images."""
+    import hashlib
+    import socket
+    import torch.multiprocessing as mp
+    sys.path.insert(0, HERE)
+    import emul_api
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = json.load(open(tmp_path / "shard0.json"))
+    r1 = json.load(open(tmp_path / "shard1.json"))
+    anchors = json.load(open(os.path.join(HERE, "golden", "anchors.json")))["Input"]
+    imgs = [ref.load_bmp(os.path.join(ref.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
+    projs = [ref.project(im) for im in imgs]
+    feats = [ref.sift_features(ref.gray(p)) for p in projs]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert r0["nfeat"] == r1["nfeat"] == anchors["nfeat"]
+    assert r0["descr_sha"] == r1["descr_sha"] == [sha(f[0]) for f in feats]
+    assert r0["keys_sha"] == r1["keys_sha"] == [sha(f[1]) for f in feats]
+    assert r0["have_proj"] == [True] * 4 and r0["proj_sha"] == [sha(p) for p in projs]
+    assert r1["have_proj"] == [False, True, False, True]          # rank 1 keeps its own, receives none
+    assert sum(r0["plan"]) == 12 and r0["plan"] == r1["plan"]
+    assert r0["match_counts"] == anchors["match_counts"] and r1["match_counts"] == {}
+    for i in range(4):
+        for j in range(4):
+            if i != j:
+                assert r0["presets"][f"{i},{j}"] == sha(emul_api.match_idx(feats[i][0], feats[j][0]).astype(np.int32))
+    assert r1["presets"] == {} and {"extract", "exchange", "match", "gather"} <= set(r0["timers"])
