@@ -270,6 +270,11 @@ def run_b200(args):
     mpix = megapixels(imgs)
     ctx = pano.Context(local_rank)
     ctx.set_match_mode(args.match_mode)
+    mode = args.mode
+    if mode == "auto":
+        mode = "sharded" if (world > 1 and args.workload.startswith("synth")) else "replicas"
+    if world > 1 and mode == "sharded":
+        return run_b200_sharded(args, ctx, L, imgs, desc, data, dist, rank, local_rank, world)
     ws = (C.c_int * n)(*[i.shape[2] for i in imgs])
     hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
 
@@ -411,32 +416,8 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    ksum = sum(k["ms"] for k in kernels.values())
     top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
-    top_name, top_k = top
-    roofline = None
-    notes = {
-        "blend.iir": "recursive Gaussian (CImg vanvliet): per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 cycles/sample (measured); parallel only across lines. Small / middle pyramid levels are latency-bound (55-60 cycles per sample per line group), the largest are HBM-bound at ~3.5 TB/s with 128-byte granules a line pitch apart (DESIGN.md 4.5). Algorithmic bytes = 16 B per plane pixel per pass (read + write, forward + backward)",
-        "sift.descr": "one warp per (keypoint, angle); gather from the L2-resident gradient map + double-precision geometry; algorithmic bytes = sum (2W+1)^2 * 8 B patch reads + 512 B per descriptor (SURVEY 8d)",
-    }
-    if top_k["ms"] > 0:
-        per_launch_ms = top_k["ms"] / top_k["launches"]
-        if top_name == "match.l1":  # FP32 CUDA-core kernel: ops, not bytes
-            ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e12
-            # non-FMA FP32 issue peak: 148 SMs x 128 lanes x sm clock
-            clk = (clocks or {}).get("sm_mhz") or 1500.0
-            peak = 148 * 128 * clk * 1e6 / 1e12
-            roofline = {"kernel": top_name, "bound": "fp32-issue", "achieved": ach, "peak": peak, "unit": "Tinstr/s",
-                        "frac": ach / peak, "traffic": None, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
-                        "share_of_kernel_time": top_k["ms"] / ksum,
-                        "note": "exact float-L1 matcher: 2 FP32 instructions (FADD sub, FADD |.|-accumulate) per dimension, no FMA possible; peak = 148 SM x 128 lanes x median SM clock"}
-        else:
-            ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e9
-            roofline = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
-                        "share_of_kernel_time": top_k["ms"] / ksum, "peak_source": peak_src,
-                        "bytes_per_launch": top_k["bytes"] / top_k["launches"], "note": notes.get(top_name)}
-            roofline.update(ncu_traffic(top_name, args.workload))
+    roofline = roofline_of(top, kernels, clocks, args.workload)
     # the HBM-bound scale-space kernels, always reported (north_star: blur GB/s)
     hbm_kernels = {}
     for name, k in kernels.items():
@@ -474,6 +455,176 @@ def run_b200(args):
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_b200_sharded(args, ctx, L, imgs, desc, data, dist, rank, local_rank, world):
+    """N > 1, one panorama job sharded over the ranks (strong scaling): image i on rank i % N, NCCL all-gather of the
+    descriptor blocks straight from HBM, directed matching problems dealt to the ranks, rank 0 runs the sequential
+    stitch loop (computervisionimagestich2_b200/dist.py: stitch_sharded_device).  Timed with CUDA events bracketed by
+    barrier + synchronize; time = max over ranks; value = job pixels / time."""
+    import hashlib
+    import torch
+    from computervisionimagestich2_b200 import dist as pdist
+    dev = torch.device("cuda", local_rank)
+    n = len(imgs)
+    mpix = megapixels(imgs)
+    mine = pdist.images_of_rank(n, world, rank)
+    keep = {i: torch.from_numpy(imgs[i]).to(dev) for i in mine}            # inputs resident in HBM on their owner
+    staged = {i: (keep[i].data_ptr(), imgs[i].shape[2], imgs[i].shape[1]) for i in mine}
+    sync = torch.cuda.synchronize
+
+    def max_over_ranks(x, op=None):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op or dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def job(staged_inputs, timers=None, want_output=False):
+        return pdist.stitch_sharded_device(ctx, imgs, dist, dev, staged=staged if staged_inputs else None,
+                                           want_output=want_output, sync=sync, timers=timers)
+
+    for _ in range(args.warmup):
+        job(True)
+    L.pano_b200_ktimer_enable(0)
+    L.pano_b200_ktimer_reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phases = {}
+    total_ms = 0.0
+    info = None
+    for _ in range(args.steps):
+        L.pano_b200_flush_l2(ctx.h)
+        sync()
+        dist.barrier()
+        sync()
+        e0.record()
+        _, info = job(True, timers=phases)
+        sync()
+        dist.barrier()
+        sync()
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    launches = int(max_over_ranks(float(L.pano_b200_ktimer_launches()), dist.ReduceOp.SUM))
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = mpix / (ms_per_step / 1e3)
+    # ---- end to end: pinned host inputs on every rank (H2D inside), panorama to pinned host memory on rank 0 ----
+    pin = {}
+    for i in mine:
+        b = imgs[i].nbytes
+        p = L.pano_b200_alloc_pinned(C.c_size_t(b))
+        C.memmove(p, imgs[i].ctypes.data, b)
+        pin[i] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (b,)).reshape(imgs[i].shape)
+    pin_imgs = [pin.get(i, imgs[i]) for i in range(n)]
+    e2e_ms, pano, e2e_steps = 0.0, None, max(1, min(args.steps, 5))
+    for it in range(1 + e2e_steps):
+        L.pano_b200_flush_l2(ctx.h)
+        sync(); dist.barrier(); sync()
+        t0 = time.perf_counter()
+        pano, _info2 = pdist.stitch_sharded_device(ctx, pin_imgs, dist, dev, want_output=True, sync=sync)
+        sync(); dist.barrier()
+        if it > 0:
+            e2e_ms += (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(e2e_ms)
+    h2d = int(max_over_ranks(float(sum(imgs[i].nbytes for i in mine)), dist.ReduceOp.SUM))
+    # ---- one instrumented step: rank 0's kernels (it holds 1/N of SIFT and matching and all of the canvas work) ----
+    L.pano_b200_ktimer_reset()
+    L.pano_b200_ktimer_enable(1)
+    job(True)
+    kernels = {}
+    if rank == 0:
+        buf = C.create_string_buffer(1 << 16)
+        L.pano_b200_ktimer_report(buf, 1 << 16)
+        kernels = json.loads(buf.value.decode())
+    L.pano_b200_ktimer_enable(0)
+    mstats = ctx.match_stats()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    pano_hash = hashlib.sha256(pano.tobytes()).hexdigest()
+    ph = {k: round(v / args.steps, 3) for k, v in phases.items()}
+    serial = ph.get("stitch", 0.0) + ph.get("gather", 0.0)
+    limiter = max(ph.items(), key=lambda kv: kv[1])[0] if ph else None
+    top = max(kernels.items(), key=lambda kv: kv[1]["ms"]) if kernels else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": data,
+        "config": {"workload": desc, "images": n, "input_mpixel": mpix, "output": list(info["size"]),
+                   "l2": "flushed (256 MB memset) between timed iterations",
+                   "parallelism": f"sharded x{world}: image i on rank i % {world}; NCCL all-gather of descriptor blocks (HBM to HBM); "
+                                  "directed matching problems dealt to the ranks; projections and match lists to rank 0; rank 0 stitches",
+                   "panorama_sha256": pano_hash, "bit_exact_vs_one_gpu": expected_synth_hash(args.workload, pano_hash),
+                   "phases_ms_rank0": ph, "limiter": f"{limiter} (rank 0: sequential stitch loop + gather = {serial:.1f} ms of {ms_per_step:.1f} ms)",
+                   "problems_per_rank": info["plan"], "nfeat": info["nfeat"]},
+        "clocks": clocks,
+        "e2e": {"value": mpix / (e2e_ms / e2e_steps / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(pano.nbytes),
+                "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roofline_of(top, kernels, clocks) if top else None,
+        "cpu_baseline": None,
+        "kernels_ms_rank0": {k: round(v["ms"], 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
+        "match_prefilter_rank0": mstats,
+    }
+    print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+ROOFLINE_NOTES = {
+    "blend.iir": "recursive Gaussian (CImg vanvliet): per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 cycles/sample (measured); parallel only across lines. Algorithmic bytes = 8 B per plane sample per pass (one read + one write, SURVEY 8d 'x-IIR r+w, y-IIR r+w'); the kernel's own forward + backward sweeps stay in shared memory",
+    "sift.descr": "one warp per (keypoint, angle); gather from the L2-resident gradient map + double-precision geometry; algorithmic bytes = sum (2W+1)^2 * 8 B patch reads + 512 B per descriptor (SURVEY 8d)",
+    "match.sad": "uint8 SAD pre-filter of the exact float-L1 matcher: 32 VABSDIFF4.U8.ACC per (query, database row) pair (one per 4 dimensions) + ~4 integer min/max for the running bounds; VABSDIFF4 issues at half rate (measured 60.7 of 64 lanes/clk/SM, tools/ubench/vsad_rate.cu), so peak = 148 SM x 64 lanes x median SM clock; 'achieved' counts the 32 VABSDIFF4 only",
+    "match.l1": "exact float-L1 matcher: 2 FP32 instructions (FADD sub, FADD |.|-accumulate) per dimension, no FMA possible; peak = 148 SM x 128 lanes x median SM clock",
+}
+
+
+def roofline_of(top, kernels, clocks, workload=None):
+    """roofline object of the dominant kernel of the instrumented pass.  HBM-bound kernels: algorithmic bytes (declared by
+    the launcher) / CUDA-event time against MEASURED_PEAKS.json; the two matcher kernels are instruction-issue
+    bound integer / FP32 CUDA-core kernels (no tensor-core form of an L1 distance exists): their figure is
+    thread-instructions per second against the issue peak of the pipe they run on."""
+    top_name, top_k = top
+    if top_k["ms"] <= 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ksum = sum(k["ms"] for k in kernels.values())
+    per_launch_ms = top_k["ms"] / top_k["launches"]
+    common = {"kernel": top_name, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
+              "share_of_kernel_time": top_k["ms"] / ksum, "note": ROOFLINE_NOTES.get(top_name), "traffic": None}
+    if top_name in ("match.l1", "match.sad"):
+        ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e12
+        clk = (clocks or {}).get("sm_mhz") or 1500.0
+        lanes = 128 if top_name == "match.l1" else 64
+        peak = 148 * lanes * clk * 1e6 / 1e12
+        r = {"bound": "fp32-issue" if top_name == "match.l1" else "int-alu-issue", "achieved": ach, "peak": peak,
+             "unit": "Tinstr/s", "frac": ach / peak, "peak_source": f"148 SM x {lanes} lanes/clk x {clk:.0f} MHz (median SM clock during the timed region)"}
+    else:
+        ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e9
+        r = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": peak_src,
+             "bytes_per_launch": top_k["bytes"] / top_k["launches"]}
+    r.update(common)
+    if workload:
+        r.update(ncu_traffic(top_name, workload))
+    return r
+
+
+def expected_synth_hash(workload, got):
+    """tests/golden/anchors.json["synth"][workload] = SHA-256 of the panorama of a synthetic workload as produced on ONE
+    GPU (bit-exact against the reference at the sizes the tests can afford; tests/test_gpu_synth.py); the sharded job
+    must reproduce it at every N."""
+    try:
+        a = json.load(open(os.path.join(ROOT, "tests", "golden", "anchors.json")))
+        want = a.get("synth", {}).get(workload)
+        return None if want is None else want == got
+    except Exception:
+        return None
 
 
 def ncu_traffic(kernel, workload):
@@ -552,6 +703,9 @@ def main():
     ap.add_argument("--workload", default="synth4k", choices=["input", "input2", "synth4k", "synth4k_r1", "synth1080", "synth8k"])
     ap.add_argument("--ref-procs", type=int, default=64)
     ap.add_argument("--match-mode", default="prefilter", choices=["prefilter", "full"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"],
+                    help="N > 1: 'sharded' = one job over all ranks (strong scaling; default for the synthetic workloads), "
+                         "'replicas' = one job per rank (weak scaling; default for the bundled sets)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-match-u8", action="store_true")
     ap.add_argument("--no-ex6", action="store_true")

@@ -494,14 +494,14 @@ void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, co
     const long plane = (long)w * h;
     if (w > 1) {
         const long nlines = (long)nplanes * h;
-        KScope ks("blend.iir", st, 16.0 * nplanes * w * h);
+        KScope ks("blend.iir", st, 8.0 * nplanes * w * h);
         iir_pipe_kernel<true, IirCoef><<<div_up(nlines, 32), 128, 0, st>>>(src, dst, w, nlines, h, plane, 1L, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
     if (h > 1) {
         const long nlines = (long)nplanes * w;
-        KScope ks("blend.iir", st, 16.0 * nplanes * w * h);
+        KScope ks("blend.iir", st, 8.0 * nplanes * w * h);
         iir_pipe_kernel<false, IirCoef><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
