@@ -64,33 +64,73 @@ def synth_scene_views_r1(n, w, h, seed=20181126):
     return views
 
 
-def synth_scene_views(n, w, h, seed=20181126, cache=True):
-    """SURVEY.md 8(d) generator (tools/synth_scene.py): fractal noise + soft-edged shapes + salt; 50 % overlap views with
-    +-8 px / +-0.5 degree / +-3 % gain jitter.  Generation takes tens of seconds at 4K, so the views are cached in the
-    temp directory (both arms of a bench run, and repeated runs, read the same bytes)."""
+def _render_views(args):
+    n, w, h, seed, only = args
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import synth_scene
-    path = os.path.join(tempfile.gettempdir(), f"pano_b200_synth_v2_{n}x{w}x{h}_{seed}.npy")
-    if cache and os.path.exists(path):
+    v = synth_scene.views(n, w, h, seed, only=only)
+    for i in only:
+        path = _view_cache_path(n, w, h, seed, i)
+        tmp = path + f".{os.getpid()}.tmp.npy"
+        np.save(tmp, v[i])
+        os.replace(tmp, path)
+    return only
+
+
+def _view_cache_path(n, w, h, seed, i):
+    return os.path.join(tempfile.gettempdir(), f"pano_b200_synth_v3_{n}x{w}x{h}_{seed}_view{i}.npy")
+
+
+def synth_scene_views(n, w, h, seed=20181126, only=None):
+    """SURVEY.md 8(d) generator (tools/synth_scene.py): fractal noise + soft-edged shapes + salt; 50 % overlap views with
+    +-8 px / +-0.5 degree / +-3 % gain jitter.  Rendering takes seconds per view (25 s at 8K), so views are rendered by a
+    process pool and cached per view in the temp directory (both arms of a bench run, and repeated runs, read the same
+    bytes).  only = the view indices wanted (a rank of a sharded job renders just the views it owns); the other entries
+    of the returned list are None."""
+    want = list(range(n)) if only is None else list(only)
+    out = [None] * n
+    missing = []
+    for i in want:
+        path = _view_cache_path(n, w, h, seed, i)
         try:
             a = np.load(path)
-            if a.shape == (n, 3, h, w):
-                return [np.ascontiguousarray(a[i]) for i in range(n)]
+            if a.shape == (3, h, w):
+                out[i] = a
+                continue
         except Exception:
             pass
-    v = synth_scene.views(n, w, h, seed)
-    if cache:
-        try:
-            tmp = path + f".{os.getpid()}.tmp.npy"
-            np.save(tmp, np.stack(v))
-            os.replace(tmp, path)
-        except Exception:
-            pass
-    return v
+        missing.append(i)
+    if missing:
+        procs = max(1, min(len(missing), (os.cpu_count() or 2) // 2, 12))
+        if procs == 1:
+            _render_views((n, w, h, seed, missing))
+        else:
+            import multiprocessing as mp
+            chunks = [missing[k::procs] for k in range(procs)]
+            with mp.get_context("spawn").Pool(procs) as pool:
+                pool.map(_render_views, [(n, w, h, seed, c) for c in chunks])
+        for i in missing:
+            out[i] = np.load(_view_cache_path(n, w, h, seed, i))
+    return out
 
 
-def load_workload(name):
+WORKLOAD_DESC = {
+    "synth4k": "synthetic 8-image 3840x2160 horizontal panorama, BASELINE.json configs[2] (the largest single-GPU configuration)",
+    "synth4k_r1": "synthetic 8-image 3840x2160 panorama, round-1 generator (pure translations)",
+    "synth1080": "synthetic 8-image 1920x1080 horizontal panorama (small variant of configs[2])",
+    "synth8k": "synthetic 24-image 7680x4320 360-degree panorama, BASELINE.json configs[3]",
+}
+
+
+SYNTH_SHAPES = {"synth4k": (8, 3840, 2160), "synth1080": (8, 1920, 1080), "synth8k": (24, 7680, 4320)}
+
+
+def load_workload(name, only=None):
+    """-> (images, description, data kind).  only (synthetic workloads): render / load just these views."""
     from computervisionimagestich2_b200 import bmpio
+    if name in SYNTH_SHAPES:
+        n, w, h = SYNTH_SHAPES[name]
+        return synth_scene_views(n, w, h, only=only), WORKLOAD_DESC[name], "synthetic"
     data = os.path.join(ROOT, "oracle", "_ref", "data")
     if name in ("input", "input2"):
         d = os.path.join(data, "Input" if name == "input" else "Input2")
@@ -99,13 +139,13 @@ def load_workload(name):
                 else "Input2/1-4.bmp 4-image panorama (1210x907), BASELINE.json configs[1]")
         return imgs, desc, "bundled reference fixtures (Input2 BMPs)" if name == "input2" else "bundled reference fixtures (Input BMPs)"
     if name == "synth4k":
-        return synth_scene_views(8, 3840, 2160), "synthetic 8-image 3840x2160 horizontal panorama, BASELINE.json configs[2] (the largest single-GPU configuration)", "synthetic"
+        return synth_scene_views(8, 3840, 2160), WORKLOAD_DESC[name], "synthetic"
     if name == "synth4k_r1":
-        return synth_scene_views_r1(8, 3840, 2160), "synthetic 8-image 3840x2160 panorama, round-1 generator (pure translations)", "synthetic"
+        return synth_scene_views_r1(8, 3840, 2160), WORKLOAD_DESC[name], "synthetic"
     if name == "synth1080":   # quick variant of the same generator (tests, smoke runs)
-        return synth_scene_views(8, 1920, 1080), "synthetic 8-image 1920x1080 horizontal panorama (small variant of configs[2])", "synthetic"
+        return synth_scene_views(8, 1920, 1080), WORKLOAD_DESC[name], "synthetic"
     if name == "synth8k":   # BASELINE.json configs[3]; sharded over the GPUs of the box (--gpus 8)
-        return synth_scene_views(24, 7680, 4320), "synthetic 24-image 7680x4320 panorama, BASELINE.json configs[3]", "synthetic"
+        return synth_scene_views(24, 7680, 4320), WORKLOAD_DESC[name], "synthetic"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -176,11 +216,24 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline (oracle/_ref = the reference itself compiled from its sources)
 # ----------------------------------------------------------------------------------------------------------------
+def ref_sample(name):
+    """The bounded sample of a workload that the CPU reference is timed on: (images, description).  The bundled sets are
+    small enough for whole jobs or a 2-image sub-panorama; for the synthetic 4K / 8K workloads even a 2-image
+    sub-panorama at full resolution takes the reference ~15 minutes per core (its matcher is O(NA NB): 21.6 k features per
+    4K view), so the sample is a 2-view panorama from the SAME generator at 1920 x 1080 -- which flatters the CPU
+    (quarter-area views have a quarter of the features, and 2 views need 3 directed matches where 8 views need 56)."""
+    if name in ("input", "input2"):
+        imgs, desc, _ = load_workload(name)
+        return imgs, desc
+    v = synth_scene_views(2, 1920, 1080)
+    return v, "2-view 1920x1080 panorama from the synthetic generator of the workload (quarter-area sample of the 3840x2160 views)"
+
+
 def _ref_worker(args):
     name, idx, reps = args
     sys.path.insert(0, ROOT)
     from oracle import ref_api
-    imgs, _, _ = load_workload(name)
+    imgs, _ = ref_sample(name)
     imgs = [imgs[i] for i in idx]
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -190,8 +243,11 @@ def _ref_worker(args):
 
 def ref_sample_plan(name, steps_total, budget_s=200.0):
     """Pick the bounded sample: the full job when it fits the time budget, else a 2-image sub-panorama."""
-    est_full = {"input": 2.5, "input2": 45.0, "synth4k": 1e9}[name]
-    est_pair = {"input": 1.0, "input2": 12.0, "synth4k": 1e9}[name]
+    if name not in ("input", "input2"):
+        n = max(1, min(steps_total, int(budget_s // 70.0)))
+        return [0, 1], "the 2-view sample (2 SIFT, 3 directed matches, 2 RANSAC, 1 blend, tail)", n
+    est_full = {"input": 2.5, "input2": 45.0}[name]
+    est_pair = {"input": 1.0, "input2": 12.0}[name]
     if steps_total * est_full <= budget_s:
         return [0, 1, 2, 3], "the full 4-image job", steps_total
     n = max(1, min(steps_total, int(budget_s // est_pair)))
@@ -203,7 +259,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import ref_api
-    name = args.workload if args.workload != "synth4k" else "input2"
+    name = args.workload
     if not ref_api.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpano_ref.so was not built (needs /root/reference at build time)"}))
         return
@@ -212,8 +268,12 @@ def run_reference(args):
     idx, what, nsteps = ref_sample_plan(name, args.steps + args.warmup)
     warm = min(args.warmup, max(0, nsteps - 1), 1)
     timed = max(1, min(args.steps, nsteps - warm))
-    imgs, desc, data = load_workload(name)
-    mpix = megapixels([imgs[i] for i in idx])
+    if name in ("input", "input2"):
+        _, desc, data = load_workload(name)
+    else:
+        desc, data = WORKLOAD_DESC.get(name, name), "synthetic"
+    simgs, sdesc = ref_sample(name)
+    mpix = megapixels([simgs[i] for i in idx])
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         if warm:
@@ -226,28 +286,27 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
         "warmup": warm, "ms_per_step": 1e3 * wall / timed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": data,
-        "config": {"workload": desc, "sample": what, "replicas": cores},
+        "config": {"workload": desc, "sample": f"{what} of {sdesc}", "replicas": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"{what} of {desc}; {cores} single-threaded process replicas of oracle/_ref (the reference has no threads), {timed} timed step(s) each"},
+                         "sample": f"{what} of {sdesc}; {cores} single-threaded process replicas of oracle/_ref (the reference has no threads), {timed} timed step(s) each"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def cpu_baseline_single(name, time_cap_s=40.0):
+def cpu_baseline_single(name, time_cap_s=80.0):
     """One core, one bounded sample (kind = reference), for the cpu_baseline object of the B200 arm."""
     from oracle import ref_api
     if not ref_api.available():
         return None
-    name = name if name != "synth4k" else "input2"
     idx, what, _ = ref_sample_plan(name, 1, budget_s=time_cap_s)
-    imgs, desc, _ = load_workload(name)
-    sub = [imgs[i] for i in idx]
+    simgs, sdesc = ref_sample(name)
+    sub = [simgs[i] for i in idx]
     t0 = time.perf_counter()
     ref_api.stitch_mem(sub)
     dt = time.perf_counter() - t0
     return {"value": megapixels(sub) / dt, "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": f"{what} of {desc}, one run on one core ({dt:.1f} s)"}
+            "sample": f"{what} of {sdesc}, one run on one core ({dt:.1f} s)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -265,16 +324,19 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import computervisionimagestich2_b200 as pano
     L = pano.lib()
+    mode = args.mode
+    if mode == "auto":
+        mode = "sharded" if (world > 1 and args.workload in SYNTH_SHAPES) else "replicas"
+    ctx = pano.Context(local_rank)
+    ctx.set_match_mode(args.match_mode)
+    if world > 1 and mode == "sharded":
+        from computervisionimagestich2_b200 import dist as pdist
+        only = pdist.images_of_rank(SYNTH_SHAPES[args.workload][0], world, rank) if args.workload in SYNTH_SHAPES else None
+        imgs, desc, data = load_workload(args.workload, only=only)    # a rank renders only the views it owns
+        return run_b200_sharded(args, ctx, L, imgs, desc, data, dist, rank, local_rank, world)
     imgs, desc, data = load_workload(args.workload)
     n = len(imgs)
     mpix = megapixels(imgs)
-    ctx = pano.Context(local_rank)
-    ctx.set_match_mode(args.match_mode)
-    mode = args.mode
-    if mode == "auto":
-        mode = "sharded" if (world > 1 and args.workload.startswith("synth")) else "replicas"
-    if world > 1 and mode == "sharded":
-        return run_b200_sharded(args, ctx, L, imgs, desc, data, dist, rank, local_rank, world)
     ws = (C.c_int * n)(*[i.shape[2] for i in imgs])
     hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
 
@@ -467,8 +529,8 @@ def run_b200_sharded(args, ctx, L, imgs, desc, data, dist, rank, local_rank, wor
     from computervisionimagestich2_b200 import dist as pdist
     dev = torch.device("cuda", local_rank)
     n = len(imgs)
-    mpix = megapixels(imgs)
     mine = pdist.images_of_rank(n, world, rank)
+    mpix = max_over_ranks_sum(dist, torch, dev, sum(imgs[i].shape[1] * imgs[i].shape[2] for i in mine) / 1e6)
     keep = {i: torch.from_numpy(imgs[i]).to(dev) for i in mine}            # inputs resident in HBM on their owner
     staged = {i: (keep[i].data_ptr(), imgs[i].shape[2], imgs[i].shape[1]) for i in mine}
     sync = torch.cuda.synchronize
@@ -575,6 +637,7 @@ ROOFLINE_NOTES = {
     "blend.iir": "recursive Gaussian (CImg vanvliet): per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 cycles/sample (measured); parallel only across lines. Algorithmic bytes = 8 B per plane sample per pass (one read + one write, SURVEY 8d 'x-IIR r+w, y-IIR r+w'); the kernel's own forward + backward sweeps stay in shared memory",
     "sift.descr": "one warp per (keypoint, angle); gather from the L2-resident gradient map + double-precision geometry; algorithmic bytes = sum (2W+1)^2 * 8 B patch reads + 512 B per descriptor (SURVEY 8d)",
     "match.sad": "uint8 SAD pre-filter of the exact float-L1 matcher: 32 VABSDIFF4.U8.ACC per (query, database row) pair (one per 4 dimensions) + ~4 integer min/max for the running bounds; VABSDIFF4 issues at half rate (measured 60.7 of 64 lanes/clk/SM, tools/ubench/vsad_rate.cu), so peak = 148 SM x 64 lanes x median SM clock; 'achieved' counts the 32 VABSDIFF4 only",
+    "match.sad_sym": "uint8 SAD pre-filter of the exact float-L1 matcher, BOTH directed problems of an image pair from one pass over the SAD matrix: 32 VABSDIFF4.U8.ACC per (row of X, row of Y) + ~5 packed 16-bit min/max/add for the two sets of running bounds + 1.5 CREDUX; VABSDIFF4 issues at half rate (measured 60.7 of 64 lanes/clk/SM, tools/ubench/vsad_rate.cu), so peak = 148 SM x 64 lanes x median SM clock; 'achieved' counts the 32 VABSDIFF4 only (the bookkeeping shares the same ALU pipe)",
     "match.l1": "exact float-L1 matcher: 2 FP32 instructions (FADD sub, FADD |.|-accumulate) per dimension, no FMA possible; peak = 148 SM x 128 lanes x median SM clock",
 }
 
@@ -598,7 +661,7 @@ def roofline_of(top, kernels, clocks, workload=None):
     per_launch_ms = top_k["ms"] / top_k["launches"]
     common = {"kernel": top_name, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
               "share_of_kernel_time": top_k["ms"] / ksum, "note": ROOFLINE_NOTES.get(top_name), "traffic": None}
-    if top_name in ("match.l1", "match.sad"):
+    if top_name in ("match.l1", "match.sad", "match.sad_sym"):
         ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e12
         clk = (clocks or {}).get("sm_mhz") or 1500.0
         lanes = 128 if top_name == "match.l1" else 64
@@ -613,6 +676,12 @@ def roofline_of(top, kernels, clocks, workload=None):
     if workload:
         r.update(ncu_traffic(top_name, workload))
     return r
+
+
+def max_over_ranks_sum(dist, torch, dev, x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t)
+    return float(t.item())
 
 
 def expected_synth_hash(workload, got):
@@ -702,7 +771,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="synth4k", choices=["input", "input2", "synth4k", "synth4k_r1", "synth1080", "synth8k"])
     ap.add_argument("--ref-procs", type=int, default=64)
-    ap.add_argument("--match-mode", default="prefilter", choices=["prefilter", "full"])
+    ap.add_argument("--match-mode", default="prefilter", choices=["prefilter", "full", "prefilter_onedir"])
     ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"],
                     help="N > 1: 'sharded' = one job over all ranks (strong scaling; default for the synthetic workloads), "
                          "'replicas' = one job per rank (weak scaling; default for the bundled sets)")

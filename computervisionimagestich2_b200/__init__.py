@@ -155,13 +155,14 @@ class Context:
         return gss, grad
 
     def set_match_mode(self, mode: str = "prefilter"):
-        """'prefilter' (default: uint8 SAD pre-filter + exact re-rank) or 'full' (exact float scan of every pair)."""
-        self._check(self.L.pano_b200_set_match_mode(self.h, {"prefilter": 0, "full": 1}[mode]), "set_match_mode")
+        """'prefilter' (default: uint8 SAD pre-filter + exact re-rank, image pairs share one SAD pass), 'full' (exact
+        float scan of every pair) or 'prefilter_onedir' (pre-filter, one SAD pass per directed problem)."""
+        self._check(self.L.pano_b200_set_match_mode(self.h, {"prefilter": 0, "full": 1, "prefilter_onedir": 2}[mode]), "set_match_mode")
 
     def match_stats(self, reset=False):
-        out = (C.c_longlong * 4)()
+        out = (C.c_longlong * 5)()
         self._check(self.L.pano_b200_match_stats(self.h, out, int(reset)), "match_stats")
-        return {"queries": out[0], "survivors": out[1], "overflow": out[2], "problems": out[3]}
+        return {"queries": out[0], "survivors": out[1], "overflow": out[2], "problems": out[3], "sym_pairs": out[4]}
 
     def match_idx(self, descA, descB):
         dA = np.ascontiguousarray(descA, np.float32)
@@ -170,6 +171,15 @@ class Context:
         n = C.c_int()
         self._check(self.L.pano_b200_match(self.h, _p(dA), len(dA), _p(dB), len(dB), _p(idx), C.byref(n)), "match")
         return idx
+
+    def match_pair(self, descA, descB):
+        """-> (getImgPair(A, B) indices [nB], getImgPair(B, A) indices [nA]) from one batch (one SAD pass by default)."""
+        dA = np.ascontiguousarray(descA, np.float32)
+        dB = np.ascontiguousarray(descB, np.float32)
+        ab = np.empty(len(dB), np.int32)
+        ba = np.empty(len(dA), np.int32)
+        self._check(self.L.pano_b200_match_pair(self.h, _p(dA), len(dA), _p(dB), len(dB), _p(ab), _p(ba)), "match_pair")
+        return ab, ba
 
     def match(self, descA, keysA, descB, keysB):
         """getImgPair: returns (A keypoints, B keypoints) of the matches in B's table order."""

@@ -256,15 +256,15 @@ int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes) {
 }
 int pano_b200_set_match_mode(pano_b200_ctx* ctx, int mode) {
     PB_API_BEGIN
-    if (mode != PANO_B200_MATCH_PREFILTER && mode != PANO_B200_MATCH_FULL) return -1;
+    if (mode != PANO_B200_MATCH_PREFILTER && mode != PANO_B200_MATCH_FULL && mode != PANO_B200_MATCH_PREFILTER_ONEDIR) return -1;
     ctx->st->set_match_mode(mode);
     return 0;
     PB_API_END
 }
-int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[4], int reset) {
+int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[5], int reset) {
     PB_API_BEGIN
     const MatchStats& m = ctx->st->match_stats();
-    if (out) { out[0] = m.queries; out[1] = m.survivors; out[2] = m.overflow; out[3] = m.problems; }
+    if (out) { out[0] = m.queries; out[1] = m.survivors; out[2] = m.overflow; out[3] = m.problems; out[4] = m.sym_pairs; }
     if (reset) ctx->st->reset_match_stats();
     return 0;
     PB_API_END
@@ -440,6 +440,22 @@ int pano_b200_match(pano_b200_ctx* ctx, const float* descrA, int nA, const float
     int c = 0;
     for (int b = 0; b < nB; ++b) { match_idx[b] = idx[b]; c += idx[b] >= 0; }
     if (nmatches) *nmatches = c;
+    return 0;
+    PB_API_END
+}
+
+int pano_b200_match_pair(pano_b200_ctx* ctx, const float* descrA, int nA, const float* descrB, int nB, int* idx_ab,
+                         int* idx_ba) {
+    PB_API_BEGIN
+    if (nA < 0 || nB < 0 || (nA > 0 && !descrA) || (nB > 0 && !descrB)) return -1;
+    FeatureTable &A = ctx->match_a, &B = ctx->match_b;
+    A.n = nA; A.descr.assign(descrA, descrA + (size_t)nA * 128); A.on_device = false; A.quantised = false;
+    B.n = nB; B.descr.assign(descrB, descrB + (size_t)nB * 128); B.on_device = false; B.quantised = false;
+    std::vector<std::pair<FeatureTable*, FeatureTable*>> probs{{&A, &B}, {&B, &A}};
+    std::vector<std::vector<int>> out;
+    ctx->st->match_batch(probs, out);
+    if (idx_ab) std::copy(out[0].begin(), out[0].end(), idx_ab);
+    if (idx_ba) std::copy(out[1].begin(), out[1].end(), idx_ba);
     return 0;
     PB_API_END
 }

@@ -107,7 +107,8 @@ __global__ void match_merge_kernel(const MatchJob* __restrict__ jobs) {
 // Pre-filter (arithmetic and proof: match_device.cuh).  Tables are quantised once per image.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) sad_quantize_kernel(const float* __restrict__ descr, int n,
-                                                           unsigned* __restrict__ q8, int* __restrict__ qe) {
+                                                           unsigned* __restrict__ q8, int* __restrict__ qe,
+                                                           int* __restrict__ emax) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= n) return;
     const float4 v = reinterpret_cast<const float4*>(descr + (size_t)row * 128)[lane];
@@ -117,13 +118,18 @@ __global__ void __launch_bounds__(128) sad_quantize_kernel(const float* __restri
     q8[(size_t)row * 32 + lane] = w;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);   // any order: the bound is rounded up
-    if (lane == 0) qe[row] = sad_row_error(e);
+    if (lane == 0) {
+        const int er = sad_row_error(e);
+        qe[row] = er;
+        if (emax) atomicMax(emax, er);
+    }
 }
 
-void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, cudaStream_t st) {
+void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, int* emax, cudaStream_t st) {
+    if (emax) PB_CUDA(cudaMemsetAsync(emax, 0, sizeof(int), st));
     if (n <= 0) return;
     KScope ks("match.quantize", st, (double)n * (512 + 128 + 4));
-    sad_quantize_kernel<<<div_up((long)n * 32, 128), 128, 0, st>>>(descr, n, q8, qe);
+    sad_quantize_kernel<<<div_up((long)n * 32, 128), 128, 0, st>>>(descr, n, q8, qe, emax);
     PB_KERNEL_CHECK();
 }
 
@@ -148,10 +154,10 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 // One VABSDIFF4.U8.ACC per four dimensions: 32 instructions per (query, row) against 256 for the float scan; the
 // accumulator starts at e(a), so SAD + e(a) costs nothing.
 template <int MODE>
-__global__ void __launch_bounds__(kST) match_sad_kernel(const MatchJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(kST) match_sad_kernel(const MatchJob* __restrict__ jobs, const int* __restrict__ which) {
     __shared__ __align__(16) unsigned tile[2][kSRows][32];
     __shared__ int terr[2][kSRows];
-    const MatchJob& J = jobs[blockIdx.z];
+    const MatchJob& J = jobs[which ? which[blockIdx.z] : blockIdx.z];
     const int NA = J.NA;
     const int nq = MODE == 0 ? J.NB : J.counters[0];
     const int rps = MODE == 0 ? J.sad_rows_per_split : J.cand_rows_per_split;
@@ -244,6 +250,159 @@ __global__ void __launch_bounds__(kST) match_sad_kernel(const MatchJob* __restri
         for (int j = 0; j < kSQ; ++j)
             if (live[j]) J.spartial[(size_t)blockIdx.y * J.NB + slot[j]] = st[j];
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Both directions of an image pair from ONE pass over the SAD matrix.  getImgPair(X, Y) (database X, queries Y) and
+// getImgPair(Y, X) need the same |X| x |Y| integer SADs; only the error terms differ.  Threads hold rows of Y in
+// registers (kSQ each), rows of X stream through shared memory exactly as in match_sad_kernel:
+//   forward  (job F: database X, queries Y): per held y, statistics over the streamed x   -- in-thread, sequential;
+//   reverse  (job R: database Y, queries X): per streamed x, statistics over the CTA's y  -- warp reduction (CREDUX),
+//            the four warps of the CTA combined through shared memory once per tile, one entry per (y block, x).
+// The running bounds are kept as PACKED 16-bit pairs (Blackwell's VIADD.16x2 / VIMNMX.U16x2 / VIADDMNMX.U16x2): the two
+// streamed rows of an iteration share one instruction, so the forward bookkeeping costs 2.5 ALU instructions per
+// (x, y) instead of 4, and the whole pass ~37 ALU-pipe instructions per (x, y) for BOTH directions against 2 x 36.
+// 16 bits suffice because SAD <= 128 * 255 = 32640 and every error bound of both tables is <= kSymErrCap (the launcher
+// checks the tables' maxima; other pairs take the one-directional kernel).  Lower bounds are stored biased by +kSymErrCap.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSymErrCap = 255;
+constexpr unsigned kSymDead = 1u << 20;   // added to the (32-bit) bounds of a held row that does not exist: never among the minima
+
+__global__ void __launch_bounds__(kST) match_sad_sym_kernel(const MatchJob* __restrict__ jobs, const int2* __restrict__ pairs) {
+    __shared__ __align__(16) unsigned tile[2][kSRows][32];
+    __shared__ int terr[2][kSRows];
+    __shared__ int rstat[kST / 32][kSRows][3];     // per warp: reverse statistics of the tile's rows
+    const int2 fr = pairs[blockIdx.z];
+    const MatchJob& F = jobs[fr.x];                // database X = F.A, queries Y = F.B
+    const MatchJob& R = jobs[fr.y];                // database Y, queries X
+    const int NX = F.NA, NY = F.NB;
+    if (blockIdx.x * (kST * kSQ) >= NY || blockIdx.y >= F.sad_nsplit) return;
+    const unsigned* __restrict__ X8 = F.A8;
+    const int* __restrict__ Xe = F.Ae;
+    const int x_begin = blockIdx.y * F.sad_rows_per_split;
+    const int x_end = min(NX, x_begin + F.sad_rows_per_split);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    unsigned q[kSQ][32];
+    int yrow[kSQ];
+    bool live[kSQ];
+    unsigned eyu[kSQ], eyl[kSQ];                   // added to a SAD: upper bound / biased lower bound of the reverse problem
+#pragma unroll
+    for (int j = 0; j < kSQ; ++j) {
+        const int y = blockIdx.x * (kST * kSQ) + j * kST + tid;
+        live[j] = y < NY;
+        yrow[j] = min(y, NY - 1);
+        const int ey = F.Be[yrow[j]];
+        eyu[j] = live[j] ? (unsigned)ey : kSymDead;
+        eyl[j] = live[j] ? (unsigned)(kSymErrCap - ey) : kSymDead;
+        const uint4* src = reinterpret_cast<const uint4*>(F.B8 + (size_t)yrow[j] * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 t = src[k];
+            q[j][4 * k] = t.x; q[j][4 * k + 1] = t.y; q[j][4 * k + 2] = t.z; q[j][4 * k + 3] = t.w;
+        }
+    }
+    // forward statistics, two streamed rows per register: low half = even row of the iteration, high half = odd row
+    unsigned flb[kSQ], fu0[kSQ], fu1[kSQ];
+#pragma unroll
+    for (int j = 0; j < kSQ; ++j) flb[j] = fu0[j] = fu1[j] = 0xffffffffu;
+
+    const int ntiles = (x_end - x_begin + kSRows - 1) / kSRows;
+    auto issue = [&](int t) {
+        const int buf = t & 1, a0 = x_begin + t * kSRows, rows = min(kSRows, x_end - a0);
+        for (int i = tid; i < rows * 8; i += kST)
+            cp_async16(&tile[buf][i >> 3][(i & 7) * 4], X8 + (size_t)(a0 + (i >> 3)) * 32 + (i & 7) * 4);
+        if (tid < rows) cp_async4(&terr[buf][tid], Xe + a0 + tid);
+        asm volatile("cp.async.commit_group;");
+    };
+    if (ntiles > 0) issue(0);
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) {
+            issue(t + 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        const int buf = t & 1, a0 = x_begin + t * kSRows, rows = min(kSRows, x_end - a0);
+#pragma unroll 1
+        for (int r = 0; r < rows; r += 2) {
+            const bool two = r + 1 < rows;
+            const unsigned e0 = (unsigned)terr[buf][r], e1 = two ? (unsigned)terr[buf][r + 1] : 0u;
+            // packed per-row constants of the forward problem; when the tile ends on an odd row the high halves are
+            // forced to 0xffff below (larger than any real bound <= 32640 + 255), with nothing added to them
+            const unsigned exu = e0 | (e1 << 16);
+            const unsigned exl = (kSymErrCap - e0) | ((two ? (kSymErrCap - e1) : 0u) << 16);
+            const unsigned deadhi = two ? 0u : 0xffff0000u;
+            unsigned acc[kSQ][2];
+#pragma unroll
+            for (int j = 0; j < kSQ; ++j) acc[j][0] = acc[j][1] = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 w0 = reinterpret_cast<const uint4*>(&tile[buf][r][0])[k];
+                const uint4 w1 = reinterpret_cast<const uint4*>(&tile[buf][r + 1][0])[k];
+#pragma unroll
+                for (int j = 0; j < kSQ; ++j) {
+                    acc[j][0] = sad4_acc(q[j][4 * k], w0.x, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k], w1.x, acc[j][1]);
+                    acc[j][0] = sad4_acc(q[j][4 * k + 1], w0.y, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k + 1], w1.y, acc[j][1]);
+                    acc[j][0] = sad4_acc(q[j][4 * k + 2], w0.z, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k + 2], w1.z, acc[j][1]);
+                    acc[j][0] = sad4_acc(q[j][4 * k + 3], w0.w, acc[j][0]); acc[j][1] = sad4_acc(q[j][4 * k + 3], w1.w, acc[j][1]);
+                }
+            }
+            // ---- forward: packed bounds of (row r, row r + 1) against the held y ----
+#pragma unroll
+            for (int j = 0; j < kSQ; ++j) {
+                const unsigned pk = (acc[j][1] * 65536u + acc[j][0]) | deadhi;   // IMAD: FMA pipe
+                const unsigned u = __vadd2(pk, exu);
+                flb[j] = __viaddmin_u16x2(pk, exl, flb[j]);
+                fu1[j] = __vminu2(fu1[j], __vmaxu2(fu0[j], u));
+                fu0[j] = __vminu2(fu0[j], u);
+            }
+            // ---- reverse: bounds of the held y's against row r (and r + 1), reduced over the warp ----
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i == 1 && !two) break;
+                unsigned lo = 0xffffffffu, hi = 0xffffffffu, lb = 0xffffffffu;   // two smallest upper bounds, smallest lower bound
+#pragma unroll
+                for (int j = 0; j < kSQ; ++j) {
+                    const unsigned u = acc[j][i] + eyu[j];
+                    hi = min(hi, max(lo, u));
+                    lo = min(lo, u);
+                    lb = min(lb, acc[j][i] + eyl[j]);
+                }
+                const unsigned m_lb = __reduce_min_sync(0xffffffffu, lb);
+                const unsigned m0 = __reduce_min_sync(0xffffffffu, lo);
+                const unsigned holders = __ballot_sync(0xffffffffu, lo == m0);
+                const unsigned rest = __reduce_min_sync(0xffffffffu, lo == m0 ? hi : lo);
+                const unsigned m1 = __popc(holders) >= 2 ? m0 : rest;
+                if (lane == 0) {
+                    rstat[warp][r + i][0] = (int)m_lb;
+                    rstat[warp][r + i][1] = (int)m0;
+                    rstat[warp][r + i][2] = (int)m1;
+                }
+            }
+        }
+        __syncthreads();   // the tile buffer is refilled by the copy issued in the next iteration; rstat is complete
+        if (tid < rows) {  // combine the warps, one entry per (y block, x row): no other CTA writes it
+            SadStat sst = sadstat_init();
+#pragma unroll
+            for (int w = 0; w < kST / 32; ++w) {
+                SadStat o;
+                o.lbmin = rstat[w][tid][0] - kSymErrCap; o.u0 = rstat[w][tid][1]; o.u1 = rstat[w][tid][2];
+                sadstat_merge(sst, o);
+            }
+            R.spartial[(size_t)blockIdx.x * NX + a0 + tid] = sst;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kSQ; ++j)
+        if (live[j]) {
+            SadStat a, b;
+            a.lbmin = (int)(flb[j] & 0xffffu) - kSymErrCap; a.u0 = (int)(fu0[j] & 0xffffu); a.u1 = (int)(fu1[j] & 0xffffu);
+            b.lbmin = (int)(flb[j] >> 16) - kSymErrCap; b.u0 = (int)(fu0[j] >> 16); b.u1 = (int)(fu1[j] >> 16);
+            sadstat_merge(a, b);
+            F.spartial[(size_t)blockIdx.y * NY + yrow[j]] = a;
+        }
 }
 
 // merges the splits' statistics, rejects what can be rejected with certainty, compacts the rest
@@ -342,10 +501,10 @@ int match_sad_num_splits(int NA, int NB, int njobs) {
     return s < 1 ? 1 : s;
 }
 
-size_t match_prefilter_ints(int NB) { return (size_t)align_up(NB, 4) * (4 + kMatchCand) + 4; }
+size_t match_prefilter_ints(int NB) { return (size_t)align_up(NB, 4) * (4 + kMatchCand); }
 
 void match_prefilter_attach(MatchJob& J, const unsigned* A8, const int* Ae, const unsigned* B8, const int* Be,
-                            int sad_nsplit, SadStat* spartial, int* scratch) {
+                            int sad_nsplit, SadStat* spartial, int* scratch, int* counters) {
     J.A8 = A8; J.Ae = Ae; J.B8 = B8; J.Be = Be;
     J.sad_rows_per_split = align_up(div_up(J.NA > 0 ? J.NA : 1, sad_nsplit > 0 ? sad_nsplit : 1), 2);
     J.sad_nsplit = div_up(J.NA > 0 ? J.NA : 1, J.sad_rows_per_split);
@@ -354,29 +513,57 @@ void match_prefilter_attach(MatchJob& J, const unsigned* A8, const int* Ae, cons
     J.cand_nsplit = div_up(J.NA > 0 ? J.NA : 1, J.cand_rows_per_split);
     J.spartial = spartial;
     const size_t n = (size_t)align_up(J.NB, 4);
-    J.counters = scratch;
-    J.surv = scratch + 4;
+    J.counters = counters;
+    J.surv = scratch;
     J.thr = J.surv + n;
     J.cand_cnt = J.thr + n;
     J.overflow = J.cand_cnt + n;
     J.cand = J.overflow + n;
 }
 
-void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, cudaStream_t st) {
+int match_prefilter_pair(MatchJob& F, MatchJob& R) {
+    // R's statistics arrive as one entry per (block of held rows of Y, row of X): its "splits" are the y blocks
+    R.sad_nsplit = div_up(F.NB, kST * kSQ);
+    return R.sad_nsplit;
+}
+int match_sym_err_cap() { return kSymErrCap; }
+int match_sym_yblocks(int NY) { return div_up(NY, kST * kSQ); }
+
+void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, const int2* d_pairs,
+                                  const int2* h_pairs, int npairs, const int* d_singles, const int* h_singles, int nsingles,
+                                  cudaStream_t st) {
     if (njobs <= 0) return;
-    int nbmax = 1, sy = 1, fy = 1, cy = 1;
-    double pairs = 0;
+    int nbmax = 1, fy = 1, cy = 1;
     for (int i = 0; i < njobs; ++i) {
         nbmax = std::max(nbmax, h_jobs[i].NB);
-        sy = std::max(sy, h_jobs[i].sad_nsplit);
         fy = std::max(fy, h_jobs[i].nsplit);
         cy = std::max(cy, h_jobs[i].cand_nsplit);
-        pairs += (double)h_jobs[i].NA * h_jobs[i].NB;
     }
     const int sx = div_up(nbmax, kST * kSQ);
-    {
+    if (npairs > 0) {   // both directions of an image pair from one pass
+        int px = 1, py = 1;
+        double pairs = 0;
+        for (int i = 0; i < npairs; ++i) {
+            const MatchJob& F = h_jobs[h_pairs[i].x];
+            px = std::max(px, div_up(F.NB, kST * kSQ));
+            py = std::max(py, F.sad_nsplit);
+            pairs += (double)F.NA * F.NB;
+        }
+        KScope ks("match.sad_sym", st, 32.0 * pairs);   // VABSDIFF4 thread-instructions (they serve two directed problems)
+        match_sad_sym_kernel<<<dim3(px, py, npairs), kST, 0, st>>>(d_jobs, d_pairs);
+        PB_KERNEL_CHECK();
+    }
+    if (nsingles > 0) {
+        int qx = 1, qy = 1;
+        double pairs = 0;
+        for (int i = 0; i < nsingles; ++i) {
+            const MatchJob& J = h_jobs[h_singles[i]];
+            qx = std::max(qx, div_up(J.NB, kST * kSQ));
+            qy = std::max(qy, J.sad_nsplit);
+            pairs += (double)J.NA * J.NB;
+        }
         KScope ks("match.sad", st, 32.0 * pairs);   // VABSDIFF4 thread-instructions
-        match_sad_kernel<0><<<dim3(sx, sy, njobs), kST, 0, st>>>(d_jobs);
+        match_sad_kernel<0><<<dim3(qx, qy, nsingles), kST, 0, st>>>(d_jobs, d_singles);
         PB_KERNEL_CHECK();
     }
     {
@@ -386,7 +573,7 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
     }
     {   // grids are sized for "every query survives"; CTAs beyond the survivor count leave at once
         KScope ks("match.cand", st, 0);
-        match_sad_kernel<1><<<dim3(sx, cy, njobs), kST, 0, st>>>(d_jobs);
+        match_sad_kernel<1><<<dim3(sx, cy, njobs), kST, 0, st>>>(d_jobs, nullptr);
         PB_KERNEL_CHECK();
     }
     {

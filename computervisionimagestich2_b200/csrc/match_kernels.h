@@ -42,14 +42,23 @@ void launch_match_batch(const MatchJob* d_jobs, const MatchJob* h_jobs, int njob
 // The same result through the pre-filter: SAD pass over the quantised tables, decision, candidate pass for the
 // surviving queries, exact float distances of the candidates, full scan of the queries whose candidate list overflowed.
 // The jobs' pre-filter fields must be set (match_prefilter_attach); counters must be zero.
-void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, cudaStream_t st);
+// pairs: (F, R) job indices with R = the reverse problem of F (F.A == R.B, F.B == R.A): one SAD pass serves both
+// (match_sad_sym_kernel); singles: the remaining job indices.  Every job appears in exactly one of the two lists.
+void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, const int2* d_pairs,
+                                  const int2* h_pairs, int npairs, const int* d_singles, const int* h_singles, int nsingles,
+                                  cudaStream_t st);
+// makes R the reverse problem of F for the symmetric pass; returns the number of SadStat rows (of R.NB entries) R needs
+int match_prefilter_pair(MatchJob& F, MatchJob& R);
+int match_sym_yblocks(int NY);
+int match_sym_err_cap();   // the symmetric pass needs every row error bound of both tables <= this
 int match_sad_num_splits(int NA, int NB, int njobs);
 // ints of scratch the pre-filter of one job needs (after the SadStat partials), and the attachment of that scratch
 size_t match_prefilter_ints(int NB);
 void match_prefilter_attach(MatchJob& J, const unsigned* A8, const int* Ae, const unsigned* B8, const int* Be,
-                            int sad_nsplit, SadStat* spartial, int* scratch);
+                            int sad_nsplit, SadStat* spartial, int* scratch, int* counters /* 4 ints, zeroed */);
 // float table [n][128] -> quantised words [n][32] + per-row error bound
-void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, cudaStream_t st);
+// emax (optional, device): receives the largest error bound of the table
+void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, int* emax, cudaStream_t st);
 
 // Scores `iters` hypotheses for each of nproblems pair lists.  pairs: concatenated lists, pair_off [nproblems+1];
 // samples [nproblems][iters][4] indices into each list; counts [nproblems][iters]; masks [nproblems][iters][words_stride]

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <map>
 #include <queue>
 #include <sstream>
 #include <thread>
@@ -178,29 +179,26 @@ void Stitcher::upload_table(FeatureTable& t) { upload_table_on(t, st_); }
 void Stitcher::quantise_table(FeatureTable& t) {
     if (t.quantised) return;
     t.d_q8.ensure(std::max<size_t>((size_t)t.n * 32, 32));
-    t.d_qe.ensure(std::max<size_t>(t.n, 1));
-    launch_sad_quantize(t.d_descr.p, t.n, t.d_q8.p, t.d_qe.p, st_);
+    t.d_qe.ensure(std::max<size_t>(t.n, 1) + 1);        // [n] = the table's largest error bound
+    int* h = h_qemax_.ensure(1);
+    launch_sad_quantize(t.d_descr.p, t.n, t.d_q8.p, t.d_qe.p, t.d_qe.p + std::max(t.n, 1), st_);
+    PB_CUDA(cudaMemcpyAsync(h, t.d_qe.p + std::max(t.n, 1), sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+    t.qemax = *h;
     t.quantised = true;
 }
 
 // Several directed matching problems (A = database, B = queries) in ONE batch of launches.  out[k][b] = row of A
-// matched by query row b, or -1 (ImageProcess.cpp:311-346).
+// matched by query row b, or -1 (ImageProcess.cpp:311-346).  Problems that come with their reverse (B, A) in the same
+// batch share one pass over the SAD matrix (match_sad_sym_kernel).
 void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTable*>>& probs,
                            std::vector<std::vector<int>>& out, int* d_out) {
     PB_CUDA(cudaSetDevice(dev_));
     const int P = (int)probs.size();
-    const bool pre = match_mode_ == 0;
+    const bool pre = match_mode_ != 1;
+    const bool sym = match_mode_ == 0;
     out.assign(P, std::vector<int>());
-    std::vector<MatchJob> jobs;
-    std::vector<int> job_of(P, -1);
-    size_t npart = 0, nidx = 0, nspart = 0, nscratch = 0;
-    std::vector<size_t> poff, ioff, soff, coff;
-    std::vector<int> nsplits, snsplits;
-    int njobs = 0;
-    for (int k = 0; k < P; ++k) {
-        FeatureTable &A = *probs[k].first, &B = *probs[k].second;
-        if (B.n > 0 && A.n >= 2) ++njobs;
-    }
+    std::vector<int> job_of(P, -1), prob_of;
     for (int k = 0; k < P; ++k) {
         FeatureTable &A = *probs[k].first, &B = *probs[k].second;
         upload_table(A);
@@ -208,24 +206,12 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         out[k].assign(B.n, -1);
         if (B.n == 0 || A.n < 2) continue;  // the reference reads an unset second neighbour when NA < 2
         if (pre) { quantise_table(A); quantise_table(B); }
-        const int ns = match_num_splits(A.n, B.n);
-        job_of[k] = (int)nsplits.size();
-        nsplits.push_back(ns);
-        poff.push_back(npart);
-        ioff.push_back(nidx);
-        npart += (size_t)ns * B.n;
-        nidx += B.n;
-        if (pre) {
-            const int sns = match_sad_num_splits(A.n, B.n, njobs);
-            snsplits.push_back(sns);
-            soff.push_back(nspart);
-            coff.push_back(nscratch);
-            nspart += (size_t)(sns + 1) * B.n;     // attach may round the split count up by one
-            nscratch += match_prefilter_ints(B.n);
-        }
+        job_of[k] = (int)prob_of.size();
+        prob_of.push_back(k);
         tm_.match_pairs_evaluated += (long)A.n * B.n;
         tm_.n_match_calls++;
     }
+    const int nj = (int)prob_of.size();
     if (d_out) {   // degenerate problems never reach a kernel: their lists are all -1
         size_t off = 0;
         for (int k = 0; k < P; ++k) {
@@ -233,35 +219,91 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
             if (job_of[k] < 0 && nb) PB_CUDA(cudaMemsetAsync(d_out + off, 0xff, nb * sizeof(int), st_));
             off += nb;
         }
-        if (nsplits.empty()) PB_CUDA(cudaStreamSynchronize(st_));
+        if (nj == 0) PB_CUDA(cudaStreamSynchronize(st_));
     }
-    if (nsplits.empty()) return;
+    if (nj == 0) return;
+    // pair every problem with its reverse where both are in the batch and both tables qualify for 16-bit bounds
+    std::vector<int> partner(nj, -1);
+    std::vector<int2> pairs;
+    std::vector<int> singles;
+    if (sym) {
+        std::map<std::pair<const FeatureTable*, const FeatureTable*>, int> open;
+        for (int q = 0; q < nj; ++q) {
+            const FeatureTable* A = probs[prob_of[q]].first;
+            const FeatureTable* B = probs[prob_of[q]].second;
+            if (A->qemax > match_sym_err_cap() || B->qemax > match_sym_err_cap() || A == B) continue;
+            auto it = open.find({B, A});
+            if (it != open.end()) {
+                partner[q] = it->second;
+                partner[it->second] = q;
+                pairs.push_back(make_int2(it->second, q));     // F = the earlier problem, R = this one
+                open.erase(it);
+            } else if (!open.count({A, B})) {
+                open[{A, B}] = q;
+            }
+        }
+    }
+    for (int q = 0; q < nj; ++q)
+        if (partner[q] < 0) singles.push_back(q);
+    std::vector<char> is_r(nj, 0);
+    for (auto& pr : pairs) is_r[pr.y] = 1;
+    // scratch layout
+    size_t npart = 0, nidx = 0, nspart = 0, nscratch = 0;
+    std::vector<size_t> poff(nj), ioff(nj), soff(nj), coff(nj);
+    std::vector<int> nsplits(nj), snsplits(nj, 1);
+    const int nlaunch_jobs = std::max<int>(1, (int)pairs.size() + (int)singles.size());
+    for (int q = 0; q < nj; ++q) {
+        FeatureTable &A = *probs[prob_of[q]].first, &B = *probs[prob_of[q]].second;
+        nsplits[q] = match_num_splits(A.n, B.n);
+        poff[q] = npart; ioff[q] = nidx;
+        npart += (size_t)nsplits[q] * B.n;
+        nidx += B.n;
+        if (pre) {
+            soff[q] = nspart; coff[q] = nscratch;
+            if (is_r[q]) {
+                nspart += (size_t)match_sym_yblocks(A.n) * B.n;   // one row of statistics per block of held rows of Y = A
+            } else {
+                snsplits[q] = match_sad_num_splits(A.n, B.n, nlaunch_jobs);
+                nspart += (size_t)(snsplits[q] + 1) * B.n;         // attach may round the split count up by one
+            }
+            nscratch += match_prefilter_ints(B.n);
+        }
+    }
     partial_.ensure(npart);
     midx_.ensure(nidx);
     if (pre) {
         spartial_.ensure(nspart);
         mscratch_.ensure(nscratch);
+        mcount_.ensure((size_t)4 * nj);
+        PB_CUDA(cudaMemsetAsync(mcount_.p, 0, (size_t)4 * nj * sizeof(int), st_));
     }
-    int* h = h_midx_.ensure(nidx + 4 * nsplits.size());
-    for (int k = 0; k < P; ++k) {
-        if (job_of[k] < 0) continue;
-        const int q = job_of[k];
-        FeatureTable &A = *probs[k].first, &B = *probs[k].second;
+    int* h = h_midx_.ensure(nidx + 4 * (size_t)nj);
+    std::vector<MatchJob> jobs(nj);
+    for (int q = 0; q < nj; ++q) {
+        FeatureTable &A = *probs[prob_of[q]].first, &B = *probs[prob_of[q]].second;
         MatchJob J = make_match_job(A.d_descr.p, A.n, B.d_descr.p, B.n, partial_.p + poff[q], nsplits[q],
                                     midx_.p + ioff[q], nullptr);
-        if (pre) {
+        if (pre)
             match_prefilter_attach(J, A.d_q8.p, A.d_qe.p, B.d_q8.p, B.d_qe.p, snsplits[q], spartial_.p + soff[q],
-                                   mscratch_.p + coff[q]);
-            PB_CUDA(cudaMemsetAsync(J.counters, 0, 4 * sizeof(int), st_));
-        }
-        jobs.push_back(J);
+                                   mscratch_.p + coff[q], mcount_.p + 4 * (size_t)q);
+        jobs[q] = J;
     }
-    MatchJob* hj = (MatchJob*)h_mjobs_.ensure(jobs.size() * sizeof(MatchJob));
+    for (auto& pr : pairs) match_prefilter_pair(jobs[pr.x], jobs[pr.y]);
+    // one upload: job table, pair list, single list
+    const size_t jb = align_up((int)(jobs.size() * sizeof(MatchJob)), 16), pb = align_up((int)(pairs.size() * sizeof(int2)), 16);
+    char* hj = h_mjobs_.ensure(jb + pb + singles.size() * sizeof(int) + 16);
     memcpy(hj, jobs.data(), jobs.size() * sizeof(MatchJob));
-    mjobs_.ensure(jobs.size());
-    PB_CUDA(cudaMemcpyAsync(mjobs_.p, hj, jobs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st_));
-    if (pre) launch_match_batch_prefilter(mjobs_.p, hj, (int)jobs.size(), st_);
-    else launch_match_batch(mjobs_.p, hj, (int)jobs.size(), st_);
+    if (!pairs.empty()) memcpy(hj + jb, pairs.data(), pairs.size() * sizeof(int2));
+    if (!singles.empty()) memcpy(hj + jb + pb, singles.data(), singles.size() * sizeof(int));
+    mjobs_.ensure(jb + pb + singles.size() * sizeof(int) + 16);
+    PB_CUDA(cudaMemcpyAsync(mjobs_.p, hj, jb + pb + singles.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+    const MatchJob* dj = reinterpret_cast<const MatchJob*>(mjobs_.p);
+    if (pre)
+        launch_match_batch_prefilter(dj, reinterpret_cast<const MatchJob*>(hj), nj, reinterpret_cast<const int2*>(mjobs_.p + jb),
+                                     reinterpret_cast<const int2*>(hj + jb), (int)pairs.size(),
+                                     reinterpret_cast<const int*>(mjobs_.p + jb + pb), reinterpret_cast<const int*>(hj + jb + pb),
+                                     (int)singles.size(), st_);
+    else launch_match_batch(dj, reinterpret_cast<const MatchJob*>(hj), nj, st_);
     PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * nidx, cudaMemcpyDeviceToHost, st_));
     if (d_out) {
         size_t off = 0;
@@ -272,13 +314,10 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
             off += nb;
         }
     }
-    if (pre)
-        for (size_t q = 0; q < jobs.size(); ++q)
-            PB_CUDA(cudaMemcpyAsync(h + nidx + 4 * q, jobs[q].counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    if (pre) PB_CUDA(cudaMemcpyAsync(h + nidx, mcount_.p, (size_t)4 * nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
-    for (int k = 0; k < P; ++k) {
-        if (job_of[k] < 0) continue;
-        const int q = job_of[k];
+    for (int q = 0; q < nj; ++q) {
+        const int k = prob_of[q];
         std::copy(h + ioff[q], h + ioff[q] + out[k].size(), out[k].begin());
         mstats_.problems++;
         mstats_.queries += (long long)out[k].size();
@@ -287,6 +326,7 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
             mstats_.overflow += h[nidx + 4 * q + 1];
         }
     }
+    mstats_.sym_pairs += (long long)pairs.size();
 }
 
 void Stitcher::match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx) {
@@ -1375,7 +1415,13 @@ int Stitcher::run() {
         WallTimer t;
         std::vector<std::pair<int, int>> wave;
         for (int i = 0; i < n; ++i)
-            for (int j = i + 1; j < n; ++j) wave.push_back({i, j});
+            for (int j = i + 1; j < n; ++j) {
+                wave.push_back({i, j});
+                // the reverse problem shares the SAD matrix: with the symmetric pass it comes almost for free, and the
+                // reference evaluates it anyway for every non-adjacent pair (below) and every tree edge (:177-178).
+                // Only the lists the reference would compute are ever consulted.
+                if (match_mode_ == 0) wave.push_back({j, i});
+            }
         run_wave(wave);
         wave.clear();
         for (int i = 0; i < n; ++i)

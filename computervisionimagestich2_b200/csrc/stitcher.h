@@ -29,6 +29,7 @@ struct FeatureTable {   // == std::map<std::vector<float>, VlSiftKeypoint> flatt
     DevBuf<unsigned> d_q8;
     DevBuf<int> d_qe;
     bool quantised = false;
+    int qemax = 0;              // largest error bound of the table (decides whether the 16-bit symmetric pass applies)
 };
 
 struct StageTimes {  // milliseconds, CUDA events on the stitcher's stream (host work between kernels included)
@@ -39,7 +40,7 @@ struct StageTimes {  // milliseconds, CUDA events on the stitcher's stream (host
 };
 
 struct MatchStats {   // pre-filter bookkeeping since the last clear(): queries, survivors of the SAD pass, full-scan fallbacks
-    long long queries = 0, survivors = 0, overflow = 0, problems = 0;
+    long long queries = 0, survivors = 0, overflow = 0, problems = 0, sym_pairs = 0;
 };
 
 class Stitcher {
@@ -96,8 +97,9 @@ class Stitcher {
     // slots (optional): imgs_[slots[i]] receives image i (the slots must exist: shard_begin); default = n appended slots
     void add_images(const u8* const* imgs, const int* w, const int* h, int n, bool on_device, const int* slots = nullptr);
     void set_lanes(int n) { want_lanes_ = n < 1 ? 1 : n; }
-    // matcher: 0 = rigorous uint8 pre-filter + exact float re-rank (default), 1 = full exact float scan.  Both give
-    // the reference's match lists bit for bit; the second is the round-1 kernel, kept as the cross-check.
+    // matcher: 0 = rigorous uint8 pre-filter + exact float re-rank, both directions of an image pair from one SAD pass
+    // (default); 1 = full exact float scan (the round-1 kernel, kept as the cross-check); 2 = pre-filter, one SAD pass
+    // per directed problem.  All give the reference's match lists bit for bit.
     void set_match_mode(int m) { match_mode_ = m; }
     int match_mode() const { return match_mode_; }
     const MatchStats& match_stats() const { return mstats_; }
@@ -168,13 +170,14 @@ class Stitcher {
     int ktab_n_ = 0;
     DevBuf<Top2> partial_;
     DevBuf<SadStat> spartial_;
-    DevBuf<int> mscratch_;
+    DevBuf<int> mscratch_, mcount_;
+    PinBuf<int> h_qemax_;
     int match_mode_ = 0;
     MatchStats mstats_;
     void quantise_table(FeatureTable& t);
     DevBuf<int> midx_;
     PinBuf<int> h_midx_;
-    DevBuf<MatchJob> mjobs_;
+    DevBuf<char> mjobs_;        // job table + pair list + single list of a matching batch
     DevBuf<u8> u8a_, u8b_, u8raw_;
     DevBuf<int> u8na_, u8nb_, u8idx_, u8d01_, u8scratch_;
     DevBuf<U8Top3> u8part_;

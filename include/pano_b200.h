@@ -132,6 +132,11 @@ int pano_b200_sift_octave_dump(pano_b200_ctx* ctx, int octave, float* gss, float
  * match_idx[b] = row of A matched by row b of B, or -1.  Returns the number of matches through *nmatches. */
 int pano_b200_match(pano_b200_ctx* ctx, const float* descrA, int nA, const float* descrB, int nB, int* match_idx,
                     int* nmatches);
+/* both directed problems of an image pair in one call, as the reference evaluates them for every stitched edge
+ * (ImageProcess.cpp:177-178): idx_ab[b] = getImgPair(A, B) (database A, queries B, nB entries), idx_ba[a] =
+ * getImgPair(B, A) (nA entries).  With the default matcher both come from ONE pass over the |A| x |B| SAD matrix. */
+int pano_b200_match_pair(pano_b200_ctx* ctx, const float* descrA, int nA, const float* descrB, int nB, int* idx_ab,
+                         int* idx_ba);
 
 /* ImageProcess::RANSAC (ImageProcess.cpp:395-436): pairs (src -> dst) -> 8 bilinear coefficients in Homography
  * constructor order (x' = H[0] x + H[1] y + H[2] x y + H[3]; y' = H[4] x + H[5] y + H[6] x y + H[7]).
@@ -209,15 +214,18 @@ void pano_b200_free_pinned(void* p);
 /* number of concurrent per-image lanes (stream + SIFT engine + host thread) used by the pipeline; default 4 */
 int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes);
 /* matcher of getImgPair (ImageProcess.cpp:273-351): PANO_B200_MATCH_PREFILTER (default) = rigorous uint8 SAD pre-filter
- * + exact float-L1 re-rank of the candidates; PANO_B200_MATCH_FULL = exact float-L1 scan of every (query, row) pair.
- * Both return the reference's match lists bit for bit (the pre-filter never drops a row the exact rule needs). */
+ * + exact float-L1 re-rank of the candidates, both directions of an image pair from one pass over the SAD matrix;
+ * PANO_B200_MATCH_FULL = exact float-L1 scan of every (query, row) pair; PANO_B200_MATCH_PREFILTER_ONEDIR = the
+ * pre-filter with one SAD pass per directed problem.  All return the reference's match lists bit for bit (the
+ * pre-filter never drops a row the exact rule needs). */
 #define PANO_B200_MATCH_PREFILTER 0
 #define PANO_B200_MATCH_FULL 1
+#define PANO_B200_MATCH_PREFILTER_ONEDIR 2
 int pano_b200_set_match_mode(pano_b200_ctx* ctx, int mode);
 /* pre-filter bookkeeping since the last reset: out[0] = queries, out[1] = queries the SAD pass could not reject,
- * out[2] = queries that fell back to the full scan (candidate list overflow), out[3] = directed problems; reset != 0
- * clears the counters after reading */
-int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[4], int reset);
+ * out[2] = queries that fell back to the full scan (candidate list overflow), out[3] = directed problems, out[4] = image
+ * pairs served by the symmetric pass; reset != 0 clears the counters after reading */
+int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[5], int reset);
 int pano_b200_flush_l2(pano_b200_ctx* ctx);           /* overwrite a 256 MB scratch buffer (2x L2) */
 int pano_b200_timer_start(pano_b200_ctx* ctx);        /* CUDA events on the context's stream */
 int pano_b200_timer_stop(pano_b200_ctx* ctx, float* ms);

@@ -73,3 +73,74 @@ def test_prefilter_vs_reference_getimgpair(ctx, ref, input_sets):
         ga, gb = ctx.match(da, ka, db, kb)
         ra, rb = ref.match(da, ka, db, kb)
         assert ga.tobytes() == ra.tobytes() and gb.tobytes() == rb.tobytes()
+
+
+# ---- both directions of an image pair from one pass over the SAD matrix (match_sad_sym_kernel) --------------------------
+def both_pair(ctx, A, B, expect_sym=True):
+    ctx.set_match_mode("full")
+    fab, fba = ctx.match_idx(A, B), ctx.match_idx(B, A)
+    ctx.set_match_mode("prefilter")
+    ctx.match_stats(reset=True)
+    ab, ba = ctx.match_pair(A, B)
+    st = ctx.match_stats(reset=True)
+    assert np.array_equal(fab, ab), f"A->B list differs at {np.nonzero(fab != ab)[0][:10]}, {st}"
+    assert np.array_equal(fba, ba), f"B->A list differs at {np.nonzero(fba != ba)[0][:10]}, {st}"
+    if expect_sym is not None and min(len(A), len(B)) >= 2:
+        assert st["sym_pairs"] == (1 if expect_sym else 0), st
+    ctx.set_match_mode("prefilter_onedir")
+    ab1, ba1 = ctx.match_pair(A, B)
+    ctx.set_match_mode("prefilter")
+    assert np.array_equal(fab, ab1) and np.array_equal(fba, ba1)
+    return ab, ba, st
+
+
+def test_symmetric_pass_equals_full_scan(ctx):
+    rng = np.random.default_rng(31)
+    A = sift_like(rng, 6007)
+    B = with_matches(rng, A, 5003, frac=0.4)
+    ab, ba, st = both_pair(ctx, A, B)
+    assert (ab >= 0).sum() > 1000 and (ba >= 0).sum() > 1000
+    assert st["queries"] == len(A) + len(B) and st["overflow"] <= 0.01 * st["queries"]
+    both_pair(ctx, A, sift_like(rng, 3001))            # unrelated tables: nothing to match in either direction
+
+
+def test_symmetric_pass_ragged_sizes(ctx):
+    """odd tile tails, partial last blocks of held rows, single-row splits, tiny tables"""
+    rng = np.random.default_rng(32)
+    A = sift_like(rng, 1400)
+    B = with_matches(rng, A, 1300)
+    for na, nb in ((2, 2), (2, 301), (3, 257), (65, 256), (127, 2), (129, 513), (1400, 3), (1, 50), (50, 1), (1399, 1299), (64, 64)):
+        both_pair(ctx, A[:na], B[:nb], expect_sym=min(na, nb) >= 2)
+
+
+def test_symmetric_pass_adversarial_and_fallback(ctx):
+    rng = np.random.default_rng(33)
+    A = sift_like(rng, 1800)
+    B = with_matches(rng, A, 1500)
+    A2, B2 = A.copy(), B.copy()
+    A2[3] = -A2[3]                                     # error bound of this row is large but finite: still <= cap? no ->
+    B2[20] = A2[10] = A2[11]                           # duplicates: d0 == d1 == 0
+    A2[50] = 0.0
+    B2[60] = 0.0
+    both_pair(ctx, A2, B2, expect_sym=False)           # the negated row's error bound exceeds the 16-bit cap: one-directional passes
+    A3, B3 = A.copy(), B.copy()
+    B3[20] = A3[10] = A3[11]
+    A3[50] = 0.0
+    B3[60] = 0.0
+    both_pair(ctx, A3, B3, expect_sym=True)
+    both_pair(ctx, np.ascontiguousarray(A * 0.01), np.ascontiguousarray(B * 0.01))       # everything quantises to 0 / 1
+    both_pair(ctx, np.ascontiguousarray(A * 1.9), np.ascontiguousarray(B * 1.9), expect_sym=None)    # clamped rows: large errors
+
+
+def test_symmetric_pass_vs_reference_getimgpair(ctx, ref, input_sets):
+    ctx.set_match_mode("prefilter")
+    tabs = [ref.sift_features(ref.gray(ref.project(img))) for img in input_sets["Input2"][:3]]
+    for i, j in ((0, 1), (1, 2), (0, 2)):
+        (da, ka), (db, kb) = tabs[i], tabs[j]
+        ab, ba = ctx.match_pair(da, db)
+        ra, rb = ref.match(da, ka, db, kb)
+        sel = ab >= 0
+        assert ka[ab[sel]].tobytes() == ra.tobytes() and kb[sel].tobytes() == rb.tobytes()
+        ra, rb = ref.match(db, kb, da, ka)
+        sel = ba >= 0
+        assert kb[ba[sel]].tobytes() == ra.tobytes() and ka[sel].tobytes() == rb.tobytes()
