@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpano_b200.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["sift_kernels.cu", "sift_engine.cu", "match_kernels.cu", "canvas_kernels.cu", "stitcher.cu", "c_api.cu",
-           "vl_sift_shim.cu", "vl_kdforest_shim.cu", "bench_kernels.cu", "match_i8_kernels.cu"]
+           "vl_sift_shim.cu", "vl_kdforest_shim.cu", "match_i8_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("PANO_B200_NVCC_EXTRA", "").split()   # e.g. -DPB_DESCR_DEBUG for an instrumented build
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
@@ -35,7 +35,10 @@ def _newest_dep() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = list(SOURCES)
+    missing = [s for s in srcs if not os.path.exists(os.path.join(CSRC, s))]
+    if missing:
+        raise RuntimeError(f"listed kernel sources are missing from {CSRC}: {missing}")
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_dep():
         return OUT
     os.makedirs(OBJ, exist_ok=True)

@@ -33,6 +33,13 @@ static_assert(sizeof(pano_b200_pair) == sizeof(KeyPair), "pair ABI");
         return -101;                                                   \
     }
 
+// results handed to the caller are malloc'ed (freed with pano_b200_free); an allocation failure becomes an error code
+static void* xmalloc(size_t n) {
+    void* p = malloc(n ? n : 1);
+    if (!p) throw std::runtime_error("out of host memory");
+    return p;
+}
+
 extern "C" {
 
 int pano_b200_device_count(void) {
@@ -73,7 +80,7 @@ int pano_b200_stitch(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* 
     if (rc) { ctx->err = S.error(); return rc; }
     *out_w = S.result_width();
     *out_h = S.result_height();
-    *out = (uint8_t*)malloc((size_t)3 * *out_w * *out_h);
+    *out = (uint8_t*)xmalloc((size_t)3 * *out_w * *out_h);
     S.copy_result(*out);
     return 0;
     PB_API_END
@@ -84,8 +91,8 @@ int pano_b200_extract(pano_b200_ctx* ctx, const uint8_t* rgb, int w, int h, uint
     FeatureTable t;
     ctx->st->extract(rgb, w, h, proj_out, t);
     *n = t.n;
-    *descr = (float*)malloc(std::max<size_t>((size_t)t.n * 128 * sizeof(float), 4));
-    *keys = (pano_b200_keypoint*)malloc(std::max<size_t>((size_t)t.n * sizeof(VlKey), 4));
+    *descr = (float*)xmalloc(std::max<size_t>((size_t)t.n * 128 * sizeof(float), 4));
+    *keys = (pano_b200_keypoint*)xmalloc(std::max<size_t>((size_t)t.n * sizeof(VlKey), 4));
     memcpy(*descr, t.descr.data(), (size_t)t.n * 128 * sizeof(float));
     memcpy(*keys, t.keys.data(), (size_t)t.n * sizeof(VlKey));
     return 0;
@@ -119,7 +126,7 @@ int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const
     if (rc) { ctx->err = S.error(); return rc; }
     *out_w = S.result_width();
     *out_h = S.result_height();
-    *out = (uint8_t*)malloc((size_t)3 * *out_w * *out_h);
+    *out = (uint8_t*)xmalloc((size_t)3 * *out_w * *out_h);
     S.copy_result(*out);
     return 0;
     PB_API_END
@@ -291,6 +298,8 @@ void pano_b200_ktimer_enable(int on) { KTimer::get().enable(on != 0); }
 void pano_b200_ktimer_reset(void) { KTimer::get().reset(); }
 long pano_b200_ktimer_launches(void) { return KTimer::get().total_launches(); }
 int pano_b200_ktimer_report(char* dst, int cap) {
+    if (!dst || cap <= 0) return -1;
+    try {
     std::ostringstream o;
     o << "{";
     bool first = true;
@@ -307,17 +316,25 @@ int pano_b200_ktimer_report(char* dst, int cap) {
     memcpy(dst, s.data(), n);
     dst[n] = 0;
     return n;
+    } catch (...) {
+        dst[0] = 0;
+        return -100;
+    }
 }
 
 int pano_b200_stitch_log(pano_b200_ctx* ctx, char* dst, int cap) {
+    if (!ctx || !dst || cap <= 0) return -1;
+    PB_API_BEGIN
     const std::string& s = ctx->st->log();
     int n = (int)s.size();
     if (n >= cap) n = cap - 1;
     memcpy(dst, s.data(), n);
     dst[n] = 0;
     return n;
+    PB_API_END
 }
 int pano_b200_stitch_times(pano_b200_ctx* ctx, pano_b200_times* t) {
+    if (!ctx || !t) return -1;
     const StageTimes& s = ctx->st->times();
     t->project = s.project; t->sift = s.sift; t->table = s.table; t->match = s.match; t->ransac = s.ransac;
     t->warp = s.warp; t->blend = s.blend; t->tail = s.tail; t->total = s.total;
@@ -326,7 +343,7 @@ int pano_b200_stitch_times(pano_b200_ctx* ctx, pano_b200_times* t) {
     return 0;
 }
 int pano_b200_stitch_nfeatures(pano_b200_ctx* ctx, int image) {
-    if (image < 0 || image >= ctx->st->num_images()) return -1;
+    if (!ctx || image < 0 || image >= ctx->st->num_images()) return -1;
     return ctx->st->features(image).n;
 }
 
@@ -375,8 +392,8 @@ int pano_b200_sift_features(pano_b200_ctx* ctx, const uint8_t* gray, int w, int 
     FeatureTable t;
     Stitcher::build_table(raw, t);
     *n = t.n;
-    *descr = (float*)malloc(std::max<size_t>((size_t)t.n * 128 * sizeof(float), 4));
-    *keys = (pano_b200_keypoint*)malloc(std::max<size_t>((size_t)t.n * sizeof(VlKey), 4));
+    *descr = (float*)xmalloc(std::max<size_t>((size_t)t.n * 128 * sizeof(float), 4));
+    *keys = (pano_b200_keypoint*)xmalloc(std::max<size_t>((size_t)t.n * sizeof(VlKey), 4));
     memcpy(*descr, t.descr.data(), (size_t)t.n * 128 * sizeof(float));
     memcpy(*keys, t.keys.data(), (size_t)t.n * sizeof(VlKey));
     return 0;
@@ -392,9 +409,9 @@ int pano_b200_sift_raw(pano_b200_ctx* ctx, const float* image, int w, int h, int
     RawFeatures& raw = ctx->last_raw;
     ctx->st->sift_raw_f32(image, w, h, p, raw);
     *n = raw.n;
-    *keys = (pano_b200_keypoint*)malloc(std::max<size_t>((size_t)raw.n * sizeof(VlKey), 4));
+    *keys = (pano_b200_keypoint*)xmalloc(std::max<size_t>((size_t)raw.n * sizeof(VlKey), 4));
     *angles = (double*)malloc(std::max<size_t>((size_t)raw.n * sizeof(double), 8));
-    *descr = (float*)malloc(std::max<size_t>((size_t)raw.n * 128 * sizeof(float), 4));
+    *descr = (float*)xmalloc(std::max<size_t>((size_t)raw.n * 128 * sizeof(float), 4));
     memcpy(*keys, raw.keys.data(), (size_t)raw.n * sizeof(VlKey));
     memcpy(*angles, raw.angles.data(), (size_t)raw.n * sizeof(double));
     memcpy(*descr, raw.descr.data(), (size_t)raw.n * 128 * sizeof(float));

@@ -296,7 +296,7 @@ __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, dou
 // INPUT, so pass 1 streams `src` again TOGETHER with the causal output Y already in `dst`, and the consumer stores
 // out = Y + yc, CImg.h:34797 -- src and dst must be distinct buffers).
 template <bool kElemContig, class Coef>
-__global__ void __launch_bounds__(128) iir_pipe_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
+__global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* dst, int N,   // src == dst is allowed (in-place y pass): no __restrict__
                                                       long nlines, int lines_per_plane, long plane_stride,
                                                       long elem_stride, Coef c) {
     constexpr bool kDeriche = std::is_same<Coef, DericheCoef>::value;

@@ -186,152 +186,6 @@ PB_HD void gradient_at(const float* __restrict__ lev, int w, int h, int pitch, i
     *ang = mod_2pi_f((float)((double)fast_atan2_f(gy, gx) + 2 * kPi));
 }
 
-// vl/sift.c:904-1037.  hist: 36 doubles, element b at hist[b * hstride] (hstride = 32 on the device where the
-// histograms of a warp's 32 keypoints are interleaved in shared memory; 1 on the host).
-// Returns the number of angles (0..4).
-PB_HD int orientations_of(const OctaveView& ov, const SiftConsts& sc, const double* __restrict__ expn_tab, int o_cur,
-                          int ko, int kis, float kx, float ky, float ksigma, double xper, double* hist, int hstride,
-                          double angles[4]) {
-    const double winf = 1.5;
-    const int w = ov.w, h = ov.h;
-    const double x = (double)kx / xper;
-    const double y = (double)ky / xper;
-    const double sigma = (double)ksigma / xper;
-    const int xi = (int)(x + 0.5);
-    const int yi = (int)(y + 0.5);
-    const int si = kis;
-    const double sigmaw = winf * sigma;
-    const double Wd = floor(3.0 * sigmaw);
-    const int W = (int)(Wd > 1 ? Wd : 1);
-    enum { nbins = 36 };
-    if (ko != o_cur) return 0;
-    if (xi < 0 || xi > w - 1 || yi < 0 || yi > h - 1 || si < sc.s_min + 1 || si > sc.s_max - 2) return 0;
-    for (int i = 0; i < nbins; ++i) hist[i * hstride] = 0;
-    const float* pt = ov.grad + 2 * ((long)(si - sc.s_min - 1) * ov.h * ov.pitch);
-    const int ys0 = (-W > -yi) ? -W : -yi, ys1 = (W < h - 1 - yi) ? W : h - 1 - yi;
-    const int xs0 = (-W > -xi) ? -W : -xi, xs1 = (W < w - 1 - xi) ? W : w - 1 - xi;
-    const double r2max = W * W + 0.6;
-    const double den = 2 * sigmaw * sigmaw;
-    for (int ys = ys0; ys <= ys1; ++ys) {
-        const float* row = pt + 2 * ((long)(yi + ys) * ov.pitch);
-        const double dy = (double)(yi + ys) - y;
-        for (int xs = xs0; xs <= xs1; ++xs) {
-            const double dx = (double)(xi + xs) - x;
-            const double r2 = dx * dx + dy * dy;
-            if (r2 >= r2max) continue;
-            const double wgt = fast_expn(expn_tab, r2 / den);
-            const double mod = row[2 * (xi + xs)];
-            const double ang = row[2 * (xi + xs) + 1];
-            const double fbin = nbins * ang / (2 * kPi);
-            const int bin = floor_d(fbin - 0.5);
-            const double rbin = fbin - bin - 0.5;
-            hist[((bin + nbins) % nbins) * hstride] += (1 - rbin) * mod * wgt;
-            hist[((bin + 1) % nbins) * hstride] += (rbin)*mod * wgt;
-        }
-    }
-    for (int iter = 0; iter < 6; iter++) {
-        double prev = hist[(nbins - 1) * hstride];
-        double first = hist[0];
-        int i;
-        for (i = 0; i < nbins - 1; i++) {
-            double newh = (prev + hist[i * hstride] + hist[((i + 1) % nbins) * hstride]) / 3.0;
-            prev = hist[i * hstride];
-            hist[i * hstride] = newh;
-        }
-        hist[i * hstride] = (prev + hist[i * hstride] + first) / 3.0;
-    }
-    double maxh = 0;
-    for (int i = 0; i < nbins; ++i) maxh = (maxh > hist[i * hstride]) ? maxh : hist[i * hstride];
-    int nangles = 0;
-    for (int i = 0; i < nbins; ++i) {
-        double h0 = hist[i * hstride];
-        double hm = hist[((i - 1 + nbins) % nbins) * hstride];
-        double hp = hist[((i + 1 + nbins) % nbins) * hstride];
-        if (h0 > 0.8 * maxh && h0 > hm && h0 > hp) {
-            double di = -0.5 * (hp - hm) / (hp + hm - 2 * h0);
-            double th = 2 * kPi * (i + di + 0.5) / nbins;
-            angles[nangles++] = th;
-            if (nangles == 4) break;
-        }
-    }
-    return nangles;
-}
-
-// vl/sift.c:1268-1438.  st0 / ct0 = sin / cos of the keypoint angle, evaluated on the HOST with glibc.
-// hist: 128 floats, bin b at hist[b * hstride].  descr: 128 contiguous floats written only when the keypoint
-// passes the bounds test; returns 1 if written, 0 if the reference would have returned early (vl/sift.c:1321-1328).
-PB_HD int descriptor_of(const OctaveView& ov, const SiftConsts& sc, const double* __restrict__ expn_tab, int o_cur,
-                        int ko, int kis, float kx, float ky, float ksigma, double xper, double angle0, double st0,
-                        double ct0, float* hist, int hstride, float* __restrict__ descr) {
-    enum { NBO = 8, NBP = 4 };
-    const int w = ov.w, h = ov.h;
-    const double x = (double)kx / xper;
-    const double y = (double)ky / xper;
-    const double sigma = (double)ksigma / xper;
-    const int xi = (int)(x + 0.5);
-    const int yi = (int)(y + 0.5);
-    const int si = kis;
-    const double SBP = sc.magnif * sigma + kEpsD;
-    const int W = (int)floor(1.4142135623730951 * SBP * (NBP + 1) / 2.0 + 0.5);
-    if (ko != o_cur || xi < 0 || xi >= w || yi < 0 || yi >= h - 1 || si < sc.s_min + 1 || si > sc.s_max - 2) return 0;
-    for (int i = 0; i < NBO * NBP * NBP; ++i) hist[i * hstride] = 0.0f;
-    const float* pt = ov.grad + 2 * ((long)(si - sc.s_min - 1) * ov.h * ov.pitch);
-    const float wsigma = (float)sc.window_size;
-    const double wden = 2.0 * wsigma * wsigma;
-    const int dy0 = (-W > 1 - yi) ? -W : 1 - yi, dy1 = (W < h - yi - 2) ? W : h - yi - 2;
-    const int dx0 = (-W > 1 - xi) ? -W : 1 - xi, dx1 = (W < w - xi - 2) ? W : w - xi - 2;
-    for (int dyi = dy0; dyi <= dy1; ++dyi) {
-        const float* row = pt + 2 * ((long)(yi + dyi) * ov.pitch);
-        const float dy = (float)((double)(yi + dyi) - y);
-        for (int dxi = dx0; dxi <= dx1; ++dxi) {
-            const float mod = row[2 * (xi + dxi)];
-            const float angle = row[2 * (xi + dxi) + 1];
-            const float theta = mod_2pi_f((float)((double)angle - angle0));
-            const float dx = (float)((double)(xi + dxi) - x);
-            const float nx = (float)((ct0 * (double)dx + st0 * (double)dy) / SBP);
-            const float ny = (float)((-st0 * (double)dx + ct0 * (double)dy) / SBP);
-            const float nt = (float)((double)((float)NBO * theta) / (2 * kPi));
-            const float win = (float)fast_expn(expn_tab, (double)(nx * nx + ny * ny) / wden);
-            const int binx = floor_f((float)((double)nx - 0.5));
-            const int biny = floor_f((float)((double)ny - 0.5));
-            const int bint = floor_f(nt);
-            const float rbinx = (float)((double)nx - ((double)binx + 0.5));
-            const float rbiny = (float)((double)ny - ((double)biny + 0.5));
-            const float rbint = nt - (float)bint;
-            for (int dbinx = 0; dbinx < 2; ++dbinx)
-                for (int dbiny = 0; dbiny < 2; ++dbiny)
-                    for (int dbint = 0; dbint < 2; ++dbint) {
-                        if (binx + dbinx >= -(NBP / 2) && binx + dbinx < (NBP / 2) && biny + dbiny >= -(NBP / 2) &&
-                            biny + dbiny < (NBP / 2)) {
-                            const float weight = win * mod * fabs_f((float)(1 - dbinx) - rbinx) *
-                                                 fabs_f((float)(1 - dbiny) - rbiny) *
-                                                 fabs_f((float)(1 - dbint) - rbint);
-                            const int bi = (biny + dbiny + NBP / 2) * (NBO * NBP) + (binx + dbinx + NBP / 2) * NBO +
-                                           ((bint + dbint) % NBO);
-                            hist[bi * hstride] += weight;
-                        }
-                    }
-        }
-    }
-    // normalize -> clamp 0.2 -> normalize (vl/sift.c:1048-1063, 1415-1436)
-    const int n = NBO * NBP * NBP;
-    float norm = 0.0f;
-    for (int i = 0; i < n; ++i) norm += hist[i * hstride] * hist[i * hstride];
-    norm = fast_sqrt_f(norm) + kEpsF;
-    for (int i = 0; i < n; ++i) hist[i * hstride] /= norm;
-    if (sc.norm_thresh != 0 && (double)norm < sc.norm_thresh) {
-        for (int i = 0; i < n; ++i) descr[i] = 0;
-        return 1;
-    }
-    for (int i = 0; i < n; ++i)
-        if ((double)hist[i * hstride] > 0.2) hist[i * hstride] = (float)0.2;
-    norm = 0.0f;
-    for (int i = 0; i < n; ++i) norm += hist[i * hstride] * hist[i * hstride];
-    norm = fast_sqrt_f(norm) + kEpsF;
-    for (int i = 0; i < n; ++i) descr[i] = hist[i * hstride] / norm;
-    return 1;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Descriptor, sample-parallel formulation (what the CUDA kernel runs).
 //

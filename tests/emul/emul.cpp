@@ -9,6 +9,7 @@
 #include <vector>
 #include <cmath>
 #include "../../computervisionimagestich2_b200/csrc/sift_device.cuh"
+#include "serial_reference.inc"
 #include "../../computervisionimagestich2_b200/csrc/match_device.cuh"
 #include "../../computervisionimagestich2_b200/csrc/canvas_device.cuh"
 #include "../../computervisionimagestich2_b200/csrc/host_numerics.h"
