@@ -354,6 +354,48 @@ class Context:
         self.L.pano_b200_stitch_times(self.h, C.byref(t))
         return pano, dict(log=buf.value.decode(), size=(ow.value, oh.value), times={f[0]: getattr(t, f[0]) for f in Times._fields_})
 
+    # ---- plane-sharded canvas stages (pano_b200_shard_stitch_planes) ------------------------------------------------
+    SEAM_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int)
+
+    def shard_stitch_planes(self, first, count, exchange=None):
+        """Everything of the stitch loop but the equalisation tail, on `count` colour planes starting at `first`.
+        exchange(values | None, is_source) -> 4 ints: called once per edge; the rank carrying plane 0 passes the seam
+        statistics in, the others receive them."""
+        def _cb(user, p, is_src):
+            try:
+                out = exchange([p[i] for i in range(4)] if is_src else None, bool(is_src))
+                for i in range(4):
+                    p[i] = int(out[i])
+                return 0
+            except Exception:   # noqa: BLE001 -- must not propagate through the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = self.SEAM_CB(_cb) if exchange is not None else self.SEAM_CB()
+        ow, oh = C.c_int(), C.c_int()
+        self._check(self.L.pano_b200_shard_stitch_planes(self.h, int(first), int(count), cb, None, C.byref(ow), C.byref(oh)),
+                    "shard_stitch_planes")
+        buf = C.create_string_buffer(1 << 16)
+        self.L.pano_b200_stitch_log(self.h, buf, 1 << 16)
+        return dict(log=buf.value.decode(), size=(ow.value, oh.value))
+
+    def shard_plane_export(self, k, out_t):
+        self._check(self.L.pano_b200_shard_plane_export(self.h, int(k), C.c_void_p(out_t.data_ptr())), "shard_plane_export")
+
+    def shard_plane_import(self, channel, in_t):
+        self._check(self.L.pano_b200_shard_plane_import(self.h, int(channel), C.c_void_p(in_t.data_ptr())), "shard_plane_import")
+
+    def shard_tail(self, want_output=True):
+        ow, oh = C.c_int(), C.c_int()
+        self._check(self.L.pano_b200_shard_tail(self.h, None, C.c_size_t(0), C.byref(ow), C.byref(oh)), "shard_tail")
+        pano = None
+        if want_output:
+            pano = np.empty((3, oh.value, ow.value), np.uint8)
+            self._check(self.L.pano_b200_result_copy(self.h, _p(pano)), "result_copy")
+        t = Times()
+        self.L.pano_b200_stitch_times(self.h, C.byref(t))
+        return pano, dict(size=(ow.value, oh.value), times={f[0]: getattr(t, f[0]) for f in Times._fields_})
+
     def pairs(self, pairs):
         """Batched independent pairs (pano_b200_pairs): [(img_a, img_b), ...] -> PAIR_RECORD array (pair = position)."""
         from .dist import PAIR_RECORD
@@ -366,6 +408,19 @@ class Context:
             ws = (C.c_int * n)(*[im.shape[2] for im in flat])
             hs = (C.c_int * n)(*[im.shape[1] for im in flat])
             self._check(self.L.pano_b200_pairs(self.h, pp, ws, hs, len(pairs), _p(rec)), "pairs")
+        return rec
+
+    def pairs_staged(self, dev_ptrs, sizes):
+        """pano_b200_pairs_staged: dev_ptrs = 2 * npairs device pointers (planar RGB in HBM), sizes = [(w, h), ...]"""
+        from .dist import PAIR_RECORD
+        n = len(dev_ptrs)
+        rec = np.zeros(n // 2, PAIR_RECORD)
+        rec["pair"] = np.arange(n // 2)
+        if n:
+            pp = (C.c_void_p * n)(*dev_ptrs)
+            ws = (C.c_int * n)(*[s[0] for s in sizes])
+            hs = (C.c_int * n)(*[s[1] for s in sizes])
+            self._check(self.L.pano_b200_pairs_staged(self.h, pp, ws, hs, n // 2, _p(rec)), "pairs_staged")
         return rec
 
     def stitch_features(self, projs, feats, match_idx=None):

@@ -109,6 +109,15 @@ int pano_b200_pairs(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w
     return rc;
     PB_API_END
 }
+int pano_b200_pairs_staged(pano_b200_ctx* ctx, const uint8_t* const* d_imgs, const int* w, const int* h, int npairs,
+                           pano_b200_pair_record* out) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    int rc = ctx->st->pairs(d_imgs, w, h, npairs, reinterpret_cast<Stitcher::PairRecord*>(out), true);
+    if (rc) ctx->err = ctx->st->error();
+    return rc;
+    PB_API_END
+}
 int pano_b200_stitch_features(pano_b200_ctx* ctx, int nimg, const uint8_t* const* proj, const int* w, const int* h,
                               const float* const* descr, const pano_b200_keypoint* const* keys, const int* nfeat,
                               const int* const* match_idx, uint8_t** out, int* out_w, int* out_h) {
@@ -180,6 +189,45 @@ int pano_b200_shard_stitch(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int
     ctx->err.clear();
     Stitcher& S = *ctx->st;
     int rc = S.run();
+    if (rc) { ctx->err = S.error(); return rc; }
+    if (out_w) *out_w = S.result_width();
+    if (out_h) *out_h = S.result_height();
+    if (out) {
+        if (out_cap < (size_t)3 * S.result_width() * S.result_height()) return -4;
+        S.copy_result(out);
+    }
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_stitch_planes(pano_b200_ctx* ctx, int first_plane, int nplanes, pano_b200_seam_exchange exchange,
+                                  void* user, int* out_w, int* out_h) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    Stitcher& S = *ctx->st;
+    int rc = S.run_planes(first_plane, nplanes, exchange, user);
+    if (rc) { ctx->err = S.error(); return rc; }
+    if (out_w) *out_w = S.result_width();
+    if (out_h) *out_h = S.result_height();
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_plane_export(pano_b200_ctx* ctx, int k, uint8_t* d_out) {
+    PB_API_BEGIN
+    ctx->st->plane_export(k, d_out);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_plane_import(pano_b200_ctx* ctx, int channel, const uint8_t* d_in) {
+    PB_API_BEGIN
+    ctx->st->plane_import(channel, d_in);
+    return 0;
+    PB_API_END
+}
+int pano_b200_shard_tail(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* out_w, int* out_h) {
+    PB_API_BEGIN
+    ctx->err.clear();
+    Stitcher& S = *ctx->st;
+    int rc = S.run_tail();
     if (rc) { ctx->err = S.error(); return rc; }
     if (out_w) *out_w = S.result_width();
     if (out_h) *out_h = S.result_height();

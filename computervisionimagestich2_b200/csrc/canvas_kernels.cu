@@ -93,6 +93,7 @@ void launch_planar_to_bmp(const u8* src, int w, int h, int stride, u8* bmp, cuda
 // ---------------------------------------------------------------------------------------------------------
 // warp + shift
 // ---------------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void warp_shift_kernel(const u8* __restrict__ src, int sw, int sh, const double* __restrict__ H8g,
                                   float offx, float offy, const u8* __restrict__ prev, int pw, int ph, int ioffx,
                                   int ioffy, u8* __restrict__ a, u8* __restrict__ b, int cw, int ch) {
@@ -106,25 +107,23 @@ __global__ void warp_shift_kernel(const u8* __restrict__ src, int sw, int sh, co
     if (a) {
         long s = warp_source(H8, x, y, offx, offy, sw, sh);
         const size_t sn = (size_t)sw * sh;
-        u8 r = 0, g = 0, bb = 0;
-        if (s >= 0) { r = src[s]; g = src[sn + s]; bb = src[2 * sn + s]; }
-        a[o] = r; a[cn + o] = g; a[2 * cn + o] = bb;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) a[c * cn + o] = s >= 0 ? src[c * sn + s] : (u8)0;
     }
     if (b) {
         int nx = x + ioffx, ny = y + ioffy;
-        u8 r = 0, g = 0, bb = 0;
-        if (nx >= 0 && nx < pw && ny >= 0 && ny < ph) {
-            const size_t pn = (size_t)pw * ph, s = (size_t)ny * pw + nx;
-            r = prev[s]; g = prev[pn + s]; bb = prev[2 * pn + s];
-        }
-        b[o] = r; b[cn + o] = g; b[2 * cn + o] = bb;
+        const bool in = nx >= 0 && nx < pw && ny >= 0 && ny < ph;
+        const size_t pn = (size_t)pw * ph, s = in ? (size_t)ny * pw + nx : 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) b[c * cn + o] = in ? prev[c * pn + s] : (u8)0;
     }
 }
 void launch_warp_shift(const u8* src, int sw, int sh, const double* H8, float offx, float offy, const u8* prev, int pw,
-                       int ph, int ioffx, int ioffy, u8* a, u8* b, int cw, int ch, cudaStream_t st) {
-    KScope ks("canvas.warp_shift", st, 12.0 * cw * ch);
+                       int ph, int ioffx, int ioffy, u8* a, u8* b, int cw, int ch, cudaStream_t st, int nch) {
+    KScope ks("canvas.warp_shift", st, 4.0 * nch * cw * ch);
     dim3 bl(64, 4), g(div_up(cw, 64), div_up(ch, 4));
-    warp_shift_kernel<<<g, bl, 0, st>>>(src, sw, sh, H8, offx, offy, prev, pw, ph, ioffx, ioffy, a, b, cw, ch);
+    if (nch == 1) warp_shift_kernel<1><<<g, bl, 0, st>>>(src, sw, sh, H8, offx, offy, prev, pw, ph, ioffx, ioffy, a, b, cw, ch);
+    else warp_shift_kernel<3><<<g, bl, 0, st>>>(src, sw, sh, H8, offx, offy, prev, pw, ph, ioffx, ioffy, a, b, cw, ch);
     PB_KERNEL_CHECK();
 }
 
@@ -167,7 +166,7 @@ void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, boo
 
 // kDoubleSeam: the src/ex6 variant keeps the seam position in double (src/ex6/ImageProcess.cpp:678-697); the root
 // variant narrows both ratios to float first (ImageProcess.cpp:684-698).
-template <bool kDoubleSeam>
+template <bool kDoubleSeam, int NCH>
 __global__ void level0_kernel(const u8* __restrict__ a, const u8* __restrict__ b, int cw, int ch,
                               const int* __restrict__ stats, float* __restrict__ G0, int* __restrict__ err_flag) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,18 +191,23 @@ __global__ void level0_kernel(const u8* __restrict__ a, const u8* __restrict__ b
     }
     const size_t n = (size_t)cw * ch, o = (size_t)y * cw + x;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         G0[c * n + o] = (float)a[c * n + o];
-        G0[(3 + c) * n + o] = (float)b[c * n + o];
+        G0[(NCH + c) * n + o] = (float)b[c * n + o];
     }
-    G0[6 * n + o] = m;
+    G0[2 * NCH * n + o] = m;
 }
 void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
-                   bool double_seam, cudaStream_t st) {
-    KScope ks("blend.level0", st, 34.0 * cw * ch);
+                   bool double_seam, cudaStream_t st, int nch) {
+    KScope ks("blend.level0", st, (10.0 * nch + 4.0) * cw * ch);
     dim3 bl(128, 2), g(div_up(cw, 128), div_up(ch, 2));
-    if (double_seam) level0_kernel<true><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
-    else level0_kernel<false><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+    if (nch == 1) {
+        if (double_seam) level0_kernel<true, 1><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+        else level0_kernel<false, 1><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+    } else {
+        if (double_seam) level0_kernel<true, 3><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+        else level0_kernel<false, 3><<<g, bl, 0, st>>>(a, b, cw, ch, stats, G0, err_flag);
+    }
     PB_KERNEL_CHECK();
 }
 
@@ -621,6 +625,7 @@ void launch_expand(const float* src, int w, int h, int nplanes, float* dst, int 
 // ---------------------------------------------------------------------------------------------------------
 // Laplacian blend + collapse of one level
 // ---------------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const float* __restrict__ Gup,
                                 const float* __restrict__ Eup, int uw, int uh, DevLinear tx, DevLinear ty,
                                 float* __restrict__ E, u8* __restrict__ out8) {
@@ -628,8 +633,8 @@ __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     const size_t n = (size_t)w * h, o = (size_t)y * w + x, un = (size_t)uw * uh;
-    const float m = G[6 * n + o];
-    // the resampling position of this pixel is shared by the nine up-sampled planes
+    const float m = G[2 * NCH * n + o];
+    // the resampling position of this pixel is shared by the 3 NCH up-sampled planes
     int px = 0, py = 0, px1 = 0;
     double ax = 0, ay = 0;
     bool has_y1 = false;
@@ -650,12 +655,12 @@ __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const
         return (float)((1 - ay) * (double)v0 + ay * (double)v1);
     };
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float la = G[c * n + o], lb = G[(3 + c) * n + o];
+    for (int c = 0; c < NCH; ++c) {
+        float la = G[c * n + o], lb = G[(NCH + c) * n + o];
         float e;
         if (Gup) {
             la = la - up(Gup + c * un);
-            lb = lb - up(Gup + (3 + c) * un);
+            lb = lb - up(Gup + (NCH + c) * un);
             const float bl = blend_px(la, lb, m);
             e = collapse_px(bl, up(Eup + c * un));
         } else {
@@ -672,11 +677,12 @@ __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const
 // kCollapseSrcRows rows), then every pixel only does the y-interpolation and the blend.  Same operations on the same
 // operands; ~15 instead of 27 double-precision interpolations per pixel.
 constexpr int kCollapseTileH = 16, kCollapseSrcRows = 12;
+template <int NCH>
 __global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __restrict__ G, int w, int h,
                                                              const float* __restrict__ Gup, const float* __restrict__ Eup,
                                                              int uw, int uh, DevLinear tx, DevLinear ty,
                                                              float* __restrict__ E, u8* __restrict__ out8) {
-    __shared__ float X[9][kCollapseSrcRows][64];
+    __shared__ float X[3 * NCH][kCollapseSrcRows][64];
     const int x = blockIdx.x * 64 + threadIdx.x;
     const int yt0 = blockIdx.y * kCollapseTileH;
     const int yt1 = (yt0 + kCollapseTileH < h ? yt0 + kCollapseTileH : h) - 1;   // last output row of the tile
@@ -689,14 +695,14 @@ __global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __rest
     const bool xin = x < w;
     // this thread's level-i values (7 planes x 4 rows) are requested first: they do not depend on the x-interpolation
     // below, which then hides their latency
-    float gv[kCollapseTileH / 4][7];
+    float gv[kCollapseTileH / 4][2 * NCH + 1];
     if (xin) {
 #pragma unroll
         for (int j = 0; j < kCollapseTileH / 4; ++j) {
             const int y = yt0 + threadIdx.y + 4 * j;
             const size_t o = (size_t)(y <= yt1 ? y : yt1) * w + x;
 #pragma unroll
-            for (int p = 0; p < 7; ++p) gv[j][p] = G[p * n + o];
+            for (int p = 0; p < 2 * NCH + 1; ++p) gv[j][p] = G[p * n + o];
         }
     }
     if (xin) {
@@ -705,8 +711,8 @@ __global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __rest
         for (int r = threadIdx.y; r < nrows; r += 4) {
             const size_t ro = (size_t)(r0 + r) * uw;
 #pragma unroll
-            for (int p = 0; p < 9; ++p) {
-                const float* plane = p < 6 ? Gup + (size_t)p * un : Eup + (size_t)(p - 6) * un;
+            for (int p = 0; p < 3 * NCH; ++p) {
+                const float* plane = p < 2 * NCH ? Gup + (size_t)p * un : Eup + (size_t)(p - 2 * NCH) * un;
                 const float a0 = plane[ro + px], a1 = plane[ro + px1];
                 X[p][r][threadIdx.x] = (float)((1 - ax) * (double)a0 + ax * (double)a1);
             }
@@ -722,34 +728,36 @@ __global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __rest
         const bool has_y1 = py < uh - 1;
         const double ay = ty.alpha[y];
         const size_t o = (size_t)y * w + x;
-        const float m = gv[j][6];
+        const float m = gv[j][2 * NCH];
         auto up = [&](int p) {
             const float v0 = X[p][pr][threadIdx.x];
             const float v1 = has_y1 ? X[p][pr + 1][threadIdx.x] : v0;
             return (float)((1 - ay) * (double)v0 + ay * (double)v1);
         };
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float la = gv[j][c] - up(c), lb = gv[j][3 + c] - up(3 + c);
-            const float e = collapse_px(blend_px(la, lb, m), up(6 + c));
+        for (int c = 0; c < NCH; ++c) {
+            const float la = gv[j][c] - up(c), lb = gv[j][NCH + c] - up(NCH + c);
+            const float e = collapse_px(blend_px(la, lb, m), up(2 * NCH + c));
             if (out8) out8[c * n + o] = (u8)e;
             else E[c * n + o] = e;
         }
     }
 }
 void launch_collapse(const float* G_i, int w, int h, const float* G_up, const float* E_up, int uw, int uh, DevLinear tx,
-                     DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st) {
-    KScope ks("blend.collapse", st, (28.0 + (out_u8 ? 3.0 : 12.0)) * w * h + 40.0 * uw * uh);
+                     DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st, int nch) {
+    KScope ks("blend.collapse", st, ((8.0 * nch + 4.0) + (out_u8 ? 1.0 : 4.0) * nch) * w * h + (8.0 * nch + 4.0 + 4.0 * nch) * uw * uh);
     // the tiled form needs the source rows of a 16-row tile to fit its shared-memory window: pos[y] advances by
     // fx = (uh - 1) / (h - 1) per output row (hostnum::linear_table), so a tile spans at most ceil(15 fx) + 3 source rows --
     // 11 for the pyramid's 2:1 steps; anything coarser takes the per-pixel kernel
     const double fx = h > 1 ? (uh - 1.0) / (h - 1.0) : 1e9;
     if (G_up && std::ceil((kCollapseTileH - 1) * fx) + 3 <= kCollapseSrcRows) {
         dim3 b(64, 4), g(div_up(w, 64), div_up(h, kCollapseTileH));
-        collapse_tiled_kernel<<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+        if (nch == 1) collapse_tiled_kernel<1><<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+        else collapse_tiled_kernel<3><<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
     } else {
         dim3 b(64, 4), g(div_up(w, 64), div_up(h, 4));
-        collapse_kernel<<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+        if (nch == 1) collapse_kernel<1><<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
+        else collapse_kernel<3><<<g, b, 0, st>>>(G_i, w, h, G_up, E_up, uw, uh, tx, ty, E_out, out_u8);
     }
     PB_KERNEL_CHECK();
 }

@@ -17,8 +17,10 @@ void launch_gray(const u8* rgb, int w, int h, float* gray_f32, int gray_pitch, u
 
 // a = warp(src image, H8, off) and b = shift(previous canvas, ioff) in one pass over the new canvas
 // (ImageProcess.cpp:596-620).  H8: device pointer to 8 doubles.  Either output may be null.
+// nch = 3: planar RGB throughout; nch = 1: one colour plane (src, prev, a, b are single planes) -- the colour planes of
+// the canvas stages are independent, which is how a sharded job splits them over ranks.
 void launch_warp_shift(const u8* src, int sw, int sh, const double* H8, float offx, float offy, const u8* prev, int pw,
-                       int ph, int ioffx, int ioffy, u8* a, u8* b, int cw, int ch, cudaStream_t st);
+                       int ph, int ioffx, int ioffy, u8* a, u8* b, int cw, int ch, cudaStream_t st, int nch = 3);
 
 // Seam statistics of the middle row (ImageProcess.cpp:659-671): stats[4] = {sum_a_x, width_mid_a, sum_overlap_x,
 // width_mid_overlap} (int32 wrap-around like the reference's int sums).
@@ -27,8 +29,9 @@ void launch_seam_stats(const u8* a, const u8* b, int cw, int ch, int* stats, boo
 // Level-0 float planes: G0[0..2] = a, G0[3..5] = b, G0[6] = seam mask (ImageProcess.cpp:678-698). err_flag set to 1
 // when the middle row is empty (the reference would loop forever / divide by zero).
 // double_seam: seam position kept in double (src/ex6/ImageProcess.cpp:678-697) instead of float.
+// nch colour planes: G0[0..nch) = a, G0[nch..2 nch) = b, G0[2 nch] = mask.
 void launch_level0(const u8* a, const u8* b, int cw, int ch, const int* stats, float* G0, int* err_flag,
-                   bool double_seam, cudaStream_t st);
+                   bool double_seam, cudaStream_t st, int nch = 3);
 
 // CImg get_blur(2, true, true) on `nplanes` planes [nplanes][h][w]: dst = blur(src) (x pass src->dst, y pass in place
 // on dst; src may equal dst).
@@ -51,8 +54,9 @@ void launch_expand(const float* src, int w, int h, int nplanes, float* dst, int 
 //   E_i = clamp( blend(Ga_i - up(Ga_{i+1}), Gb_i - up(Gb_{i+1}), M_i) + up(E_{i+1}) )
 // G_i: 7 planes [7][h][w] (a rgb, b rgb, mask); G_up: 7 planes of level i+1 (uw x uh) or null for the top level;
 // E_up: 3 planes of level i+1 or null; E_out: 3 float planes, or out_u8 (level 0: truncating store, planar u8).
+// With nch colour planes the level has 2 nch + 1 planes and E has nch.
 void launch_collapse(const float* G_i, int w, int h, const float* G_up, const float* E_up, int uw, int uh, DevLinear tx,
-                     DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st);
+                     DevLinear ty, float* E_out, u8* out_u8, cudaStream_t st, int nch = 3);
 
 // Equalisation tail (equalization.cpp:74-131 + ImageProcess.cpp:237-268)
 void launch_luma_hist(const u8* rgb, int w, int h, int* hist256, cudaStream_t st);

@@ -513,20 +513,22 @@ void Stitcher::warp_shift(const u8* src, int sw, int sh, const double* H8, float
 // ------------------------------------------------------------------------------------------------------------
 // multiband blend (ImageProcess.cpp:648-773) on device buffers
 // ------------------------------------------------------------------------------------------------------------
-int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out, bool defer_check) {
+int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out, bool defer_check, int nch,
+                           bool own_stats) {
+    const int NP = 2 * nch + 1;   // float planes per pyramid level: a, b (nch each) and the mask
     std::vector<int> lw, lh;
     const bool ex6 = profile_.ex6();
     const int L = stitch::blend_levels(cw, ch, lw, lh, ex6);
     if (L < 1) { err_ = "blend: canvas too small"; return -2; }
-    // level storage: 7 planes per level
+    // level storage: NP planes per level
     std::vector<size_t> goff(L + 1, 0);
-    for (int i = 0; i < L; ++i) goff[i + 1] = goff[i] + (size_t)7 * lw[i] * lh[i];
+    for (int i = 0; i < L; ++i) goff[i + 1] = goff[i] + (size_t)NP * lw[i] * lh[i];
     pyr_.ensure(goff[L]);
-    tmpf_.ensure((size_t)7 * lw[0] * lh[0]);
-    if (ex6) tmpf2_.ensure((size_t)7 * lw[0] * lh[0]);
+    tmpf_.ensure((size_t)NP * lw[0] * lh[0]);
+    if (ex6) tmpf2_.ensure((size_t)NP * lw[0] * lh[0]);
     if (L > 1) {
-        E_[0].ensure((size_t)3 * lw[1] * lh[1]);
-        E_[1].ensure((size_t)3 * lw[1] * lh[1]);
+        E_[0].ensure((size_t)nch * lw[1] * lh[1]);
+        E_[1].ensure((size_t)nch * lw[1] * lh[1]);
     }
     // resampling tables for every level transition, packed and uploaded once
     std::vector<int> ti;
@@ -600,20 +602,29 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
 
     const IirCoef coef = make_iir(2.0f);
     const DericheCoef dcoef = make_deriche(2.0f);
-    launch_seam_stats(d_a, d_b, cw, ch, stats_.p, ex6, st_);
-    launch_level0(d_a, d_b, cw, ch, stats_.p, pyr_.p, err_flag, ex6, st_);
+    // the seam statistics come from colour plane 0 (ImageProcess.cpp:659-671).  In a plane-sharded job only the rank that
+    // carries plane 0 computes them; seam_exchange_ hands them to the others (16 bytes per edge).
+    if (own_stats) launch_seam_stats(d_a, d_b, cw, ch, stats_.p, ex6, st_);
+    if (seam_exchange_) {
+        int* hs = h_stats_.ensure(4);
+        if (own_stats) {
+            PB_CUDA(cudaMemcpyAsync(hs, stats_.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+            PB_CUDA(cudaStreamSynchronize(st_));
+        }
+        if (seam_exchange_(seam_user_, hs, own_stats ? 1 : 0) != 0) { err_ = "seam statistics exchange failed"; return -9; }
+        if (!own_stats) PB_CUDA(cudaMemcpyAsync(stats_.p, hs, 4 * sizeof(int), cudaMemcpyHostToDevice, st_));
+    }
+    launch_level0(d_a, d_b, cw, ch, stats_.p, pyr_.p, err_flag, ex6, st_, nch);
     // REDUCE chain (ImageProcess.cpp:705-715)
     for (int i = 1; i < L; ++i) {
-        const size_t nprev = (size_t)7 * lw[i - 1] * lh[i - 1];
-        (void)nprev;
-        if (ex6) launch_deriche_blur(pyr_.p + goff[i - 1], tmpf2_.p, tmpf_.p, lw[i - 1], lh[i - 1], 7, dcoef, st_);
-        else launch_iir_blur(pyr_.p + goff[i - 1], tmpf_.p, lw[i - 1], lh[i - 1], 7, coef, st_);
+        if (ex6) launch_deriche_blur(pyr_.p + goff[i - 1], tmpf2_.p, tmpf_.p, lw[i - 1], lh[i - 1], NP, dcoef, st_);
+        else launch_iir_blur(pyr_.p + goff[i - 1], tmpf_.p, lw[i - 1], lh[i - 1], NP, coef, st_);
         const LevelTab& t = lt[i - 1];
         DevMovAvg mx{tab_i_.p + t.mx_start, tab_i_.p + t.mx_src, tab_f_.p + t.mx_wgt,
                      lw[i] == lw[i - 1] ? 1.0f : (float)lw[i - 1]};
         DevMovAvg my{tab_i_.p + t.my_start, tab_i_.p + t.my_src, tab_f_.p + t.my_wgt,
                      lh[i] == lh[i - 1] ? 1.0f : (float)lh[i - 1]};
-        launch_reduce(tmpf_.p, lw[i - 1], lh[i - 1], 7, pyr_.p + goff[i], lw[i], lh[i], mx, my, st_);
+        launch_reduce(tmpf_.p, lw[i - 1], lh[i - 1], NP, pyr_.p + goff[i], lw[i], lh[i], mx, my, st_);
     }
     // Laplacian + blend + collapse, top-down (ImageProcess.cpp:727-771)
     const float* Eup = nullptr;
@@ -631,10 +642,10 @@ int Stitcher::blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_o
             uw = lw[i + 1]; uh = lh[i + 1];
         }
         if (i == 0) {
-            launch_collapse(Gi, lw[0], lh[0], Gup, Eup, uw, uh, lx, ly, nullptr, d_out, st_);
+            launch_collapse(Gi, lw[0], lh[0], Gup, Eup, uw, uh, lx, ly, nullptr, d_out, st_, nch);
         } else {
             float* Eo = E_[eb].p;
-            launch_collapse(Gi, lw[i], lh[i], Gup, Eup, uw, uh, lx, ly, Eo, nullptr, st_);
+            launch_collapse(Gi, lw[i], lh[i], Gup, Eup, uw, uh, lx, ly, Eo, nullptr, st_, nch);
             Eup = Eo;
             eb ^= 1;
         }
@@ -1062,11 +1073,11 @@ void Stitcher::add_images(const u8* const* imgs, const int* w, const int* h, int
 
 // Independent pairs: readFile of all 2K images on the lanes, the 2K directed matching problems in one launch, the RANSAC
 // problems of the adjacent directions in one launch.  Nothing is stitched.
-int Stitcher::pairs(const u8* const* imgs, const int* w, const int* h, int npairs, PairRecord* out) {
+int Stitcher::pairs(const u8* const* imgs, const int* w, const int* h, int npairs, PairRecord* out, bool on_device) {
     PB_CUDA(cudaSetDevice(dev_));
     clear();
     if (npairs <= 0) return 0;
-    add_images(imgs, w, h, 2 * npairs, false);
+    add_images(imgs, w, h, 2 * npairs, on_device);
     std::vector<std::pair<FeatureTable*, FeatureTable*>> probs;
     for (int p = 0; p < npairs; ++p) {
         FeatureTable &A = imgs_[2 * p]->feat, &B = imgs_[2 * p + 1]->feat;
@@ -1245,7 +1256,8 @@ int Stitcher::stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d
         err_ = "degenerate canvas";
         return -4;
     }
-    const size_t cn = (size_t)3 * cp.new_w * cp.new_h;
+    const int nch = cplanes_;   // colour planes this stitcher carries through the canvas stages (3, or 1 in a plane-sharded job)
+    const size_t cn = (size_t)nch * cp.new_w * cp.new_h;
     {
         WallTimer t;
         a_.ensure(cn);
@@ -1255,8 +1267,8 @@ int Stitcher::stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d
         memcpy(hh, bwd, 8 * sizeof(double));
         PB_CUDA(cudaMemcpyAsync(H8_.p, hh, 8 * sizeof(double), cudaMemcpyHostToDevice, st_));
         PB_CUDA(cudaEventRecord(ev_h8_, st_));
-        launch_warp_shift(D.proj.p, D.w, D.h, H8_.p, cp.min_x, cp.min_y, res_[cur_].p, rw_, rh_, (int)cp.min_x,
-                          (int)cp.min_y, a_.p, b_.p, cp.new_w, cp.new_h, st_);
+        launch_warp_shift(D.proj.p + (size_t)cplane0_ * D.w * D.h, D.w, D.h, H8_.p, cp.min_x, cp.min_y, res_[cur_].p, rw_, rh_,
+                          (int)cp.min_x, (int)cp.min_y, a_.p, b_.p, cp.new_w, cp.new_h, st_, nch);
         // no synchronisation here: the blend's host-side table construction overlaps this kernel (tm_.warp is then the
         // issue time only; the kernel's own time is in the per-kernel report)
         tm_.warp += t.ms();
@@ -1266,7 +1278,7 @@ int Stitcher::stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d
     {
         WallTimer t;
         res_[cur_ ^ 1].ensure(cn);
-        int rc = blend_device(a_.p, b_.p, cp.new_w, cp.new_h, res_[cur_ ^ 1].p, true);
+        int rc = blend_device(a_.p, b_.p, cp.new_w, cp.new_h, res_[cur_ ^ 1].p, true, nch, cplane0_ == 0);
         if (rc) return rc;
         cur_ ^= 1;
         rw_ = cp.new_w; rh_ = cp.new_h;
@@ -1446,8 +1458,9 @@ int Stitcher::run() {
         Image& s = *imgs_[start];
         rw_ = s.w; rh_ = s.h;
         cur_ = 0;
-        res_[0].ensure((size_t)3 * rw_ * rh_);
-        PB_CUDA(cudaMemcpyAsync(res_[0].p, s.proj.p, (size_t)3 * rw_ * rh_, cudaMemcpyDeviceToDevice, st_));
+        res_[0].ensure((size_t)cplanes_ * rw_ * rh_);
+        PB_CUDA(cudaMemcpyAsync(res_[0].p, s.proj.p + (size_t)cplane0_ * rw_ * rh_, (size_t)cplanes_ * rw_ * rh_,
+                                cudaMemcpyDeviceToDevice, st_));
     }
     H8_.ensure(8);
     {   // the stitching order depends on the adjacency alone: plan it now and evaluate, in one launch, the directed
@@ -1490,6 +1503,11 @@ int Stitcher::run() {
         const int rc = check_blend_flag();
         if (rc) return rc;
     }
+    log_ = log.str();
+    if (skip_tail_) {   // plane-sharded job: the equalisation needs all three planes (run_tail after plane_import)
+        tm_.total += ttot.ms();
+        return 0;
+    }
     {
         WallTimer t;
         res_[cur_ ^ 1].ensure((size_t)3 * rw_ * rh_);
@@ -1497,8 +1515,57 @@ int Stitcher::run() {
         cur_ ^= 1;
         tm_.tail += t.ms();
     }
-    log_ = log.str();
     tm_.total += ttot.ms();
+    return 0;
+}
+
+// ---- plane-sharded canvas stages: the colour planes of warp / shift / blend are independent -----------
+int Stitcher::run_planes(int first, int count, SeamExchange cb, void* user) {
+    if (profile_.ex6()) { err_ = "plane sharding: the ex6 seam statistics need all three planes"; return -10; }
+    if (!((count == 3 && first == 0) || (count == 1 && first >= 0 && first < 3))) { err_ = "plane sharding: planes must be 0..2"; return -10; }
+    cplane0_ = first; cplanes_ = count;
+    seam_exchange_ = cb; seam_user_ = user;
+    skip_tail_ = true;
+    int rc;
+    try {
+        rc = run();
+    } catch (...) {
+        cplane0_ = 0; cplanes_ = 3; seam_exchange_ = nullptr; seam_user_ = nullptr; skip_tail_ = false;
+        throw;
+    }
+    seam_exchange_ = nullptr; seam_user_ = nullptr; skip_tail_ = false;
+    planes_first_ = first; planes_count_ = count;
+    cplane0_ = 0; cplanes_ = 3;
+    return rc;
+}
+void Stitcher::plane_export(int k, u8* d_out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (k < 0 || k >= planes_count_) throw std::runtime_error("plane_export: plane out of range");
+    PB_CUDA(cudaMemcpyAsync(d_out, res_[cur_].p + (size_t)k * rw_ * rh_, (size_t)rw_ * rh_, cudaMemcpyDeviceToDevice, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+void Stitcher::plane_import(int channel, const u8* d_in) {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (channel < 0 || channel >= 3) throw std::runtime_error("plane_import: channel out of range");
+    const size_t n = (size_t)rw_ * rh_;
+    if (planes_count_ != 3) {   // first import: lay the canvas out as three planes, own planes in place
+        res_[cur_ ^ 1].ensure(3 * n);
+        PB_CUDA(cudaMemcpyAsync(res_[cur_ ^ 1].p + (size_t)planes_first_ * n, res_[cur_].p, (size_t)planes_count_ * n,
+                                cudaMemcpyDeviceToDevice, st_));
+        cur_ ^= 1;
+        planes_first_ = 0; planes_count_ = 3;
+    }
+    PB_CUDA(cudaMemcpyAsync(res_[cur_].p + (size_t)channel * n, d_in, n, cudaMemcpyDeviceToDevice, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+int Stitcher::run_tail() {
+    PB_CUDA(cudaSetDevice(dev_));
+    if (planes_count_ != 3) { err_ = "run_tail: the canvas does not hold all three planes"; return -10; }
+    WallTimer t;
+    res_[cur_ ^ 1].ensure((size_t)3 * rw_ * rh_);
+    equalize_mix_device(res_[cur_].p, rw_, rh_, res_[cur_ ^ 1].p);
+    cur_ ^= 1;
+    tm_.tail += t.ms();
     return 0;
 }
 

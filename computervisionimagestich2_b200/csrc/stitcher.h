@@ -116,11 +116,19 @@ class Stitcher {
     void shard_export(int i, float* d_descr_out, VlKey* keys_out, u8* d_proj_out);
     void shard_import(int i, int w, int h, int n, const float* d_descr, const VlKey* keys, const u8* d_proj);
     void shard_match(const int* I, const int* J, int nprob, int* d_idx_out);
+    // plane-sharded canvas stages: run() on `count` colour planes starting at `first` (3 planes from 0 = everything but
+    // the tail; 1 plane = a third of the pixel work).  cb hands the 16-byte seam statistics of plane 0 to the stitchers
+    // that do not carry it: called once per edge on every participant, is_source = 1 where stats4 holds the values.
+    typedef int (*SeamExchange)(void* user, int* stats4, int is_source);
+    int run_planes(int first, int count, SeamExchange cb, void* user);
+    void plane_export(int k, u8* d_out);              // plane k of this stitcher's result -> device buffer
+    void plane_import(int channel, const u8* d_in);   // colour plane `channel` computed elsewhere
+    int run_tail();                                   // equalisation + mix on the assembled canvas
     int image_width(int i) const { return imgs_[i]->w; }
     int image_height(int i) const { return imgs_[i]->h; }
     // ---- batched independent pairs (BASELINE configs[4]): imgs[2p], imgs[2p+1]; see pano_b200_pairs ----------------
     struct PairRecord { long long pair; int nfeat[2], nmatch[2], has_h[2]; double H[2][8]; };
-    int pairs(const u8* const* imgs, const int* w, const int* h, int npairs, PairRecord* out);
+    int pairs(const u8* const* imgs, const int* w, const int* h, int npairs, PairRecord* out, bool on_device = false);
     // inputs staged in HBM once (outside any timed region), then stitched any number of times
     void stage_images(const u8* const* imgs, const int* w, const int* h, int n);
     int run_staged();
@@ -145,7 +153,10 @@ class Stitcher {
     };
     // defer_check: inside run() the empty-middle-row flag accumulates in blend_flag_ and is read once after the last edge
     // (no host round trip per blend); the stage API checks at once
-    int blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out, bool defer_check = false);
+    // nch: colour planes in d_a / d_b / d_out (3, or 1 in a plane-sharded job); own_stats: this stitcher carries plane 0
+    // and computes the seam statistics itself
+    int blend_device(const u8* d_a, const u8* d_b, int cw, int ch, u8* d_out, bool defer_check = false, int nch = 3,
+                     bool own_stats = true);
     int check_blend_flag();
     void equalize_mix_device(const u8* d_rgb, int w, int h, u8* d_out);
     void ensure_ktab(int short_side);
@@ -196,6 +207,12 @@ class Stitcher {
     DevBuf<float> tab_f_;
     DevBuf<double> tab_d_;
     int cur_ = 0, rw_ = 0, rh_ = 0;
+    int cplane0_ = 0, cplanes_ = 3;            // colour planes carried through warp / shift / blend
+    int planes_first_ = 0, planes_count_ = 3;  // what res_[cur_] holds after run_planes
+    bool skip_tail_ = false;
+    SeamExchange seam_exchange_ = nullptr;
+    void* seam_user_ = nullptr;
+    PinBuf<int> h_stats_;
     struct Lane {   // per-worker resources for concurrent feature extraction
         cudaStream_t st = nullptr;
         std::unique_ptr<SiftEngine> eng;

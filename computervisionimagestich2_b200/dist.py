@@ -193,18 +193,36 @@ def _pad_gather(dist, t, cap, dst=None):
     return outs
 
 
-def stitch_sharded_device(engine, images, dist, device, profile="root", staged=None, want_output=True, sync=None, timers=None):
+_PLANE_GROUPS = {}
+
+
+def plane_group(dist, world):
+    """NCCL / gloo sub-group of the ranks that carry the canvas planes (0, 1, 2); created once, by every rank"""
+    key = (id(dist), world)
+    if key not in _PLANE_GROUPS:
+        _PLANE_GROUPS[key] = dist.new_group(ranks=[0, 1, 2])
+    return _PLANE_GROUPS[key]
+
+
+def stitch_sharded_device(engine, images, dist, device, profile="root", staged=None, want_output=True, sync=None, timers=None,
+                          planes="auto"):
     """images: list of n planar uint8 arrays (only the entries this rank owns are read), or staged = {i: (device_ptr, w, h)}
     for inputs already resident in HBM.  Returns (panorama | None, info).  `sync()` must wait for the device (torch
     collectives run on torch's stream, the engine on its own; each hand-over is a host synchronisation).  `timers`
-    (dict) receives the phase wall times of this rank in ms."""
+    (dict) receives the phase wall times of this rank in ms.  planes: "auto" = with 3 or more ranks (root profile) the
+    canvas stages of the sequential stitch loop are split by colour plane over ranks 0, 1, 2 -- the planes of warp /
+    shift / blend are independent except for the 16-byte seam statistics of plane 0, broadcast once per edge, and the
+    final equalisation, for which rank 0 collects the other two planes; "off" = rank 0 carries all three."""
     import time
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
-    n = len(images) if images is not None else max(staged) + 1
+    n = len(images)
     sync = sync or (lambda: None)
     tm = timers if timers is not None else {}
     t0 = time.perf_counter()
+    use_planes = planes != "off" and world >= 3 and profile != "ex6"
+    canvas_ranks = [0, 1, 2] if use_planes else [0]
+    pg = plane_group(dist, world) if use_planes else None
 
     def lap(name):
         nonlocal t0
@@ -229,7 +247,7 @@ def stitch_sharded_device(engine, images, dist, device, profile="root", staged=N
     meta = meta.cpu().numpy()
     W, H, NF = [int(x) for x in meta[:, 0]], [int(x) for x in meta[:, 1]], [int(x) for x in meta[:, 2]]
     owner = [i % world for i in range(n)]
-    # ---- descriptors + keypoints: all-gather; projections: gather to rank 0 ----------------------------------------
+    # ---- descriptors + keypoints: all-gather; projections: to the canvas ranks only ---------------------------------
     rows_of = [sum(NF[i] for i in images_of_rank(n, world, r)) for r in range(world)]
     cap_rows = max(max(rows_of), 1)
     send_d = torch.empty((cap_rows, 128), dtype=torch.float32, device=device)
@@ -240,13 +258,15 @@ def stitch_sharded_device(engine, images, dist, device, profile="root", staged=N
     ro = po = 0
     for i in mine:
         engine.shard_export(i, send_d[ro:ro + NF[i]] if NF[i] else None, keys_mine[ro:ro + NF[i]] if NF[i] else None,
-                            send_p[po:po + 3 * W[i] * H[i]] if (send_p is not None and rank != 0) else None)
+                            send_p[po:po + 3 * W[i] * H[i]] if send_p is not None else None)
         ro += NF[i]
         po += 3 * W[i] * H[i]
     all_d = _pad_gather(dist, send_d.view(-1), cap_rows * 128).view(world, cap_rows, 128)
     kbytes = torch.from_numpy(keys_mine.view(np.uint8).copy()).to(device)
     all_k = _pad_gather(dist, kbytes, cap_rows * KEY_DTYPE.itemsize).cpu().numpy()
-    all_p = _pad_gather(dist, send_p, cap_px, dst=0) if world > 1 else None
+    all_p = None
+    if world > 1:
+        all_p = _pad_gather(dist, send_p, cap_px) if use_planes else _pad_gather(dist, send_p, cap_px, dst=0)
     sync()
     ro = [0] * world
     po = [0] * world
@@ -254,12 +274,12 @@ def stitch_sharded_device(engine, images, dist, device, profile="root", staged=N
         r = owner[i]
         if r != rank:
             k = np.frombuffer(all_k[r].tobytes(), KEY_DTYPE, NF[i], ro[r] * KEY_DTYPE.itemsize)
-            proj = all_p[r][po[r]:po[r] + 3 * W[i] * H[i]] if rank == 0 else None
+            proj = all_p[r][po[r]:po[r] + 3 * W[i] * H[i]] if rank in canvas_ranks else None
             engine.shard_import(i, W[i], H[i], NF[i], all_d[r, ro[r]:ro[r] + NF[i]], k, proj)
         ro[r] += NF[i]
         po[r] += 3 * W[i] * H[i]
     lap("exchange")
-    # ---- matching: directed problems dealt to the ranks, lists gathered on rank 0 ------------------------------------
+    # ---- matching: directed problems dealt to the ranks, lists to the canvas ranks --------------------------------------
     problems = chain_wave(n) if profile == "ex6" else all_directed(n)
     plan = deal_problems(problems, NF, world)
     len_of = [sum(NF[j] for (_, j) in plan[r]) for r in range(world)]
@@ -267,9 +287,14 @@ def stitch_sharded_device(engine, images, dist, device, profile="root", staged=N
     out_idx = torch.empty(cap_idx, dtype=torch.int32, device=device)
     engine.shard_match([p[0] for p in plan[rank]], [p[1] for p in plan[rank]], out_idx)
     lap("match")
-    got = _pad_gather(dist, out_idx, cap_idx, dst=0) if world > 1 else [out_idx]
-    info = dict(nfeat=NF, world=world, plan=[len(p) for p in plan])
-    if rank != 0:
+    if world == 1:
+        got = [out_idx]
+    elif use_planes:
+        got = _pad_gather(dist, out_idx, cap_idx)
+    else:
+        got = _pad_gather(dist, out_idx, cap_idx, dst=0)
+    info = dict(nfeat=NF, world=world, plan=[len(p) for p in plan], canvas_ranks=canvas_ranks)
+    if rank not in canvas_ranks:
         lap("gather")
         dist.barrier()
         return None, info
@@ -283,10 +308,36 @@ def stitch_sharded_device(engine, images, dist, device, profile="root", staged=N
             engine.shard_preset(i, j, idx)
             counts[(i, j)] = int((idx >= 0).sum())
     lap("gather")
-    pano, sinfo = engine.shard_stitch(want_output=want_output)
-    lap("stitch")
-    info.update(sinfo)
     info["match_counts"] = counts
+    if not use_planes:
+        pano, sinfo = engine.shard_stitch(want_output=want_output)
+        lap("stitch")
+        info.update(sinfo)
+        dist.barrier()
+        return pano, info
+
+    def exchange(vals, is_source):
+        t = torch.tensor(vals, dtype=torch.int32, device=device) if is_source else torch.zeros(4, dtype=torch.int32, device=device)
+        dist.broadcast(t, src=0, group=pg)
+        return t.cpu().tolist()
+
+    sinfo = engine.shard_stitch_planes(rank, 1, exchange)
+    lap("stitch")
+    cw, ch = sinfo["size"]
+    plane = torch.empty(cw * ch, dtype=torch.uint8, device=device)
+    pano = None
+    if rank == 0:
+        for c in (1, 2):
+            dist.recv(plane, src=c)
+            sync()
+            engine.shard_plane_import(c, plane)
+        pano, tinfo = engine.shard_tail(want_output=want_output)
+        sinfo.update(tinfo)
+    else:
+        engine.shard_plane_export(0, plane)
+        dist.send(plane, dst=0)
+    lap("collect")
+    info.update(sinfo)
     dist.barrier()
     return pano, info
 

@@ -94,6 +94,9 @@ typedef struct pano_b200_pair_record {
 } pano_b200_pair_record;
 int pano_b200_pairs(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int npairs,
                     pano_b200_pair_record* out);
+/* the same with the 2 * npairs input images already resident in HBM (d_imgs[k] = device pointers, planar RGB) */
+int pano_b200_pairs_staged(pano_b200_ctx* ctx, const uint8_t* const* d_imgs, const int* w, const int* h, int npairs,
+                           pano_b200_pair_record* out);
 /* Inputs staged in HBM once, then stitched any number of times with no host<->device pixel traffic
  * (device-resident throughput measurement); pano_b200_result_copy downloads the last result. */
 int pano_b200_stage_images(pano_b200_ctx* ctx, const uint8_t* const* imgs, const int* w, const int* h, int n);
@@ -207,6 +210,18 @@ int pano_b200_shard_preset(pano_b200_ctx* ctx, int i, int j, const int* idx, int
 /* the sequential part (adjacency, order, RANSAC, warp, blend, equalisation) on the job's images with the preset lists;
  * out (optional, host) receives the panorama when out_cap is large enough (else -4) */
 int pano_b200_shard_stitch(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* out_w, int* out_h);
+
+/* ---- plane-sharded canvas stages.  The colour planes of warp / shift / blend are independent except for the seam
+ *      statistics of plane 0 (16 bytes per stitched edge, ImageProcess.cpp:659-671) and the final equalisation, so up to
+ *      three ranks that hold the same images and match lists can each carry one plane.  exchange() is called once per
+ *      edge on every participant: is_source = 1 on the rank carrying plane 0 (stats4 holds the values to send), 0
+ *      elsewhere (stats4 receives them); it returns 0 on success. */
+typedef int (*pano_b200_seam_exchange)(void* user, int* stats4, int is_source);
+int pano_b200_shard_stitch_planes(pano_b200_ctx* ctx, int first_plane, int nplanes, pano_b200_seam_exchange exchange,
+                                  void* user, int* out_w, int* out_h);       /* everything but the equalisation tail */
+int pano_b200_shard_plane_export(pano_b200_ctx* ctx, int k, uint8_t* d_out);   /* plane k of this rank's result (device) */
+int pano_b200_shard_plane_import(pano_b200_ctx* ctx, int channel, const uint8_t* d_in);
+int pano_b200_shard_tail(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* out_w, int* out_h);
 
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */

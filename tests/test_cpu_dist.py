@@ -285,3 +285,61 @@ def test_sharded_device_exchange_world2_gloo(ref, tmp_path):
             if i != j:
                 assert r0["presets"][f"{i},{j}"] == sha(emul_api.match_idx(feats[i][0], feats[j][0]).astype(np.int32))
     assert r1["presets"] == {} and {"extract", "exchange", "match", "gather"} <= set(r0["timers"])
+
+
+# ---- plane-sharded canvas stages: world_size 3 over gloo, fake engine ------------------------------------------------
+class OraclePlaneEngine(OracleShardEngine):
+    """adds the plane-stitch interface: records the lock-step seam exchange and the plane collection"""
+
+    def shard_stitch_planes(self, first, count, exchange):
+        self.first = first
+        self.seen = []
+        for edge in range(self.n - 1):                    # one exchange per stitched edge, in lock step on all three ranks
+            vals = exchange([100 + edge, 7, 50 + edge, 3] if first == 0 else None, first == 0)
+            self.seen.append([int(v) for v in vals])
+        return dict(log="", size=(5, 4))
+
+    def shard_plane_export(self, k, out_t):
+        out_t.numpy()[:] = 10 + self.first
+
+    def shard_plane_import(self, channel, in_t):
+        self.imported = getattr(self, "imported", {})
+        self.imported[channel] = int(in_t.numpy()[0])
+
+    def shard_tail(self, want_output=True):
+        return None, dict(tail=True)
+
+
+def _plane_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    from computervisionimagestich2_b200 import dist as pdist
+    from oracle import ref_api
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    imgs = [ref_api.load_bmp(os.path.join(ref_api.REF_DATA, "Input", f"{i}.bmp")) for i in range(1, 5)]
+    eng = OraclePlaneEngine()
+    _, info = pdist.stitch_sharded_device(eng, imgs, dist, "cpu")
+    rec = {"canvas_ranks": info["canvas_ranks"], "seen": getattr(eng, "seen", None), "imported": getattr(eng, "imported", None),
+           "npresets": len(eng.presets), "have_proj": [eng.im[i]["proj"] is not None for i in range(4)], "tail": info.get("tail")}
+    with open(os.path.join(out_dir, f"plane{rank}.json"), "w") as f:
+        json.dump(rec, f)
+    dist.destroy_process_group()
+
+
+def test_plane_sharded_stitch_world3_gloo(ref, tmp_path):
+    """With three ranks the canvas stages split by colour plane: every canvas rank gets all projections and all 12 match
+    lists, the seam statistics of plane 0 reach ranks 1 and 2 edge by edge, rank 0 collects planes 1 and 2 and runs the tail."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_plane_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    r = [json.load(open(tmp_path / f"plane{k}.json")) for k in range(3)]
+    want = [[100 + e, 7, 50 + e, 3] for e in range(3)]
+    for k in range(3):
+        assert r[k]["canvas_ranks"] == [0, 1, 2] and r[k]["npresets"] == 12 and r[k]["have_proj"] == [True] * 4
+        assert r[k]["seen"] == want
+    assert r[0]["imported"] == {"1": 11, "2": 12} and r[0]["tail"] is True
+    assert r[1]["imported"] is None and r[2]["imported"] is None
