@@ -241,6 +241,14 @@ class Context:
         self._check(self.L.pano_b200_equalize_mix(self.h, _p(img), w, h, _p(out)), "equalize_mix")
         return out
 
+    def color_transfer(self, src, tem):
+        """the reference's `transfer tran(src, tem, out)` (Reinhard l-alpha-beta transfer): -> out like src"""
+        s, t = _u8(src), _u8(tem)
+        out = np.empty_like(s)
+        self._check(self.L.pano_b200_color_transfer(self.h, _p(s), s.shape[2], s.shape[1], _p(t), t.shape[2], t.shape[1], _p(out)),
+                    "color_transfer")
+        return out
+
     def cimg_blur2(self, planes, deriche=False):
         """get_blur(2, true, true) (Van Vliet; root variant) or get_blur(2) (Deriche; src/ex6)."""
         p = np.ascontiguousarray(planes, np.float32)

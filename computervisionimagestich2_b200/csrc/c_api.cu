@@ -238,6 +238,14 @@ int pano_b200_shard_tail(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* 
     return 0;
     PB_API_END
 }
+int pano_b200_color_transfer(pano_b200_ctx* ctx, const uint8_t* src, int w, int h, const uint8_t* tem, int tw, int th,
+                             uint8_t* out) {
+    PB_API_BEGIN
+    if (!src || !tem || !out || w <= 0 || h <= 0 || tw <= 0 || th <= 0) return -1;
+    ctx->st->color_transfer(src, w, h, tem, tw, th, out);
+    return 0;
+    PB_API_END
+}
 int pano_b200_stitch_bmp(pano_b200_ctx* ctx, const uint8_t* const* files, const size_t* sizes, int n, uint8_t** out_bmp,
                          size_t* out_size) {
     PB_API_BEGIN

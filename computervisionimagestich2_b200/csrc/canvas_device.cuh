@@ -245,4 +245,54 @@ PB_HD u8 luma_bin(u8 r, u8 g, u8 b) {
     return (u8)Y;
 }
 
+// --- Reinhard l-alpha-beta colour transfer (the reference's class transfer, transfer.cpp:125-225) -----------------------
+// Per-pixel halves, in the reference's promotion order (double constants x float operands, results narrowed to float
+// where the reference assigns to a float).  logf / pow are library functions: glibc's on the host, CUDA's on the device --
+// each within an ulp of the true value, not necessarily of each other, which is why this stage's parity bar on the GPU
+// is "within 1 LSB" (BASELINE.json north_star) rather than bit-exact; on the host the bodies reproduce the reference.
+PB_HD void rgb_to_lab(float R, float G, float B, float* L, float* a, float* b) {
+    float l = (float)(0.3811 * (double)R + 0.5783 * (double)G + 0.0402 * (double)B);
+    float m = (float)(0.1967 * (double)R + 0.7244 * (double)G + 0.0782 * (double)B);
+    float s = (float)(0.0241 * (double)R + 0.1288 * (double)G + 0.8444 * (double)B);
+    if (l == 0) l = 1;
+    if (m == 0) m = 1;
+    if (s == 0) s = 1;
+    // `log(l)` on a float with `using namespace std` is std::log(float) = logf; `log(10)` is the double overload
+    // (transfer.cpp:187-189).  Host: glibc's logf.  Device: the correctly rounded float log via the double routine
+    // (CUDA's logf is a 1-ulp approximation of its own; glibc's is within 0.82 ulp -- neither is the other).
+    const double ln10 = log(10.0);
+#ifdef __CUDA_ARCH__
+    l = (float)((double)(float)log((double)l) / ln10);
+    m = (float)((double)(float)log((double)m) / ln10);
+    s = (float)((double)(float)log((double)s) / ln10);
+#else
+    l = (float)((double)logf(l) / ln10);
+    m = (float)((double)logf(m) / ln10);
+    s = (float)((double)logf(s) / ln10);
+#endif
+    const float paraA = (float)(1.0 / sqrt(3.0)), paraB = (float)(1.0 / sqrt(6.0)), paraC = (float)(1.0 / sqrt(2.0));
+    *L = paraA * ((l + m) + s);
+    *a = (float)((double)(paraB * l + paraB * m) - (2.0 * (double)paraB) * (double)s);
+    *b = paraC * l - paraC * m;
+}
+PB_HD void lab_to_rgb(float L, float a, float b, float* R, float* G, float* B) {
+    const float paraA = (float)(sqrt(3.0) / 3.0), paraB = (float)(sqrt(6.0) / 6.0), paraC = (float)(sqrt(2.0) / 2.0);
+    float l = (paraA * L + paraB * a) + paraC * b;
+    float m = (paraA * L + paraB * a) - paraC * b;
+    float s = (float)((double)(paraA * L) - (2.0 * (double)paraB) * (double)a);
+    l = (float)pow(10.0, (double)l);
+    m = (float)pow(10.0, (double)m);
+    s = (float)pow(10.0, (double)s);
+    float r = (float)((4.4679 * (double)l - 3.5873 * (double)m) + 0.1193 * (double)s);
+    float g = (float)(((-1.2186) * (double)l + 2.3809 * (double)m) - 0.1624 * (double)s);
+    float bb = (float)((0.0497 * (double)l - 0.2439 * (double)m) + 1.2045 * (double)s);
+    *R = r > 0.0f ? (r < 255.0f ? r : 255.0f) : 0.0f;
+    *G = g > 0.0f ? (g < 255.0f ? g : 255.0f) : 0.0f;
+    *B = bb > 0.0f ? (bb < 255.0f ? bb : 255.0f) : 0.0f;
+}
+// statistics matching (transfer.cpp:166-172): ((v - meanSrc) * sdTemplate) / sdSrc + meanTemplate, all float
+PB_HD float lab_match(float v, float mean_src, float sd_src, float mean_tem, float sd_tem) {
+    return ((v - mean_src) * sd_tem) / sd_src + mean_tem;
+}
+
 }  // namespace pb

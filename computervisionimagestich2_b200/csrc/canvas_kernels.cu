@@ -806,4 +806,80 @@ void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out
     PB_KERNEL_CHECK();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Reinhard colour transfer (transfer.cpp:4-13, 125-225)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void lab_forward_kernel(const u8* __restrict__ rgb, size_t n, float* __restrict__ lab) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float L, a, b;
+    rgb_to_lab((float)rgb[i], (float)rgb[n + i], (float)rgb[2 * n + i], &L, &a, &b);
+    lab[i] = L; lab[n + i] = a; lab[2 * n + i] = b;
+}
+// The reference sums every plane in raster order into a FLOAT accumulator (transfer.cpp:129-160): the value depends on
+// the order, so the sum is kept serial -- one warp per plane: the lanes fetch 32 consecutive samples with one coalesced
+// load, then every lane walks them in order through shuffles (all lanes hold the same accumulator).  mode 0: sum of v;
+// mode 1: sum of (v - mean)^2 with mean = stats[plane] (separately rounded difference, product and sum).
+__global__ void __launch_bounds__(32) lab_serial_sum_kernel(const float* __restrict__ lab, size_t n, int mode,
+                                                            const float* __restrict__ mean, float* __restrict__ out) {
+    const float* p = lab + (size_t)blockIdx.x * n;
+    const int lane = threadIdx.x;
+    const float mu = mode ? mean[blockIdx.x] : 0.0f;
+    float acc = 0.0f;
+    for (size_t base = 0; base < n; base += 32) {
+        const size_t i = base + lane;
+        float v = i < n ? p[i] : 0.0f;
+        if (mode) { const float d = v - mu; v = d * d; }
+        const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+        if (cnt == 32) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc += __shfl_sync(0xffffffffu, v, k);
+        } else {
+            for (int k = 0; k < cnt; ++k) acc += __shfl_sync(0xffffffffu, v, k);
+        }
+    }
+    if (lane == 0) out[blockIdx.x] = acc;
+}
+// stats layout (floats): [0..2] sum src, [3..5] sum tem, [6..8] mean src, [9..11] mean tem, [12..14] sumsq src,
+// [15..17] sumsq tem, [18..20] sd src, [21..23] sd tem
+__global__ void lab_finish_stats_kernel(float* __restrict__ st, float n_src, float n_tem, int stage) {
+    const int c = threadIdx.x;
+    if (c >= 3) return;
+    if (stage == 0) { st[6 + c] = st[c] / n_src; st[9 + c] = st[3 + c] / n_tem; }
+    else { st[18 + c] = sqrtf(st[12 + c] / n_src); st[21 + c] = sqrtf(st[15 + c] / n_tem); }
+}
+__global__ void lab_inverse_kernel(const float* __restrict__ lab, size_t n, const float* __restrict__ st, u8* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = lab_match(lab[c * n + i], st[6 + c], st[18 + c], st[9 + c], st[21 + c]);
+    float R, G, B;
+    lab_to_rgb(v[0], v[1], v[2], &R, &G, &B);
+    out[i] = (u8)R; out[n + i] = (u8)G; out[2 * n + i] = (u8)B;
+}
+void launch_color_transfer(const u8* src, int w, int h, const u8* tem, int tw, int th, float* lab_src, float* lab_tem,
+                           float* stats24, u8* out, cudaStream_t st) {
+    const size_t n = (size_t)w * h, nt = (size_t)tw * th;
+    {
+        KScope ks("transfer.lab", st, 15.0 * (n + nt));
+        lab_forward_kernel<<<div_up((long)n, 256), 256, 0, st>>>(src, n, lab_src);
+        lab_forward_kernel<<<div_up((long)nt, 256), 256, 0, st>>>(tem, nt, lab_tem);
+        PB_KERNEL_CHECK();
+    }
+    {
+        KScope ks("transfer.stats", st, 8.0 * 3 * (n + nt));
+        lab_serial_sum_kernel<<<3, 32, 0, st>>>(lab_src, n, 0, nullptr, stats24);
+        lab_serial_sum_kernel<<<3, 32, 0, st>>>(lab_tem, nt, 0, nullptr, stats24 + 3);
+        lab_finish_stats_kernel<<<1, 32, 0, st>>>(stats24, (float)(w * h), (float)(tw * th), 0);
+        lab_serial_sum_kernel<<<3, 32, 0, st>>>(lab_src, n, 1, stats24 + 6, stats24 + 12);
+        lab_serial_sum_kernel<<<3, 32, 0, st>>>(lab_tem, nt, 1, stats24 + 9, stats24 + 15);
+        lab_finish_stats_kernel<<<1, 32, 0, st>>>(stats24, (float)(w * h), (float)(tw * th), 1);
+        PB_KERNEL_CHECK();
+    }
+    KScope ks("transfer.map", st, 15.0 * n);
+    lab_inverse_kernel<<<div_up((long)n, 256), 256, 0, st>>>(lab_src, n, stats24, out);
+    PB_KERNEL_CHECK();
+}
+
 }  // namespace pb

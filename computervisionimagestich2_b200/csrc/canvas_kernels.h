@@ -64,4 +64,10 @@ void launch_luma_hist(const u8* rgb, int w, int h, int* hist256, cudaStream_t st
 void launch_equalize_mix(const u8* rgb, int w, int h, const int* lut256, u8* out, double num, double den,
                          cudaStream_t st);
 
+// Reinhard l-alpha-beta colour transfer (the reference's class transfer, transfer.cpp): out = src recoloured to the
+// per-channel mean / deviation of tem in l-alpha-beta space.  lab_src / lab_tem: scratch of 3 * w * h / 3 * tw * th
+// floats; stats24: 24 floats of scratch.  The plane sums keep the reference's serial float order (one warp per plane).
+void launch_color_transfer(const u8* src, int w, int h, const u8* tem, int tw, int th, float* lab_src, float* lab_tem,
+                           float* stats24, u8* out, cudaStream_t st);
+
 }  // namespace pb

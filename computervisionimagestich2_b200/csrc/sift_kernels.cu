@@ -81,21 +81,50 @@ __global__ void __launch_bounds__(256) blur_h_kernel(const float* __restrict__ s
     constexpr int WP = (W + 3) / 4 * 4;
     constexpr int TX = 512, TY = 8;
     constexpr int L = TX + 2 * WP;
-    __shared__ __align__(16) float tile[TY][L];
+    __shared__ __align__(128) float tile[TY][L];
+    __shared__ unsigned long long bar;
     const int tile_x0 = blockIdx.x * TX;
     const int tile_y0 = blockIdx.y * TY;
     const int tid = threadIdx.y * 128 + threadIdx.x;
-    for (int r = 0; r < TY; ++r) {
-        int y = tile_y0 + r;
-        if (y >= h) break;
-        const float* row = src + (long)y * pitch;
-        for (int c = tid; c < L; c += 256) {
-            int gx = tile_x0 - WP + c;
-            gx = gx < 0 ? 0 : (gx > w - 1 ? w - 1 : gx);
-            tile[r][c] = row[gx];
+    const int rows = min(TY, h - tile_y0);
+    // Interior tiles (no column clamping needed): every tile row is one contiguous, 16-byte aligned run of L floats in
+    // HBM, fetched by ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) whose completion is counted in bytes on an mbarrier
+    // -- no per-element LDG / STS, no clamp arithmetic.  Tiles touching the left or right image border replicate the edge
+    // column (vl_imconvcol_vf pads by continuity, vl/imopv.c:137-198) with the element-wise fill.
+    const bool interior = tile_x0 - WP >= 0 && tile_x0 - WP + L <= pitch && tile_x0 + TX + WP <= w;
+    if (interior) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned b = (unsigned)__cvta_generic_to_shared(&bar);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((unsigned)(rows * L * 4)) : "memory");
+            for (int r = 0; r < rows; ++r)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (unsigned)__cvta_generic_to_shared(&tile[r][0])),
+                             "l"(src + (long)(tile_y0 + r) * pitch + (tile_x0 - WP)), "r"((unsigned)(L * 4)), "r"(b)
+                             : "memory");
+        }
+        unsigned ok;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok)
+                         : "r"((unsigned)__cvta_generic_to_shared(&bar)), "r"(0u)
+                         : "memory");
+        } while (!ok);
+    } else {
+        for (int r = 0; r < rows; ++r) {
+            const float* row = src + (long)(tile_y0 + r) * pitch;
+            for (int c = tid; c < L; c += 256) {
+                int gx = tile_x0 - WP + c;
+                gx = gx < 0 ? 0 : (gx > w - 1 ? w - 1 : gx);
+                tile[r][c] = row[gx];
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const int xl = threadIdx.x * 4;
     const int x0 = tile_x0 + xl;
     if (x0 >= w) return;

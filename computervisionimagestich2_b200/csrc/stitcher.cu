@@ -711,6 +711,19 @@ void Stitcher::equalize_mix(const u8* rgb, int w, int h, u8* out) {
     PB_CUDA(cudaStreamSynchronize(st_));
 }
 
+// transfer tran(src, tem, out) (transfer.cpp:4-13), host buffers
+void Stitcher::color_transfer(const u8* src, int w, int h, const u8* tem, int tw, int th, u8* out) {
+    PB_CUDA(cudaSetDevice(dev_));
+    const size_t n = (size_t)w * h, nt = (size_t)tw * th;
+    a_.ensure(3 * n); b_.ensure(3 * nt); tmp8_.ensure(3 * n);
+    pyr_.ensure(3 * n); tmpf_.ensure(std::max<size_t>(3 * nt, 64)); tab_f_.ensure(64);
+    PB_CUDA(cudaMemcpyAsync(a_.p, src, 3 * n, cudaMemcpyHostToDevice, st_));
+    PB_CUDA(cudaMemcpyAsync(b_.p, tem, 3 * nt, cudaMemcpyHostToDevice, st_));
+    launch_color_transfer(a_.p, w, h, b_.p, tw, th, pyr_.p, tmpf_.p, tab_f_.p, tmp8_.p, st_);
+    PB_CUDA(cudaMemcpyAsync(out, tmp8_.p, 3 * n, cudaMemcpyDeviceToHost, st_));
+    PB_CUDA(cudaStreamSynchronize(st_));
+}
+
 void Stitcher::cimg_blur2(const float* src, int w, int h, int c, float* dst) {
     PB_CUDA(cudaSetDevice(dev_));
     size_t n = (size_t)w * h * c;

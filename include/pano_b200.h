@@ -223,6 +223,13 @@ int pano_b200_shard_plane_export(pano_b200_ctx* ctx, int k, uint8_t* d_out);   /
 int pano_b200_shard_plane_import(pano_b200_ctx* ctx, int channel, const uint8_t* d_in);
 int pano_b200_shard_tail(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* out_w, int* out_h);
 
+/* ---- Reinhard l-alpha-beta colour transfer: the reference's `transfer tran(src, tem, out)` (transfer.cpp:4-13; its
+ *      call site ImageProcess.cpp:180-182 is commented out in the reference, so this is a stage of its own).  src, tem,
+ *      out: planar RGB uint8 in host memory; out has the size of src.  Parity: within 1 LSB of the reference (device
+ *      log / pow are within 1 ulp of glibc's, not identical); the plane sums keep the reference's serial float order. */
+int pano_b200_color_transfer(pano_b200_ctx* ctx, const uint8_t* src, int w, int h, const uint8_t* tem, int tw, int th,
+                             uint8_t* out);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
 void pano_b200_free_pinned(void* p);

@@ -224,3 +224,11 @@ def equalize_mix(img, ex6=False):
     out = np.empty_like(img)
     (lib().emul_equalize_mix_ex6 if ex6 else lib().emul_equalize_mix)(_p(img), w, h, _p(out))
     return out
+
+
+def color_transfer(src, tem):
+    s = np.ascontiguousarray(src, np.uint8)
+    t = np.ascontiguousarray(tem, np.uint8)
+    out = np.empty_like(s)
+    lib().emul_color_transfer(_p(s), s.shape[2], s.shape[1], _p(t), t.shape[2], t.shape[1], _p(out))
+    return out
