@@ -489,6 +489,12 @@ class Context:
                                                     _p(B) if B is not None else None, nB, reps, C.byref(ms)), "bench_match_u8")
         return ms.value
 
+    def bench_match_u8_peak(self):
+        """after bench_match_u8: (ms per repetition of the MMA-only run of the same kernel, K steps of 32 bytes per tile)"""
+        ms, ks = C.c_float(), C.c_int()
+        self._check(self.L.pano_b200_bench_match_u8_peak(self.h, C.byref(ms), C.byref(ks)), "bench_match_u8_peak")
+        return ms.value, ks.value
+
     # ---- pipeline -------------------------------------------------------------------------------------------------
     def stitch(self, imgs):
         """ImageProcess(dir, n) on in-memory planar RGB images -> (panorama [3][H][W] u8, info dict)."""

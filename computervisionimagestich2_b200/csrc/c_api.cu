@@ -246,6 +246,13 @@ int pano_b200_color_transfer(pano_b200_ctx* ctx, const uint8_t* src, int w, int 
     return 0;
     PB_API_END
 }
+int pano_b200_bench_match_u8_peak(pano_b200_ctx* ctx, float* ms, int* ksteps) {
+    PB_API_BEGIN
+    if (ms) *ms = ctx->st->last_u8_mma_only_ms_;
+    if (ksteps) *ksteps = ctx->st->last_u8_ksteps_;
+    return 0;
+    PB_API_END
+}
 int pano_b200_stitch_bmp(pano_b200_ctx* ctx, const uint8_t* const* files, const size_t* sizes, int n, uint8_t** out_bmp,
                          size_t* out_size) {
     PB_API_BEGIN

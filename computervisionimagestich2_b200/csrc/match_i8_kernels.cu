@@ -166,7 +166,7 @@ __device__ __forceinline__ void mma_loop(SmemLayout& S, unsigned tmem, int ntile
 
 __global__ void __launch_bounds__(640, 1)
 match_u8_kernel(const unsigned char* __restrict__ Ablk, int NA, const unsigned char* __restrict__ Bblk, int NB,
-                int rows_per_split, int ext_steps, U8Top3* __restrict__ partial) {
+                int rows_per_split, int ext_steps, U8Top3* __restrict__ partial, int mma_only) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,6 +241,12 @@ match_u8_kernel(const unsigned char* __restrict__ Ablk, int NA, const unsigned c
             const int b = t % kBuf;
             mbar_wait(&S.tmem_full[b], (unsigned)((t / kBuf) & 1));
             tc_fence_after();
+            if (mma_only) {   // tensor-pipe peak measurement: the accumulators are released unread (no LDTM, no max tree)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.tmem_empty[b]);
+                continue;
+            }
             const unsigned taddr = tmem + ((unsigned)(ew * 32) << 16) + (unsigned)((b * kQB + qb) * kND + part * (kND / 2));
             int va[32], vb[32];
 #define PB_LDTM(v, col)                                                                                                      \
@@ -486,7 +492,8 @@ int match_u8_num_splits(int NA, int NB) {
     return std::max(1, want);
 }
 
-void launch_match_u8(const U8Table& A, const U8Table& B, U8Top3* partial, int nsplit, int* idx, int* d01, cudaStream_t st) {
+void launch_match_u8(const U8Table& A, const U8Table& B, U8Top3* partial, int nsplit, int* idx, int* d01, cudaStream_t st,
+                     bool mma_only) {
     const int NA = A.n, NB = B.n;
     if (NB <= 0) return;
     if (NA <= 0) {
@@ -502,10 +509,12 @@ void launch_match_u8(const U8Table& A, const U8Table& B, U8Top3* partial, int ns
     int rps = align_up(div_up(NA, nsplit), 256);   // splits start on block boundaries of the blocked layout
     nsplit = div_up(NA, rps);
     {
-        KScope ks("match_u8.mma", st, 2.0 * 128.0 * (double)NA * (double)NB);
-        match_u8_kernel<<<dim3(div_up(NB, kQB * kMQ), nsplit), 640, smem, st>>>(A.blk, NA, B.blk, NB, rps, A.ext_steps, partial);
+        KScope ks(mma_only ? "match_u8.mma_only" : "match_u8.mma", st, 2.0 * 128.0 * (double)NA * (double)NB);
+        match_u8_kernel<<<dim3(div_up(NB, kQB * kMQ), nsplit), 640, smem, st>>>(A.blk, NA, B.blk, NB, rps, A.ext_steps, partial,
+                                                                             mma_only ? 1 : 0);
         PB_KERNEL_CHECK();
     }
+    if (mma_only) return;   // peak measurement: the same UTCIMMA stream with the epilogue reduced to releasing the accumulators
     KScope ks2("match_u8.finish", st, 0);
     match_u8_finish_kernel<<<div_up(NB, 4), 128, 0, st>>>(partial, nsplit, A.blk, A.norm, NA, B.blk, B.norm, NB, idx, d01);
     PB_KERNEL_CHECK();

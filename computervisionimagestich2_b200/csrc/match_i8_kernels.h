@@ -35,6 +35,8 @@ void u8_table_prepare(U8Table& t, int* scratch2, cudaStream_t st);
 int match_u8_num_splits(int NA, int NB);
 // A = database, B = queries (both prepared).  idx[b] = row of A or -1 (ratio rule 4 d0 < d1 on squared distances);
 // d01 (optional) [NB][3] = d0, d1, index of the nearest row regardless of the rule.  partial: nsplit * NB entries.
-void launch_match_u8(const U8Table& A, const U8Table& B, U8Top3* partial, int nsplit, int* idx, int* d01, cudaStream_t st);
+// mma_only: tensor-pipe peak measurement -- the same TMA + UTCIMMA stream, accumulators released unread, no results
+void launch_match_u8(const U8Table& A, const U8Table& B, U8Top3* partial, int nsplit, int* idx, int* d01, cudaStream_t st,
+                     bool mma_only = false);
 
 }  // namespace pb

@@ -83,6 +83,10 @@ class Stitcher {
     void match_u8(const u8* A, int nA, const u8* B, int nB, int* idx, int* d01);
     // ms per repetition of the matcher kernels on resident tables (A, B row-major host tables, or NULL = uniform bytes)
     float bench_match_u8(const u8* A, int nA, const u8* B, int nB, int reps);
+    // set by bench_match_u8: ms per repetition of the MMA-only run (tensor-pipe peak of the kernel's own instruction
+    // stream) and the K steps of 32 bytes each MMA tile runs (4 descriptor steps + the norm extension)
+    float last_u8_mma_only_ms_ = 0;
+    int last_u8_ksteps_ = 4;
     // Reinhard colour transfer of `src` towards `tem` (the reference's class transfer, dead code there: SURVEY 8f rank 3)
     void color_transfer(const u8* src, int w, int h, const u8* tem, int tw, int th, u8* out);
     void cimg_blur2(const float* src, int w, int h, int c, float* dst);    // get_blur(2,true,true), host buffers

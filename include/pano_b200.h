@@ -230,6 +230,11 @@ int pano_b200_shard_tail(pano_b200_ctx* ctx, uint8_t* out, size_t out_cap, int* 
 int pano_b200_color_transfer(pano_b200_ctx* ctx, const uint8_t* src, int w, int h, const uint8_t* tem, int tw, int th,
                              uint8_t* out);
 
+/* after pano_b200_bench_match_u8: *ms = ms per repetition of the SAME kernel with the epilogue reduced to releasing the
+ * accumulators (TMA + UTCIMMA only: the tensor-pipe peak this tile shape can reach), *ksteps = K steps of 32 bytes per
+ * MMA tile (4 descriptor steps + the norm-extension steps), i.e. int8 ops issued = 2 * 32 * ksteps * nA * nB */
+int pano_b200_bench_match_u8_peak(pano_b200_ctx* ctx, float* ms, int* ksteps);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
 void pano_b200_free_pinned(void* p);
