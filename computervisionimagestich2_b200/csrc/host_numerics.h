@@ -226,8 +226,8 @@ inline void cimg_svd(const Mat& A, Mat& U, std::vector<double>& S, Mat& V) {
     }
 }
 
-// x = pinv(A) * b, A (4 cols x n rows), b (n) -> x (4).  CImg.h:25293-25302 + operator* (12244-12262).
-inline void pinv_solve(const Mat& A, const std::vector<double>& b, double* x) {
+// P = pinv(A), A (4 cols x n rows) -> P (n cols x 4 rows).  CImg.h:25293-25302.
+inline Mat pinv(const Mat& A) {
     Mat U, V;
     std::vector<double> S;
     cimg_svd(A, U, S, V);
@@ -247,12 +247,20 @@ inline void pinv_solve(const Mat& A, const std::vector<double>& b, double* x) {
             for (int k = 0; k < W; ++k) value += V(k, j) * U(k, i);
             P(i, j) = value;
         }
+    return P;
+}
+// x = P * b (operator*, CImg.h:12244-12262)
+inline void pinv_apply(const Mat& P, const std::vector<double>& b, double* x) {
+    const int H = P.w, W = P.h;
     for (int j = 0; j < W; ++j) {
         double value = 0;
         for (int k = 0; k < H; ++k) value += P(k, j) * b[k];
         x[j] = value;
     }
 }
+// x = pinv(A) * b.  The reference solves its two right-hand sides (x' and y', ImageProcess.cpp:500-529) with two
+// get_solve calls on the same A; the pseudo-inverse depends on A alone, so callers with both sides use pinv once.
+inline void pinv_solve(const Mat& A, const std::vector<double>& b, double* x) { pinv_apply(pinv(A), b, x); }
 
 // ---- CImg van Vliet recursive Gaussian, order 0 (CImg.h:35045-35065) ---------------------------------------------
 struct VanVliet {

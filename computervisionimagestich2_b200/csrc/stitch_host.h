@@ -92,9 +92,10 @@ inline bool refit(const KeyPair* pairs, const std::vector<int>& inl, double* H8)
         A(3, i) = 1.0;
         b[i] = (double)p.dst.x;
     }
-    hostnum::pinv_solve(A, b, H8);
+    const hostnum::Mat P = hostnum::pinv(A);   // one SVD for both right-hand sides: same bits as two get_solve calls
+    hostnum::pinv_apply(P, b, H8);
     for (int i = 0; i < n; ++i) b[i] = (double)pairs[inl[i]].dst.y;
-    hostnum::pinv_solve(A, b, H8 + 4);
+    hostnum::pinv_apply(P, b, H8 + 4);
     return true;
 }
 

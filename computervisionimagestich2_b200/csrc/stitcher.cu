@@ -452,16 +452,31 @@ bool Stitcher::ransac(const std::vector<const std::vector<KeyPair>*>& problems, 
     PB_CUDA(cudaMemcpyAsync(counts.data(), r_counts_.p, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, rst_));
     PB_CUDA(cudaMemcpyAsync(masks.data(), r_masks_.p, masks.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, rst_));
     PB_CUDA(cudaStreamSynchronize(rst_));
-    for (int p = 0; p < P; ++p) {
+    // selection + least-squares refit (SVD of an n x 4 system) per problem: independent, so the problems of a call -- the
+    // two directions of an edge, or all directions of a batch of pairs -- run on host threads
+    std::vector<char> okp(P, 1);
+    auto finish = [&](int p) {
         const int n = (int)problems[p]->size();
         int best = stitch::select_hypothesis(counts.data() + (size_t)p * iters, iters);
-        if (best < 0) { err_ = "RANSAC found no inliers"; return false; }
+        if (best < 0) { okp[p] = 0; return; }
         const unsigned* m = masks.data() + ((size_t)p * iters + best) * words;
         std::vector<int> inl;
         for (int i = 0; i < n; ++i)
             if (m[i >> 5] >> (i & 31) & 1u) inl.push_back(i);
-        if (!stitch::refit(problems[p]->data(), inl, H8s.data() + (size_t)p * 8)) return false;
+        if (!stitch::refit(problems[p]->data(), inl, H8s.data() + (size_t)p * 8)) okp[p] = 0;
+    };
+    const int nthr = std::min(P, 8);
+    if (nthr <= 1) {
+        for (int p = 0; p < P; ++p) finish(p);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; ++t)
+            th.emplace_back([&, t] { for (int p = t; p < P; p += nthr) finish(p); });
+        for (int p = 0; p < P; p += nthr) finish(p);
+        for (auto& t : th) t.join();
     }
+    for (int p = 0; p < P; ++p)
+        if (!okp[p]) { err_ = "RANSAC found no inliers"; return false; }
     return true;
 }
 
