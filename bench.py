@@ -105,10 +105,15 @@ def synth_scene_views(n, w, h, seed=20181126, only=None):
         if procs == 1:
             _render_views((n, w, h, seed, missing))
         else:
-            import multiprocessing as mp
+            # child interpreters running THIS file's renderer entry (not a multiprocessing pool: a spawned pool worker
+            # re-imports the caller's main module, which for an unguarded script means running the script again)
+            import subprocess
             chunks = [missing[k::procs] for k in range(procs)]
-            with mp.get_context("spawn").Pool(procs) as pool:
-                pool.map(_render_views, [(n, w, h, seed, c) for c in chunks])
+            kids = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--render-views",
+                                      ",".join(map(str, (n, w, h, seed))), ",".join(map(str, c))]) for c in chunks]
+            for k in kids:
+                if k.wait() != 0:
+                    raise RuntimeError("synthetic view renderer failed")
         for i in missing:
             out[i] = np.load(_view_cache_path(n, w, h, seed, i))
     return out
@@ -725,11 +730,13 @@ def run_b200_pairs(args, ctx, L, dist, rank, local_rank, world):
     need = sorted({p % distinct for p in mine})
     procs = max(1, min(len(need), (os.cpu_count() or 2) // max(1, world), 8))
     if procs > 1:
-        import multiprocessing as mp
-        with mp.get_context("spawn").Pool(procs) as pool:
-            got = pool.map(_render_pair, [(i, w, h) for i in need])
-    else:
-        got = [_render_pair((i, w, h)) for i in need]
+        import subprocess
+        kids = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--render-pairs", f"{w},{h}",
+                                  ",".join(map(str, need[k::procs]))]) for k in range(procs)]
+        for k in kids:
+            if k.wait() != 0:
+                raise RuntimeError("synthetic pair renderer failed")
+    got = [_render_pair((i, w, h)) for i in need]   # cached by the children above
     scenes = dict(zip(need, got))
     staged = {i: torch.from_numpy(scenes[i]).to(dev) for i in need}            # [2][3][h][w] per distinct pair, in HBM
     pinned = {}
@@ -918,6 +925,15 @@ def bench_pairs(ctx, npairs=8, w=1920, h=1080, reps=3):
 
 
 def main():
+    if len(sys.argv) == 4 and sys.argv[1] == "--render-views":   # renderer child of synth_scene_views
+        n, w, h, seed = map(int, sys.argv[2].split(","))
+        _render_views((n, w, h, seed, [int(x) for x in sys.argv[3].split(",")]))
+        return
+    if len(sys.argv) == 4 and sys.argv[1] == "--render-pairs":   # renderer child of the pairs workload
+        w, h = map(int, sys.argv[2].split(","))
+        for i in map(int, sys.argv[3].split(",")):
+            _render_pair((i, w, h))
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

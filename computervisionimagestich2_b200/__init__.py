@@ -157,12 +157,13 @@ class Context:
     def set_match_mode(self, mode: str = "prefilter"):
         """'prefilter' (default: uint8 SAD pre-filter + exact re-rank, image pairs share one SAD pass), 'full' (exact
         float scan of every pair) or 'prefilter_onedir' (pre-filter, one SAD pass per directed problem)."""
-        self._check(self.L.pano_b200_set_match_mode(self.h, {"prefilter": 0, "full": 1, "prefilter_onedir": 2}[mode]), "set_match_mode")
+        self._check(self.L.pano_b200_set_match_mode(self.h, {"prefilter": 0, "full": 1, "prefilter_onedir": 2, "prefilter_fullsad": 3}[mode]), "set_match_mode")
 
     def match_stats(self, reset=False):
-        out = (C.c_longlong * 5)()
-        self._check(self.L.pano_b200_match_stats(self.h, out, int(reset)), "match_stats")
-        return {"queries": out[0], "survivors": out[1], "overflow": out[2], "problems": out[3], "sym_pairs": out[4]}
+        out = (C.c_longlong * 9)()
+        self._check(self.L.pano_b200_match_stats_ex(self.h, out, 9, int(reset)), "match_stats")
+        return {"queries": out[0], "survivors": out[1], "overflow": out[2], "problems": out[3], "sym_pairs": out[4],
+                "group_pairs": out[5], "group_exact": out[6], "group_accepts": out[7], "group_overflow": out[8]}
 
     def match_idx(self, descA, descB):
         dA = np.ascontiguousarray(descA, np.float32)

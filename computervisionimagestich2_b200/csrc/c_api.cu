@@ -326,7 +326,9 @@ int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes) {
 }
 int pano_b200_set_match_mode(pano_b200_ctx* ctx, int mode) {
     PB_API_BEGIN
-    if (mode != PANO_B200_MATCH_PREFILTER && mode != PANO_B200_MATCH_FULL && mode != PANO_B200_MATCH_PREFILTER_ONEDIR) return -1;
+    if (mode != PANO_B200_MATCH_PREFILTER && mode != PANO_B200_MATCH_FULL && mode != PANO_B200_MATCH_PREFILTER_ONEDIR &&
+        mode != PANO_B200_MATCH_PREFILTER_FULLSAD)
+        return -1;
     ctx->st->set_match_mode(mode);
     return 0;
     PB_API_END
@@ -335,6 +337,16 @@ int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[5], int reset) {
     PB_API_BEGIN
     const MatchStats& m = ctx->st->match_stats();
     if (out) { out[0] = m.queries; out[1] = m.survivors; out[2] = m.overflow; out[3] = m.problems; out[4] = m.sym_pairs; }
+    if (reset) ctx->st->reset_match_stats();
+    return 0;
+    PB_API_END
+}
+int pano_b200_match_stats_ex(pano_b200_ctx* ctx, long long* out, int n, int reset) {
+    PB_API_BEGIN
+    const MatchStats& m = ctx->st->match_stats();
+    const long long v[9] = {m.queries, m.survivors, m.overflow, m.problems, m.sym_pairs, m.group_pairs, m.group_exact,
+                            m.group_accepts, m.group_overflow};
+    for (int i = 0; out && i < n && i < 9; ++i) out[i] = v[i];
     if (reset) ctx->st->reset_match_stats();
     return 0;
     PB_API_END

@@ -24,6 +24,12 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define PB_CUDA(x) ::pb::cuda_check((x), #x, __FILE__, __LINE__)
 #define PB_KERNEL_CHECK() ::pb::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
 
+// Host-side timeline for diagnostics: PANO_B200_TRACE=1 makes every PB_TRACE(tag) print "trace <thread> <ms> <tag>" on
+// stderr (ms since the first trace point of the process).  Off: one predictable branch.
+bool trace_on();
+void trace_point(const char* tag, long a = -1);
+#define PB_TRACE(...) do { if (::pb::trace_on()) ::pb::trace_point(__VA_ARGS__); } while (0)
+
 inline int div_up(long a, long b) { return (int)((a + b - 1) / b); }
 inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
 

@@ -113,4 +113,74 @@ PB_HD bool sad_certain_reject(const SadStat& s, int eb, int* thr) {
     return false;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Second level of the pre-filter: a GROUPED lower bound of the SAD, 8 instructions per (row, row) instead of 32
+// (match_kernels.cu: match_group_sym_kernel).
+//
+// A SIFT descriptor is 4 x 4 spatial cells x 8 orientation bins, dimension = bin + 8 (cx + 4 cy) (vl/sift.c:1268-1438).
+// Group g = (bin, cx / 2, cy / 2) collects the SAME orientation bin of a 2 x 2 block of cells: 32 groups of 4
+// dimensions.  With A_g = sum of the row's quantised bytes over group g (<= 1020) and its top 8 bits f_g = A_g >> 2:
+//        SAD(a, b) = sum_i |qa_i - qb_i|  >=  sum_g |A_g(a) - A_g(b)|            (triangle inequality inside each group)
+//                                         >=  sum_g (4 |f_g(a) - f_g(b)| - 3)     (A_g = 4 f_g + r, 0 <= r <= 3)
+//                                         =   4 S(a, b) - 96,   S = SAD of the two 32-byte group vectors.          (**)
+// On SIFT tables 4 S - 96 is ~0.83 of the SAD (orientation-selective, spatially smooth), which is far tighter than the
+// certain-reject test of a query needs: once an upper bound u1 of the second-nearest distance is known (from ANY two
+// rows), the query is certainly rejected as soon as every row has SAD - e(a) >= tau(u1, e(b)) below, i.e. about HALF of
+// u1.  A row whose grouped bound already proves SAD - e(a) >= tau is SKIPPED (no exact SAD); all other rows get the exact
+// SAD and enter the statistics as before.  For the decision,
+//        min_a (SAD - e(a))  >=  min(lbmin over the exactly evaluated rows, tau),      u1 = second smallest over ANY rows,
+// so sad_certain_reject stays rigorous; queries it does not reject go to the candidate pass (exact SAD of every row)
+// exactly as before.  tau is monotone in u1, so a tau computed from the FINAL u1 is <= every tau used while skipping.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGrpBytes = 32;          // groups per row
+constexpr int kGrpShift = 2;           // f_g = A_g >> 2
+constexpr int kGrpSlack = 3 * 32;      // (**)
+constexpr int kGrpErrCap = 255;        // rows with a larger quantisation error bound do not take the grouped pass
+constexpr int kGrpBias = 128;          // 2 * (kGrpErrCap + 1) / 4: keeps the packed 16-bit comparison non-negative
+PB_HD int sad_group_of_dim(int d) {
+    const int bin = d & 7, cx = (d >> 3) & 3, cy = d >> 5;
+    return bin + 8 * ((cx >> 1) + 2 * (cy >> 1));
+}
+// q: the row's 128 quantised bytes -> g: 32 group bytes
+PB_HD void sad_group_bytes(const unsigned char* q, unsigned char* g) {
+    int sum[kGrpBytes];
+    for (int i = 0; i < kGrpBytes; ++i) sum[i] = 0;
+    for (int d = 0; d < 128; ++d) sum[sad_group_of_dim(d)] += q[d];
+    for (int i = 0; i < kGrpBytes; ++i) g[i] = (unsigned char)(sum[i] >> kGrpShift);
+}
+// smallest lbmin with which sad_certain_reject(SadStat{lbmin, *, u1}, eb) returns true (plus one unit of margin; the
+// decision itself is always taken by sad_certain_reject, so this value only steers how many rows are skipped)
+PB_HD int sad_tau(int u1, int eb) {
+    if (u1 >= (1 << 24)) return 1 << 24;
+    const double half = ((double)u1 + (double)eb) * (1.0 + kSadGamma) / (2.0 * (1.0 - kSadGamma));
+    return (int)half + eb + 2;
+}
+// Skip test of the pair (x, y) in quarter units: with ex4 = ceil(e(x) / 4), ey4 likewise,
+//        S - ex4 - ey4 >= c4   ==>   4 S - 96 - e(x) >= tau        for  c4 = ceil((tau + 96 - e(y)) / 4)   [query y, row x]
+// (4 ex4 >= e(x), 4 ey4 >= e(y)).  Stored biased for the packed unsigned 16-bit compare:
+//        (S + w16(x) + w16(y))  >=  max(c16(y), c16(x)),   w16 = 64 - e4,   c16 = min(c4 + 128, 65535).
+// CERTAIN ACCEPT.  Row r0 was evaluated exactly (u0 = SAD + e(r0)); every other row has SAD - e(a) >= `others` (the
+// smaller of tau -- the skip guarantee -- and the smallest exact lower bound among the other evaluated rows: l0 <= l1 are
+// the two smallest SAD - e(a) over the evaluated rows as a multiset, so without r0's own entry the minimum is l1 if r0
+// holds l0, else l0).  By (*):  S d(r0) <= D0 := (u0 + e(b))(1 + 2^-16)  and  S d(r) >= L1 := (others - e(b))(1 - 2^-16)
+// for r != r0.  If 2 D0 (1 + 2^-10) < L1 then r0 is the unique nearest row and d0 / d1 < 0.5 / (1 + 2^-10); the
+// reference's double quotient and its float rounding (relative 2^-24) stay below 0.5: the query is CERTAINLY accepted with
+// row r0 -- no exact float arithmetic is needed.
+PB_HD bool sad_certain_accept(int u0, int e_r0, int l0, int l1, int tau, int eb) {
+    if (u0 >= (1 << 24)) return false;                 // no row was evaluated
+    int others = (u0 - 2 * e_r0 == l0) ? l1 : l0;
+    if (tau < others) others = tau;
+    double L1 = (double)others - (double)eb;
+    if (!(L1 > 0.0)) return false;
+    L1 *= (1.0 - kSadGamma);
+    const double D0 = ((double)u0 + (double)eb) * (1.0 + kSadGamma);
+    return 2.0 * D0 * (1.0 + 1.0 / 1024.0) < L1;
+}
+PB_HD unsigned sad_w16(int e) { return (unsigned)(64 - ((e + 3) >> 2)); }               // e <= kGrpErrCap
+PB_HD unsigned sad_c16(int tau, int e) {
+    const long c4 = ((long)tau + kGrpSlack - e + 3) >> 2;                               // tau > e: the numerator is positive
+    const long c = c4 + kGrpBias;
+    return (unsigned)(c < 0 ? 0 : (c > 65535 ? 65535 : c));
+}
+
 }  // namespace pb

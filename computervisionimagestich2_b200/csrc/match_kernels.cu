@@ -20,18 +20,33 @@ constexpr int kQ = 128;   // queries per CTA (one per thread)
 constexpr int kTA = 32;   // database rows per shared-memory tile
 
 // LIST: scan only the queries of J.overflow[0 .. J.counters[1]) (the pre-filter's fallback); partial is then indexed
-// by list position.
-template <bool LIST>
+// by list position.  A short list (at most 1 / kListFine of the queries -- the usual case: a few dozen) would leave the
+// machine empty with the database split sized for ALL queries, so it takes kListFine times as many splits; the partial
+// buffer holds both layouts (kListFine x the splits, 1 / kListFine of the positions).  FINE selects which of the two
+// layouts a launch serves; the other launch's CTAs leave at once.
+constexpr int kListFine = 16;
+__device__ __forceinline__ bool list_layout(const MatchJob& J, int count, int& nsplit, int& rps, int& pstride) {
+    nsplit = J.nsplit; rps = J.rows_per_split; pstride = J.NB;
+    if ((long)count * kListFine > J.NB) return false;
+    const int fine = min(J.nsplit * kListFine, max(1, J.NA / (2 * kTA)));   // at least two tiles per split
+    if (fine <= nsplit) return false;
+    rps = ((J.NA + fine - 1) / fine + 3) & ~3;
+    nsplit = (J.NA + rps - 1) / rps;
+    pstride = J.NB / kListFine;
+    return true;
+}
+template <bool LIST, bool FINE = false>
 __global__ void __launch_bounds__(kQ) match_l1_kernel(const MatchJob* __restrict__ jobs) {
     __shared__ __align__(16) float tile[kTA][128];
     const MatchJob& J = jobs[blockIdx.z];
     const float* __restrict__ A = J.A;
     const float* __restrict__ B = J.B;
-    const int NA = J.NA, rows_per_split = J.rows_per_split;
+    const int NA = J.NA;
     const int NB = LIST ? J.counters[1] : J.NB;    // number of queries scanned
-    const int pstride = J.NB;
+    int nsplit = J.nsplit, rows_per_split = J.rows_per_split, pstride = J.NB;
+    if (LIST && list_layout(J, NB, nsplit, rows_per_split, pstride) != FINE) return;
     Top2* __restrict__ partial = J.partial;
-    if (blockIdx.x * kQ >= NB || blockIdx.y >= J.nsplit) return;   // grid is sized for the largest job of the batch
+    if (blockIdx.x * kQ >= NB || blockIdx.y >= nsplit) return;   // grid is sized for the largest job of the batch
     const int pos = blockIdx.x * kQ + threadIdx.x;
     const int b = LIST ? J.overflow[min(pos, NB - 1)] : pos;
     const int a_begin = blockIdx.y * rows_per_split;
@@ -89,8 +104,10 @@ template <bool LIST>
 __global__ void match_merge_kernel(const MatchJob* __restrict__ jobs) {
     const MatchJob& J = jobs[blockIdx.y];
     const Top2* __restrict__ partial = J.partial;
-    const int nsplit = J.nsplit, NA = J.NA, pstride = J.NB;
+    const int NA = J.NA;
     const int NB = LIST ? J.counters[1] : J.NB;
+    int nsplit = J.nsplit, rps = 0, pstride = J.NB;
+    if (LIST) list_layout(J, NB, nsplit, rps, pstride);
     int* __restrict__ idx = J.idx;
     float* __restrict__ d01 = J.d01;
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,28 +125,44 @@ __global__ void match_merge_kernel(const MatchJob* __restrict__ jobs) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) sad_quantize_kernel(const float* __restrict__ descr, int n,
                                                            unsigned* __restrict__ q8, int* __restrict__ qe,
-                                                           int* __restrict__ emax) {
+                                                           int* __restrict__ emax, unsigned* __restrict__ g8,
+                                                           unsigned short* __restrict__ w16) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= n) return;
     const float4 v = reinterpret_cast<const float4*>(descr + (size_t)row * 128)[lane];
     double e = 0.0;
-    const unsigned w = sad_quantize(v.x, &e) | (sad_quantize(v.y, &e) << 8) | (sad_quantize(v.z, &e) << 16) |
-                       (sad_quantize(v.w, &e) << 24);
-    q8[(size_t)row * 32 + lane] = w;
+    const unsigned b0 = sad_quantize(v.x, &e), b1 = sad_quantize(v.y, &e), b2 = sad_quantize(v.z, &e), b3 = sad_quantize(v.w, &e);
+    q8[(size_t)row * 32 + lane] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);   // any order: the bound is rounded up
+    const int er = sad_row_error(e);
     if (lane == 0) {
-        const int er = sad_row_error(e);
         qe[row] = er;
         if (emax) atomicMax(emax, er);
     }
+    if (g8) {
+        // grouped vector (match_device.cuh, sad_group_of_dim): lane = 4 consecutive bins of cell lane / 2; the 2 x 2 block
+        // of cells differs in lane bits 2 (cx) and 8 (cy)
+        unsigned s0 = b0, s1 = b1, s2 = b2, s3 = b3;
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2); s3 += __shfl_xor_sync(0xffffffffu, s3, 2);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 8); s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 8);
+        if ((lane & 10) == 0) {
+            const int word = (lane & 1) + 2 * (((lane >> 2) & 1) + 2 * (lane >> 4));
+            g8[(size_t)row * 8 + word] = (s0 >> kGrpShift) | ((s1 >> kGrpShift) << 8) | ((s2 >> kGrpShift) << 16) |
+                                         ((s3 >> kGrpShift) << 24);
+        }
+        if (lane == 0) w16[row] = (unsigned short)(er <= kGrpErrCap ? sad_w16(er) : 0u);
+    }
 }
 
-void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, int* emax, cudaStream_t st) {
+void launch_sad_quantize(const float* descr, int n, unsigned* q8, int* qe, int* emax, cudaStream_t st, unsigned* g8,
+                         unsigned short* w16) {
     if (emax) PB_CUDA(cudaMemsetAsync(emax, 0, sizeof(int), st));
     if (n <= 0) return;
-    KScope ks("match.quantize", st, (double)n * (512 + 128 + 4));
-    sad_quantize_kernel<<<div_up((long)n * 32, 128), 128, 0, st>>>(descr, n, q8, qe, emax);
+    KScope ks("match.quantize", st, (double)n * (512 + 128 + 4 + 32 + 2));
+    sad_quantize_kernel<<<div_up((long)n * 32, 128), 128, 0, st>>>(descr, n, q8, qe, emax, g8, w16);
     PB_KERNEL_CHECK();
 }
 
@@ -405,9 +438,282 @@ __global__ void __launch_bounds__(kST) match_sad_sym_kernel(const MatchJob* __re
         }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Grouped pass (match_device.cuh, second level of the pre-filter).
+//   match_seed_kernel:      per query, exact SAD against a strided sample of the database -> u1 (a valid upper bound of the
+//                           second-nearest distance) and the packed skip threshold c16 derived from tau(u1).
+//   match_group_sym_kernel: both directions of an image pair.  Threads hold the 32-byte GROUP vectors of kGY rows of Y in
+//                           registers; group vectors of X stream through shared memory.  Per (x, y): 8 VABSDIFF4 give S,
+//                           and the pair is skipped when S + w16(x) + w16(y) >= max(c16(y), c16(x)) -- both directed
+//                           problems then know SAD - e(row) >= tau(query).  Two streamed rows share every bookkeeping
+//                           instruction (packed 16-bit halves).  The few pairs that fail the test get the exact 128-byte
+//                           SAD, computed by the whole warp (lane = word), and enter the statistics of both problems:
+//                           forward in the holder's registers, reverse through global atomics (lb: min; u0 / u1: the
+//                           displaced-value rule keeps the two smallest of a multiset under any interleaving).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSeedRows = 512;   // sampled database rows per query
+constexpr int kGY = 4;           // held rows of Y per thread
+constexpr int kGRows = 64;       // streamed rows of X per tile
+
+__global__ void __launch_bounds__(128) match_seed_kernel(const MatchJob* __restrict__ jobs, const int* __restrict__ which) {
+    __shared__ __align__(16) unsigned tile[32][32];
+    __shared__ int terr[32];
+    const MatchJob& J = jobs[which[blockIdx.z]];
+    const int NA = J.NA, NB = J.NB, tid = threadIdx.x;
+    if (blockIdx.x * 128 >= NB) return;
+    const int b = min(blockIdx.x * 128 + tid, NB - 1);
+    unsigned q[32];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(J.B8 + (size_t)b * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 t = src[k];
+            q[4 * k] = t.x; q[4 * k + 1] = t.y; q[4 * k + 2] = t.z; q[4 * k + 3] = t.w;
+        }
+    }
+    const int stride = max(1, NA / kSeedRows);
+    const int nrows = (NA + stride - 1) / stride;
+    SadStat st = sadstat_init();
+    for (int r0 = 0; r0 < nrows; r0 += 32) {
+        const int rows = min(32, nrows - r0);
+        __syncthreads();
+        for (int i = tid; i < rows * 8; i += 128)
+            reinterpret_cast<uint4*>(&tile[i >> 3][0])[i & 7] =
+                reinterpret_cast<const uint4*>(J.A8 + (size_t)(r0 + (i >> 3)) * stride * 32)[i & 7];
+        if (tid < rows) terr[tid] = J.Ae[(size_t)(r0 + tid) * stride];
+        __syncthreads();
+#pragma unroll 1
+        for (int r = 0; r < rows; ++r) {
+            const int ea = terr[r];
+            unsigned acc = (unsigned)ea;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 w = reinterpret_cast<const uint4*>(&tile[r][0])[k];
+                acc = sad4_acc(q[4 * k], w.x, acc); acc = sad4_acc(q[4 * k + 1], w.y, acc);
+                acc = sad4_acc(q[4 * k + 2], w.z, acc); acc = sad4_acc(q[4 * k + 3], w.w, acc);
+            }
+            sadstat_push(st, (int)acc, ea);
+        }
+    }
+    if (blockIdx.x * 128 + tid < NB) {
+        const int eb = J.Be[b];
+        J.seed_u1[b] = st.u1;
+        J.c16[b] = (unsigned short)sad_c16(sad_tau(st.u1, eb), eb);
+    }
+}
+
+// two smallest of a multiset under concurrent insertion: the value displaced from (or refused by) slot 0 goes to slot 1
+__device__ __forceinline__ void atomic_top2(int* u0, int* u1, int v) {
+    const int old = atomicMin(u0, v);
+    atomicMin(u1, old > v ? old : v);
+}
+// the same for keys (value << 32 | row); returns the second-smallest VALUE after the insertion
+__device__ __forceinline__ int atomic_top2_key(unsigned long long* p0, unsigned long long* p1, unsigned long long v) {
+    const unsigned long long old = atomicMin(p0, v);
+    const unsigned long long d = old > v ? old : v;
+    const unsigned long long old1 = atomicMin(p1, d);
+    return (int)((old1 < d ? old1 : d) >> 32);
+}
+
+// Queue of the row pairs the grouped bound could not skip: entry = pair index << 52 | x << 26 | y.
+struct GroupQueue {
+    unsigned long long* items;
+    int* count;          // entries appended so far (may exceed cap: the excess is dropped and the batch is redone without the grouped pass)
+    int cap;
+};
+constexpr int kGQLocal = 2048;   // entries a CTA collects in shared memory between flushes
+
+__global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __restrict__ jobs, const int2* __restrict__ pairs,
+                                                             GroupQueue gq) {
+    __shared__ __align__(16) unsigned tile[2][kGRows][8];
+    __shared__ __align__(16) unsigned short xw[2][kGRows], xc[2][kGRows];
+    __shared__ unsigned long long qbuf[kGQLocal];
+    __shared__ int qn, qbase;
+    const int2 fr = pairs[blockIdx.z];
+    const MatchJob& F = jobs[fr.x];                // database X = F.A, queries Y = F.B
+    const MatchJob& R = jobs[fr.y];                // database Y, queries X
+    const int NX = F.NA, NY = F.NB;
+    if (blockIdx.x * (128 * kGY) >= NY || blockIdx.y >= F.grp_nsplit) return;
+    const unsigned* __restrict__ Xg = F.Ag;
+    const unsigned short* __restrict__ Xw = F.Aw;
+    const unsigned short* __restrict__ Xc = R.c16;
+    const int x_begin = blockIdx.y * F.grp_rows_per_split;
+    const int x_end = min(NX, x_begin + F.grp_rows_per_split);
+    const int tid = threadIdx.x;
+    const unsigned long long ztag = (unsigned long long)blockIdx.z << 52;
+
+    unsigned g[kGY][8];
+    int yrow[kGY];
+    bool live[kGY];
+    unsigned wy[kGY], cy[kGY];                     // replicated in both halves: w16(y), c16(y)
+#pragma unroll
+    for (int j = 0; j < kGY; ++j) {
+        const int y = blockIdx.x * (128 * kGY) + j * 128 + tid;
+        live[j] = y < NY;
+        yrow[j] = min(y, NY - 1);
+        const uint4* src = reinterpret_cast<const uint4*>(F.Bg + (size_t)yrow[j] * 8);
+        const uint4 t0 = src[0], t1 = src[1];
+        g[j][0] = t0.x; g[j][1] = t0.y; g[j][2] = t0.z; g[j][3] = t0.w;
+        g[j][4] = t1.x; g[j][5] = t1.y; g[j][6] = t1.z; g[j][7] = t1.w;
+        wy[j] = live[j] ? (unsigned)F.Bw[yrow[j]] * 0x10001u : 0x7f007f00u;   // a row that does not exist never fails
+        cy[j] = live[j] ? (unsigned)F.c16[yrow[j]] * 0x10001u : 0u;
+    }
+    if (tid == 0) qn = 0;
+
+    // appends the CTA's collected pairs to the global queue (called by all threads, between two barriers)
+    auto flush = [&]() {
+        const int n = min(qn, kGQLocal);
+        if (tid == 0) qbase = n > 0 ? atomicAdd(gq.count, n) : 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 128)
+            if (qbase + i < gq.cap) gq.items[qbase + i] = qbuf[i];
+        __syncthreads();
+        if (tid == 0) qn = 0;
+    };
+
+    const int ntiles = (x_end - x_begin + kGRows - 1) / kGRows;
+    auto issue = [&](int t) {   // tables are padded to a multiple of kGRows rows: whole tiles are always readable
+        const int buf = t & 1, a0 = x_begin + t * kGRows;
+        cp_async16(&tile[buf][tid >> 1][(tid & 1) * 4], Xg + (size_t)(a0 + (tid >> 1)) * 8 + (tid & 1) * 4);
+        if (tid < 8) cp_async16(&xw[buf][tid * 8], Xw + a0 + tid * 8);
+        else if (tid < 16) cp_async16(&xc[buf][(tid - 8) * 8], Xc + a0 + (tid - 8) * 8);
+        asm volatile("cp.async.commit_group;");
+    };
+    if (ntiles > 0) issue(0);
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) {
+            issue(t + 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        const int buf = t & 1, a0 = x_begin + t * kGRows, rows = min(kGRows, x_end - a0);
+#pragma unroll 1
+        for (int r = 0; r < rows; r += 2) {
+            const bool two = r + 1 < rows;
+            const unsigned deadhi = two ? 0u : 0xffff0000u;
+            const unsigned xwp = *reinterpret_cast<const unsigned*>(&xw[buf][r]);
+            const unsigned xcp = *reinterpret_cast<const unsigned*>(&xc[buf][r]);
+            const uint4 a0w = reinterpret_cast<const uint4*>(&tile[buf][r][0])[0];
+            const uint4 a1w = reinterpret_cast<const uint4*>(&tile[buf][r][0])[1];
+            const uint4 b0w = reinterpret_cast<const uint4*>(&tile[buf][r + 1][0])[0];
+            const uint4 b1w = reinterpret_cast<const uint4*>(&tile[buf][r + 1][0])[1];
+            unsigned Z[kGY], P[kGY], bad = 0u;
+#pragma unroll
+            for (int j = 0; j < kGY; ++j) {
+                unsigned s0 = 0u, s1 = 0u;
+                s0 = sad4_acc(g[j][0], a0w.x, s0); s1 = sad4_acc(g[j][0], b0w.x, s1);
+                s0 = sad4_acc(g[j][1], a0w.y, s0); s1 = sad4_acc(g[j][1], b0w.y, s1);
+                s0 = sad4_acc(g[j][2], a0w.z, s0); s1 = sad4_acc(g[j][2], b0w.z, s1);
+                s0 = sad4_acc(g[j][3], a0w.w, s0); s1 = sad4_acc(g[j][3], b0w.w, s1);
+                s0 = sad4_acc(g[j][4], a1w.x, s0); s1 = sad4_acc(g[j][4], b1w.x, s1);
+                s0 = sad4_acc(g[j][5], a1w.y, s0); s1 = sad4_acc(g[j][5], b1w.y, s1);
+                s0 = sad4_acc(g[j][6], a1w.z, s0); s1 = sad4_acc(g[j][6], b1w.z, s1);
+                s0 = sad4_acc(g[j][7], a1w.w, s0); s1 = sad4_acc(g[j][7], b1w.w, s1);
+                const unsigned pk = s1 * 65536u + s0;                          // IMAD: FMA pipe
+                Z[j] = __vadd2(__vadd2(pk, wy[j]), xwp) | deadhi;
+                P[j] = __vmaxu2(cy[j], xcp);
+                bad |= __vminu2(Z[j], P[j]) ^ P[j];                            // a half differs iff its Z < P
+            }
+            if (bad != 0u) {
+                // ---- rare (~0.1 % of the pairs): the grouped bound cannot skip the pair -> queue it for the exact SAD ----
+#pragma unroll
+                for (int j = 0; j < kGY; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const unsigned z = i ? (Z[j] >> 16) : (Z[j] & 0xffffu), pth = i ? (P[j] >> 16) : (P[j] & 0xffffu);
+                        if (live[j] && z < pth) {
+                            const unsigned long long item = ztag | ((unsigned long long)(a0 + r + i) << 26) | (unsigned)yrow[j];
+                            const int pos = atomicAdd(&qn, 1);
+                            if (pos < kGQLocal) qbuf[pos] = item;
+                            else {   // the local buffer is full (degenerate tables): straight to the global queue
+                                const int gp = atomicAdd(gq.count, 1);
+                                if (gp < gq.cap) gq.items[gp] = item;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // the tile buffer is refilled by the copy issued in the next iteration; qn is stable
+        if (qn >= kGQLocal / 2) flush();
+    }
+    flush();
+}
+
+// exact 128-byte SAD of the queued pairs, eight lanes per pair (lane = 16 bytes), statistics of both directed problems
+// through atomics: the two smallest keys (SAD + e(a)) << 32 | a and the two smallest SAD - e(a) (displaced-value rule).
+// A value that is not below the CURRENT second smallest can never enter the final pair (the slots only decrease), so it
+// is dropped after a plain read: ~2 ln(n) of a query's n queued pairs reach an atomic.
+__device__ __forceinline__ void group_stat_push(int* s6, int sad, int e, int row) {
+    const int lb = sad - e;
+    if (lb < __ldcg(s6 + 5)) atomic_top2(s6 + 4, s6 + 5, lb);
+    const unsigned long long key = ((unsigned long long)(unsigned)(sad + e) << 32) | (unsigned)row;
+    if (key < __ldcg(reinterpret_cast<const unsigned long long*>(s6) + 1))
+        atomic_top2_key(reinterpret_cast<unsigned long long*>(s6), reinterpret_cast<unsigned long long*>(s6) + 1, key);
+}
+__global__ void __launch_bounds__(256) match_group_exact_kernel(const MatchJob* __restrict__ jobs, const int2* __restrict__ pairs,
+                                                               GroupQueue gq) {
+    const int sub = threadIdx.x & 7;
+    const int ngroups = (gridDim.x * blockDim.x) >> 3;
+    const int n = min(*gq.count, gq.cap);
+    const int nround = (n + ngroups - 1) / ngroups * ngroups;   // whole warps stay in the loop: the shuffles need all lanes
+    for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; it < nround; it += ngroups) {
+        const bool ok = it < n;
+        const unsigned long long item = gq.items[ok ? it : 0];
+        const int2 fr = pairs[(int)(item >> 52)];
+        const MatchJob& F = jobs[fr.x];
+        const MatchJob& R = jobs[fr.y];
+        const int x = (int)((item >> 26) & 0x3ffffffu), y = (int)(item & 0x3ffffffu);
+        const uint4 a = reinterpret_cast<const uint4*>(F.A8 + (size_t)x * 32)[sub];
+        const uint4 b = reinterpret_cast<const uint4*>(F.B8 + (size_t)y * 32)[sub];
+        unsigned d = sad4_acc(a.x, b.x, 0u);
+        d = sad4_acc(a.y, b.y, d); d = sad4_acc(a.z, b.z, d); d = sad4_acc(a.w, b.w, d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (!ok) continue;
+        if (sub == 0) group_stat_push(F.stat6 + 6 * (size_t)y, (int)d, F.Ae[x], x);        // forward: database row x, query y
+        else if (sub == 1) group_stat_push(R.stat6 + 6 * (size_t)x, (int)d, F.Be[y], y);   // reverse: database row y, query x
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int total = *gq.count;
+        atomicAdd(&jobs[pairs[0].x].counters[2], min(total, gq.cap));      // bookkeeping: exact SADs of the batch ...
+        if (total > gq.cap) atomicAdd(&jobs[pairs[0].x].counters[3], 1 << 30);   // ... and the overflow flag (host redoes the batch)
+    }
+}
+
+// decision of the grouped pass: exact statistics of the evaluated rows + the skip guarantee + the seed's bound
+__global__ void match_group_decide_kernel(const MatchJob* __restrict__ jobs, const int* __restrict__ which) {
+    const MatchJob& J = jobs[which[blockIdx.y]];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= J.NB) return;
+    const int* s6 = J.stat6 + 6 * (size_t)b;
+    const int i0 = s6[0], u0 = s6[1], u1x = s6[3], l0 = s6[4], l1 = s6[5];   // keys are (value << 32 | row): little-endian halves
+    const int eb = J.Be[b];
+    SadStat s;
+    s.u0 = u0;
+    s.u1 = min(u1x, J.seed_u1[b]);                  // each is the second smallest over a set of distinct rows
+    const int tau = sad_tau(s.u1, eb);              // every skipped row has SAD - e(a) >= tau(u1 at that time) >= tau(final u1)
+    s.lbmin = min(l0, tau);
+    int thr = 0;
+    J.idx[b] = -1;
+    if (sad_certain_reject(s, eb, &thr)) return;
+    if (u0 < (1 << 24) && sad_certain_accept(u0, J.Ae[i0], l0, l1, tau, eb)) {
+        J.idx[b] = i0;
+        atomicAdd(&J.counters[3], 1);
+        return;
+    }
+    const int slot = atomicAdd(&J.counters[0], 1);
+    J.surv[slot] = b;
+    J.thr[slot] = thr;
+    J.cand_cnt[slot] = 0;
+}
+
 // merges the splits' statistics, rejects what can be rejected with certainty, compacts the rest
-__global__ void match_sad_decide_kernel(const MatchJob* __restrict__ jobs) {
-    const MatchJob& J = jobs[blockIdx.y];
+__global__ void match_sad_decide_kernel(const MatchJob* __restrict__ jobs, const int* __restrict__ which) {
+    const MatchJob& J = jobs[which ? which[blockIdx.y] : blockIdx.y];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= J.NB) return;
     SadStat s = J.spartial[b];
@@ -529,9 +835,29 @@ int match_prefilter_pair(MatchJob& F, MatchJob& R) {
 int match_sym_err_cap() { return kSymErrCap; }
 int match_sym_yblocks(int NY) { return div_up(NY, kST * kSQ); }
 
+size_t match_group_ints(int NB) { return (size_t)align_up(NB, 4) * 7 + match_group_pad_rows(NB) / 2 + 16; }
+void match_group_attach(MatchJob& J, const unsigned* Ag, const unsigned short* Aw, const unsigned* Bg, const unsigned short* Bw,
+                        int nsplit, int* scratch) {
+    J.Ag = Ag; J.Aw = Aw; J.Bg = Bg; J.Bw = Bw;
+    J.grp_rows_per_split = align_up(div_up(J.NA > 0 ? J.NA : 1, nsplit > 0 ? nsplit : 1), kGRows);
+    J.grp_nsplit = div_up(J.NA > 0 ? J.NA : 1, J.grp_rows_per_split);
+    const size_t n4 = (size_t)align_up(J.NB, 4);
+    J.stat6 = scratch;                              // 8-byte aligned keys: the scratch of a job starts 16-byte aligned
+    J.seed_u1 = scratch + 6 * n4;
+    J.c16 = reinterpret_cast<unsigned short*>(scratch + 7 * n4);
+}
+int match_group_yblocks(int NY) { return div_up(NY, 128 * kGY); }
+int match_group_num_splits(int NA, int yblocks_total) {
+    const int want = div_up(148 * 8, yblocks_total > 0 ? yblocks_total : 1);   // ~8 CTAs per SM over the whole batch
+    const int maxs = div_up(NA, 4 * kGRows);                                   // at least four tiles per split
+    const int s = want < maxs ? want : maxs;
+    return s < 1 ? 1 : s;
+}
+int match_group_err_cap() { return kGrpErrCap; }
+
 void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, const int2* d_pairs,
                                   const int2* h_pairs, int npairs, const int* d_singles, const int* h_singles, int nsingles,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, bool grouped, unsigned long long* gq_items, int* gq_count, int gq_cap) {
     if (njobs <= 0) return;
     int nbmax = 1, fy = 1, cy = 1;
     for (int i = 0; i < njobs; ++i) {
@@ -540,7 +866,37 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
         cy = std::max(cy, h_jobs[i].cand_nsplit);
     }
     const int sx = div_up(nbmax, kST * kSQ);
-    if (npairs > 0) {   // both directions of an image pair from one pass
+    const int* d_pairjobs = reinterpret_cast<const int*>(d_pairs);   // the 2 * npairs job indices of the pair list
+    if (npairs > 0 && grouped) {
+        int px = 1, py = 1, nb = 1;
+        double pairs = 0, seed = 0;
+        for (int i = 0; i < npairs; ++i) {
+            const MatchJob& F = h_jobs[h_pairs[i].x];
+            px = std::max(px, match_group_yblocks(F.NB));
+            py = std::max(py, F.grp_nsplit);
+            nb = std::max(nb, std::max(F.NA, F.NB));
+            pairs += (double)F.NA * F.NB;
+            seed += 32.0 * std::min(F.NA, 2 * kSeedRows) * F.NB + 32.0 * std::min(F.NB, 2 * kSeedRows) * F.NA;
+        }
+        {
+            KScope ks("match.seed", st, seed);
+            match_seed_kernel<<<dim3(div_up(nb, 128), 1, 2 * npairs), 128, 0, st>>>(d_jobs, d_pairjobs);
+            PB_KERNEL_CHECK();
+        }
+        {
+            KScope ks("match.group_sym", st, 8.0 * pairs);   // VABSDIFF4 thread-instructions of the grouped bound
+            match_group_sym_kernel<<<dim3(px, py, npairs), 128, 0, st>>>(d_jobs, d_pairs, GroupQueue{gq_items, gq_count, gq_cap});
+            PB_KERNEL_CHECK();
+        }
+        {
+            KScope ks("match.group_exact", st, 0);
+            match_group_exact_kernel<<<148 * 8, 256, 0, st>>>(d_jobs, d_pairs, GroupQueue{gq_items, gq_count, gq_cap});
+            PB_KERNEL_CHECK();
+        }
+        KScope ks("match.decide", st, 0);
+        match_group_decide_kernel<<<dim3(div_up(nb, 128), 2 * npairs), 128, 0, st>>>(d_jobs, d_pairjobs);
+        PB_KERNEL_CHECK();
+    } else if (npairs > 0) {   // both directions of an image pair from one pass
         int px = 1, py = 1;
         double pairs = 0;
         for (int i = 0; i < npairs; ++i) {
@@ -549,8 +905,13 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
             py = std::max(py, F.sad_nsplit);
             pairs += (double)F.NA * F.NB;
         }
-        KScope ks("match.sad_sym", st, 32.0 * pairs);   // VABSDIFF4 thread-instructions (they serve two directed problems)
-        match_sad_sym_kernel<<<dim3(px, py, npairs), kST, 0, st>>>(d_jobs, d_pairs);
+        {
+            KScope ks("match.sad_sym", st, 32.0 * pairs);   // VABSDIFF4 thread-instructions (they serve two directed problems)
+            match_sad_sym_kernel<<<dim3(px, py, npairs), kST, 0, st>>>(d_jobs, d_pairs);
+            PB_KERNEL_CHECK();
+        }
+        KScope ks("match.decide", st, 0);
+        match_sad_decide_kernel<<<dim3(div_up(nbmax, 128), 2 * npairs), 128, 0, st>>>(d_jobs, d_pairjobs);
         PB_KERNEL_CHECK();
     }
     if (nsingles > 0) {
@@ -562,13 +923,13 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
             qy = std::max(qy, J.sad_nsplit);
             pairs += (double)J.NA * J.NB;
         }
-        KScope ks("match.sad", st, 32.0 * pairs);   // VABSDIFF4 thread-instructions
-        match_sad_kernel<0><<<dim3(qx, qy, nsingles), kST, 0, st>>>(d_jobs, d_singles);
-        PB_KERNEL_CHECK();
-    }
-    {
+        {
+            KScope ks("match.sad", st, 32.0 * pairs);   // VABSDIFF4 thread-instructions
+            match_sad_kernel<0><<<dim3(qx, qy, nsingles), kST, 0, st>>>(d_jobs, d_singles);
+            PB_KERNEL_CHECK();
+        }
         KScope ks("match.decide", st, 0);
-        match_sad_decide_kernel<<<dim3(div_up(nbmax, 128), njobs), 128, 0, st>>>(d_jobs);
+        match_sad_decide_kernel<<<dim3(div_up(nbmax, 128), nsingles), 128, 0, st>>>(d_jobs, d_singles);
         PB_KERNEL_CHECK();
     }
     {   // grids are sized for "every query survives"; CTAs beyond the survivor count leave at once
@@ -581,9 +942,11 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
         match_exact_kernel<<<dim3(div_up((long)nbmax * 32, 128), njobs), 128, 0, st>>>(d_jobs);
         PB_KERNEL_CHECK();
     }
-    {
+    {   // full float scan of the queries whose candidate list overflowed: short lists (the usual case) with fine splits
         KScope ks("match.l1", st, 0);
-        match_l1_kernel<true><<<dim3(div_up(nbmax, kQ), fy, njobs), kQ, 0, st>>>(d_jobs);
+        match_l1_kernel<true, true><<<dim3(div_up(div_up(nbmax, kListFine), kQ), fy * kListFine, njobs), kQ, 0, st>>>(d_jobs);
+        PB_KERNEL_CHECK();
+        match_l1_kernel<true, false><<<dim3(div_up(nbmax, kQ), fy, njobs), kQ, 0, st>>>(d_jobs);
         PB_KERNEL_CHECK();
     }
     KScope ks2("match.merge", st, 0);

@@ -276,8 +276,10 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out, bo
         launch_refine(ov, sc, ob.cand.p, counts_.p + oi, ob.cand_cap, ob.refined.p, xper, st_);
         launch_gradient(ov, sc, ob.grad.p, st_);
     }
+    PB_TRACE("sift.pyramid.issued");
     PB_CUDA(cudaMemcpyAsync(h_counts_.p, counts_.p, sizeof(int) * O, cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
+    PB_TRACE("sift.pyramid.done");
     // 2. refined candidates -> host (sigma needs pow), rare overflow handled by the octave-at-a-time path
     std::vector<int> cnt(O);
     size_t total = 0;
@@ -298,6 +300,7 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out, bo
             off += cnt[oi];
         }
     PB_CUDA(cudaStreamSynchronize(st_));
+    PB_TRACE("sift.keys.downloaded", (long)total);
     off = 0;
     for (int oi = 0; oi < O; ++oi)
         if (cnt[oi] > 0) {
@@ -338,10 +341,12 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out, bo
     int* h_na = (int*)h_nang_.ensure((size_t)nk * sizeof(int));
     double* h_an = (double*)h_ang_.ensure((size_t)nk * 4 * sizeof(double));
     PB_CUDA(cudaMemcpyAsync(keyin_.p, hk, (size_t)nk * sizeof(KeyIn), cudaMemcpyHostToDevice, st_));
+    PB_TRACE("sift.orient.launch", nk);
     launch_orient(os, sc, expn_tab_.p, keyin_.p, nk, order_k_.p, nangles_.p, angles_.p, st_);
     PB_CUDA(cudaMemcpyAsync(h_na, nangles_.p, (size_t)nk * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(h_an, angles_.p, (size_t)nk * 4 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
+    PB_TRACE("sift.orient.done");
     for (int oi = 0; oi < O; ++oi) {
         OctaveBuf& ob = oct_[oi];
         const int n = (int)ob.keys.size();
@@ -382,10 +387,12 @@ void SiftEngine::extract(const float* d_img, int img_pitch, RawFeatures& out, bo
     }
     order_j_.ensure(nj);
     PB_CUDA(cudaMemcpyAsync(order_j_.p, h_oj, nj * sizeof(int), cudaMemcpyHostToDevice, st_));
+    PB_TRACE("sift.descr.launch", (long)nj);
     launch_descr(os, sc, expn_tab_.p, keyin_.p, jobs_.p, (int)nj, order_j_.p, descr_.p, written_.p, patch_bytes, st_);
     PB_CUDA(cudaMemcpyAsync(hd, descr_.p, nj * 128 * sizeof(float), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaMemcpyAsync(hw, written_.p, nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
+    PB_TRACE("sift.descr.done");
     // 5. assemble in the reference's insertion order (octave, keypoint, angle), dropping descriptors the reference
     //    leaves unwritten
     if (copy_descr) out.descr.reserve(nj * 128);

@@ -12,6 +12,18 @@
 
 namespace pb {
 
+bool trace_on() {
+    static const bool on = [] { const char* e = getenv("PANO_B200_TRACE"); return e && *e && *e != '0'; }();
+    return on;
+}
+void trace_point(const char* tag, long a) {
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const unsigned tid = (unsigned)(std::hash<std::thread::id>()(std::this_thread::get_id()) % 997u);
+    if (a >= 0) fprintf(stderr, "trace %3u %10.3f %s %ld\n", tid, ms, tag, a);
+    else fprintf(stderr, "trace %3u %10.3f %s\n", tid, ms, tag);
+}
+
 namespace {
 struct WallTimer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -181,7 +193,10 @@ void Stitcher::quantise_table(FeatureTable& t) {
     t.d_q8.ensure(std::max<size_t>((size_t)t.n * 32, 32));
     t.d_qe.ensure(std::max<size_t>(t.n, 1) + 1);        // [n] = the table's largest error bound
     int* h = h_qemax_.ensure(1);
-    launch_sad_quantize(t.d_descr.p, t.n, t.d_q8.p, t.d_qe.p, t.d_qe.p + std::max(t.n, 1), st_);
+    const size_t padded = match_group_pad_rows(t.n);
+    t.d_g8.ensure(padded * 8);
+    t.d_w16.ensure(padded);
+    launch_sad_quantize(t.d_descr.p, t.n, t.d_q8.p, t.d_qe.p, t.d_qe.p + std::max(t.n, 1), st_, t.d_g8.p, t.d_w16.p);
     PB_CUDA(cudaMemcpyAsync(h, t.d_qe.p + std::max(t.n, 1), sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
     t.qemax = *h;
@@ -196,7 +211,9 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
     PB_CUDA(cudaSetDevice(dev_));
     const int P = (int)probs.size();
     const bool pre = match_mode_ != 1;
-    const bool sym = match_mode_ == 0;
+    const bool sym = match_mode_ == 0 || match_mode_ == 3;
+    const bool grouped = match_mode_ == 0 && !no_group_;   // pairs take the grouped pass (mode 3: the full SAD pass for both directions)
+    const StageTimes tm_before = tm_;
     out.assign(P, std::vector<int>());
     std::vector<int> job_of(P, -1), prob_of;
     for (int k = 0; k < P; ++k) {
@@ -232,6 +249,7 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
             const FeatureTable* A = probs[prob_of[q]].first;
             const FeatureTable* B = probs[prob_of[q]].second;
             if (A->qemax > match_sym_err_cap() || B->qemax > match_sym_err_cap() || A == B) continue;
+            if (grouped && (A->qemax > match_group_err_cap() || B->qemax > match_group_err_cap())) continue;
             auto it = open.find({B, A});
             if (it != open.end()) {
                 partner[q] = it->second;
@@ -248,8 +266,11 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
     std::vector<char> is_r(nj, 0);
     for (auto& pr : pairs) is_r[pr.y] = 1;
     // scratch layout
-    size_t npart = 0, nidx = 0, nspart = 0, nscratch = 0;
-    std::vector<size_t> poff(nj), ioff(nj), soff(nj), coff(nj);
+    size_t npart = 0, nidx = 0, nspart = 0, nscratch = 0, ngroup = 0, gq_cap = 0;
+    std::vector<size_t> poff(nj), ioff(nj), soff(nj), coff(nj), goff(nj, 0);
+    int group_yblocks = 0;
+    if (grouped)
+        for (auto& pr : pairs) group_yblocks += match_group_yblocks(probs[prob_of[pr.x]].second->n);
     std::vector<int> nsplits(nj), snsplits(nj, 1);
     const int nlaunch_jobs = std::max<int>(1, (int)pairs.size() + (int)singles.size());
     for (int q = 0; q < nj; ++q) {
@@ -260,7 +281,10 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         nidx += B.n;
         if (pre) {
             soff[q] = nspart; coff[q] = nscratch;
-            if (is_r[q]) {
+            if (grouped && partner[q] >= 0) {
+                goff[q] = ngroup;                                  // statistics through atomics: no per-split partials
+                ngroup += match_group_ints(B.n);
+            } else if (is_r[q]) {
                 nspart += (size_t)match_sym_yblocks(A.n) * B.n;   // one row of statistics per block of held rows of Y = A
             } else {
                 snsplits[q] = match_sad_num_splits(A.n, B.n, nlaunch_jobs);
@@ -272,10 +296,19 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
     partial_.ensure(npart);
     midx_.ensure(nidx);
     if (pre) {
-        spartial_.ensure(nspart);
+        spartial_.ensure(std::max<size_t>(nspart, 1));
         mscratch_.ensure(nscratch);
-        mcount_.ensure((size_t)4 * nj);
-        PB_CUDA(cudaMemsetAsync(mcount_.p, 0, (size_t)4 * nj * sizeof(int), st_));
+        if (ngroup) {
+            gscratch_.ensure(ngroup);
+            PB_CUDA(cudaMemsetAsync(gscratch_.p, 0x7f, ngroup * sizeof(int), st_));
+            // queue of the row pairs the grouped bound cannot skip: ~0.07 % of the pairs on SIFT tables; room for 0.25 %
+            double rowpairs = 0;
+            for (auto& pr : pairs) rowpairs += (double)probs[prob_of[pr.x]].first->n * probs[prob_of[pr.x]].second->n;
+            gq_cap = (size_t)std::min(std::max(rowpairs * 0.0025, 262144.0), 512.0 * 1024 * 1024);
+            gqueue_.ensure(gq_cap);
+        }
+        mcount_.ensure((size_t)4 * nj + 4);           // [4 * nj]: entries in the grouped pass's queue
+        PB_CUDA(cudaMemsetAsync(mcount_.p, 0, ((size_t)4 * nj + 4) * sizeof(int), st_));
     }
     int* h = h_midx_.ensure(nidx + 4 * (size_t)nj);
     std::vector<MatchJob> jobs(nj);
@@ -286,9 +319,13 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         if (pre)
             match_prefilter_attach(J, A.d_q8.p, A.d_qe.p, B.d_q8.p, B.d_qe.p, snsplits[q], spartial_.p + soff[q],
                                    mscratch_.p + coff[q], mcount_.p + 4 * (size_t)q);
+        if (grouped && partner[q] >= 0)
+            match_group_attach(J, A.d_g8.p, A.d_w16.p, B.d_g8.p, B.d_w16.p, match_group_num_splits(A.n, group_yblocks),
+                               gscratch_.p + goff[q]);
         jobs[q] = J;
     }
-    for (auto& pr : pairs) match_prefilter_pair(jobs[pr.x], jobs[pr.y]);
+    if (!grouped)
+        for (auto& pr : pairs) match_prefilter_pair(jobs[pr.x], jobs[pr.y]);
     // one upload: job table, pair list, single list
     const size_t jb = align_up((int)(jobs.size() * sizeof(MatchJob)), 16), pb = align_up((int)(pairs.size() * sizeof(int2)), 16);
     char* hj = h_mjobs_.ensure(jb + pb + singles.size() * sizeof(int) + 16);
@@ -302,7 +339,7 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         launch_match_batch_prefilter(dj, reinterpret_cast<const MatchJob*>(hj), nj, reinterpret_cast<const int2*>(mjobs_.p + jb),
                                      reinterpret_cast<const int2*>(hj + jb), (int)pairs.size(),
                                      reinterpret_cast<const int*>(mjobs_.p + jb + pb), reinterpret_cast<const int*>(hj + jb + pb),
-                                     (int)singles.size(), st_);
+                                     (int)singles.size(), st_, grouped, gqueue_.p, mcount_.p + 4 * (size_t)nj, (int)gq_cap);
     else launch_match_batch(dj, reinterpret_cast<const MatchJob*>(hj), nj, st_);
     PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * nidx, cudaMemcpyDeviceToHost, st_));
     if (d_out) {
@@ -316,6 +353,15 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
     }
     if (pre) PB_CUDA(cudaMemcpyAsync(h + nidx, mcount_.p, (size_t)4 * nj * sizeof(int), cudaMemcpyDeviceToHost, st_));
     PB_CUDA(cudaStreamSynchronize(st_));
+    if (grouped && !pairs.empty() && (h[nidx + 4 * (size_t)pairs[0].x + 3] >> 30)) {
+        // the queue overflowed (tables on which the grouped bound skips little): the batch is redone with the full SAD pass
+        tm_ = tm_before;
+        no_group_ = true;
+        try { match_batch(probs, out, d_out); } catch (...) { no_group_ = false; throw; }
+        no_group_ = false;
+        mstats_.group_overflow++;
+        return;
+    }
     for (int q = 0; q < nj; ++q) {
         const int k = prob_of[q];
         std::copy(h + ioff[q], h + ioff[q] + out[k].size(), out[k].begin());
@@ -324,9 +370,12 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         if (pre) {
             mstats_.survivors += h[nidx + 4 * q];
             mstats_.overflow += h[nidx + 4 * q + 1];
+            mstats_.group_exact += h[nidx + 4 * q + 2];
+            mstats_.group_accepts += h[nidx + 4 * q + 3] & ((1 << 30) - 1);
         }
     }
     mstats_.sym_pairs += (long long)pairs.size();
+    if (grouped) mstats_.group_pairs += (long long)pairs.size();
 }
 
 void Stitcher::match_idx(FeatureTable& A, FeatureTable& B, std::vector<int>& idx) {
@@ -1013,6 +1062,7 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
             im.w = iw; im.h = ih;
             const size_t np = (size_t)iw * ih;
             WallTimer t0;
+            PB_TRACE("lane.image.begin", i);
             const u8* d_rgb = imgs[i];
             if (!on_device) {
                 L.in_rgb.ensure(3 * np);
@@ -1040,8 +1090,10 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
             L.eng->extract(L.gray32.p, pitch, raw, false);   // descriptors stay in the engine's pinned buffer
             L.t_sift += t1.ms();
             WallTimer t2;
+            PB_TRACE("lane.table.begin", i);
             std::vector<int> sel;
             build_table(raw, im.feat, &sel, false);            // ... and the table's device copy is gathered below
+            PB_TRACE("lane.table.sorted", i);
             if (raw.d_descr && !sel.empty()) {
                 // the descriptors are still in the engine's device buffer: gather the sorted rows there instead of
                 // sending the 1.2 MB table back over PCIe from pageable memory
@@ -1059,6 +1111,7 @@ void Stitcher::lane_work(Lane& L, int first, int step, const u8* const* imgs, co
                 im.feat.on_device = true; im.feat.quantised = false;
             }
             L.t_table += t2.ms();
+            PB_TRACE("lane.image.end", i);
         }
     } catch (const std::exception& e) {
         L.err = e.what();
@@ -1282,7 +1335,9 @@ int Stitcher::stitch_edge(int src, int dst, int pre, const std::vector<int>& s2d
     {
         WallTimer t;
         std::vector<const std::vector<KeyPair>*> probs{&d2s, &s2d};
+        PB_TRACE("edge.ransac.begin", (long)d2s.size());
         if (!ransac(probs, H)) return -3;
+        PB_TRACE("edge.ransac.end");
         tm_.ransac += t.ms();
     }
     const double* fwd = H.data();       // RANSAC(dstToSrcPair)
@@ -1471,7 +1526,9 @@ int Stitcher::run() {
                 // Only the lists the reference would compute are ever consulted.
                 if (match_mode_ == 0) wave.push_back({j, i});
             }
+        PB_TRACE("run.match.wave1.begin", (long)wave.size());
         run_wave(wave);
+        PB_TRACE("run.match.wave1.end");
         wave.clear();
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < i; ++j)
@@ -1531,13 +1588,16 @@ int Stitcher::run() {
             adj[src][dst] = adj[dst][src] = 0;
             wait.push(dst);
             log << src << " " << dst << "\n";
+            PB_TRACE("run.edge.begin", dst);
             int rc = stitch_edge(src, dst, pre, midx[src][dst], midx[dst][src]);
+            PB_TRACE("run.edge.issued", dst);
             if (rc) return rc;
             pre = dst;
         }
     }
     {
         const int rc = check_blend_flag();
+        PB_TRACE("run.edges.done");
         if (rc) return rc;
     }
     log_ = log.str();

@@ -30,6 +30,9 @@ struct FeatureTable {   // == std::map<std::vector<float>, VlSiftKeypoint> flatt
     DevBuf<int> d_qe;
     bool quantised = false;
     int qemax = 0;              // largest error bound of the table (decides whether the 16-bit symmetric pass applies)
+    // grouped pass: 32 group bytes per row and w16, both readable in whole 64-row tiles (match_group_pad_rows)
+    DevBuf<unsigned> d_g8;
+    DevBuf<unsigned short> d_w16;
 };
 
 struct StageTimes {  // milliseconds, CUDA events on the stitcher's stream (host work between kernels included)
@@ -41,6 +44,9 @@ struct StageTimes {  // milliseconds, CUDA events on the stitcher's stream (host
 
 struct MatchStats {   // pre-filter bookkeeping since the last clear(): queries, survivors of the SAD pass, full-scan fallbacks
     long long queries = 0, survivors = 0, overflow = 0, problems = 0, sym_pairs = 0;
+    long long group_pairs = 0, group_exact = 0;   // image pairs through the grouped pass; exact SADs it evaluated
+    long long group_accepts = 0;                  // queries accepted with certainty by the grouped pass (no float arithmetic)
+    long long group_overflow = 0;                 // batches redone with the full SAD pass because the pair queue overflowed
 };
 
 class Stitcher {
@@ -187,7 +193,9 @@ class Stitcher {
     int ktab_n_ = 0;
     DevBuf<Top2> partial_;
     DevBuf<SadStat> spartial_;
-    DevBuf<int> mscratch_, mcount_;
+    DevBuf<int> mscratch_, mcount_, gscratch_;
+    DevBuf<unsigned long long> gqueue_;
+    bool no_group_ = false;
     PinBuf<int> h_qemax_;
     int match_mode_ = 0;
     MatchStats mstats_;

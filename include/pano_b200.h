@@ -248,11 +248,16 @@ int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes);
 #define PANO_B200_MATCH_PREFILTER 0
 #define PANO_B200_MATCH_FULL 1
 #define PANO_B200_MATCH_PREFILTER_ONEDIR 2
+#define PANO_B200_MATCH_PREFILTER_FULLSAD 3   /* pre-filter with the full 128-byte SAD of every row pair (no grouped bound) */
 int pano_b200_set_match_mode(pano_b200_ctx* ctx, int mode);
 /* pre-filter bookkeeping since the last reset: out[0] = queries, out[1] = queries the SAD pass could not reject,
  * out[2] = queries that fell back to the full scan (candidate list overflow), out[3] = directed problems, out[4] = image
  * pairs served by the symmetric pass; reset != 0 clears the counters after reading */
 int pano_b200_match_stats(pano_b200_ctx* ctx, long long out[5], int reset);
+/* the same counters plus out[5] = image pairs through the grouped pass, out[6] = exact SADs the grouped pass evaluated
+ * (of out[5] pairs' |X| x |Y| row pairs), out[7] = queries it accepted with certainty, out[8] = batches redone with
+ * the full SAD pass because its pair queue overflowed; fills min(n, 9) entries */
+int pano_b200_match_stats_ex(pano_b200_ctx* ctx, long long* out, int n, int reset);
 int pano_b200_flush_l2(pano_b200_ctx* ctx);           /* overwrite a 256 MB scratch buffer (2x L2) */
 int pano_b200_timer_start(pano_b200_ctx* ctx);        /* CUDA events on the context's stream */
 int pano_b200_timer_stop(pano_b200_ctx* ctx, float* ms);

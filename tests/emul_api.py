@@ -132,6 +132,19 @@ def match_idx_prefilter(dA, dB, cand_cap=0):
     return idx, {"survivors": int(st[0]), "overflow": int(st[1]), "max_candidates": int(st[2]), "unbounded_rows": int(st[3])}
 
 
+def match_pair_grouped(dX, dY, sample_rows=0, cand_cap=0):
+    """The grouped pass (seed, grouped bound, exact SAD of the pairs it cannot skip, decision, candidates, exact re-rank)
+    for both directions of one image pair on the CPU.  Returns (idx of getImgPair(X, Y), idx of getImgPair(Y, X), stats)."""
+    dX = np.ascontiguousarray(dX, np.float32)
+    dY = np.ascontiguousarray(dY, np.float32)
+    ixy = np.empty(len(dY), np.int32)
+    iyx = np.empty(len(dX), np.int32)
+    st = np.zeros(4, np.int64)
+    lib().emul_match_grouped(_p(dX), len(dX), _p(dY), len(dY), _p(ixy), _p(iyx), _p(st), int(sample_rows), int(cand_cap))
+    return ixy, iyx, {"survivors": int(st[0]), "exact": int(st[1]), "pairs": int(st[2]), "unqualified": int(st[3]) & 1,
+                      "accepts": int(st[3]) >> 1}
+
+
 def _pairs(src, dst):
     p = np.empty(len(src), PAIR_DTYPE)
     p["src"] = src

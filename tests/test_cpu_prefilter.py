@@ -132,3 +132,98 @@ def test_prefilter_vs_reference_on_input_sets(ref, input_sets):
         qb = np.nonzero(pre >= 0)[0]
         assert ka[pre[qb]].tobytes() == ra.tobytes() and kb[qb].tobytes() == rb.tobytes()
         assert st["overflow"] == 0 and st["survivors"] <= 2 * len(qb) + 16
+
+
+# ---- grouped pass (second level: 32 group bytes per row, match_device.cuh (**)) ---------------------------------------
+def check_grouped(X, Y, sample_rows=0, cand_cap=0):
+    fxy, fyx = emul.match_idx(X, Y), emul.match_idx(Y, X)
+    gxy, gyx, st = emul.match_pair_grouped(X, Y, sample_rows, cand_cap)
+    assert st["unqualified"] == 0
+    assert np.array_equal(fxy, gxy), f"grouped pass changed getImgPair(X, Y): {np.nonzero(fxy != gxy)[0][:10]} {st}"
+    assert np.array_equal(fyx, gyx), f"grouped pass changed getImgPair(Y, X): {np.nonzero(fyx != gyx)[0][:10]} {st}"
+    return fxy, fyx, st
+
+
+def test_group_bound_holds():
+    """SAD(a, b) >= 4 * S(a, b) - 96 for the 2 x 2-cell / same-bin grouping, on arbitrary byte rows"""
+    rng = np.random.default_rng(31)
+    q = rng.integers(0, 256, (300, 128)).astype(np.int64)
+    q[:40] = rng.integers(0, 4, (40, 128))          # tiny values: the slack dominates
+    q[40:60] = 255
+    d = np.arange(128)
+    grp = (d & 7) + 8 * ((((d >> 3) & 3) >> 1) + 2 * ((d >> 5) >> 1))
+    assert sorted(np.bincount(grp)) == [4] * 32
+    G = np.zeros((len(q), 32), np.int64)
+    for k in range(128):
+        G[:, grp[k]] += q[:, k]
+    assert G.max() <= 1020
+    F = G >> 2
+    for a in range(0, len(q), 7):
+        sad = np.abs(q - q[a]).sum(1)
+        S = np.abs(F - F[a]).sum(1)
+        assert np.all(sad >= 4 * S - 96)
+
+
+def test_grouped_equals_full_scan_both_directions():
+    rng = np.random.default_rng(32)
+    X = sift_like(rng, 900)
+    Y = with_matches(rng, X, 700)
+    fxy, fyx, st = check_grouped(X, Y)
+    assert (fxy >= 0).sum() > 100 and (fyx >= 0).sum() > 100
+    assert st["accepts"] > 0.5 * ((fxy >= 0).sum() + (fyx >= 0).sum())   # most true matches need no float arithmetic at all
+    assert st["exact"] < 0.2 * st["pairs"]            # the bound does skip (synthetic tables are far less structured than SIFT)
+    # a small sample (loose thresholds) and a tiny candidate capacity (overflow -> full scan) change nothing
+    check_grouped(X[:300], Y[:250], sample_rows=4, cand_cap=1)
+    # unrelated tables: nothing matches, (almost) nothing survives
+    _, _, st = check_grouped(X, sift_like(rng, 400))
+    assert st["survivors"] < 0.1 * 1300
+
+
+def test_grouped_adversarial_and_degenerate():
+    rng = np.random.default_rng(33)
+    X = sift_like(rng, 400)
+    Y = with_matches(rng, X, 300)
+    X2, Y2 = X.copy(), Y.copy()
+    X2[10] = X2[11]                                   # duplicates: d0 == d1 ties
+    Y2[20] = X2[10]
+    X2[50] = 0.0
+    Y2[60] = 0.0
+    Y2[4, :8] = -0.02                                 # negative values are clamped by the quantiser, their error is accounted
+    check_grouped(X2, Y2)
+    check_grouped(np.ascontiguousarray(X * 0.01), np.ascontiguousarray(Y * 0.01))   # everything quantises to 0 / 1
+    for nx, ny in ((2, 1), (2, 2), (3, 130), (65, 64), (129, 2), (1, 5), (5, 1)):
+        check_grouped(X[:nx], Y[:ny])
+    X3 = X.copy()
+    X3[5] *= 3.0                                      # a row whose error bound exceeds the cap: the pair does not qualify
+    _, _, st = emul.match_pair_grouped(X3, Y)
+    assert st["unqualified"] == 1
+
+
+def test_grouped_vs_reference_on_input_sets(ref, input_sets):
+    tabs = [ref.sift_features(ref.gray(ref.project(img))) for img in input_sets["Input"][:3]]
+    for i, j in ((0, 1), (1, 2), (0, 2)):
+        (dx, kx), (dy, ky) = tabs[i], tabs[j]
+        gxy, gyx, st = emul.match_pair_grouped(dx, dy)
+        ra, rb = ref.match(dx, kx, dy, ky)
+        q = np.nonzero(gxy >= 0)[0]
+        assert kx[gxy[q]].tobytes() == ra.tobytes() and ky[q].tobytes() == rb.tobytes()
+        ra, rb = ref.match(dy, ky, dx, kx)
+        q = np.nonzero(gyx >= 0)[0]
+        assert ky[gyx[q]].tobytes() == ra.tobytes() and kx[q].tobytes() == rb.tobytes()
+        assert st["exact"] < 0.02 * st["pairs"]       # real SIFT tables: the grouped bound skips almost every row pair
+
+
+def test_grouped_near_the_ratio_threshold():
+    """d0 / d1 straddles 0.5 (and 0.25, where the certain-accept rule stops being certain): such queries must reach the
+    exact pass, and the accept rule must never fire on a query the exact rule rejects"""
+    rng = np.random.default_rng(34)
+    X = sift_like(rng, 260)
+    Y = []
+    for i in range(200):
+        a0, a1 = X[rng.choice(260, 2, replace=False)]
+        t = (1.0 / 3.0 if i % 2 else 0.2) + rng.normal(0, 2e-3)
+        Y.append((1 - t) * a0 + t * a1)
+    Y = np.ascontiguousarray(np.array(Y, np.float32))
+    fxy, fyx, st = check_grouped(X, Y)
+    assert 0 < (fxy >= 0).sum() < len(Y)
+    assert st["accepts"] < (fxy >= 0).sum() + (fyx >= 0).sum()

@@ -87,10 +87,13 @@ def both_pair(ctx, A, B, expect_sym=True):
     assert np.array_equal(fba, ba), f"B->A list differs at {np.nonzero(fba != ba)[0][:10]}, {st}"
     if expect_sym is not None and min(len(A), len(B)) >= 2:
         assert st["sym_pairs"] == (1 if expect_sym else 0), st
-    ctx.set_match_mode("prefilter_onedir")
-    ab1, ba1 = ctx.match_pair(A, B)
+        # default mode: symmetric pairs take the grouped pass (or, when its pair queue overflows, are redone without it)
+        assert st["group_pairs"] + st["group_overflow"] == st["sym_pairs"], st
+    for mode in ("prefilter_onedir", "prefilter_fullsad"):   # one SAD pass per direction / full 128-byte SAD for both
+        ctx.set_match_mode(mode)
+        ab1, ba1 = ctx.match_pair(A, B)
+        assert np.array_equal(fab, ab1) and np.array_equal(fba, ba1), mode
     ctx.set_match_mode("prefilter")
-    assert np.array_equal(fab, ab1) and np.array_equal(fba, ba1)
     return ab, ba, st
 
 
@@ -101,6 +104,9 @@ def test_symmetric_pass_equals_full_scan(ctx):
     ab, ba, st = both_pair(ctx, A, B)
     assert (ab >= 0).sum() > 1000 and (ba >= 0).sum() > 1000
     assert st["queries"] == len(A) + len(B) and st["overflow"] <= 0.01 * st["queries"]
+    # unstructured random tables: the grouped bound skips far fewer pairs than on SIFT tables, so the pair queue (sized for
+    # 0.25 % of the pairs) overflows and the batch is redone with the full SAD pass -- the fallback is part of the contract
+    assert st["group_pairs"] + st["group_overflow"] == 1, st
     both_pair(ctx, A, sift_like(rng, 3001))            # unrelated tables: nothing to match in either direction
 
 
@@ -128,16 +134,24 @@ def test_symmetric_pass_adversarial_and_fallback(ctx):
     A3[50] = 0.0
     B3[60] = 0.0
     both_pair(ctx, A3, B3, expect_sym=True)
-    both_pair(ctx, np.ascontiguousarray(A * 0.01), np.ascontiguousarray(B * 0.01))       # everything quantises to 0 / 1
+    _, _, st = both_pair(ctx, np.ascontiguousarray(A * 0.01), np.ascontiguousarray(B * 0.01))   # everything quantises to 0 / 1:
+    assert st["group_overflow"] == 1, st                                                       # ... the bound skips nothing -> redo
     both_pair(ctx, np.ascontiguousarray(A * 1.9), np.ascontiguousarray(B * 1.9), expect_sym=None)    # clamped rows: large errors
 
 
 def test_symmetric_pass_vs_reference_getimgpair(ctx, ref, input_sets):
+    """real SIFT tables: the grouped pass proper (no queue overflow), few exact SADs, most matches accepted without float
+    arithmetic -- and the reference's match lists bit for bit"""
     ctx.set_match_mode("prefilter")
     tabs = [ref.sift_features(ref.gray(ref.project(img))) for img in input_sets["Input2"][:3]]
     for i, j in ((0, 1), (1, 2), (0, 2)):
         (da, ka), (db, kb) = tabs[i], tabs[j]
+        ctx.match_stats(reset=True)
         ab, ba = ctx.match_pair(da, db)
+        st = ctx.match_stats(reset=True)
+        assert st["group_pairs"] == 1 and st["group_overflow"] == 0, st
+        assert 0 < st["group_exact"] < 0.01 * len(da) * len(db), st
+        assert st["group_accepts"] <= (ab >= 0).sum() + (ba >= 0).sum(), st
         ra, rb = ref.match(da, ka, db, kb)
         sel = ab >= 0
         assert ka[ab[sel]].tobytes() == ra.tobytes() and kb[sel].tobytes() == rb.tobytes()

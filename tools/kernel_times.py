@@ -36,3 +36,4 @@ print(desc, "->", ow.value, "x", oh.value)
 for name, v in sorted(k.items(), key=lambda kv: -kv[1]["ms"]):
     gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0
     print(f"{name:22s} {v['ms']:9.3f} ms {v['launches']:5d} launches  {gb:9.1f} G(B|op)/s")
+print("match stats", ctx.match_stats())
