@@ -496,6 +496,11 @@ def run_b200(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     roofline = roofline_of(top, kernels, clocks, args.workload)
+    # the largest HBM-streaming kernel as well, when the dominant kernel is an instruction-issue-bound matcher kernel
+    roofline_hbm = None
+    hbm_only = {k: v for k, v in kernels.items() if v["bytes"] > 0 and not k.startswith(("match", "ransac", "sift.refine", "sift.orient", "sift.descr"))}
+    if hbm_only and roofline and roofline.get("bound") != "hbm":
+        roofline_hbm = roofline_of(max(hbm_only.items(), key=lambda kv: kv[1]["ms"]), kernels, clocks, args.workload)
     # the HBM-bound scale-space kernels, always reported (north_star: blur GB/s)
     hbm_kernels = {}
     for name, k in kernels.items():
@@ -521,6 +526,7 @@ def run_b200(args):
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,
         "stages_ms_last_step": stages,
         "kernels_ms": {k: round(v["ms"], 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
@@ -649,8 +655,14 @@ def run_b200_sharded(args, ctx, L, imgs, desc, data, dist, rank, local_rank, wor
     dist.destroy_process_group()
 
 
+_IIR_NOTE = ("recursive Gaussian (CImg vanvliet), {axis} pass: per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 "
+             "cycles/sample (measured); parallel only across lines. Algorithmic bytes = 8 B per plane sample per pass (one read + one "
+             "write, SURVEY 8d 'x-IIR r+w, y-IIR r+w'); the kernel itself moves 16 B (the forward result goes through HBM before the "
+             "backward sweep: a line does not fit on chip). {extra}")
 ROOFLINE_NOTES = {
-    "blend.iir": "recursive Gaussian (CImg vanvliet): per line a serial 3rd-order recurrence in double, dependent chain DMUL+3 DADD = 32 cycles/sample (measured); parallel only across lines. Algorithmic bytes = 8 B per plane sample per pass (one read + one write, SURVEY 8d 'x-IIR r+w, y-IIR r+w'); the kernel's own forward + backward sweeps stay in shared memory",
+    "blend.iir_x": _IIR_NOTE.format(axis="x", extra="Lines = rows x planes: only 2.3 k x 7 lines of up to 18 k samples on the last edge, i.e. 3.4 warps per SM -- the pass is bound by the per-line latency (2 N x ~65 cycles), not by bandwidth"),
+    "blend.iir_y": _IIR_NOTE.format(axis="y", extra="Lines = columns x planes (126 k lines on the last edge): ncu shows long_scoreboard + mio_throttle stalls, DRAM at 47 %"),
+    "match.group_sym": "grouped lower bound of the uint8 SAD pre-filter, both directed problems of an image pair per pass: 8 VABSDIFF4.U8.ACC per (row of X, row of Y) on 32-byte group vectors + 2.5 packed 16-bit add / max / min / xor for the skip test (10.5 ALU-pipe instructions per row pair against 37 for the full SAD pass); VABSDIFF4 issues at half rate (measured 60.7 of 64 lanes/clk/SM, tools/ubench/vsad_rate.cu), so peak = 148 SM x 64 lanes x median SM clock; 'achieved' counts the 8 VABSDIFF4 only -- with the bookkeeping on the same pipe the pipe carries 1.31 x that",
     "sift.descr": "one warp per (keypoint, angle); gather from the L2-resident gradient map + double-precision geometry; algorithmic bytes = sum (2W+1)^2 * 8 B patch reads + 512 B per descriptor (SURVEY 8d)",
     "match.sad": "uint8 SAD pre-filter of the exact float-L1 matcher: 32 VABSDIFF4.U8.ACC per (query, database row) pair (one per 4 dimensions) + ~4 integer min/max for the running bounds; VABSDIFF4 issues at half rate (measured 60.7 of 64 lanes/clk/SM, tools/ubench/vsad_rate.cu), so peak = 148 SM x 64 lanes x median SM clock; 'achieved' counts the 32 VABSDIFF4 only",
     "match.sad_sym": "uint8 SAD pre-filter of the exact float-L1 matcher, BOTH directed problems of an image pair from one pass over the SAD matrix: 32 VABSDIFF4.U8.ACC per (row of X, row of Y) + ~5 packed 16-bit min/max/add for the two sets of running bounds + 1.5 CREDUX; VABSDIFF4 issues at half rate (measured 60.7 of 64 lanes/clk/SM, tools/ubench/vsad_rate.cu), so peak = 148 SM x 64 lanes x median SM clock; 'achieved' counts the 32 VABSDIFF4 only (the bookkeeping shares the same ALU pipe)",
@@ -677,7 +689,7 @@ def roofline_of(top, kernels, clocks, workload=None):
     per_launch_ms = top_k["ms"] / top_k["launches"]
     common = {"kernel": top_name, "avg_launch_ms": per_launch_ms, "launches": top_k["launches"],
               "share_of_kernel_time": top_k["ms"] / ksum, "note": ROOFLINE_NOTES.get(top_name), "traffic": None}
-    if top_name in ("match.l1", "match.sad", "match.sad_sym"):
+    if top_name in ("match.l1", "match.sad", "match.sad_sym", "match.group_sym"):
         ach = top_k["bytes"] / (top_k["ms"] * 1e-3) / 1e12
         clk = (clocks or {}).get("sm_mhz") or 1500.0
         lanes = 128 if top_name == "match.l1" else 64
@@ -861,12 +873,14 @@ def ncu_traffic(kernel, workload):
     """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/
     r01_ncu_traffic.json, written by tools/summarize_ncu.py): the capture is of ONE launch -- the largest -- so its own
     algorithmic bytes are given beside it; `traffic` stays None when no capture of this kernel / workload exists."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))[workload][kernel]
-        return {"traffic": t["dram_bytes"], "traffic_launch": t["launch"], "traffic_launch_algorithmic_bytes": t["algorithmic_bytes"],
-                "traffic_source": t["source"]}
-    except Exception:
-        return {}
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))[workload][kernel]
+            return {"traffic": t["dram_bytes"], "traffic_launch": t["launch"], "traffic_launch_algorithmic_bytes": t["algorithmic_bytes"],
+                    "traffic_source": t["source"]}
+        except Exception:
+            continue
+    return {}
 
 
 def sift_summary(kernels, stages, mpix):

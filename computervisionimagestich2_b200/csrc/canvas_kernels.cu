@@ -262,8 +262,7 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
 __device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-constexpr int kIirNSVanVliet = 4;  // tiles in flight per CTA (4.2 KB each); 8 measured slower (22.1 vs 20.0 ms on 8 x 4K)
-constexpr int kIirNSDeriche = 4;   // Deriche keeps two rings (input and causal output)
+constexpr int kIirNSDeriche = 4;   // tiles in flight per CTA (4.2 KB each); Deriche keeps two rings (input and causal output)
 constexpr int kIirPitch = 33;      // floats between consecutive elements of a tile
 }  // namespace
 
@@ -272,6 +271,9 @@ constexpr int kIirPitch = 33;      // floats between consecutive elements of a t
 // (F2F: ~19 cycles latency, ~10 issue cycles per warp on a unit shared by the SM, tools/ubench/f2f_lat.cu) this plain
 // form measures 38 cycles in isolation and 62 in the kernel.  Integer-pipe conversions and hand software pipelining
 // were both tried and were slower (87 and 51 cycles).
+// (Conversions on the integer pipe -- tools/ubench/cvt_exact.cuh, bit-identical to F2F -- were measured inside this kernel in
+// round 2: x pass 2.60 -> 3.20 (widening only) -> 4.12 ms (both), y pass 1.83 -> 1.99 -> 2.43 ms on a 17997 x 2268 blend.
+// ncu: the XU pipe is at 19 % in both passes; the conversions are not the limiter.)
 template <bool FWD>
 __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, double& v3, const IirCoef& c) {
 #pragma unroll
@@ -299,12 +301,12 @@ __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, dou
 // so pass 1 streams `dst` back in); DericheCoef = Deriche (fp32 state; causal and anticausal runs both filter the
 // INPUT, so pass 1 streams `src` again TOGETHER with the causal output Y already in `dst`, and the consumer stores
 // out = Y + yc, CImg.h:34797 -- src and dst must be distinct buffers).
-template <bool kElemContig, class Coef>
+template <bool kElemContig, class Coef, int NS>
 __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* dst, int N,   // src == dst is allowed (in-place y pass): no __restrict__
                                                       long nlines, int lines_per_plane, long plane_stride,
                                                       long elem_stride, Coef c) {
     constexpr bool kDeriche = std::is_same<Coef, DericheCoef>::value;
-    constexpr int kIirNS = kDeriche ? kIirNSDeriche : kIirNSVanVliet;
+    constexpr int kIirNS = NS;
     __shared__ float tiles[kIirNS][32 * kIirPitch];
     // Deriche, pass 1: the causal output Y of the same tile, streamed back beside the input so that the consumer forms
     // out = Y + yc itself (a read-modify-write in the storer exposes one HBM latency per tile)
@@ -493,20 +495,30 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* 
     }
 }
 
+template <bool X>
+static void launch_iir_pass(int ns, int grid, cudaStream_t st, const float* src, float* dst, int N, long nlines, int lpp,
+                            long plane, long estride, const IirCoef& coef) {
+    if (ns >= 10) iir_pipe_kernel<X, IirCoef, 10><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
+    else if (ns >= 8) iir_pipe_kernel<X, IirCoef, 8><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
+    else if (ns >= 6) iir_pipe_kernel<X, IirCoef, 6><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
+    else iir_pipe_kernel<X, IirCoef, 4><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
+}
 void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st) {
+    static const int ns_x = [] { const char* e = getenv("PANO_B200_IIR_NS_X"); return e ? atoi(e) : 4; }();
+    static const int ns_y = [] { const char* e = getenv("PANO_B200_IIR_NS_Y"); return e ? atoi(e) : 4; }();
     const float* ysrc = src;
     const long plane = (long)w * h;
     if (w > 1) {
         const long nlines = (long)nplanes * h;
-        KScope ks("blend.iir", st, 8.0 * nplanes * w * h);
-        iir_pipe_kernel<true, IirCoef><<<div_up(nlines, 32), 128, 0, st>>>(src, dst, w, nlines, h, plane, 1L, coef);
+        KScope ks("blend.iir_x", st, 8.0 * nplanes * w * h);
+        launch_iir_pass<true>(ns_x, div_up(nlines, 32), st, src, dst, w, nlines, h, plane, 1L, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
     if (h > 1) {
         const long nlines = (long)nplanes * w;
-        KScope ks("blend.iir", st, 8.0 * nplanes * w * h);
-        iir_pipe_kernel<false, IirCoef><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
+        KScope ks("blend.iir_y", st, 8.0 * nplanes * w * h);
+        launch_iir_pass<false>(ns_y, div_up(nlines, 32), st, ysrc, dst, h, nlines, w, plane, (long)w, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
@@ -522,14 +534,14 @@ void launch_deriche_blur(const float* src, float* tmp, float* dst, int w, int h,
         const long nlines = (long)nplanes * h;
         float* xdst = h > 1 ? tmp : dst;
         KScope ks("blend.deriche", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<true, DericheCoef><<<div_up(nlines, 32), 128, 0, st>>>(src, xdst, w, nlines, h, plane, 1L, coef);
+        iir_pipe_kernel<true, DericheCoef, kIirNSDeriche><<<div_up(nlines, 32), 128, 0, st>>>(src, xdst, w, nlines, h, plane, 1L, coef);
         PB_KERNEL_CHECK();
         ysrc = xdst;
     }
     if (h > 1) {
         const long nlines = (long)nplanes * w;
         KScope ks("blend.deriche", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<false, DericheCoef><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
+        iir_pipe_kernel<false, DericheCoef, kIirNSDeriche><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }

@@ -373,7 +373,10 @@ void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cu
 // order (optional): slot -> keypoint index, largest window first.  The window radius grows with sigma (13^2 .. 49^2
 // samples and more), one warp works on one keypoint, and the kernel ends when its slowest warp does: issued in array
 // order the big ones land anywhere and the tail of the launch runs at a fraction of the machine.
-__global__ void __launch_bounds__(128) orient_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
+#ifndef PB_ORIENT_MINB
+#define PB_ORIENT_MINB 6   // 80 registers, small spills: 7.2 -> 5.6 ms on 8 x 4K (the kernel waits on FP64 latencies; more resident warps hide them)
+#endif
+__global__ void __launch_bounds__(128, PB_ORIENT_MINB) orient_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
                                                      const KeyIn* __restrict__ keys, int nkeys,
                                                      const int* __restrict__ order,
                                                      int* __restrict__ nangles, double* __restrict__ angles) {
@@ -510,7 +513,10 @@ struct DescWarpSmem {
     float hist[128];
 };
 // order (optional): slot -> job index, largest patch first (841 .. 13 k samples per descriptor; see orient_kernel)
-__global__ void __launch_bounds__(128) descr_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
+#ifndef PB_DESCR_MINB
+#define PB_DESCR_MINB 1
+#endif
+__global__ void __launch_bounds__(128, PB_DESCR_MINB) descr_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
                                                     const KeyIn* __restrict__ keys, const DescJob* __restrict__ jobs,
                                                     int njobs, const int* __restrict__ order, float* __restrict__ descr,
                                                     int* __restrict__ written) {
