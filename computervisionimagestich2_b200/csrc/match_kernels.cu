@@ -561,14 +561,16 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
     if (tid == 0) qn = 0;
 
     // appends the CTA's collected pairs to the global queue (called by all threads, between two barriers)
+    // Called by ALL threads right after a barrier, i.e. with no append in flight.  qn is reset between the two barriers:
+    // after the first one every thread has read it, after the second one threads start appending again.
     auto flush = [&]() {
         const int n = min(qn, kGQLocal);
         if (tid == 0) qbase = n > 0 ? atomicAdd(gq.count, n) : 0;
         __syncthreads();
+        if (tid == 0) qn = 0;
         for (int i = tid; i < n; i += 128)
             if (qbase + i < gq.cap) gq.items[qbase + i] = qbuf[i];
         __syncthreads();
-        if (tid == 0) qn = 0;
     };
 
     const int ntiles = (x_end - x_begin + kGRows - 1) / kGRows;
@@ -636,9 +638,11 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
                 }
             }
         }
-        __syncthreads();   // the tile buffer is refilled by the copy issued in the next iteration; qn is stable
-        if (qn >= kGQLocal / 2) flush();
+        // barrier: the tile buffer is refilled by the copy issued in the next iteration.  The flush decision is taken BY the
+        // barrier (a thread that reads qn on its own could see appends of threads already in the next tile)
+        if (__syncthreads_or(qn >= kGQLocal / 2)) flush();
     }
+    __syncthreads();
     flush();
 }
 

@@ -158,3 +158,22 @@ def test_symmetric_pass_vs_reference_getimgpair(ctx, ref, input_sets):
         ra, rb = ref.match(db, kb, da, ka)
         sel = ba >= 0
         assert kb[ba[sel]].tobytes() == ra.tobytes() and ka[sel].tobytes() == rb.tobytes()
+
+
+def test_grouped_pass_dense_queue(ctx):
+    """clustered tables: every query fails the grouped bound against the ~50 rows of its own cluster, so a CTA collects
+    tens of thousands of pairs and flushes its shared-memory queue many times inside the pass (and falls through to the
+    direct global append when a tile adds more than the local buffer holds); the lists must still equal the full scan,
+    run after run"""
+    rng = np.random.default_rng(35)
+    centres = sift_like(rng, 40)
+    X = np.repeat(centres, 50, axis=0) + rng.normal(0, 2e-4, (2000, 128)).astype(np.float32)
+    Y = np.repeat(centres, 45, axis=0) + rng.normal(0, 2e-4, (1800, 128)).astype(np.float32)
+    X = np.ascontiguousarray(np.abs(X), np.float32)
+    Y = np.ascontiguousarray(np.abs(Y[rng.permutation(len(Y))]), np.float32)
+    ab, ba, st = both_pair(ctx, X, Y)
+    assert st["group_pairs"] == 1 and st["group_overflow"] == 0, st
+    assert st["group_exact"] >= 40 * 50 * 45, st
+    for _ in range(5):
+        ab2, ba2 = ctx.match_pair(X, Y)
+        assert np.array_equal(ab, ab2) and np.array_equal(ba, ba2)
