@@ -38,7 +38,10 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "sm__cycles_elapsed.max"]
+        "sm__cycles_elapsed.max", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__warps_eligible.avg.per_cycle_active", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
 
 
 def full(rep, out, title):
