@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kST) match_sad_sym_kernel(const MatchJob* __re
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kSeedRows = 512;   // sampled database rows per query
 constexpr int kGY = 4;           // held rows of Y per thread
-constexpr int kGRows = 64;       // streamed rows of X per tile
+constexpr int kGRows = 128;      // streamed rows of X per tile (a barrier per tile: 64-row tiles spent 11 % of the samples at it)
 
 __global__ void __launch_bounds__(128) match_seed_kernel(const MatchJob* __restrict__ jobs, const int* __restrict__ which) {
     __shared__ __align__(16) unsigned tile[32][32];
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
     unsigned g[kGY][8];
     int yrow[kGY];
     bool live[kGY];
-    unsigned wy[kGY], cy[kGY];                     // replicated in both halves: w16(y), c16(y)
+    unsigned wy[kGY], cy[kGY];                     // w16(y); c16(y) replicated in both halves
 #pragma unroll
     for (int j = 0; j < kGY; ++j) {
         const int y = blockIdx.x * (128 * kGY) + j * 128 + tid;
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
         const uint4 t0 = src[0], t1 = src[1];
         g[j][0] = t0.x; g[j][1] = t0.y; g[j][2] = t0.z; g[j][3] = t0.w;
         g[j][4] = t1.x; g[j][5] = t1.y; g[j][6] = t1.z; g[j][7] = t1.w;
-        wy[j] = live[j] ? (unsigned)F.Bw[yrow[j]] * 0x10001u : 0x7f007f00u;   // a row that does not exist never fails
+        wy[j] = live[j] ? (unsigned)F.Bw[yrow[j]] : 0x7f00u;   // accumulator start: w16(y); a row that does not exist never fails
         cy[j] = live[j] ? (unsigned)F.c16[yrow[j]] * 0x10001u : 0u;
     }
     if (tid == 0) qn = 0;
@@ -576,9 +576,11 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
     const int ntiles = (x_end - x_begin + kGRows - 1) / kGRows;
     auto issue = [&](int t) {   // tables are padded to a multiple of kGRows rows: whole tiles are always readable
         const int buf = t & 1, a0 = x_begin + t * kGRows;
-        cp_async16(&tile[buf][tid >> 1][(tid & 1) * 4], Xg + (size_t)(a0 + (tid >> 1)) * 8 + (tid & 1) * 4);
-        if (tid < 8) cp_async16(&xw[buf][tid * 8], Xw + a0 + tid * 8);
-        else if (tid < 16) cp_async16(&xc[buf][(tid - 8) * 8], Xc + a0 + (tid - 8) * 8);
+#pragma unroll
+        for (int i = tid; i < kGRows * 2; i += 128)
+            cp_async16(&tile[buf][i >> 1][(i & 1) * 4], Xg + (size_t)(a0 + (i >> 1)) * 8 + (i & 1) * 4);
+        if (tid < kGRows / 8) cp_async16(&xw[buf][tid * 8], Xw + a0 + tid * 8);
+        else if (tid < kGRows / 4) cp_async16(&xc[buf][(tid - kGRows / 8) * 8], Xc + a0 + (tid - kGRows / 8) * 8);
         asm volatile("cp.async.commit_group;");
     };
     if (ntiles > 0) issue(0);
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
             unsigned Z[kGY], P[kGY], bad = 0u;
 #pragma unroll
             for (int j = 0; j < kGY; ++j) {
-                unsigned s0 = 0u, s1 = 0u;
+                unsigned s0 = wy[j], s1 = wy[j];   // the accumulators start at w16(y): S + w16(y) costs nothing
                 s0 = sad4_acc(g[j][0], a0w.x, s0); s1 = sad4_acc(g[j][0], b0w.x, s1);
                 s0 = sad4_acc(g[j][1], a0w.y, s0); s1 = sad4_acc(g[j][1], b0w.y, s1);
                 s0 = sad4_acc(g[j][2], a0w.z, s0); s1 = sad4_acc(g[j][2], b0w.z, s1);
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
                 s0 = sad4_acc(g[j][6], a1w.z, s0); s1 = sad4_acc(g[j][6], b1w.z, s1);
                 s0 = sad4_acc(g[j][7], a1w.w, s0); s1 = sad4_acc(g[j][7], b1w.w, s1);
                 const unsigned pk = s1 * 65536u + s0;                          // IMAD: FMA pipe
-                Z[j] = __vadd2(__vadd2(pk, wy[j]), xwp) | deadhi;
+                Z[j] = __vadd2(pk, xwp) | deadhi;
                 P[j] = __vmaxu2(cy[j], xcp);
                 bad |= __vminu2(Z[j], P[j]) ^ P[j];                            // a half differs iff its Z < P
             }
@@ -852,7 +854,9 @@ void match_group_attach(MatchJob& J, const unsigned* Ag, const unsigned short* A
 }
 int match_group_yblocks(int NY) { return div_up(NY, 128 * kGY); }
 int match_group_num_splits(int NA, int yblocks_total) {
-    const int want = div_up(148 * 8, yblocks_total > 0 ? yblocks_total : 1);   // ~8 CTAs per SM over the whole batch
+    // ~8 waves of the 6 CTAs an SM holds (80 registers): with one split the 8 x 4K batch is 1400 CTAs = 1.6 waves, and the
+    // half-empty second wave costs ~20 % of the pass
+    const int want = div_up(148 * 6 * 8, yblocks_total > 0 ? yblocks_total : 1);
     const int maxs = div_up(NA, 4 * kGRows);                                   // at least four tiles per split
     const int s = want < maxs ? want : maxs;
     return s < 1 ? 1 : s;

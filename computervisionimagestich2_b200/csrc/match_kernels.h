@@ -34,12 +34,12 @@ struct MatchJob {
     int* overflow;          // [NB] query rows with more than kMatchCand candidates: full exact scan
     int* counters;          // [0] survivors, [1] overflow queries, [2] exact SADs of the grouped pass, [3] certain accepts
     // ---- grouped pass (second level of the pre-filter, match_device.cuh); null unless the job takes it ----
-    const unsigned* Ag;     // [NA padded to 64][8] words = 32 group bytes per row
+    const unsigned* Ag;     // [NA padded to whole tiles][8] words = 32 group bytes per row
     const unsigned short* Aw;   // [NA padded] w16 of each row
     const unsigned* Bg;
     const unsigned short* Bw;
     int* seed_u1;           // [NB] upper bound of the second-nearest SAD + e from the sampled rows
-    unsigned short* c16;    // [NB padded to 64] packed skip threshold of each query
+    unsigned short* c16;    // [NB padded to whole tiles] packed skip threshold of each query
     int* stat6;             // [NB][6] over the exactly evaluated rows (atomics; initialised to 0x7f bytes): two smallest keys
                             // (SAD + e(a)) << 32 | a as 64-bit values, then the two smallest SAD - e(a)
     int grp_rows_per_split, grp_nsplit;
@@ -69,7 +69,7 @@ void match_group_attach(MatchJob& J, const unsigned* Ag, const unsigned short* A
 int match_group_yblocks(int NY);
 int match_group_num_splits(int NA, int yblocks_total);
 int match_group_err_cap();
-inline size_t match_group_pad_rows(int n) { return (size_t)(n + 63) / 64 * 64 + 64; }   // rows readable by whole-tile copies
+inline size_t match_group_pad_rows(int n) { return (size_t)(n + 127) / 128 * 128 + 128; }   // rows readable by whole-tile copies
 // makes R the reverse problem of F for the symmetric pass; returns the number of SadStat rows (of R.NB entries) R needs
 int match_prefilter_pair(MatchJob& F, MatchJob& R);
 int match_sym_yblocks(int NY);
