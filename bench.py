@@ -433,7 +433,7 @@ def run_b200(args):
     buf = C.create_string_buffer(1 << 16)
     L.pano_b200_ktimer_report(buf, 1 << 16)
     L.pano_b200_ktimer_enable(0)
-    L.pano_b200_set_lanes(ctx.h, 4)
+    L.pano_b200_set_lanes(ctx.h, 8)
     kernels = json.loads(buf.value.decode())
     # --- north-star stage (3): the uint8 / tcgen05 matcher on resident SIFT-like tables (kernel only) ----------------
     match_u8 = None

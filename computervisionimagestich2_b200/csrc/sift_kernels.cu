@@ -374,7 +374,7 @@ void launch_gradient(const OctaveView& ov, const SiftConsts& sc, float* grad, cu
 // samples and more), one warp works on one keypoint, and the kernel ends when its slowest warp does: issued in array
 // order the big ones land anywhere and the tail of the launch runs at a fraction of the machine.
 #ifndef PB_ORIENT_MINB
-#define PB_ORIENT_MINB 6   // 80 registers, small spills: 7.2 -> 5.6 ms on 8 x 4K (the kernel waits on FP64 latencies; more resident warps hide them)
+#define PB_ORIENT_MINB 1
 #endif
 __global__ void __launch_bounds__(128, PB_ORIENT_MINB) orient_kernel(OctaveSet os, SiftConsts sc, const double* __restrict__ expn_tab,
                                                      const KeyIn* __restrict__ keys, int nkeys,
@@ -458,37 +458,58 @@ __global__ void __launch_bounds__(128, PB_ORIENT_MINB) orient_kernel(OctaveSet o
     hist[lane] = h0;
     if (lane < nbins - 32) hist[lane + 32] = h1;
     __syncwarp();
-    // vl/sift.c:1000-1036 on a private copy (every lane computes the same thing; lane 0 stores)
-    double hh[nbins];
-#pragma unroll
-    for (int i = 0; i < nbins; ++i) hh[i] = hist[i];
+    // vl/sift.c:1000-1036.  The reference's in-place loop carries the OLD value of the previous bin (`prev`), i.e. every pass
+    // computes new[i] = ((old[i-1] + old[i]) + old[i+1]) / 3 from the old histogram alone (circular): lane = bin, the same
+    // operations in the same order per bin, 2 divisions per lane and pass instead of 36.  (The first version ran the serial
+    // loop redundantly in every lane on a private 36-double copy: 216 divisions and 167 registers per thread.)
+    const bool two = lane < nbins - 32;   // lanes 0..3 also own bins 32..35
+    double c0 = h0, c1 = h1;
     for (int iter = 0; iter < 6; iter++) {
-        double prev = hh[nbins - 1];
-        const double first = hh[0];
-#pragma unroll
-        for (int i = 0; i < nbins - 1; i++) {
-            const double newh = (prev + hh[i] + hh[i + 1]) / 3.0;
-            prev = hh[i];
-            hh[i] = newh;
+        const double a0 = hist[(lane + nbins - 1) % nbins], b0v = hist[lane + 1];   // lane + 1 <= 32 < nbins
+        const double n0 = ((a0 + c0) + b0v) / 3.0;
+        double n1 = 0.0;
+        if (two) {
+            const double a1 = hist[lane + 31], b1 = hist[(lane + 33) % nbins];
+            n1 = ((a1 + c1) + b1) / 3.0;
         }
-        hh[nbins - 1] = (prev + hh[nbins - 1] + first) / 3.0;
+        __syncwarp();
+        hist[lane] = c0 = n0;
+        if (two) hist[lane + 32] = c1 = n1;
+        __syncwarp();
     }
-    double maxh = 0;
+    double maxh = (c0 > 0.0) ? c0 : 0.0;                        // running maximum from 0 (vl/sift.c:1010-1012); max is order-free
+    if (two) maxh = (maxh > c1) ? maxh : c1;
 #pragma unroll
-    for (int i = 0; i < nbins; ++i) maxh = (maxh > hh[i]) ? maxh : hh[i];
-    int na = 0;
-    double out[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < nbins; ++i) {
-        const double c0 = hh[i], hm = hh[(i - 1 + nbins) % nbins], hp = hh[(i + 1) % nbins];
-        if (na < 4 && c0 > 0.8 * maxh && c0 > hm && c0 > hp) {
-            const double di = -0.5 * (hp - hm) / (hp + hm - 2 * c0);
-            out[na++] = 2 * kPi * (i + di + 0.5) / nbins;
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double m = __shfl_xor_sync(0xffffffffu, maxh, o);
+        maxh = (maxh > m) ? maxh : m;
     }
-    if (lane == 0) {
-        nangles[ki] = na;
-        for (int j = 0; j < 4; ++j) angles[ki * 4 + j] = out[j];
+    // peaks in bin order, at most 4 (vl/sift.c:1015-1036)
+    bool pk0, pk1 = false;
+    double ang0, ang1 = 0.0;
+    {
+        const double hm = hist[(lane + nbins - 1) % nbins], hp = hist[lane + 1];
+        pk0 = c0 > 0.8 * maxh && c0 > hm && c0 > hp;
+        const double di = -0.5 * (hp - hm) / (hp + hm - 2 * c0);
+        ang0 = 2 * kPi * (lane + di + 0.5) / nbins;
+    }
+    if (two) {
+        const double hm = hist[lane + 31], hp = hist[(lane + 33) % nbins];
+        pk1 = c1 > 0.8 * maxh && c1 > hm && c1 > hp;
+        const double di = -0.5 * (hp - hm) / (hp + hm - 2 * c1);
+        ang1 = 2 * kPi * ((lane + 32) + di + 0.5) / nbins;
+    }
+    const unsigned m0 = __ballot_sync(0xffffffffu, pk0), m1 = __ballot_sync(0xffffffffu, pk1);
+    const int n0 = __popc(m0), na = min(4, n0 + __popc(m1));
+    if (lane == 0) nangles[ki] = na;
+    if (lane < 4 && lane >= na) angles[ki * 4 + lane] = 0;
+    if (pk0) {
+        const int r = __popc(m0 & ((1u << lane) - 1u));
+        if (r < 4) angles[ki * 4 + r] = ang0;
+    }
+    if (pk1) {
+        const int r = n0 + __popc(m1 & ((1u << lane) - 1u));
+        if (r < 4) angles[ki * 4 + r] = ang1;
     }
 }
 void launch_orient(const OctaveSet& os, const SiftConsts& sc, const double* expn_tab, const KeyIn* keys, int nkeys,

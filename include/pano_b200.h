@@ -238,7 +238,7 @@ int pano_b200_bench_match_u8_peak(pano_b200_ctx* ctx, float* ms, int* ksteps);
 /* ---- measurement helpers --------------------------------------------------------------------------------------- */
 void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory for timed host<->device copies */
 void pano_b200_free_pinned(void* p);
-/* number of concurrent per-image lanes (stream + SIFT engine + host thread) used by the pipeline; default 4 */
+/* number of concurrent per-image lanes (stream + SIFT engine + host thread) used by the pipeline; default 8 */
 int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes);
 /* matcher of getImgPair (ImageProcess.cpp:273-351): PANO_B200_MATCH_PREFILTER (default) = rigorous uint8 SAD pre-filter
  * + exact float-L1 re-rank of the candidates, both directions of an image pair from one pass over the SAD matrix;

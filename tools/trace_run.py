@@ -15,6 +15,8 @@ def main():
     ws = (C.c_int * n)(*[i.shape[2] for i in imgs]); hs = (C.c_int * n)(*[i.shape[1] for i in imgs])
     ctx._check(L.pano_b200_stage_images(ctx.h, ptrs, ws, hs, n), "stage")
     ow, oh = C.c_int(), C.c_int()
+    if os.environ.get("LANES"):
+        L.pano_b200_set_lanes(ctx.h, int(os.environ["LANES"]))
     for r in range(4):
         L.pano_b200_flush_l2(ctx.h)
         print(f"trace === run {r} begin", file=sys.stderr, flush=True)
