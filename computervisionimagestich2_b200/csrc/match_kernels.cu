@@ -518,8 +518,9 @@ __device__ __forceinline__ int atomic_top2_key(unsigned long long* p0, unsigned 
 // Queue of the row pairs the grouped bound could not skip: entry = pair index << 52 | x << 26 | y.
 struct GroupQueue {
     unsigned long long* items;
-    int* count;          // entries appended so far (may exceed cap: the excess is dropped and the batch is redone without the grouped pass)
-    int cap;
+    unsigned long long* count;   // entries appended so far (may exceed cap: the excess is dropped and the batch is redone
+                                 // without the grouped pass); 64 bits: a 24 x 8K batch has 10^12 row pairs
+    unsigned long long cap;
 };
 constexpr int kGQLocal = 2048;   // entries a CTA collects in shared memory between flushes
 
@@ -528,7 +529,8 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
     __shared__ __align__(16) unsigned tile[2][kGRows][8];
     __shared__ __align__(16) unsigned short xw[2][kGRows], xc[2][kGRows];
     __shared__ unsigned long long qbuf[kGQLocal];
-    __shared__ int qn, qbase;
+    __shared__ int qn;
+    __shared__ unsigned long long qbase;
     const int2 fr = pairs[blockIdx.z];
     const MatchJob& F = jobs[fr.x];                // database X = F.A, queries Y = F.B
     const MatchJob& R = jobs[fr.y];                // database Y, queries X
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
     // after the first one every thread has read it, after the second one threads start appending again.
     auto flush = [&]() {
         const int n = min(qn, kGQLocal);
-        if (tid == 0) qbase = n > 0 ? atomicAdd(gq.count, n) : 0;
+        if (tid == 0) qbase = n > 0 ? atomicAdd(gq.count, (unsigned long long)n) : 0ull;
         __syncthreads();
         if (tid == 0) qn = 0;
         for (int i = tid; i < n; i += 128)
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(128) match_group_sym_kernel(const MatchJob* __
                             const int pos = atomicAdd(&qn, 1);
                             if (pos < kGQLocal) qbuf[pos] = item;
                             else {   // the local buffer is full (degenerate tables): straight to the global queue
-                                const int gp = atomicAdd(gq.count, 1);
+                                const unsigned long long gp = atomicAdd(gq.count, 1ull);
                                 if (gp < gq.cap) gq.items[gp] = item;
                             }
                         }
@@ -662,10 +664,10 @@ __device__ __forceinline__ void group_stat_push(int* s6, int sad, int e, int row
 __global__ void __launch_bounds__(256) match_group_exact_kernel(const MatchJob* __restrict__ jobs, const int2* __restrict__ pairs,
                                                                GroupQueue gq) {
     const int sub = threadIdx.x & 7;
-    const int ngroups = (gridDim.x * blockDim.x) >> 3;
-    const int n = min(*gq.count, gq.cap);
-    const int nround = (n + ngroups - 1) / ngroups * ngroups;   // whole warps stay in the loop: the shuffles need all lanes
-    for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; it < nround; it += ngroups) {
+    const unsigned long long ngroups = (gridDim.x * blockDim.x) >> 3;
+    const unsigned long long n = min(*gq.count, gq.cap);
+    const unsigned long long nround = (n + ngroups - 1) / ngroups * ngroups;   // whole warps stay in the loop: the shuffles need all lanes
+    for (unsigned long long it = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; it < nround; it += ngroups) {
         const bool ok = it < n;
         const unsigned long long item = gq.items[ok ? it : 0];
         const int2 fr = pairs[(int)(item >> 52)];
@@ -684,8 +686,8 @@ __global__ void __launch_bounds__(256) match_group_exact_kernel(const MatchJob* 
         else if (sub == 1) group_stat_push(R.stat6 + 6 * (size_t)x, (int)d, F.Be[y], y);   // reverse: database row y, query x
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const int total = *gq.count;
-        atomicAdd(&jobs[pairs[0].x].counters[2], min(total, gq.cap));      // bookkeeping: exact SADs of the batch ...
+        const unsigned long long total = *gq.count;
+        atomicAdd(&jobs[pairs[0].x].counters[2], (int)min(min(total, gq.cap), 0x7fffffffull));   // bookkeeping: exact SADs of the batch ...
         if (total > gq.cap) atomicAdd(&jobs[pairs[0].x].counters[3], 1 << 30);   // ... and the overflow flag (host redoes the batch)
     }
 }
@@ -865,7 +867,8 @@ int match_group_err_cap() { return kGrpErrCap; }
 
 void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, const int2* d_pairs,
                                   const int2* h_pairs, int npairs, const int* d_singles, const int* h_singles, int nsingles,
-                                  cudaStream_t st, bool grouped, unsigned long long* gq_items, int* gq_count, int gq_cap) {
+                                  cudaStream_t st, bool grouped, unsigned long long* gq_items, unsigned long long* gq_count,
+                                  size_t gq_cap) {
     if (njobs <= 0) return;
     int nbmax = 1, fy = 1, cy = 1;
     for (int i = 0; i < njobs; ++i) {
@@ -893,12 +896,12 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
         }
         {
             KScope ks("match.group_sym", st, 8.0 * pairs);   // VABSDIFF4 thread-instructions of the grouped bound
-            match_group_sym_kernel<<<dim3(px, py, npairs), 128, 0, st>>>(d_jobs, d_pairs, GroupQueue{gq_items, gq_count, gq_cap});
+            match_group_sym_kernel<<<dim3(px, py, npairs), 128, 0, st>>>(d_jobs, d_pairs, GroupQueue{gq_items, gq_count, (unsigned long long)gq_cap});
             PB_KERNEL_CHECK();
         }
         {
             KScope ks("match.group_exact", st, 0);
-            match_group_exact_kernel<<<148 * 8, 256, 0, st>>>(d_jobs, d_pairs, GroupQueue{gq_items, gq_count, gq_cap});
+            match_group_exact_kernel<<<148 * 8, 256, 0, st>>>(d_jobs, d_pairs, GroupQueue{gq_items, gq_count, (unsigned long long)gq_cap});
             PB_KERNEL_CHECK();
         }
         KScope ks("match.decide", st, 0);

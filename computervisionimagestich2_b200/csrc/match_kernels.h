@@ -60,7 +60,7 @@ void launch_match_batch(const MatchJob* d_jobs, const MatchJob* h_jobs, int njob
 void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs, int njobs, const int2* d_pairs,
                                   const int2* h_pairs, int npairs, const int* d_singles, const int* h_singles, int nsingles,
                                   cudaStream_t st, bool grouped = false, unsigned long long* gq_items = nullptr,
-                                  int* gq_count = nullptr /* zeroed */, int gq_cap = 0);
+                                  unsigned long long* gq_count = nullptr /* zeroed */, size_t gq_cap = 0);
 // grouped pass: ints of scratch one job needs, the attachment of that scratch (which the caller fills with 0x7f bytes
 // before the launch), the number of database splits for a batch with `yblocks_total` blocks of held rows
 size_t match_group_ints(int NB);

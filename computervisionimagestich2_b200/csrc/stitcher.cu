@@ -304,7 +304,7 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
             // queue of the row pairs the grouped bound cannot skip: ~0.07 % of the pairs on SIFT tables; room for 0.25 %
             double rowpairs = 0;
             for (auto& pr : pairs) rowpairs += (double)probs[prob_of[pr.x]].first->n * probs[prob_of[pr.x]].second->n;
-            gq_cap = (size_t)std::min(std::max(rowpairs * 0.0025, 262144.0), 512.0 * 1024 * 1024);
+            gq_cap = (size_t)std::min(std::max(rowpairs * 0.0025, 262144.0), 1024.0 * 1024 * 1024);   // at most 8 GB
             gqueue_.ensure(gq_cap);
         }
         mcount_.ensure((size_t)4 * nj + 4);           // [4 * nj]: entries in the grouped pass's queue
@@ -339,7 +339,8 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         launch_match_batch_prefilter(dj, reinterpret_cast<const MatchJob*>(hj), nj, reinterpret_cast<const int2*>(mjobs_.p + jb),
                                      reinterpret_cast<const int2*>(hj + jb), (int)pairs.size(),
                                      reinterpret_cast<const int*>(mjobs_.p + jb + pb), reinterpret_cast<const int*>(hj + jb + pb),
-                                     (int)singles.size(), st_, grouped, gqueue_.p, mcount_.p + 4 * (size_t)nj, (int)gq_cap);
+                                     (int)singles.size(), st_, grouped, gqueue_.p,
+                                     reinterpret_cast<unsigned long long*>(mcount_.p + 4 * (size_t)nj), gq_cap);
     else launch_match_batch(dj, reinterpret_cast<const MatchJob*>(hj), nj, st_);
     PB_CUDA(cudaMemcpyAsync(h, midx_.p, sizeof(int) * nidx, cudaMemcpyDeviceToHost, st_));
     if (d_out) {
