@@ -451,7 +451,10 @@ __global__ void __launch_bounds__(kST) match_sad_sym_kernel(const MatchJob* __re
 //                           forward in the holder's registers, reverse through global atomics (lb: min; u0 / u1: the
 //                           displaced-value rule keeps the two smallest of a multiset under any interleaving).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSeedRows = 512;   // sampled database rows per query
+// sampled database rows per query: NA / 48 within [512, 2048] -- the second-smallest of n samples sits at the 2 / n quantile,
+// so a larger table needs a larger sample for the same tightness of the seed (72 k rows at 512 samples: 0.19 % of the pairs
+// fail the grouped bound against 0.08 % for 25 k rows)
+__host__ __device__ inline int seed_rows(int NA) { const int k = NA / 48; return k < 512 ? 512 : (k > 2048 ? 2048 : k); }
 constexpr int kGY = 4;           // held rows of Y per thread
 constexpr int kGRows = 128;      // streamed rows of X per tile (a barrier per tile: 64-row tiles spent 11 % of the samples at it)
 
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(128) match_seed_kernel(const MatchJob* __restr
             q[4 * k] = t.x; q[4 * k + 1] = t.y; q[4 * k + 2] = t.z; q[4 * k + 3] = t.w;
         }
     }
-    const int stride = max(1, NA / kSeedRows);
+    const int stride = max(1, NA / seed_rows(NA));
     const int nrows = (NA + stride - 1) / stride;
     SadStat st = sadstat_init();
     for (int r0 = 0; r0 < nrows; r0 += 32) {
@@ -887,7 +890,7 @@ void launch_match_batch_prefilter(const MatchJob* d_jobs, const MatchJob* h_jobs
             py = std::max(py, F.grp_nsplit);
             nb = std::max(nb, std::max(F.NA, F.NB));
             pairs += (double)F.NA * F.NB;
-            seed += 32.0 * std::min(F.NA, 2 * kSeedRows) * F.NB + 32.0 * std::min(F.NB, 2 * kSeedRows) * F.NA;
+            seed += 32.0 * std::min(F.NA, 2 * seed_rows(F.NA)) * F.NB + 32.0 * std::min(F.NB, 2 * seed_rows(F.NB)) * F.NA;
         }
         {
             KScope ks("match.seed", st, seed);

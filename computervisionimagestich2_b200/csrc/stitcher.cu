@@ -301,10 +301,10 @@ void Stitcher::match_batch(const std::vector<std::pair<FeatureTable*, FeatureTab
         if (ngroup) {
             gscratch_.ensure(ngroup);
             PB_CUDA(cudaMemsetAsync(gscratch_.p, 0x7f, ngroup * sizeof(int), st_));
-            // queue of the row pairs the grouped bound cannot skip: ~0.07 % of the pairs on SIFT tables; room for 0.25 %
+            // queue of the row pairs the grouped bound cannot skip: 0.07 - 0.2 % of the pairs on SIFT tables; room for 0.5 %
             double rowpairs = 0;
             for (auto& pr : pairs) rowpairs += (double)probs[prob_of[pr.x]].first->n * probs[prob_of[pr.x]].second->n;
-            gq_cap = (size_t)std::min(std::max(rowpairs * 0.0025, 262144.0), 1024.0 * 1024 * 1024);   // at most 8 GB
+            gq_cap = (size_t)std::min(std::max(rowpairs * 0.005, 262144.0), 1024.0 * 1024 * 1024);   // at most 8 GB
             gqueue_.ensure(gq_cap);
         }
         mcount_.ensure((size_t)4 * nj + 4);           // [4 * nj]: entries in the grouped pass's queue

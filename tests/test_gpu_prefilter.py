@@ -105,7 +105,7 @@ def test_symmetric_pass_equals_full_scan(ctx):
     assert (ab >= 0).sum() > 1000 and (ba >= 0).sum() > 1000
     assert st["queries"] == len(A) + len(B) and st["overflow"] <= 0.01 * st["queries"]
     # unstructured random tables: the grouped bound skips far fewer pairs than on SIFT tables, so the pair queue (sized for
-    # 0.25 % of the pairs) overflows and the batch is redone with the full SAD pass -- the fallback is part of the contract
+    # 0.5 % of the pairs) overflows and the batch is redone with the full SAD pass -- the fallback is part of the contract
     assert st["group_pairs"] + st["group_overflow"] == 1, st
     both_pair(ctx, A, sift_like(rng, 3001))            # unrelated tables: nothing to match in either direction
 
