@@ -274,8 +274,58 @@ constexpr int kIirPitch = 33;      // floats between consecutive elements of a t
 // (Conversions on the integer pipe -- tools/ubench/cvt_exact.cuh, bit-identical to F2F -- were measured inside this kernel in
 // round 2: x pass 2.60 -> 3.20 (widening only) -> 4.12 ms (both), y pass 1.83 -> 1.99 -> 2.43 ms on a 17997 x 2268 blend.
 // ncu: the XU pipe is at 19 % in both passes; the conversions are not the limiter.)
-template <bool FWD>
-__device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, double& v3, const IirCoef& c) {
+// PHASED (y pass): three phases over the 32 samples of the tile, all in registers -- widen (independent conversions,
+// pipelined), the recurrence alone (DMUL + 3 DADD per sample, nothing else on the chain), narrow + store.  In the one-loop
+// form ptxas places the F2F.F64.F32 of a sample (~19 cycles) right before the DADD that needs it, between two links of the
+// chain; it also re-merges the phases when they are only written as separate loops, so the chain is made to DEPEND on all
+// the conversions: `zero` is a kernel argument that is 0 at run time, OR-ed (masked) into the state before the first link.
+template <bool FWD, bool PHASED, bool ROWMAJOR>
+__device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, double& v3, const IirCoef& c, int zero) {
+    if (ROWMAJOR) {
+        // x pass: the lane's 32 samples are contiguous in shared memory (line pitch 36 floats: 16-byte aligned, and the
+        // eight lanes of a 128-bit wavefront cover all 32 banks): 8 LDS.128 + 8 STS.128 per tile instead of 32 + 32.  ncu
+        // of the [element][line] form: the consumer spends ~40 % of its samples waiting to issue its LDS / STS behind the
+        // loader's and the storer's traffic on the same MIO queue.
+        float4* t4 = reinterpret_cast<float4*>(t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int kk = FWD ? k : 7 - k;
+            const float4 in = t4[kk];
+            const float f[4] = {FWD ? in.x : in.w, FWD ? in.y : in.z, FWD ? in.z : in.y, FWD ? in.w : in.x};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double v0 = (double)f[i];
+                if (!FWD) v0 *= c.sum;
+                v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+                o[i] = (float)v0;
+                v3 = v2; v2 = v1; v1 = v0;
+            }
+            t4[kk] = FWD ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[3], o[2], o[1], o[0]);
+        }
+        return;
+    }
+    if (PHASED) {
+        double d[32];
+        unsigned seen = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            d[e] = (double)t[(FWD ? e : 31 - e) * kIirPitch];
+            if (!FWD) d[e] *= c.sum;
+            seen |= (unsigned)__double2loint(d[e]);
+        }
+        v1 = __hiloint2double(__double2hiint(v1), __double2loint(v1) | (int)(seen & (unsigned)zero));
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            double v0 = d[e];
+            v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
+            d[e] = v0;
+            v3 = v2; v2 = v1; v1 = v0;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) t[(FWD ? e : 31 - e) * kIirPitch] = (float)d[e];
+        return;
+    }
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
         float* p = t + (FWD ? e : 31 - e) * kIirPitch;
@@ -301,13 +351,18 @@ __device__ __forceinline__ void iir_tile32(float* t, double& v1, double& v2, dou
 // so pass 1 streams `dst` back in); DericheCoef = Deriche (fp32 state; causal and anticausal runs both filter the
 // INPUT, so pass 1 streams `src` again TOGETHER with the causal output Y already in `dst`, and the consumer stores
 // out = Y + yc, CImg.h:34797 -- src and dst must be distinct buffers).
-template <bool kElemContig, class Coef, int NS>
+template <bool kElemContig, class Coef, int NS, bool PHASE = false, bool ROWM = false>
 __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* dst, int N,   // src == dst is allowed (in-place y pass): no __restrict__
                                                       long nlines, int lines_per_plane, long plane_stride,
-                                                      long elem_stride, Coef c) {
+                                                      long elem_stride, Coef c, int zero) {
     constexpr bool kDeriche = std::is_same<Coef, DericheCoef>::value;
     constexpr int kIirNS = NS;
-    __shared__ float tiles[kIirNS][32 * kIirPitch];
+    constexpr bool kPhased = PHASE && !kDeriche;
+    // Van Vliet x pass: tiles are [line][element] with a line pitch of 36 floats (see iir_tile32); every other form keeps
+    // [element][line] with pitch 33.  kLS / kES: floats between consecutive lines / elements of a tile.
+    constexpr bool kRowMajor = kElemContig && !kDeriche && ROWM;
+    constexpr int kLS = kRowMajor ? 36 : 1, kES = kRowMajor ? 1 : kIirPitch;
+    __shared__ __align__(16) float tiles[kIirNS][kRowMajor ? 32 * 36 : 32 * kIirPitch];
     // Deriche, pass 1: the causal output Y of the same tile, streamed back beside the input so that the consumer forms
     // out = Y + yc itself (a read-modify-write in the storer exposes one HBM latency per tile)
     __shared__ float ytiles[kDeriche ? kIirNS : 1][kDeriche ? 32 * kIirPitch : 1];
@@ -362,20 +417,20 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* 
         for (int q = 0; q < 2 * T; ++q) {
             const int s = q % kIirNS;
             mbar_wait(&full[s], (unsigned)((q / kIirNS) & 1));
-            float* t = &tiles[s][lane];
+            float* t = &tiles[s][lane * kLS];
             const bool fwd = q < T;
             const int tile = fwd ? q : 2 * T - 1 - q;
             const int ne = (N - tile * 32) < 32 ? (N - tile * 32) : 32;
             if (fwd) {
                 if (q == 0) v1 = v2 = v3 = (double)t[0] / c.sumsq;
-                if (tile == T - 1) iplus = (double)t[(ne - 1) * kIirPitch];
+                if (tile == T - 1) iplus = (double)t[(ne - 1) * kES];
                 if (ne == 32) {
-                    iir_tile32<true>(t, v1, v2, v3, c);
+                    iir_tile32<true, kPhased, kRowMajor>(t, v1, v2, v3, c, zero);
                 } else {
                     for (int e = 0; e < ne; ++e) {
-                        double v0 = (double)t[e * kIirPitch];
+                        double v0 = (double)t[e * kES];
                         v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
-                        t[e * kIirPitch] = (float)v0;
+                        t[e * kES] = (float)v0;
                         v3 = v2; v2 = v1; v1 = v0;
                     }
                 }
@@ -387,18 +442,18 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* 
                     const double v0 = (c.M[0] * unp + c.M[1] * unp1 + c.M[2] * unp2 + vplus) * c.sum;
                     const double n1 = (c.M[3] * unp + c.M[4] * unp1 + c.M[5] * unp2 + vplus) * c.sum;
                     const double n2 = (c.M[6] * unp + c.M[7] * unp1 + c.M[8] * unp2 + vplus) * c.sum;
-                    t[e * kIirPitch] = (float)v0;
+                    t[e * kES] = (float)v0;
                     v3 = n2; v2 = n1; v1 = v0;
                     --e;
                 }
                 if (e == 31) {
-                    iir_tile32<false>(t, v1, v2, v3, c);
+                    iir_tile32<false, kPhased, kRowMajor>(t, v1, v2, v3, c, zero);
                 } else {
                     for (; e >= 0; --e) {
-                        double v0 = (double)t[e * kIirPitch];
+                        double v0 = (double)t[e * kES];
                         v0 *= c.sum;
                         v0 += v1 * c.f1; v0 += v2 * c.f2; v0 += v3 * c.f3;
-                        t[e * kIirPitch] = (float)v0;
+                        t[e * kES] = (float)v0;
                         v3 = v2; v2 = v1; v1 = v0;
                     }
                 }
@@ -423,8 +478,9 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* 
         mybase = p * plane_stride + ((line_ok ? l : 0) - p * lines_per_plane);
     }
     // smem offset (floats) of this lane's first tile element and the stride between the elements it touches
-    const int s_off = kElemContig ? lane * kIirPitch : lane;
-    const int s_step = kElemContig ? 1 : kIirPitch;
+    // x pass: lane = element, the loop runs over the lines; y pass: lane = line, the loop runs over the elements
+    const int s_off = kElemContig ? lane * kES : lane * kLS;
+    const int s_step = kElemContig ? kLS : kES;
     const long g_step = kElemContig ? (long)N : elem_stride;   // HBM stride between those elements
     if (warp == 1) {
         for (int pass = 0; pass < 2; ++pass) {
@@ -495,30 +551,28 @@ __global__ void __launch_bounds__(128) iir_pipe_kernel(const float* src, float* 
     }
 }
 
+// x pass: row-major tiles, 128-bit shared accesses in the consumer; y pass: conversions ahead of the chain (iir_tile32).
+// Measured on a 17997 x 2268 blend (11 levels): x 2.58 -> 2.38 ms, y 1.83 -> 1.71 ms; the other way round (phased x,
+// either layout) is slower: 2.70 / 2.57 ms.
 template <bool X>
-static void launch_iir_pass(int ns, int grid, cudaStream_t st, const float* src, float* dst, int N, long nlines, int lpp,
-                            long plane, long estride, const IirCoef& coef) {
-    if (ns >= 10) iir_pipe_kernel<X, IirCoef, 10><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
-    else if (ns >= 8) iir_pipe_kernel<X, IirCoef, 8><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
-    else if (ns >= 6) iir_pipe_kernel<X, IirCoef, 6><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
-    else iir_pipe_kernel<X, IirCoef, 4><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef);
+static void launch_iir_pass(int grid, cudaStream_t st, const float* src, float* dst, int N, long nlines, int lpp, long plane,
+                            long estride, const IirCoef& coef) {
+    iir_pipe_kernel<X, IirCoef, 4, !X, X><<<grid, 128, 0, st>>>(src, dst, N, nlines, lpp, plane, estride, coef, 0);
 }
 void launch_iir_blur(const float* src, float* dst, int w, int h, int nplanes, const IirCoef& coef, cudaStream_t st) {
-    static const int ns_x = [] { const char* e = getenv("PANO_B200_IIR_NS_X"); return e ? atoi(e) : 4; }();
-    static const int ns_y = [] { const char* e = getenv("PANO_B200_IIR_NS_Y"); return e ? atoi(e) : 4; }();
     const float* ysrc = src;
     const long plane = (long)w * h;
     if (w > 1) {
         const long nlines = (long)nplanes * h;
         KScope ks("blend.iir_x", st, 8.0 * nplanes * w * h);
-        launch_iir_pass<true>(ns_x, div_up(nlines, 32), st, src, dst, w, nlines, h, plane, 1L, coef);
+        launch_iir_pass<true>(div_up(nlines, 32), st, src, dst, w, nlines, h, plane, 1L, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
     if (h > 1) {
         const long nlines = (long)nplanes * w;
         KScope ks("blend.iir_y", st, 8.0 * nplanes * w * h);
-        launch_iir_pass<false>(ns_y, div_up(nlines, 32), st, ysrc, dst, h, nlines, w, plane, (long)w, coef);
+        launch_iir_pass<false>(div_up(nlines, 32), st, ysrc, dst, h, nlines, w, plane, (long)w, coef);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
@@ -534,14 +588,14 @@ void launch_deriche_blur(const float* src, float* tmp, float* dst, int w, int h,
         const long nlines = (long)nplanes * h;
         float* xdst = h > 1 ? tmp : dst;
         KScope ks("blend.deriche", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<true, DericheCoef, kIirNSDeriche><<<div_up(nlines, 32), 128, 0, st>>>(src, xdst, w, nlines, h, plane, 1L, coef);
+        iir_pipe_kernel<true, DericheCoef, kIirNSDeriche><<<div_up(nlines, 32), 128, 0, st>>>(src, xdst, w, nlines, h, plane, 1L, coef, 0);
         PB_KERNEL_CHECK();
         ysrc = xdst;
     }
     if (h > 1) {
         const long nlines = (long)nplanes * w;
         KScope ks("blend.deriche", st, 16.0 * nplanes * w * h);
-        iir_pipe_kernel<false, DericheCoef, kIirNSDeriche><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef);
+        iir_pipe_kernel<false, DericheCoef, kIirNSDeriche><<<div_up(nlines, 32), 128, 0, st>>>(ysrc, dst, h, nlines, w, plane, (long)w, coef, 0);
         PB_KERNEL_CHECK();
         ysrc = dst;
     }
