@@ -1262,12 +1262,15 @@ int Stitcher::stitch_bmp(const u8* const* files, const size_t* sizes, int n, u8*
         std::unique_ptr<Staged> s(new Staged());
         s->w = w; s->h = h;
         s->rgb.ensure((size_t)3 * w * h);
-        bmp_raw_.ensure(stride * h);
-        PB_CUDA(cudaMemcpyAsync(bmp_raw_.p, f + off, stride * h, cudaMemcpyHostToDevice, st_));
-        launch_bmp_to_planar(bmp_raw_.p, (int)stride, w, h, bottom_up, s->rgb.p, st_);
-        PB_CUDA(cudaStreamSynchronize(st_));   // bmp_raw_ is reused by the next file
+        // every file has its own raw buffer: the upload of file i + 1 (a blocking copy out of pageable memory) runs while
+        // the decode kernel of file i executes, and nothing waits per file
+        s->raw.ensure(stride * h);
+        PB_CUDA(cudaMemcpyAsync(s->raw.p, f + off, stride * h, cudaMemcpyHostToDevice, st_));
+        launch_bmp_to_planar(s->raw.p, (int)stride, w, h, bottom_up, s->rgb.p, st_);
         staged_.push_back(std::move(s));
     }
+    PB_CUDA(cudaStreamSynchronize(st_));   // the lanes read the decoded images on their own streams
+    for (auto& s : staged_) s->raw.release();
     const int rc = run_staged();
     if (rc) return rc;
     const int w = rw_, h = rh_;

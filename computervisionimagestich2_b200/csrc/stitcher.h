@@ -247,9 +247,9 @@ class Stitcher {
     std::vector<PresetMatch> preset_;
     std::vector<std::unique_ptr<Lane>> lanes_;
     int want_lanes_ = 8;   // 8 x 4K job: 97.5 / 93.1 / 88.9 / 86.6 / 84.3 ms with 2 / 3 / 4 / 6 / 8 lanes (the host phases of one image overlap the kernels of the others)
-    struct Staged { int w, h; DevBuf<u8> rgb; };
+    struct Staged { int w, h; DevBuf<u8> rgb, raw; };   // raw: the BMP pixel area as uploaded (stitch_bmp), freed after decoding
     std::vector<std::unique_ptr<Staged>> staged_;
-    DevBuf<u8> bmp_raw_, bmp_out_;
+    DevBuf<u8> bmp_out_;
     DevBuf<char> flush_;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     std::string log_, err_;
