@@ -611,7 +611,7 @@ void launch_deriche_blur(const float* src, float* tmp, float* dst, int w, int h,
 // (A form with the plane count at compile time and all 9 x 7 tap loads of a thread issued before the first use was measured
 // on a 17997 x 2268 blend: 1.24 ms against 0.99 ms for this loop over 11 launches -- its 109 registers halve the resident
 // threads.)
-__global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ src, int w, int h, int nplanes,
+__global__ void __launch_bounds__(256, 8) reduce_kernel(const float* __restrict__ src, int w, int h, int nplanes,
                                                     float* __restrict__ dst, int nw, int nh, DevMovAvg tx, DevMovAvg ty) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -745,9 +745,12 @@ __global__ void collapse_kernel(const float* __restrict__ G, int w, int h, const
 // (64 x 16 output pixels) first fills shared memory with the x-interpolated source rows it needs (nine planes, at most
 // kCollapseSrcRows rows), then every pixel only does the y-interpolation and the blend.  Same operations on the same
 // operands; ~15 instead of 27 double-precision interpolations per pixel.
+// Occupancy: both this kernel and the reduce wait on loads (ncu: long_scoreboard 7.7 / 10.8 per issue, DRAM at 22-25 %), so
+// they are capped at 48 / 32 registers (5 / 8 CTAs of 256 threads per SM, a few spilled words): collapse 1.31 -> 1.00 ms,
+// reduce 0.99 -> 0.84 ms over the levels of a 17997 x 2268 blend (6 CTAs for the collapse: 1.10 ms).
 constexpr int kCollapseTileH = 16, kCollapseSrcRows = 12;
 template <int NCH>
-__global__ void __launch_bounds__(256) collapse_tiled_kernel(const float* __restrict__ G, int w, int h,
+__global__ void __launch_bounds__(256, 5) collapse_tiled_kernel(const float* __restrict__ G, int w, int h,
                                                              const float* __restrict__ Gup, const float* __restrict__ Eup,
                                                              int uw, int uh, DevLinear tx, DevLinear ty,
                                                              float* __restrict__ E, u8* __restrict__ out8) {
