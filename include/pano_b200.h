@@ -240,11 +240,13 @@ void* pano_b200_alloc_pinned(size_t bytes);           /* page-locked host memory
 void pano_b200_free_pinned(void* p);
 /* number of concurrent per-image lanes (stream + SIFT engine + host thread) used by the pipeline; default 8 */
 int pano_b200_set_lanes(pano_b200_ctx* ctx, int nlanes);
-/* matcher of getImgPair (ImageProcess.cpp:273-351): PANO_B200_MATCH_PREFILTER (default) = rigorous uint8 SAD pre-filter
- * + exact float-L1 re-rank of the candidates, both directions of an image pair from one pass over the SAD matrix;
- * PANO_B200_MATCH_FULL = exact float-L1 scan of every (query, row) pair; PANO_B200_MATCH_PREFILTER_ONEDIR = the
- * pre-filter with one SAD pass per directed problem.  All return the reference's match lists bit for bit (the
- * pre-filter never drops a row the exact rule needs). */
+/* matcher of getImgPair (ImageProcess.cpp:273-351): PANO_B200_MATCH_PREFILTER (default) = rigorous two-level uint8
+ * pre-filter (grouped lower bound on 32 group bytes per row, exact 128-byte SAD of the row pairs it cannot skip, certain
+ * reject / certain accept) + exact float-L1 re-rank of the undecided queries, both directions of an image pair from one
+ * pass; PANO_B200_MATCH_PREFILTER_FULLSAD = the same with the full SAD of every row pair; PANO_B200_MATCH_PREFILTER_ONEDIR
+ * = one full-SAD pass per directed problem; PANO_B200_MATCH_FULL = exact float-L1 scan of every (query, row) pair.  All
+ * return the reference's match lists bit for bit (the pre-filter never drops a row the exact rule needs and decides a
+ * query without float arithmetic only where the reference's decision is certain). */
 #define PANO_B200_MATCH_PREFILTER 0
 #define PANO_B200_MATCH_FULL 1
 #define PANO_B200_MATCH_PREFILTER_ONEDIR 2
